@@ -1,0 +1,714 @@
+// ResNet encoder for sm_100a: BatchNorm-folded conv (+bias, +residual, +ReLU) as an implicit GEMM on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA.
+//
+// Replaces models/resnet.py:202-217.  Activations are bf16 NHWC, weights bf16
+// (Cout, kh, kw, Cin) with the eval-mode BatchNorm scale folded in, accumulation fp32.
+//
+// im2col is never materialised: the A tile of one k-block is ONE 4-D TMA box {64 channels, TW, TH, TB}
+// of the NHWC activation tensor, shifted by the filter tap; out-of-bounds box elements are zero-filled by
+// the TMA unit, which is exactly the convolution's zero padding.  Stride-2 convolutions use one tensor
+// map per input parity (pixel stride 2 in the map), so every load stays a plain tiled box.  The 7x7/2 stem
+// (Cin = 18 -> 32) reads a physically padded input as "pixel pairs" (2 taps x 32 ch = one 128-byte row).
+//
+// Kernel = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (one elected thread) + TMEM owner, warps 2-5
+// epilogue (TMEM -> registers -> bias/residual/ReLU -> bf16 NHWC).  smem ring of STAGES x (A 16 KB + B BN*128 B),
+// 128-byte swizzle on both the TMA and the UMMA descriptor side.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <vector>
+#include <map>
+#include <cstring>
+
+namespace {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (int it = 0; it < 4096; ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        if (mbar_try_wait(bar, parity)) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) __trap();     // 2 s
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major operand tile, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address  [0,14)
+    d |= (uint64_t)0 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+// ------------------------------------------------------------------ tcgen05 implicit-GEMM conv
+struct ConvGeom {
+    int kind;        // 0 = generic (Cin % 64 == 0), 1 = stem pixel-pair layout
+    int ksize, stride, pad;
+    int cin;         // channels per pixel in the A tensor
+    int Ho, Wo, B, cout;
+    int TW, TH, TB;  // output tile (TW*TH*TB == 128)
+    int tiles_w, tiles_h, tiles_b;
+    int nkb;         // number of 64-wide k-blocks
+    int relu;
+};
+
+struct ConvMaps {
+    CUtensorMap a[4];   // activation maps (stride 1: [0]; stride 2: [ph*2+pw]; stem: [ph])
+    CUtensorMap b;      // weights [Cout][K]
+};
+
+constexpr int CONV_THREADS = 192;
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, const float* __restrict__ bias,
+                    const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out) {
+    constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[BN];
+    const uint32_t tiles = smem_u32(smem_raw);
+    const uint32_t tile_base = (tiles + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % g.tiles_w; t /= g.tiles_w;
+    const int th = t % g.tiles_h; t /= g.tiles_h;
+    const int tb = t;
+    const int wo0 = tw * g.TW, ho0 = th * g.TH, b0 = tb * g.TB;
+    const int n0 = blockIdx.y * BN;
+
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x >= 64) {
+        for (int i = threadIdx.x - 64; i < BN; i += CONV_THREADS - 64) bias_s[i] = (n0 + i < g.cout) ? bias[n0 + i] : 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int cpb = g.cin >> 6;   // 64-channel blocks per tap (generic)
+            for (int kb = 0; kb < g.nkb; ++kb) {
+                const int st = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
+                const uint32_t fb = full0 + 8 * st;
+                mbar_expect_tx(fb, STAGE_BYTES);
+                int mi, c0, c1, c2;
+                if (g.kind == 0) {
+                    const int tap = kb / cpb, cb = kb - tap * cpb;
+                    const int kh = tap / g.ksize, kw = tap - kh * g.ksize;
+                    const int dw = kw - g.pad, dh = kh - g.pad;
+                    c0 = cb * 64;
+                    if (g.stride == 1) { mi = 0; c1 = wo0 + dw; c2 = ho0 + dh; }
+                    else {
+                        const int pw = dw & 1, phh = dh & 1;
+                        mi = phh * 2 + pw;
+                        c1 = wo0 + ((dw - pw) >> 1);
+                        c2 = ho0 + ((dh - phh) >> 1);
+                    }
+                } else {
+                    const int kh = kb >> 2, q = kb & 3;
+                    mi = kh & 1; c0 = 0; c1 = wo0 + q; c2 = ho0 + (kh >> 1);
+                }
+                tma_load_4d(sa, &maps.a[mi], fb, c0, c1, c2, b0);
+                tma_load_2d(sb, &maps.b, fb, kb * 64, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int kb = 0; kb < g.nkb; ++kb) {
+                const int st = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(full0 + 8 * st, ph);
+                tcgen05_fence_after();
+                const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
+                const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                umma_commit(empty0 + 8 * st);
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                   // tile row = output pixel
+        const int ltw = row % g.TW, lth = (row / g.TW) % g.TH, ltb = row / (g.TW * g.TH);
+        const int wo = wo0 + ltw, ho = ho0 + lth, b = b0 + ltb;
+        const bool valid = (wo < g.Wo) && (ho < g.Ho) && (b < g.B);
+        const size_t pix = ((size_t)b * g.Ho + ho) * g.Wo + wo;
+        mbar_wait(tfull, 0);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (valid && n0 + c0 < g.cout) {
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_s[c0 + i];
+                if (res) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res + pix * g.cout + n0 + c0);
+                    uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+                        f[2 * i] += __bfloat162float(h.x);
+                        f[2 * i + 1] += __bfloat162float(h.y);
+                    }
+                }
+                if (g.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                    o[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* op = reinterpret_cast<uint4*>(out + pix * g.cout + n0 + c0);
+                op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ SIMT direct convolution (debug cross-check)
+__global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                 const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res,
+                                 __nv_bfloat16* __restrict__ y, int B, int H, int W, int cin, int cout, int ks,
+                                 int stride, int pad, int Ho, int Wo, int relu) {
+    const size_t total = (size_t)B * Ho * Wo * cout;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int co = (int)(e % cout);
+        size_t p = e / cout;
+        const int wo = (int)(p % Wo); p /= Wo;
+        const int ho = (int)(p % Ho);
+        const int b = (int)(p / Ho);
+        float acc = 0.f;
+        for (int kh = 0; kh < ks; ++kh) {
+            const int ih = ho * stride + kh - pad;
+            if (ih < 0 || ih >= H) continue;
+            for (int kw = 0; kw < ks; ++kw) {
+                const int iw = wo * stride + kw - pad;
+                if (iw < 0 || iw >= W) continue;
+                const __nv_bfloat16* xp = x + (((size_t)b * H + ih) * W + iw) * cin;
+                const __nv_bfloat16* wp = w + (((size_t)co * ks + kh) * ks + kw) * cin;
+                for (int c = 0; c < cin; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
+            }
+        }
+        acc += bias[co];
+        if (res) acc += __bfloat162float(res[e]);
+        if (relu) acc = fmaxf(acc, 0.f);
+        y[e] = __float2bfloat16_rn(acc);
+    }
+}
+
+// ------------------------------------------------------------------ layout / pooling kernels
+// fp32 NCHW -> bf16 NHWC with channel padding and spatial zero border (stem input).
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
+                                        int H, int W, int Cp, int Hp, int Wp, int top, int left) {
+    // one thread per (b, h, w): reads C strided planes (coalesced over w), writes Cp contiguous bf16
+    const size_t total = (size_t)B * H * W;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(e % W);
+        size_t p = e / W;
+        const int h = (int)(p % H);
+        const int b = (int)(p / H);
+        __nv_bfloat16* o = y + (((size_t)b * Hp + h + top) * Wp + w + left) * Cp;
+        const float* xi = x + ((size_t)b * C * H + h) * W + w;
+        for (int c0 = 0; c0 < Cp; c0 += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ca = c0 + 2 * i, cb = ca + 1;
+                const float fa = ca < C ? __ldg(xi + (size_t)ca * H * W) : 0.f;
+                const float fb = cb < C ? __ldg(xi + (size_t)cb * H * W) : 0.f;
+                __nv_bfloat162 hh = __floats2bfloat162_rn(fa, fb);
+                pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            *reinterpret_cast<uint4*>(o + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+// 3x3 stride-2 pad-1 max pooling on bf16 NHWC, 8 channels per thread.
+__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                               int C, int Ho, int Wo) {
+    const int C8 = C / 8;
+    const size_t total = (size_t)B * Ho * Wo * C8;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(e % C8);
+        size_t p = e / C8;
+        const int wo = (int)(p % Wo); p /= Wo;
+        const int ho = (int)(p % Ho);
+        const int b = (int)(p / Ho);
+        float m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+        for (int kh = 0; kh < 3; ++kh) {
+            const int ih = ho * 2 + kh - 1;
+            if (ih < 0 || ih >= H) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iw = wo * 2 + kw - 1;
+                if (iw < 0 || iw >= W) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + c8 * 8));
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&vv[i]);
+                    m[2 * i] = fmaxf(m[2 * i], __bfloat162float(h.x));
+                    m[2 * i + 1] = fmaxf(m[2 * i + 1], __bfloat162float(h.y));
+                }
+            }
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(m[2 * i], m[2 * i + 1]);
+            o[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(y + (((size_t)b * Ho + ho) * Wo + wo) * C + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// global average pool bf16 NHWC -> fp32 (B, C)
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    const __nv_bfloat16* p = x + (size_t)b * HW * C + c;
+    for (int i = 0; i < HW; ++i) s += __bfloat162float(p[(size_t)i * C]);
+    y[(size_t)b * C + c] = s / (float)HW;
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* fn) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        HF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess) return hf::fail(HF_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        cached = (EncodeTiledFn)p;
+    }
+    *fn = cached;
+    return HF_OK;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+    EncodeTiledFn fn;
+    int rc = get_encode_fn(&fn);
+    if (rc) return rc;
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return hf::fail(HF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]",
+                        (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                        (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                        box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return HF_OK;
+}
+
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+struct ConvPlan {
+    ConvGeom g;
+    ConvMaps maps;
+    int bn;
+    dim3 grid;
+    size_t smem;
+    int stages;
+};
+
+// x: NHWC activation (generic) or the padded stem input; returns launch plan.
+// Generic: x (B,H,W,cin), cin % 64 == 0.  Stem (kind 1): x is (B,Hp,Wp,32) with 3 zero rows/cols before the
+// image, ksize 7, stride 2, pad 3; H, W are the UNPADDED sizes.
+int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H, int W, int cin, int cout, int ks,
+              int stride, int pad, int relu, int Hp, int Wp) {
+    ConvGeom& g = p->g;
+    g.kind = kind; g.ksize = ks; g.stride = stride; g.pad = pad; g.cin = cin; g.B = B; g.cout = cout; g.relu = relu;
+    g.Ho = (H + 2 * pad - ks) / stride + 1;
+    g.Wo = (W + 2 * pad - ks) / stride + 1;
+    g.TW = std::min(16, pow2_ceil(g.Wo));
+    g.TH = std::min(128 / g.TW, pow2_ceil(g.Ho));
+    g.TB = 128 / (g.TW * g.TH);
+    g.tiles_w = hf::div_up(g.Wo, g.TW); g.tiles_h = hf::div_up(g.Ho, g.TH); g.tiles_b = hf::div_up(B, g.TB);
+    if (cout % 64) return hf::fail(HF_ERR_UNSUPPORTED, "conv: cout %d is not a multiple of 64", cout);
+    const uint32_t box[4] = {64, (uint32_t)g.TW, (uint32_t)g.TH, (uint32_t)g.TB};
+    int ktot;
+    if (kind == 0) {
+        if (cin % 64) return hf::fail(HF_ERR_UNSUPPORTED, "conv: cin %d is not a multiple of 64", cin);
+        if (stride != 1 && stride != 2) return hf::fail(HF_ERR_UNSUPPORTED, "conv: stride %d", stride);
+        g.nkb = ks * ks * (cin / 64);
+        ktot = ks * ks * cin;
+        const uint64_t eb = 2;
+        if (stride == 1) {
+            const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+            const uint64_t st[3] = {cin * eb, (uint64_t)W * cin * eb, (uint64_t)H * W * cin * eb};
+            int rc = encode_map(&p->maps.a[0], x, 4, dims, st, box);
+            if (rc) return rc;
+        } else {
+            for (int ph = 0; ph < 2; ++ph)
+                for (int pw = 0; pw < 2; ++pw) {
+                    if (ph >= H || pw >= W) continue;
+                    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)((W - pw + 1) / 2), (uint64_t)((H - ph + 1) / 2), (uint64_t)B};
+                    const uint64_t st[3] = {2 * cin * eb, 2 * (uint64_t)W * cin * eb, (uint64_t)H * W * cin * eb};
+                    const uint8_t* base = (const uint8_t*)x + ((size_t)ph * W + pw) * cin * eb;
+                    int rc = encode_map(&p->maps.a[ph * 2 + pw], base, 4, dims, st, box);
+                    if (rc) return rc;
+                }
+        }
+    } else {
+        if (ks != 7 || stride != 2 || pad != 3 || cin != 32 || (Wp & 1)) return hf::fail(HF_ERR_UNSUPPORTED, "stem conv: unsupported geometry");
+        g.nkb = 7 * 4;
+        ktot = 7 * 8 * 32;
+        for (int ph = 0; ph < 2; ++ph) {
+            const uint64_t dims[4] = {64, (uint64_t)(Wp / 2), (uint64_t)((Hp - ph + 1) / 2), (uint64_t)B};
+            const uint64_t st[3] = {128, 2 * (uint64_t)Wp * 64, (uint64_t)Hp * Wp * 64};
+            const uint8_t* base = (const uint8_t*)x + (size_t)ph * Wp * 64;
+            int rc = encode_map(&p->maps.a[ph], base, 4, dims, st, box);
+            if (rc) return rc;
+        }
+    }
+    p->bn = (cout % 128 == 0) ? 128 : 64;
+    {
+        const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout};
+        const uint64_t st[1] = {(uint64_t)ktot * 2};
+        const uint32_t bx[2] = {64, (uint32_t)p->bn};
+        int rc = encode_map(&p->maps.b, w, 2, dims, st, bx);
+        if (rc) return rc;
+    }
+    p->stages = (p->bn == 128) ? 3 : 4;
+    p->smem = (size_t)p->stages * (128 * 128 + p->bn * 128) + 1024;
+    p->grid = dim3(g.tiles_w * g.tiles_h * g.tiles_b, cout / p->bn);
+    return HF_OK;
+}
+
+int launch_conv(const ConvPlan& p, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* out, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        attr = true;
+    }
+    if (p.bn == 128)
+        conv_tcgen05_kernel<128, 3><<<p.grid, CONV_THREADS, p.smem, s>>>(p.maps, p.g, bias, res, out);
+    else
+        conv_tcgen05_kernel<64, 4><<<p.grid, CONV_THREADS, p.smem, s>>>(p.maps, p.g, bias, res, out);
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
+
+int launch_simt(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, const __nv_bfloat16* res,
+                __nv_bfloat16* y, int B, int H, int W, int cin, int cout, int ks, int stride, int pad, int relu,
+                cudaStream_t s, int Ho_override = 0, int Wo_override = 0) {
+    const int Ho = Ho_override ? Ho_override : (H + 2 * pad - ks) / stride + 1;
+    const int Wo = Wo_override ? Wo_override : (W + 2 * pad - ks) / stride + 1;
+    const size_t total = (size_t)B * Ho * Wo * cout;
+    int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 64);
+    conv_simt_kernel<<<blocks, 256, 0, s>>>(x, w, bias, res, y, B, H, W, cin, cout, ks, stride, pad, Ho, Wo, relu);
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
+
+}  // namespace
+
+struct hf_encoder {
+    std::vector<hf_enc_op> ops;
+    std::vector<__nv_bfloat16*> w;        // device weights (tcgen05 packing: stem repacked to pixel pairs)
+    std::vector<__nv_bfloat16*> w_plain;  // device weights in plain (cout,k,k,cin) order for the SIMT path
+    std::vector<float*> bias;
+    std::vector<int> w_cin;               // cin of each weight as given
+    int in_channels, stem_cin, feat_dim, impl;
+    // plan cache for one (B,H,W,workspace)
+    int pB, pH, pW;
+    void* pws;
+    std::vector<ConvPlan> plans;
+};
+
+namespace {
+constexpr int STEM_CP = 32;
+
+struct BufShape { int H, W, C; };
+
+// walk the op list to derive every buffer's shape
+int infer_shapes(const hf_encoder* h, int B, int H, int W, std::map<int, BufShape>& shp, size_t* max_act) {
+    shp.clear();
+    size_t mx = 0;
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+        const hf_enc_op& op = h->ops[i];
+        BufShape in;
+        if (i == 0) in = {H, W, h->stem_cin};
+        else {
+            if (!shp.count(op.src)) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu reads unwritten buffer %d", i, op.src);
+            in = shp[op.src];
+        }
+        BufShape out = in;
+        if (op.kind == HF_OP_CONV) {
+            out.H = (in.H + 2 * op.pad - op.ksize) / op.stride + 1;
+            out.W = (in.W + 2 * op.pad - op.ksize) / op.stride + 1;
+            out.C = op.cout;
+            if (i > 0 && op.cin != in.C) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu cin %d != buffer channels %d", i, op.cin, in.C);
+        } else if (op.kind == HF_OP_MAXPOOL3x3S2) {
+            out.H = (in.H + 2 - 3) / 2 + 1; out.W = (in.W + 2 - 3) / 2 + 1;
+        } else if (op.kind == HF_OP_GLOBAL_AVGPOOL) {
+            continue;
+        }
+        shp[op.dst] = out;
+        mx = std::max(mx, (size_t)B * out.H * out.W * out.C * 2);
+    }
+    *max_act = (mx + 1023) & ~(size_t)1023;
+    return HF_OK;
+}
+
+int num_buffers(const hf_encoder* h) {
+    int n = 0;
+    for (auto& op : h->ops) { n = std::max(n, op.dst + 1); n = std::max(n, op.src + 1); n = std::max(n, op.res + 1); }
+    return n;
+}
+
+size_t stem_in_bytes(int B, int H, int W) { return (((size_t)B * (H + 6) * (W + 8) * STEM_CP * 2) + 1023) & ~(size_t)1023; }
+
+}  // namespace
+
+extern "C" int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int num_ops, const uint16_t* const* weights,
+                                 const float* const* bias, int num_weights, int in_channels, int stem_cin, int feat_dim) {
+    if (!out || !ops || num_ops < 1) return hf::fail(HF_ERR_INVALID, "hf_encoder_create: null argument");
+    if (ops[0].kind != HF_OP_CONV || ops[0].ksize != 7 || ops[0].stride != 2 || ops[0].pad != 3 || stem_cin != STEM_CP ||
+        in_channels > STEM_CP)
+        return hf::fail(HF_ERR_UNSUPPORTED, "hf_encoder_create: first op must be the 7x7/2 stem with <=32 input channels padded to 32");
+    hf_encoder* h = new hf_encoder();
+    h->ops.assign(ops, ops + num_ops);
+    h->in_channels = in_channels; h->stem_cin = stem_cin; h->feat_dim = feat_dim; h->impl = 0;
+    h->pB = h->pH = h->pW = 0; h->pws = nullptr;
+    h->w.resize(num_weights); h->w_plain.resize(num_weights); h->bias.resize(num_weights); h->w_cin.resize(num_weights);
+    for (int i = 0; i < num_ops; ++i) {
+        const hf_enc_op& op = ops[i];
+        if (op.kind != HF_OP_CONV) continue;
+        const int wi = op.weight_index;
+        if (wi < 0 || wi >= num_weights) { delete h; return hf::fail(HF_ERR_INVALID, "hf_encoder_create: weight index %d", wi); }
+        const size_t n = (size_t)op.cout * op.ksize * op.ksize * op.cin;
+        int rc;
+        if ((rc = hf::upload((uint16_t**)&h->w_plain[wi], weights[wi], n))) return rc;
+        if ((rc = hf::upload(&h->bias[wi], bias[wi], (size_t)op.cout))) return rc;
+        h->w_cin[wi] = op.cin;
+        if (i == 0) {
+            // stem: (cout,7,7,32) -> (cout,7,8,32) with a zero 8th tap so that two taps x 32 ch form one 128-byte k-block
+            std::vector<uint16_t> pk((size_t)op.cout * 7 * 8 * STEM_CP, 0);
+            for (int co = 0; co < op.cout; ++co)
+                for (int kh = 0; kh < 7; ++kh)
+                    for (int kw = 0; kw < 7; ++kw)
+                        memcpy(&pk[(((size_t)co * 7 + kh) * 8 + kw) * STEM_CP], &weights[wi][(((size_t)co * 7 + kh) * 7 + kw) * STEM_CP], STEM_CP * 2);
+            if ((rc = hf::upload((uint16_t**)&h->w[wi], pk.data(), pk.size()))) return rc;
+        } else {
+            h->w[wi] = h->w_plain[wi];
+        }
+    }
+    *out = h;
+    return HF_OK;
+}
+
+extern "C" void hf_encoder_destroy(hf_encoder_t* h) {
+    if (!h) return;
+    for (size_t i = 0; i < h->w.size(); ++i) {
+        if (h->w[i] && h->w[i] != h->w_plain[i]) cudaFree(h->w[i]);
+        if (h->w_plain[i]) cudaFree(h->w_plain[i]);
+        if (h->bias[i]) cudaFree(h->bias[i]);
+    }
+    delete h;
+}
+
+extern "C" int hf_encoder_set_impl(hf_encoder_t* h, int impl) {
+    if (!h || impl < 0 || impl > 1) return hf::fail(HF_ERR_INVALID, "hf_encoder_set_impl: bad argument");
+    h->impl = impl;
+    return HF_OK;
+}
+
+extern "C" size_t hf_encoder_workspace_bytes(const hf_encoder_t* h, int B, int H, int W) {
+    std::map<int, BufShape> shp;
+    size_t max_act = 0;
+    if (infer_shapes(h, B, H, W, shp, &max_act)) return 0;
+    return stem_in_bytes(B, H, W) + (size_t)num_buffers(h) * max_act + 1024;
+}
+
+extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, int H, int W, float* feats, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+    if (!h || !input || !feats || !workspace) return hf::fail(HF_ERR_INVALID, "hf_encoder_forward: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    std::map<int, BufShape> shp;
+    size_t max_act = 0;
+    int rc = infer_shapes(h, B, H, W, shp, &max_act);
+    if (rc) return rc;
+    const size_t need = hf_encoder_workspace_bytes(h, B, H, W);
+    if (workspace_bytes < need) return hf::fail(HF_ERR_INVALID, "hf_encoder_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
+    uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    __nv_bfloat16* stem_in = (__nv_bfloat16*)ws;
+    const size_t sib = stem_in_bytes(B, H, W);
+    auto buf = [&](int id) { return (__nv_bfloat16*)(ws + sib + (size_t)id * max_act); };
+    const int Hp = H + 6, Wp = W + 8;
+
+    // (re)build the launch plans when the geometry or workspace changes
+    if (h->pB != B || h->pH != H || h->pW != W || h->pws != workspace) {
+        h->plans.assign(h->ops.size(), ConvPlan());
+        for (size_t i = 0; i < h->ops.size(); ++i) {
+            const hf_enc_op& op = h->ops[i];
+            if (op.kind != HF_OP_CONV) continue;
+            if (i == 0) rc = plan_conv(&h->plans[i], 1, stem_in, h->w[op.weight_index], B, H, W, STEM_CP, op.cout, 7, 2, 3, op.relu, Hp, Wp);
+            else {
+                const BufShape in = shp[op.src];
+                if (op.cin % 64 != 0) return hf::fail(HF_ERR_UNSUPPORTED, "encoder: conv %zu has cin %d (must be a multiple of 64)", i, op.cin);
+                rc = plan_conv(&h->plans[i], 0, buf(op.src), h->w[op.weight_index], B, in.H, in.W, op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, 0, 0);
+            }
+            if (rc) return rc;
+        }
+        // zero the padded stem input once: borders and channel padding stay zero, the interior is rewritten per call
+        HF_CUDA(cudaMemsetAsync(stem_in, 0, sib, stream));
+        h->pB = B; h->pH = H; h->pW = W; h->pws = workspace;
+    }
+    {
+        const size_t total = (size_t)B * H * W;
+        int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+        nchw_to_nhwc_pad_kernel<<<blocks, 256, 0, stream>>>(input, stem_in, B, h->in_channels, H, W, STEM_CP, Hp, Wp, 3, 3);
+        HF_LAUNCH_CHECK();
+    }
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+        const hf_enc_op& op = h->ops[i];
+        if (op.kind == HF_OP_CONV) {
+            const __nv_bfloat16* res = op.res >= 0 ? buf(op.res) : nullptr;
+            if (h->impl == 0) {
+                rc = launch_conv(h->plans[i], h->bias[op.weight_index], res, buf(op.dst), stream);
+            } else if (i == 0) {
+                // SIMT path reads the physically padded input as a pad-0 convolution with the true output size
+                rc = launch_simt(stem_in, h->w_plain[op.weight_index], h->bias[op.weight_index], res, buf(op.dst), B, Hp, Wp,
+                                 STEM_CP, op.cout, 7, 2, 0, op.relu, stream, h->plans[i].g.Ho, h->plans[i].g.Wo);
+            } else {
+                const BufShape in = shp[op.src];
+                rc = launch_simt(buf(op.src), h->w_plain[op.weight_index], h->bias[op.weight_index], res, buf(op.dst), B, in.H, in.W,
+                                 op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, stream);
+            }
+            if (rc) return rc;
+        } else if (op.kind == HF_OP_MAXPOOL3x3S2) {
+            const BufShape in = shp[op.src], o = shp[op.dst];
+            const size_t total = (size_t)B * o.H * o.W * (in.C / 8);
+            int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+            maxpool_kernel<<<blocks, 256, 0, stream>>>(buf(op.src), buf(op.dst), B, in.H, in.W, in.C, o.H, o.W);
+            HF_LAUNCH_CHECK();
+        } else if (op.kind == HF_OP_GLOBAL_AVGPOOL) {
+            const BufShape in = shp[op.src];
+            dim3 grid(hf::div_up(in.C, 128), B);
+            avgpool_kernel<<<grid, 128, 0, stream>>>(buf(op.src), feats, B, in.H * in.W, in.C);
+            HF_LAUNCH_CHECK();
+        }
+    }
+    return HF_OK;
+}
+
+extern "C" int hf_conv2d_nhwc(const uint16_t* x, const uint16_t* w, const float* bias, const uint16_t* res, uint16_t* y,
+                              int B, int H, int W, int cin, int cout, int ksize, int stride, int pad, int relu, int impl,
+                              void* stream) {
+    if (!x || !w || !bias || !y) return hf::fail(HF_ERR_INVALID, "hf_conv2d_nhwc: null argument");
+    if (impl == 1)
+        return launch_simt((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (const __nv_bfloat16*)res,
+                           (__nv_bfloat16*)y, B, H, W, cin, cout, ksize, stride, pad, relu, (cudaStream_t)stream);
+    ConvPlan p;
+    int rc = plan_conv(&p, 0, x, w, B, H, W, cin, cout, ksize, stride, pad, relu, 0, 0);
+    if (rc) return rc;
+    return launch_conv(p, bias, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, (cudaStream_t)stream);
+}

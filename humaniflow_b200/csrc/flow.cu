@@ -1,0 +1,740 @@
+// Ancestor-conditioned SO(3) normalising flow for sm_100a: one launch walks the whole kinematic tree.
+//
+// Replaces: models/humaniflow_model.py:116-186,286-320;
+// models/norm_flows/pyro_conditional_norm_flow.py:21-129; local_diffeo_transformed_distribution.py:72-142;
+// transforms/{conditional_spline_coupling,scaled_radial_tanh,so3_exp,to}_transform.py;
+// utils/rigid_transform_utils.py:142-314; pyro 1.7.0 SplineCoupling/ConditionalDenseNN/Permute [upstream].
+//
+// Design: a CTA owns NR rows (samples) and keeps every activation of those rows in shared memory for all
+// 23 joints (image-level features, the rotations already drawn for the ancestors, contexts, hidden
+// layers).  Dense layers are fp32 register-tiled GEMMs (4 outputs x NR/4 rows per thread, K split across
+// the 16 warps and reduced through shared memory); weights (3.4 MB for the whole tree, L2-resident) are
+// streamed with 128-bit read-only loads, each element exactly once per CTA.  fp32 everywhere the
+// reference is fp32, fp64 for the exp/log maps and the radial-tanh inverse, as in the reference.
+#include "common.cuh"
+#include <vector>
+#include <cmath>
+
+#define HF_FJ 23          // max body parts
+#define HF_FANC 23        // max ancestors per joint
+#define HF_NT 512         // threads per CTA
+#define HF_NW 16          // warps per CTA
+
+namespace {
+
+constexpr int FEATS = 256, CTX = 64, H1 = 64, H2 = 32, H3 = 32, NRAW = 62, NBINS = 8;
+// coupling block layout (floats, k-major matrices [K][O])
+constexpr int OFF_W0 = 0, OFF_B0 = 65 * 64, OFF_W1 = OFF_B0 + 64, OFF_B1 = OFF_W1 + 64 * 32,
+              OFF_W2 = OFF_B1 + 32, OFF_B2 = OFF_W2 + 32 * 32, OFF_W3 = OFF_B2 + 32, OFF_B3 = OFF_W3 + 32 * 64,
+              COUPLING_FLOATS = OFF_B3 + 64;
+
+struct FlowParams {
+    const float* pack;
+    const float* betaW;     // [nb][FEATS]
+    int J, nb, T;
+    float radius, base_std;
+    int off_ctxW[HF_FJ], off_ctxB[HF_FJ], off_nn[HF_FJ][2];
+    int anc_cnt[HF_FJ];
+    signed char anc[HF_FJ][HF_FANC];
+};
+
+__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expm1f(x); }
+
+// ---- register-tiled partial GEMM of one warp: part[32][NR] = sum_{k in [k0,k1)} W[k][ob*32 + :] x X[k][:] ----
+template <int NR, typename XRow>
+__device__ __forceinline__ void warp_gemm(const float* __restrict__ W, int ldw, int ob, int k0, int k1, XRow xrow,
+                                          float* __restrict__ part, int lane) {
+    constexpr int SPL = NR / 4;
+    const int oi = lane & 7, sq = lane >> 3;
+    float acc[4][SPL];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int s = 0; s < SPL; ++s) acc[i][s] = 0.f;
+    const float* wp = W + ob * 32 + oi * 4;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * ldw));
+        const float2* xp = reinterpret_cast<const float2*>(xrow(k) + sq * SPL);
+#pragma unroll
+        for (int q = 0; q < SPL / 2; ++q) {
+            const float2 x = xp[q];
+            acc[0][2 * q] = fmaf(w.x, x.x, acc[0][2 * q]); acc[0][2 * q + 1] = fmaf(w.x, x.y, acc[0][2 * q + 1]);
+            acc[1][2 * q] = fmaf(w.y, x.x, acc[1][2 * q]); acc[1][2 * q + 1] = fmaf(w.y, x.y, acc[1][2 * q + 1]);
+            acc[2][2 * q] = fmaf(w.z, x.x, acc[2][2 * q]); acc[2][2 * q + 1] = fmaf(w.z, x.y, acc[2][2 * q + 1]);
+            acc[3][2 * q] = fmaf(w.w, x.x, acc[3][2 * q]); acc[3][2 * q + 1] = fmaf(w.w, x.y, acc[3][2 * q + 1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2* pp = reinterpret_cast<float2*>(part + (oi * 4 + i) * NR + sq * SPL);
+#pragma unroll
+        for (int q = 0; q < SPL / 2; ++q) pp[q] = make_float2(acc[i][2 * q], acc[i][2 * q + 1]);
+    }
+}
+
+// A dense layer over the CTA: OT output tiles of 32, K split over HF_NW/OT warps, partials in scratch,
+// then bias + activation into dst[O][NR].  ACT: 0 none, 1 ELU, 2 ReLU.  Ends with __syncthreads().
+template <int NR, int OT, int ACT, typename XRow>
+__device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias, int K,
+                                            XRow xrow, float* scratch, float* dst) {
+    constexpr int NS = HF_NW / OT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ob = warp / NS, sp = warp - ob * NS;
+    const int chunk = (K + NS - 1) / NS;
+    const int k0 = min(sp * chunk, K), k1 = min(k0 + chunk, K);
+    warp_gemm<NR>(W, OT * 32, ob, k0, k1, xrow, scratch + warp * 32 * NR, lane);
+    __syncthreads();
+    for (int e = threadIdx.x; e < OT * 32 * NR; e += HF_NT) {
+        const int o = e / NR, s = e - o * NR;
+        const int ob2 = o >> 5, ol = o & 31;
+        float a = __ldg(bias + o);
+        const float* p = scratch + ((ob2 * NS) * 32 + ol) * NR + s;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) a += p[q * 32 * NR];
+        if (ACT == 1) a = elu(a);
+        if (ACT == 2) a = fmaxf(a, 0.f);
+        dst[o * NR + s] = a;
+    }
+    __syncthreads();
+}
+
+// ---- rational-linear spline (pyro _monotonic_rational_spline, order='linear') for one scalar ----
+struct SplineBin {
+    float in_w, in_cw, in_ch, in_h, d0, d1, lam;
+};
+
+// raw: pointer to this row's NN outputs with stride `rs` between consecutive outputs; d in {0,1}
+__device__ __forceinline__ SplineBin spline_select(const float* raw, int rs, int d, float input, float bound,
+                                                   bool inverse) {
+    const float lo = -bound, hi = bound;
+    float w[NBINS], h[NBINS];
+    {   // softmax widths / heights
+        float mw = -INFINITY, mh = -INFINITY;
+#pragma unroll
+        for (int b = 0; b < NBINS; ++b) {
+            w[b] = raw[(d * NBINS + b) * rs];
+            h[b] = raw[(2 * NBINS + d * NBINS + b) * rs];
+            mw = fmaxf(mw, w[b]); mh = fmaxf(mh, h[b]);
+        }
+        float sw = 0.f, sh = 0.f;
+#pragma unroll
+        for (int b = 0; b < NBINS; ++b) {
+            w[b] = expf(w[b] - mw); sw += w[b];
+            h[b] = expf(h[b] - mh); sh += h[b];
+        }
+#pragma unroll
+        for (int b = 0; b < NBINS; ++b) {
+            w[b] = 1e-3f + 0.992f * (w[b] / sw);
+            h[b] = 1e-3f + 0.992f * (h[b] / sh);
+        }
+    }
+    float kw[NBINS + 1], kh[NBINS + 1];
+    {
+        float cw = 0.f, ch = 0.f;
+        kw[0] = lo; kh[0] = lo;
+#pragma unroll
+        for (int b = 0; b < NBINS; ++b) {
+            cw += w[b]; ch += h[b];
+            kw[b + 1] = (hi - lo) * cw + lo;
+            kh[b + 1] = (hi - lo) * ch + lo;
+        }
+        kw[NBINS] = hi; kh[NBINS] = hi;
+    }
+    int idx = -1;
+#pragma unroll
+    for (int b = 0; b <= NBINS; ++b) idx += (input >= (inverse ? kh[b] : kw[b]) + 1e-6f) ? 1 : 0;
+    idx = max(0, min(idx, NBINS - 1));
+    SplineBin r;
+    r.in_w = 0.f; r.in_cw = 0.f; r.in_ch = 0.f; r.in_h = 0.f;
+#pragma unroll
+    for (int b = 0; b < NBINS; ++b)
+        if (b == idx) { r.in_w = kw[b + 1] - kw[b]; r.in_cw = kw[b]; r.in_ch = kh[b]; r.in_h = kh[b + 1] - kh[b]; }
+    // derivatives: softplus + min, padded with 1 - min at both ends; lambdas: sigmoid, affine
+    auto deriv = [&](int i) -> float {   // i in [0, NBINS]
+        if (i == 0 || i == NBINS) return 0.999f;
+        float x = raw[(4 * NBINS + d * (NBINS - 1) + (i - 1)) * rs];
+        float sp = (x > 20.f) ? x : log1pf(expf(x));
+        return 1e-3f + sp;
+    };
+    r.d0 = deriv(idx);
+    r.d1 = deriv(idx + 1);
+    float l = raw[(4 * NBINS + 2 * (NBINS - 1) + d * NBINS + idx) * rs];
+    l = 1.f / (1.f + expf(-l));
+    r.lam = 0.95f * l + 0.025f;
+    return r;
+}
+
+__device__ __forceinline__ float spline_forward(const float* raw, int rs, int d, float x, float bound) {
+    if (!(x >= -bound && x <= bound)) return x;
+    SplineBin b = spline_select(raw, rs, d, x, bound, false);
+    const float delta = b.in_h / b.in_w;
+    const float wb = sqrtf(b.d0 / b.d1);
+    const float wc = (b.lam * b.d0 + (1.f - b.lam) * wb * b.d1) / delta;
+    const float ya = b.in_ch, yb = b.in_h + b.in_ch;
+    const float yc = ((1.f - b.lam) * ya + b.lam * wb * yb) / ((1.f - b.lam) + b.lam * wb);
+    const float theta = (x - b.in_cw) / b.in_w;
+    float num, den;
+    if (theta <= b.lam) {
+        num = ya * (b.lam - theta) + wc * yc * theta;
+        den = (b.lam - theta) + wc * theta;
+    } else {
+        num = wc * yc * (1.f - theta) + wb * yb * (theta - b.lam);
+        den = wc * (1.f - theta) + wb * (theta - b.lam);
+    }
+    return num / den;
+}
+
+// inverse spline; *fwd_logdet receives the FORWARD log|dy/dx| evaluated through the inverse formulas
+// (pyro Spline._inverse caches -logabsdet of the inverse direction).
+__device__ __forceinline__ float spline_inverse(const float* raw, int rs, int d, float y, float bound,
+                                                float* fwd_logdet) {
+    if (!(y >= -bound && y <= bound)) { *fwd_logdet = 0.f; return y; }
+    SplineBin b = spline_select(raw, rs, d, y, bound, true);
+    const float delta = b.in_h / b.in_w;
+    const float wb = sqrtf(b.d0 / b.d1);
+    const float wc = (b.lam * b.d0 + (1.f - b.lam) * wb * b.d1) / delta;
+    const float ya = b.in_ch, yb = b.in_h + b.in_ch;
+    const float yc = ((1.f - b.lam) * ya + b.lam * wb * yb) / ((1.f - b.lam) + b.lam * wb);
+    float num, den, dnum;
+    if (y <= yc) {
+        num = b.lam * (ya - y);
+        den = (wc - 1.f) * y + ya - wc * yc;
+        dnum = wc * b.lam * (yc - ya) * b.in_w;
+    } else {
+        num = (wc - b.lam * wb) * y + b.lam * wb * yb - wc * yc;
+        den = (wc - wb) * y + wb * yb - wc * yc;
+        dnum = wb * wc * (1.f - b.lam) * (yb - yc) * b.in_w;
+    }
+    const float theta = num / den;
+    *fwd_logdet = -(logf(dnum) - 2.f * logf(fabsf(den)));
+    return theta * b.in_w + b.in_cw;
+}
+
+// ---- exp / log maps ----
+__device__ __forceinline__ void so3_exp_f64(double x, double y, double z, float* R) {
+    // utils/rigid_transform_utils.py:182-201
+    double th = sqrt(x * x + y * y + z * z);
+    double alpha, beta;
+    if (th > 1e-10) { alpha = sin(th) / th; beta = (1.0 - cos(th)) / (th * th); }
+    else { alpha = 1.0 - 1.0 / 6.0; beta = 0.5 - 1.0 / 24.0; }   // reference substitutes theta=1 in the Taylor terms
+    double xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+    R[0] = (float)(1.0 + beta * (-(yy + zz))); R[1] = (float)(-alpha * z + beta * xy); R[2] = (float)(alpha * y + beta * xz);
+    R[3] = (float)(alpha * z + beta * xy); R[4] = (float)(1.0 + beta * (-(xx + zz))); R[5] = (float)(-alpha * x + beta * yz);
+    R[6] = (float)(-alpha * y + beta * xz); R[7] = (float)(alpha * x + beta * yz); R[8] = (float)(1.0 + beta * (-(xx + yy)));
+}
+
+__device__ __forceinline__ void so3_exp_f64d(double x, double y, double z, double* R) {
+    double th = sqrt(x * x + y * y + z * z);
+    double alpha, beta;
+    if (th > 1e-10) { alpha = sin(th) / th; beta = (1.0 - cos(th)) / (th * th); }
+    else { alpha = 1.0 - 1.0 / 6.0; beta = 0.5 - 1.0 / 24.0; }
+    double xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+    R[0] = 1.0 + beta * (-(yy + zz)); R[1] = -alpha * z + beta * xy; R[2] = alpha * y + beta * xz;
+    R[3] = alpha * z + beta * xy; R[4] = 1.0 + beta * (-(xx + zz)); R[5] = -alpha * x + beta * yz;
+    R[6] = -alpha * y + beta * xz; R[7] = alpha * x + beta * yz; R[8] = 1.0 + beta * (-(xx + yy));
+}
+
+__device__ __forceinline__ void rodrigues_f32(float x, float y, float z, float* o) {
+    float ex = x + 1e-8f, ey = y + 1e-8f, ez = z + 1e-8f;
+    float angle = sqrtf(ex * ex + ey * ey + ez * ez);
+    float rx = x / angle, ry = y / angle, rz = z / angle;
+    float s = sinf(angle), c1 = 1.f - cosf(angle);
+    float xx = rx * rx, yy = ry * ry, zz = rz * rz, xy = rx * ry, xz = rx * rz, yz = ry * rz;
+    o[0] = 1.f + c1 * (-(yy + zz)); o[1] = -s * rz + c1 * xy;        o[2] = s * ry + c1 * xz;
+    o[3] = s * rz + c1 * xy;        o[4] = 1.f + c1 * (-(xx + zz)); o[5] = -s * rx + c1 * yz;
+    o[6] = -s * ry + c1 * xz;       o[7] = s * rx + c1 * yz;        o[8] = 1.f + c1 * (-(xx + yy));
+}
+
+// utils/rigid_transform_utils.py:204-279 (returns the axis-angle vector)
+__device__ void so3_log_f64(const double* r, double* x) {
+    const double PI = 3.14159265358979323846;
+    double c = 0.5 * (r[0] + r[4] + r[8] - 1.0);
+    c = fmin(fmax(c, -1.0), 1.0);
+    double th = acos(c);
+    double ratio = th / sin(th);
+    if (th < 1e-20) ratio = 1.0 + th * th / 6.0;
+    // vee(ratio * 0.5 (R - R^T)) = (-m12, m02, -m01)
+    x[0] = -ratio * 0.5 * (r[5] - r[7]);
+    x[1] = ratio * 0.5 * (r[2] - r[6]);
+    x[2] = -ratio * 0.5 * (r[1] - r[3]);
+    if (fabs(PI - th) < 1e-2) {
+        double k = th * th / (1.0 - cos(th));
+        double q1 = k * (r[0] - 1.0), q2 = k * (r[4] - 1.0), q3 = k * (r[8] - 1.0);
+        double a1 = sqrt(fmax(q1 - q2 - q3, 1e-8) / 2.0);
+        double a2 = sqrt(fmax(-q1 + q2 - q3, 1e-8) / 2.0);
+        double a3 = sqrt(fmax(-q1 - q2 + q3, 1e-8) / 2.0);
+        double best = 1e300;
+        int bi = 0;
+        for (int s = 0; s < 8; ++s) {      // order of itertools.product([0,1], repeat=3) * 2 - 1; first minimum wins
+            double sx = (s & 4) ? 1.0 : -1.0, sy = (s & 2) ? 1.0 : -1.0, sz = (s & 1) ? 1.0 : -1.0;
+            double E[9];
+            so3_exp_f64d(sx * a1, sy * a2, sz * a3, E);
+            double d = 0.0;
+            for (int e = 0; e < 9; ++e) { double t = r[e] - E[e]; d += t * t; }
+            if (d < best) { best = d; bi = s; }
+        }
+        x[0] = ((bi & 4) ? 1.0 : -1.0) * a1;
+        x[1] = ((bi & 2) ? 1.0 : -1.0) * a2;
+        x[2] = ((bi & 1) ? 1.0 : -1.0) * a3;
+    }
+}
+
+// log((2 - 2cos t)/t^2) in fp64 (utils/rigid_transform_utils.py:298-314)
+__device__ __forceinline__ double so3_log_abs_det(double x, double y, double z) {
+    double n = sqrt(x * x + y * y + z * z);
+    double ratio = (n > 1e-10) ? (2.0 - 2.0 * cos(n)) / (n * n) : (1.0 - 1.0 / 12.0);
+    return log(ratio);
+}
+
+// image-level features of the CTA's rows: Fs[o][s] = ELU(img_base[img][o] + sum_l betaW[l][o] beta[s][l])
+template <int NR>
+__device__ __forceinline__ void image_feats(const FlowParams& P, const float* __restrict__ img_base,
+                                            const float* __restrict__ betas, const int* __restrict__ img_index,
+                                            int r0, int R, float* Fs) {
+    for (int e = threadIdx.x; e < FEATS * NR; e += HF_NT) {
+        const int s = e / FEATS, o = e - s * FEATS;
+        const int r = r0 + s;
+        float a = 0.f;
+        if (r < R) {
+            a = __ldg(img_base + (size_t)__ldg(img_index + r) * FEATS + o);
+            for (int l = 0; l < P.nb; ++l) a = fmaf(__ldg(P.betaW + l * FEATS + o), __ldg(betas + (size_t)r * P.nb + l), a);
+            a = elu(a);
+        }
+        Fs[o * NR + s] = a;
+    }
+}
+
+// context input row k of joint j: image features then the ancestors' rotations (row-major 3x3 each)
+struct CtxRow {
+    const float* Fs; const float* Ps; const signed char* anc; int NR;
+    __device__ __forceinline__ const float* operator()(int k) const {
+        if (k < FEATS) return Fs + k * NR;
+        int q = k - FEATS, a = q / 9;
+        return Ps + (anc[a] * 9 + (q - a * 9)) * NR;
+    }
+};
+struct PlainRow {
+    const float* X; int NR;
+    __device__ __forceinline__ const float* operator()(int k) const { return X + k * NR; }
+};
+
+template <int NR>
+struct SmemLayout {
+    static constexpr int Fs = 0;                          // [FEATS][NR]
+    static constexpr int Ps = Fs + FEATS * NR;            // [HF_FJ*9][NR]
+    static constexpr int Cs = Ps + HF_FJ * 9 * NR;        // [CTX+1][NR]
+    static constexpr int Ha = Cs + (CTX + 1) * NR;        // [64][NR]
+    static constexpr int Hb = Ha + 64 * NR;               // [32][NR]
+    static constexpr int Hc = Hb + 32 * NR;               // [32][NR]
+    static constexpr int Raw = Hc + 32 * NR;              // [64][NR]
+    static constexpr int Zs = Raw + 64 * NR;              // [3][NR]
+    static constexpr int Scratch = Zs + 4 * NR;           // [HF_NW][32][NR]
+    static constexpr int Total = Scratch + HF_NW * 32 * NR;
+};
+
+// the 4-layer hypernet of one coupling: Cs (context + x1 in row CTX) -> Raw[64][NR]
+template <int NR>
+__device__ __forceinline__ void coupling_nn(const float* __restrict__ cw, float* sm) {
+    using L = SmemLayout<NR>;
+    dense_layer<NR, 2, 2>(cw + OFF_W0, cw + OFF_B0, CTX + 1, PlainRow{sm + L::Cs, NR}, sm + L::Scratch, sm + L::Ha);
+    dense_layer<NR, 1, 2>(cw + OFF_W1, cw + OFF_B1, H1, PlainRow{sm + L::Ha, NR}, sm + L::Scratch, sm + L::Hb);
+    dense_layer<NR, 1, 2>(cw + OFF_W2, cw + OFF_B2, H2, PlainRow{sm + L::Hb, NR}, sm + L::Scratch, sm + L::Hc);
+    dense_layer<NR, 2, 0>(cw + OFF_W3, cw + OFF_B3, H3, PlainRow{sm + L::Hc, NR}, sm + L::Scratch, sm + L::Raw);
+}
+
+// =====================================  sampling  =====================================
+template <int NR>
+__global__ void __launch_bounds__(HF_NT, 1)
+flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict__ img_base, const float* __restrict__ betas,
+                   const int* __restrict__ img_index, const float* __restrict__ base_noise, int R, int Rn,
+                   float* __restrict__ rotmats, float* __restrict__ axisangle_pe) {
+    using L = SmemLayout<NR>;
+    extern __shared__ __align__(16) float sm[];
+    const int r0 = blockIdx.x * NR;
+    const int tid = threadIdx.x;
+    image_feats<NR>(P, img_base, betas, img_index, r0, R, sm + L::Fs);
+    __syncthreads();
+    for (int j = 0; j < P.J; ++j) {
+        const int Kc = FEATS + 9 * P.anc_cnt[j];
+        dense_layer<NR, 2, 1>(P.pack + P.off_ctxW[j], P.pack + P.off_ctxB[j], Kc,
+                              CtxRow{sm + L::Fs, sm + L::Ps, P.anc[j], NR}, sm + L::Scratch, sm + L::Cs);
+        // base sample (zero for point-estimate rows); first permutation is the identity
+        if (tid < NR) {
+            const int r = r0 + tid;
+            float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+            if (r < Rn) {
+                const float* z = base_noise + ((size_t)r * P.J + j) * 3;
+                z0 = z[0]; z1 = z[1]; z2 = z[2];
+            }
+            sm[L::Zs + tid] = z0; sm[L::Zs + NR + tid] = z1; sm[L::Zs + 2 * NR + tid] = z2;
+            sm[L::Cs + CTX * NR + tid] = z0;
+        }
+        __syncthreads();
+        for (int t = 0; t < P.T; ++t) {
+            coupling_nn<NR>(P.pack + P.off_nn[j][t], sm);
+            // spline on the two trailing coordinates, then rotate the vector for the next Permute
+            // (pyro_conditional_norm_flow.py:46-62: with <=2 transforms the only non-identity Permute is [1,2,0],
+            //  applied to the running vector before the second coupling).
+            if (tid < 2 * NR) {
+                const int s = tid >> 1, d = tid & 1;
+                const float x = sm[L::Zs + (1 + d) * NR + s];
+                sm[L::Ha + d * NR + s] = spline_forward(sm + L::Raw + s, NR, d, x, P.radius);
+            }
+            __syncthreads();
+            if (tid < NR) {
+                const float y0 = sm[L::Zs + tid], y1 = sm[L::Ha + tid], y2 = sm[L::Ha + NR + tid];
+                if (t + 1 < P.T) {     // next permutation relative to the current order is always [1,2,0]
+                    sm[L::Zs + tid] = y1; sm[L::Zs + NR + tid] = y2; sm[L::Zs + 2 * NR + tid] = y0;
+                    sm[L::Cs + CTX * NR + tid] = y1;
+                } else {
+                    sm[L::Zs + tid] = y0; sm[L::Zs + NR + tid] = y1; sm[L::Zs + 2 * NR + tid] = y2;
+                }
+            }
+            __syncthreads();
+        }
+        // radial tanh -> exp map -> store (shared copy feeds the descendants' contexts)
+        if (tid < NR) {
+            const int r = r0 + tid;
+            float x = sm[L::Zs + tid], y = sm[L::Zs + NR + tid], z = sm[L::Zs + 2 * NR + tid];
+            const float n = sqrtf(x * x + y * y + z * z);
+            if (n > 1e-7f) {
+                const float th = tanhf(n / P.radius);
+                x = th * (x / n) * P.radius; y = th * (y / n) * P.radius; z = th * (z / n) * P.radius;
+            }
+            float Rm[9];
+            if (r < Rn) so3_exp_f64((double)x, (double)y, (double)z, Rm);
+            else rodrigues_f32(x, y, z, Rm);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) sm[L::Ps + (j * 9 + e) * NR + tid] = Rm[e];
+            if (r < R) {
+                float* o = rotmats + ((size_t)r * P.J + j) * 9;
+#pragma unroll
+                for (int e = 0; e < 9; ++e) o[e] = Rm[e];
+                if (r >= Rn && axisangle_pe) {
+                    float* a = axisangle_pe + ((size_t)(r - Rn) * P.J + j) * 3;
+                    a[0] = x; a[1] = y; a[2] = z;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================  contexts for teacher forcing  =====================================
+template <int NR>
+__global__ void __launch_bounds__(HF_NT, 1)
+flow_context_kernel(const __grid_constant__ FlowParams P, const float* __restrict__ img_base, const float* __restrict__ betas,
+                    const int* __restrict__ img_index, const float* __restrict__ anc_rotmats, int R,
+                    float* __restrict__ ctx_out) {
+    using L = SmemLayout<NR>;
+    extern __shared__ __align__(16) float sm[];
+    const int r0 = blockIdx.x * NR;
+    const int j = blockIdx.y;
+    image_feats<NR>(P, img_base, betas, img_index, r0, R, sm + L::Fs);
+    for (int e = threadIdx.x; e < P.J * 9 * NR; e += HF_NT) {
+        const int s = e / (P.J * 9), q = e - s * (P.J * 9);
+        const int r = r0 + s;
+        sm[L::Ps + q * NR + s] = (r < R) ? anc_rotmats[(size_t)r * P.J * 9 + q] : 0.f;
+    }
+    __syncthreads();
+    const int Kc = FEATS + 9 * P.anc_cnt[j];
+    dense_layer<NR, 2, 1>(P.pack + P.off_ctxW[j], P.pack + P.off_ctxB[j], Kc,
+                          CtxRow{sm + L::Fs, sm + L::Ps, P.anc[j], NR}, sm + L::Scratch, sm + L::Cs);
+    for (int e = threadIdx.x; e < CTX * NR; e += HF_NT) {
+        const int s = e / CTX, o = e - s * CTX;
+        const int r = r0 + s;
+        if (r < R) ctx_out[((size_t)r * P.J + j) * CTX + o] = sm[L::Cs + o * NR + s];
+    }
+}
+
+// =====================================  log_prob  =====================================
+// CTA = (joint, NR/3 rows); the three pre-images of each target rotation are 3 rows of the coupling MLPs.
+// ALGEBRA = true evaluates the so(3) density of a given vector instead (single candidate per row).
+template <int NR, bool ALGEBRA>
+__global__ void __launch_bounds__(HF_NT, 1)
+flow_logprob_kernel(const __grid_constant__ FlowParams P, const float* __restrict__ ctx, int ctx_row_stride, int joint_first,
+                    int joint_count, const double* __restrict__ rot, const float* __restrict__ valg, int R,
+                    float* __restrict__ out) {
+    using L = SmemLayout<NR>;
+    constexpr int NC = ALGEBRA ? 1 : 3;
+    constexpr int RT = NR / NC;               // target rows per CTA
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float s_lp[NR];                // running log_prob per candidate
+    __shared__ int s_mask[NR];
+    const int jj = blockIdx.y, j = joint_first + jj;
+    const int r0 = blockIdx.x * RT;
+    const int tid = threadIdx.x;
+    const double PI = 3.14159265358979323846;
+    // contexts, replicated per candidate: candidate c of row s lives in column c*RT + s
+    for (int e = tid; e < CTX * NR; e += HF_NT) {
+        const int col = e / CTX, o = e - col * CTX;
+        const int r = r0 + (col % RT);
+        sm[L::Cs + o * NR + col] = (r < R) ? ctx[(size_t)r * ctx_row_stride + j * CTX + o] : 0.f;
+    }
+    if (tid < RT) {
+        const int r = r0 + tid;
+        double x[3] = {0.0, 0.0, 0.0};
+        if (r < R) {
+            if (ALGEBRA) {
+                const float* v = valg + ((size_t)r * joint_count + jj) * 3;
+                x[0] = v[0]; x[1] = v[1]; x[2] = v[2];
+            } else {
+                double rm[9];
+                const double* rp = rot + ((size_t)r * joint_count + jj) * 9;
+                for (int e = 0; e < 9; ++e) rm[e] = rp[e];
+                so3_log_f64(rm, x);
+            }
+        }
+        for (int c = 0; c < NC; ++c) {
+            double v[3] = {x[0], x[1], x[2]};
+            int mask = 1;
+            if (c > 0) {   // so3_xset k = -1 (c=1), +1 (c=2); masked by |.| < radius, masked-out -> 0 (so3_exp_transform.py:36-41)
+                const double n = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+                const double k = (c == 1) ? -1.0 : 1.0;
+                const double f = (n + 2.0 * PI * k);
+                v[0] = x[0] / n * f; v[1] = x[1] / n * f; v[2] = x[2] / n * f;
+                const double vn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+                mask = (vn < (double)P.radius) ? 1 : 0;   // NaN (n == 0) compares false
+                if (!mask) { v[0] = v[1] = v[2] = 0.0; }
+            }
+            const int col = c * RT + tid;
+            float lp = ALGEBRA ? 0.f : -(float)so3_log_abs_det(v[0], v[1], v[2]);
+            // ToTransform: fp64 -> fp32; then invert the radial tanh in fp64 (scaled_radial_tanh_transform.py:41-59)
+            const float y0 = (float)v[0], y1 = (float)v[1], y2 = (float)v[2];
+            const double dy0 = y0, dy1 = y1, dy2 = y2;
+            const double yn = sqrt(dy0 * dy0 + dy1 * dy1 + dy2 * dy2);
+            float x0 = y0, x1 = y1, x2 = y2;
+            if (yn > 1e-7) {
+                const double a = atanh(yn / (double)P.radius);
+                x0 = (float)(a * (dy0 / yn) * (double)P.radius);
+                x1 = (float)(a * (dy1 / yn) * (double)P.radius);
+                x2 = (float)(a * (dy2 / yn) * (double)P.radius);
+            }
+            const float xn32 = sqrtf(x0 * x0 + x1 * x1 + x2 * x2), yn32 = sqrtf(y0 * y0 + y1 * y1 + y2 * y2);
+            float ld = 0.f;
+            if (yn32 > 1e-7f) {
+                const float q = yn32 / P.radius;
+                ld = 2.f * (logf(yn32) - logf(xn32)) + log1pf(-(q * q));
+            }
+            lp = lp + (0.0f - ld);
+            s_lp[col] = lp;
+            s_mask[col] = mask;
+            sm[L::Zs + col] = x0; sm[L::Zs + NR + col] = x1; sm[L::Zs + 2 * NR + col] = x2;
+            sm[L::Cs + CTX * NR + col] = x0;   // conditioning coordinate of the last coupling
+        }
+    }
+    __syncthreads();
+    for (int t = P.T - 1; t >= 0; --t) {
+        coupling_nn<NR>(P.pack + P.off_nn[j][t], sm);
+        if (tid < 2 * NR) {
+            const int s = tid >> 1, d = tid & 1;
+            float ld;
+            const float y = sm[L::Zs + (1 + d) * NR + s];
+            sm[L::Ha + d * NR + s] = spline_inverse(sm + L::Raw + s, NR, d, y, P.radius, &ld);
+            sm[L::Hb + d * NR + s] = ld;
+        }
+        __syncthreads();
+        if (tid < NR) {
+            s_lp[tid] = s_lp[tid] - (sm[L::Hb + tid] + sm[L::Hb + NR + tid]);
+            const float x0 = sm[L::Zs + tid], x1 = sm[L::Ha + tid], x2 = sm[L::Ha + NR + tid];
+            if (t > 0) {   // undo Permute [1,2,0]: current = prev[[1,2,0]]  =>  prev = (cur[2], cur[0], cur[1])
+                sm[L::Zs + tid] = x2; sm[L::Zs + NR + tid] = x0; sm[L::Zs + 2 * NR + tid] = x1;
+                sm[L::Cs + CTX * NR + tid] = x2;
+            } else {
+                sm[L::Zs + tid] = x0; sm[L::Zs + NR + tid] = x1; sm[L::Zs + 2 * NR + tid] = x2;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < RT) {
+        const int r = r0 + tid;
+        const float sc = P.base_std;
+        const float log_scale = logf(sc), half_log_2pi = 0.91893853320467274178f;
+        float terms[NC];
+        for (int c = 0; c < NC; ++c) {
+            const int col = c * RT + tid;
+            float b = 0.f;
+            for (int e = 0; e < 3; ++e) {
+                const float x = sm[L::Zs + e * NR + col];
+                b += -(x * x) / (2.f * sc * sc) - log_scale - half_log_2pi;
+            }
+            terms[c] = s_mask[col] ? (s_lp[col] + b) : -INFINITY;
+        }
+        float res = terms[0];
+        if (!ALGEBRA) {
+            float m = fmaxf(terms[0], fmaxf(terms[NC > 1 ? 1 : 0], terms[NC > 2 ? 2 : 0]));
+            float ssum = 0.f;
+            for (int c = 0; c < NC; ++c) ssum += expf(terms[c] - m);
+            res = m + logf(ssum);
+        }
+        if (r < R) out[(size_t)r * joint_count + jj] = res;
+    }
+}
+
+}  // namespace
+
+struct hf_flow {
+    hf_flow_config cfg;
+    FlowParams P;
+    float* pack;
+    float* betaW;
+};
+
+namespace {
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    HF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return HF_OK;
+}
+
+int pick_rows(int R) {
+    if (R <= 148 * 8) return 8;
+    if (R <= 148 * 16) return 16;
+    if (R <= 148 * 24) return 24;
+    return 32;
+}
+
+}  // namespace
+
+extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const int* ancestors,
+                              const int* anc_offsets, const float* beta_weight, const float* const* ctx_weight,
+                              const float* const* ctx_bias, const float* const* nn_weight,
+                              const float* const* nn_bias) {
+    if (!out || !cfg) return hf::fail(HF_ERR_INVALID, "hf_flow_create: null argument");
+    if (cfg->num_joints < 1 || cfg->num_joints > HF_FJ || cfg->feats_dim != FEATS || cfg->context_dim != CTX ||
+        cfg->num_transforms < 1 || cfg->num_transforms > 2 || cfg->hidden[0] != H1 || cfg->hidden[1] != H2 ||
+        cfg->hidden[2] != H3 || cfg->num_bins != NBINS || cfg->num_betas < 1 || cfg->num_betas > 16)
+        return hf::fail(HF_ERR_UNSUPPORTED,
+                        "hf_flow_create: kernels are specialised to feats 256, context 64, hidden [64,32,32], 8 bins, "
+                        "<=2 spline couplings, <=23 joints (got feats %d ctx %d T %d hidden [%d,%d,%d] bins %d J %d)",
+                        cfg->feats_dim, cfg->context_dim, cfg->num_transforms, cfg->hidden[0], cfg->hidden[1],
+                        cfg->hidden[2], cfg->num_bins, cfg->num_joints);
+    hf_flow* h = new hf_flow();
+    h->cfg = *cfg;
+    FlowParams& P = h->P;
+    P.J = cfg->num_joints; P.nb = cfg->num_betas; P.T = cfg->num_transforms;
+    P.radius = cfg->radius; P.base_std = cfg->base_std;
+    std::vector<float> pack;
+    for (int j = 0; j < P.J; ++j) {
+        const int a = anc_offsets[j + 1] - anc_offsets[j];
+        if (a < 0 || a > HF_FANC) { delete h; return hf::fail(HF_ERR_INVALID, "hf_flow_create: joint %d has %d ancestors", j, a); }
+        P.anc_cnt[j] = a;
+        for (int q = 0; q < a; ++q) {
+            int an = ancestors[anc_offsets[j] + q];
+            if (an < 0 || an >= j) { delete h; return hf::fail(HF_ERR_INVALID, "hf_flow_create: ancestor %d of joint %d is not an earlier joint", an, j); }
+            P.anc[j][q] = (signed char)an;
+        }
+        const int Kc = FEATS + 9 * a;
+        P.off_ctxW[j] = (int)pack.size();
+        pack.resize(pack.size() + (size_t)Kc * CTX);
+        for (int k = 0; k < Kc; ++k)
+            for (int o = 0; o < CTX; ++o) pack[P.off_ctxW[j] + k * CTX + o] = ctx_weight[j][(size_t)o * Kc + k];
+        P.off_ctxB[j] = (int)pack.size();
+        pack.insert(pack.end(), ctx_bias[j], ctx_bias[j] + CTX);
+        for (int t = 0; t < P.T; ++t) {
+            const int base = (int)pack.size();
+            P.off_nn[j][t] = base;
+            pack.resize(pack.size() + COUPLING_FLOATS, 0.f);
+            const int li = (j * P.T + t) * 4;
+            const int Ks[4] = {CTX + 1, H1, H2, H3}, Os[4] = {H1, H2, H3, NRAW}, Op[4] = {64, 32, 32, 64};
+            const int offW[4] = {OFF_W0, OFF_W1, OFF_W2, OFF_W3}, offB[4] = {OFF_B0, OFF_B1, OFF_B2, OFF_B3};
+            for (int l = 0; l < 4; ++l) {
+                for (int k = 0; k < Ks[l]; ++k)
+                    for (int o = 0; o < Os[l]; ++o)
+                        pack[base + offW[l] + k * Op[l] + o] = nn_weight[li + l][(size_t)o * Ks[l] + k];
+                for (int o = 0; o < Os[l]; ++o) pack[base + offB[l] + o] = nn_bias[li + l][o];
+            }
+        }
+    }
+    std::vector<float> bw((size_t)P.nb * FEATS);
+    for (int l = 0; l < P.nb; ++l)
+        for (int o = 0; o < FEATS; ++o) bw[l * FEATS + o] = beta_weight[(size_t)o * P.nb + l];
+    int rc;
+    if ((rc = hf::upload(&h->pack, pack.data(), pack.size()))) return rc;
+    if ((rc = hf::upload(&h->betaW, bw.data(), bw.size()))) return rc;
+    P.pack = h->pack; P.betaW = h->betaW;
+    *out = h;
+    return HF_OK;
+}
+
+extern "C" void hf_flow_destroy(hf_flow_t* h) {
+    if (!h) return;
+    cudaFree(h->pack); cudaFree(h->betaW);
+    delete h;
+}
+
+#define HF_DISPATCH_ROWS(NRv, ...)                            \
+    switch (NRv) {                                            \
+        case 8:  { constexpr int NR = 8;  __VA_ARGS__; } break; \
+        case 16: { constexpr int NR = 16; __VA_ARGS__; } break; \
+        case 24: { constexpr int NR = 24; __VA_ARGS__; } break; \
+        default: { constexpr int NR = 32; __VA_ARGS__; } break; \
+    }
+
+extern "C" int hf_flow_sample(const hf_flow_t* h, const float* img_base, const float* betas, const int* img_index,
+                              const float* base_noise, int R, int Rn, float* rotmats, float* axisangle_pe,
+                              void* stream) {
+    if (!h || !img_base || !betas || !img_index || !rotmats) return hf::fail(HF_ERR_INVALID, "hf_flow_sample: null argument");
+    if (Rn < 0 || Rn > R || (Rn > 0 && !base_noise)) return hf::fail(HF_ERR_INVALID, "hf_flow_sample: bad row split R=%d Rn=%d", R, Rn);
+    if (R <= 0) return HF_OK;
+    const int nr = pick_rows(R);
+    HF_DISPATCH_ROWS(nr, {
+        const size_t smem = SmemLayout<NR>::Total * sizeof(float);
+        int rc = set_smem(flow_sample_kernel<NR>, smem);
+        if (rc) return rc;
+        flow_sample_kernel<NR><<<hf::div_up(R, NR), HF_NT, smem, (cudaStream_t)stream>>>(
+            h->P, img_base, betas, img_index, base_noise, R, Rn, rotmats, axisangle_pe);
+    });
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
+
+extern "C" int hf_flow_context(const hf_flow_t* h, const float* img_base, const float* betas, const int* img_index,
+                               const float* anc_rotmats, int R, float* ctx_out, void* stream) {
+    if (!h || !img_base || !betas || !img_index || !anc_rotmats || !ctx_out) return hf::fail(HF_ERR_INVALID, "hf_flow_context: null argument");
+    if (R <= 0) return HF_OK;
+    constexpr int NR = 8;
+    const size_t smem = SmemLayout<NR>::Total * sizeof(float);
+    int rc = set_smem(flow_context_kernel<NR>, smem);
+    if (rc) return rc;
+    dim3 grid(hf::div_up(R, NR), h->P.J);
+    flow_context_kernel<NR><<<grid, HF_NT, smem, (cudaStream_t)stream>>>(h->P, img_base, betas, img_index, anc_rotmats, R, ctx_out);
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
+
+extern "C" int hf_flow_log_prob(const hf_flow_t* h, const float* ctx, int ctx_row_stride, int joint_first,
+                                int joint_count, const double* rot_f64, int R, float* out, void* stream) {
+    if (!h || !ctx || !rot_f64 || !out) return hf::fail(HF_ERR_INVALID, "hf_flow_log_prob: null argument");
+    if (joint_first < 0 || joint_count < 1 || joint_first + joint_count > h->P.J)
+        return hf::fail(HF_ERR_INVALID, "hf_flow_log_prob: joints [%d,%d) out of range", joint_first, joint_first + joint_count);
+    if (R <= 0) return HF_OK;
+    constexpr int NR = 24;
+    const size_t smem = SmemLayout<NR>::Total * sizeof(float);
+    int rc = set_smem(flow_logprob_kernel<NR, false>, smem);
+    if (rc) return rc;
+    dim3 grid(hf::div_up(R, NR / 3), joint_count);
+    flow_logprob_kernel<NR, false><<<grid, HF_NT, smem, (cudaStream_t)stream>>>(h->P, ctx, ctx_row_stride, joint_first,
+                                                                              joint_count, rot_f64, nullptr, R, out);
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
+
+extern "C" int hf_flow_algebra_log_prob(const hf_flow_t* h, const float* ctx, int ctx_row_stride, int joint_first,
+                                        int joint_count, const float* v, int R, float* out, void* stream) {
+    if (!h || !ctx || !v || !out) return hf::fail(HF_ERR_INVALID, "hf_flow_algebra_log_prob: null argument");
+    if (joint_first < 0 || joint_count < 1 || joint_first + joint_count > h->P.J)
+        return hf::fail(HF_ERR_INVALID, "hf_flow_algebra_log_prob: joints [%d,%d) out of range", joint_first, joint_first + joint_count);
+    if (R <= 0) return HF_OK;
+    constexpr int NR = 8;
+    const size_t smem = SmemLayout<NR>::Total * sizeof(float);
+    int rc = set_smem(flow_logprob_kernel<NR, true>, smem);
+    if (rc) return rc;
+    dim3 grid(hf::div_up(R, NR), joint_count);
+    flow_logprob_kernel<NR, true><<<grid, HF_NT, smem, (cudaStream_t)stream>>>(h->P, ctx, ctx_row_stride, joint_first,
+                                                                             joint_count, nullptr, v, R, out);
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}

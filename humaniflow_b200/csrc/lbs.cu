@@ -1,0 +1,380 @@
+// SMPL linear blend skinning for sm_100a: shape+pose blend, joint regression, kinematic chain,
+// skinning and the reference's 90-joint assembly.
+//
+// Replaces models/smpl.py:27-41 and, beneath it, smplx 0.1.26 lbs()/batch_rigid_transform()/
+// vertices2joints()/VertexJointSelector.
+//
+// HBM layout (built once by hf_smpl_create, immutable, ~19 MB -> L2 resident on B200):
+//   blend [KB][3][Vp]  KB = num_betas + 9*(J-1); row l<nb = shapedirs[:,c,l], row nb+k = posedirs[k][3v+c]
+//   vtemp [3][Vp]      v_template, structure-of-arrays so that a warp's 32 vertices are 128 contiguous bytes
+//   J0 [J][3], Jd [J][3][nb]   J_regressor folded through v_template / shapedirs (fp64 on the host)
+//   sj/sw [nslots][Vp] sparse skinning weights (SMPL: <=4 influences per vertex)
+// Per call (workspace): F [M][KP] blend coefficients (betas | vec(R_i - I)), A [M][J][3][4] relative transforms.
+#include "common.cuh"
+#include <vector>
+#include <cmath>
+
+#define HF_MAXJ 24
+#define HF_MAXB 16
+
+struct hf_smpl {
+    int V, Vp, nb, J, KB, KP, nslots, nvj, nextra, nnz;
+    float *blend, *vtemp, *J0, *Jd, *sw;
+    int *sj, *vj, *csr_ptr, *csr_col;
+    float* csr_val;
+    int parents[HF_MAXJ];
+};
+
+namespace {
+
+struct Parents { int p[HF_MAXJ]; };
+
+// One thread per sample: joints from betas, 24-step chain of rigid transforms, relative transforms,
+// blend coefficients.  Tiny (M threads); layouts chosen for the skinning kernel that follows.
+__global__ void lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats,
+                                const float* __restrict__ transl, const float* __restrict__ J0,
+                                const float* __restrict__ Jd, Parents par, int M, int J, int nb, int KP,
+                                int J_out, float* __restrict__ F, float* __restrict__ A,
+                                float* __restrict__ joints) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float beta[HF_MAXB];
+    for (int l = 0; l < nb; ++l) beta[l] = betas[(size_t)m * nb + l];
+    float Jl[HF_MAXJ][3];
+    for (int i = 0; i < J; ++i)
+        for (int c = 0; c < 3; ++c) {
+            float a = J0[i * 3 + c];
+            for (int l = 0; l < nb; ++l) a = fmaf(Jd[(i * 3 + c) * nb + l], beta[l], a);
+            Jl[i][c] = a;
+        }
+    float tr[3] = {0.f, 0.f, 0.f};
+    if (transl) { tr[0] = transl[m * 3]; tr[1] = transl[m * 3 + 1]; tr[2] = transl[m * 3 + 2]; }
+    float* Fm = F + (size_t)m * KP;
+    for (int l = 0; l < nb; ++l) Fm[l] = beta[l];
+    for (int k = nb + 9 * (J - 1); k < KP; ++k) Fm[k] = 0.f;
+    float G[HF_MAXJ][12];
+    for (int i = 0; i < J; ++i) {
+        float R[9];
+        const float* Rm = rotmats + ((size_t)m * J + i) * 9;
+        for (int e = 0; e < 9; ++e) R[e] = Rm[e];
+        if (i > 0)
+            for (int e = 0; e < 9; ++e) Fm[nb + (i - 1) * 9 + e] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
+        float t[3];
+        int p = par.p[i];
+        for (int c = 0; c < 3; ++c) t[c] = (i == 0) ? Jl[0][c] : Jl[i][c] - Jl[p][c];
+        float* g = G[i];
+        if (i == 0) {
+            for (int r = 0; r < 3; ++r) {
+                g[r * 4 + 0] = R[r * 3 + 0]; g[r * 4 + 1] = R[r * 3 + 1]; g[r * 4 + 2] = R[r * 3 + 2];
+                g[r * 4 + 3] = t[r];
+            }
+        } else {
+            const float* gp = G[p];
+            for (int r = 0; r < 3; ++r) {
+                float a0 = gp[r * 4 + 0], a1 = gp[r * 4 + 1], a2 = gp[r * 4 + 2];
+                g[r * 4 + 0] = a0 * R[0] + a1 * R[3] + a2 * R[6];
+                g[r * 4 + 1] = a0 * R[1] + a1 * R[4] + a2 * R[7];
+                g[r * 4 + 2] = a0 * R[2] + a1 * R[5] + a2 * R[8];
+                g[r * 4 + 3] = a0 * t[0] + a1 * t[1] + a2 * t[2] + gp[r * 4 + 3];
+            }
+        }
+        float* Am = A + ((size_t)m * J + i) * 12;
+        float* jo = joints + ((size_t)m * J_out + i) * 3;
+        for (int r = 0; r < 3; ++r) {
+            Am[r * 4 + 0] = g[r * 4 + 0]; Am[r * 4 + 1] = g[r * 4 + 1]; Am[r * 4 + 2] = g[r * 4 + 2];
+            Am[r * 4 + 3] = g[r * 4 + 3] - (g[r * 4 + 0] * Jl[i][0] + g[r * 4 + 1] * Jl[i][1] + g[r * 4 + 2] * Jl[i][2]);
+            jo[r] = g[r * 4 + 3] + tr[r];
+        }
+    }
+}
+
+// Tile = 128 vertices x TS samples.  Thread (vl, sg) owns one vertex and SPT samples: the blend
+// contraction runs as SPT*3 independent FMA chains per thread with the basis read coalesced from L2
+// (the SG sample groups of a CTA share the lines through L1) and coefficients broadcast from smem.
+template <int SPT, int SG>
+__global__ void __launch_bounds__(128 * SG, 1)
+lbs_skin_kernel(const float* __restrict__ blend, const float* __restrict__ vtemp,
+                const int* __restrict__ sj, const float* __restrict__ sw, const float* __restrict__ F,
+                const float* __restrict__ A, const float* __restrict__ transl, int M, int V, int Vp, int KB,
+                int KP, int J, int nslots, float* __restrict__ vertices) {
+    constexpr int TS = SPT * SG;
+    extern __shared__ __align__(16) float smem[];
+    float* Fs = smem;                 // [KP][TS]
+    float* As = smem + KP * TS;       // [TS][J*12]
+    const int J12 = J * 12;
+    const int m0 = blockIdx.y * TS;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < TS * KP; idx += 128 * SG) {
+        int s = idx / KP, k = idx - s * KP;
+        int m = m0 + s;
+        Fs[k * TS + s] = (m < M) ? F[(size_t)m * KP + k] : 0.f;
+    }
+    for (int idx = tid; idx < TS * J12; idx += 128 * SG) {
+        int s = idx / J12;
+        int m = m0 + s;
+        As[idx] = (m < M) ? A[(size_t)m * J12 + (idx - s * J12)] : 0.f;
+    }
+    __syncthreads();
+
+    const int vl = tid & 127, sg = tid >> 7;
+    const int v = blockIdx.x * 128 + vl;          // < Vp always (arrays are padded)
+    float acc[SPT][3];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) acc[s][0] = acc[s][1] = acc[s][2] = 0.f;
+    const float* bp = blend + v;
+    const float* fs = Fs + sg * SPT;
+#pragma unroll 4
+    for (int k = 0; k < KB; ++k) {
+        float p0 = __ldg(bp + (size_t)(k * 3 + 0) * Vp);
+        float p1 = __ldg(bp + (size_t)(k * 3 + 1) * Vp);
+        float p2 = __ldg(bp + (size_t)(k * 3 + 2) * Vp);
+        const float4* f4 = reinterpret_cast<const float4*>(fs + k * TS);
+#pragma unroll
+        for (int q = 0; q < SPT / 4; ++q) {
+            float4 f = f4[q];
+            acc[q * 4 + 0][0] = fmaf(p0, f.x, acc[q * 4 + 0][0]); acc[q * 4 + 0][1] = fmaf(p1, f.x, acc[q * 4 + 0][1]); acc[q * 4 + 0][2] = fmaf(p2, f.x, acc[q * 4 + 0][2]);
+            acc[q * 4 + 1][0] = fmaf(p0, f.y, acc[q * 4 + 1][0]); acc[q * 4 + 1][1] = fmaf(p1, f.y, acc[q * 4 + 1][1]); acc[q * 4 + 1][2] = fmaf(p2, f.y, acc[q * 4 + 1][2]);
+            acc[q * 4 + 2][0] = fmaf(p0, f.z, acc[q * 4 + 2][0]); acc[q * 4 + 2][1] = fmaf(p1, f.z, acc[q * 4 + 2][1]); acc[q * 4 + 2][2] = fmaf(p2, f.z, acc[q * 4 + 2][2]);
+            acc[q * 4 + 3][0] = fmaf(p0, f.w, acc[q * 4 + 3][0]); acc[q * 4 + 3][1] = fmaf(p1, f.w, acc[q * 4 + 3][1]); acc[q * 4 + 3][2] = fmaf(p2, f.w, acc[q * 4 + 3][2]);
+        }
+    }
+    const float t0 = vtemp[v], t1 = vtemp[Vp + v], t2 = vtemp[2 * Vp + v];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) { acc[s][0] += t0; acc[s][1] += t1; acc[s][2] += t2; }
+
+    // skinning: v = sum_k w_k (R_k p + t_k), A rows gathered from smem (vertices of a warp mostly
+    // share joints, so the 128-bit loads are broadcasts).
+    constexpr int HS = (SPT >= 8) ? 8 : SPT;
+#pragma unroll
+    for (int h0 = 0; h0 < SPT; h0 += HS) {
+        float o[HS][3];
+#pragma unroll
+        for (int s = 0; s < HS; ++s) o[s][0] = o[s][1] = o[s][2] = 0.f;
+        for (int slot = 0; slot < nslots; ++slot) {
+            const int j = sj[slot * Vp + v];
+            const float w = sw[slot * Vp + v];
+            const float* a0 = As + (sg * SPT + h0) * J12 + j * 12;
+#pragma unroll
+            for (int s = 0; s < HS; ++s) {
+                const float4* a = reinterpret_cast<const float4*>(a0 + s * J12);
+                float4 r0 = a[0], r1 = a[1], r2 = a[2];
+                float px = acc[h0 + s][0], py = acc[h0 + s][1], pz = acc[h0 + s][2];
+                o[s][0] = fmaf(w, fmaf(r0.x, px, fmaf(r0.y, py, fmaf(r0.z, pz, r0.w))), o[s][0]);
+                o[s][1] = fmaf(w, fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w))), o[s][1]);
+                o[s][2] = fmaf(w, fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))), o[s][2]);
+            }
+        }
+        if (v < V) {
+#pragma unroll
+            for (int s = 0; s < HS; ++s) {
+                int m = m0 + sg * SPT + h0 + s;
+                if (m < M) {
+                    float tx = 0.f, ty = 0.f, tz = 0.f;
+                    if (transl) { tx = transl[m * 3]; ty = transl[m * 3 + 1]; tz = transl[m * 3 + 2]; }
+                    float* out = vertices + ((size_t)m * V + v) * 3;
+                    __stcs(out + 0, o[s][0] + tx);
+                    __stcs(out + 1, o[s][1] + ty);
+                    __stcs(out + 2, o[s][2] + tz);
+                }
+            }
+        }
+    }
+}
+
+// joints[J .. J+nvj) = picked vertices; joints[J+nvj ..) = sparse regressors applied to the final vertices.
+__global__ void lbs_extra_joints_kernel(const float* __restrict__ vertices, const int* __restrict__ vj,
+                                        const int* __restrict__ csr_ptr, const int* __restrict__ csr_col,
+                                        const float* __restrict__ csr_val, int M, int V, int J, int nvj,
+                                        int nextra, int J_out, float* __restrict__ joints) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int per = nvj + nextra;
+    if (idx >= M * per) return;
+    int m = idx / per, r = idx - m * per;
+    const float* vm = vertices + (size_t)m * V * 3;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (r < nvj) {
+        const float* p = vm + (size_t)vj[r] * 3;
+        x = p[0]; y = p[1]; z = p[2];
+    } else {
+        int row = r - nvj;
+        for (int e = csr_ptr[row]; e < csr_ptr[row + 1]; ++e) {
+            const float* p = vm + (size_t)csr_col[e] * 3;
+            float w = csr_val[e];
+            x = fmaf(w, p[0], x); y = fmaf(w, p[1], y); z = fmaf(w, p[2], z);
+        }
+    }
+    float* o = joints + ((size_t)m * J_out + J + r) * 3;
+    o[0] = x; o[1] = y; o[2] = z;
+}
+
+__global__ void rodrigues_kernel(const float* __restrict__ aa, float* __restrict__ R, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // smplx batch_rodrigues: angle = ||v + 1e-8||, axis = v / angle, R = I + sin K + (1-cos) K^2 (fp32)
+    float x = aa[i * 3], y = aa[i * 3 + 1], z = aa[i * 3 + 2];
+    float ex = x + 1e-8f, ey = y + 1e-8f, ez = z + 1e-8f;
+    float angle = sqrtf(ex * ex + ey * ey + ez * ez);
+    float rx = x / angle, ry = y / angle, rz = z / angle;
+    float s = sinf(angle), c1 = 1.f - cosf(angle);
+    float* o = R + (size_t)i * 9;
+    // K = [[0,-rz,ry],[rz,0,-rx],[-ry,rx,0]];  K^2 = r r^T - |r|^2 I
+    float xx = rx * rx, yy = ry * ry, zz = rz * rz, xy = rx * ry, xz = rx * rz, yz = ry * rz;
+    o[0] = 1.f + c1 * (-(yy + zz)); o[1] = -s * rz + c1 * xy;        o[2] = s * ry + c1 * xz;
+    o[3] = s * rz + c1 * xy;        o[4] = 1.f + c1 * (-(xx + zz)); o[5] = -s * rx + c1 * yz;
+    o[6] = -s * ry + c1 * xz;       o[7] = s * rx + c1 * yz;        o[8] = 1.f + c1 * (-(xx + yy));
+}
+
+constexpr int kSPT = 16, kSG = 4;
+
+}  // namespace
+
+extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float* v_template,
+                              const float* shapedirs, const float* posedirs, const float* J_regressor,
+                              const float* lbs_weights, const int* parents, const int* vertex_joint_ids,
+                              int nvj, const float* extra_regressors, int nextra) {
+    if (!out || V <= 0 || nb <= 0 || nb > HF_MAXB || J <= 1 || J > HF_MAXJ)
+        return hf::fail(HF_ERR_INVALID, "hf_smpl_create: bad sizes V=%d nb=%d J=%d", V, nb, J);
+    if (parents[0] != -1) return hf::fail(HF_ERR_INVALID, "hf_smpl_create: parents[0] must be -1");
+    for (int i = 1; i < J; ++i)
+        if (parents[i] < 0 || parents[i] >= i)
+            return hf::fail(HF_ERR_INVALID, "hf_smpl_create: parents[%d]=%d is not an earlier joint", i, parents[i]);
+    hf_smpl* h = new hf_smpl();
+    h->V = V; h->nb = nb; h->J = J; h->nvj = nvj; h->nextra = nextra;
+    h->Vp = hf::div_up(V, 128) * 128;
+    h->KB = nb + 9 * (J - 1);
+    h->KP = hf::div_up(h->KB, 4) * 4;
+    for (int i = 0; i < J; ++i) h->parents[i] = parents[i];
+    const int Vp = h->Vp, KB = h->KB;
+    std::vector<float> blend((size_t)KB * 3 * Vp, 0.f), vt((size_t)3 * Vp, 0.f);
+    for (int v = 0; v < V; ++v)
+        for (int c = 0; c < 3; ++c) {
+            vt[(size_t)c * Vp + v] = v_template[v * 3 + c];
+            for (int l = 0; l < nb; ++l)
+                blend[((size_t)l * 3 + c) * Vp + v] = shapedirs[((size_t)v * 3 + c) * nb + l];
+            for (int k = 0; k < 9 * (J - 1); ++k)
+                blend[((size_t)(nb + k) * 3 + c) * Vp + v] = posedirs[(size_t)k * V * 3 + v * 3 + c];
+        }
+    // joint regressor folded through the shape space (fp64 accumulation)
+    std::vector<float> J0((size_t)J * 3), Jd((size_t)J * 3 * nb);
+    for (int i = 0; i < J; ++i)
+        for (int c = 0; c < 3; ++c) {
+            double a = 0.0;
+            std::vector<double> d(nb, 0.0);
+            for (int v = 0; v < V; ++v) {
+                double w = J_regressor[(size_t)i * V + v];
+                if (w == 0.0) continue;
+                a += w * v_template[v * 3 + c];
+                for (int l = 0; l < nb; ++l) d[l] += w * shapedirs[((size_t)v * 3 + c) * nb + l];
+            }
+            J0[i * 3 + c] = (float)a;
+            for (int l = 0; l < nb; ++l) Jd[(i * 3 + c) * nb + l] = (float)d[l];
+        }
+    // sparse skinning weights
+    int nslots = 1;
+    for (int v = 0; v < V; ++v) {
+        int n = 0;
+        for (int j = 0; j < J; ++j) n += lbs_weights[(size_t)v * J + j] != 0.f;
+        if (n > nslots) nslots = n;
+    }
+    h->nslots = nslots;
+    std::vector<int> sj((size_t)nslots * Vp, 0);
+    std::vector<float> sw((size_t)nslots * Vp, 0.f);
+    for (int v = 0; v < V; ++v) {
+        int n = 0;
+        for (int j = 0; j < J; ++j) {
+            float w = lbs_weights[(size_t)v * J + j];
+            if (w != 0.f) { sj[(size_t)n * Vp + v] = j; sw[(size_t)n * Vp + v] = w; ++n; }
+        }
+    }
+    // extra joint regressors -> CSR
+    std::vector<int> ptr(nextra + 1, 0), col;
+    std::vector<float> val;
+    for (int r = 0; r < nextra; ++r) {
+        for (int v = 0; v < V; ++v) {
+            float w = extra_regressors[(size_t)r * V + v];
+            if (w != 0.f) { col.push_back(v); val.push_back(w); }
+        }
+        ptr[r + 1] = (int)col.size();
+    }
+    h->nnz = (int)col.size();
+    if (col.empty()) { col.push_back(0); val.push_back(0.f); }
+    for (int r = 0; r < nvj; ++r)
+        if (vertex_joint_ids[r] < 0 || vertex_joint_ids[r] >= V) {
+            delete h;
+            return hf::fail(HF_ERR_INVALID, "hf_smpl_create: vertex_joint_ids[%d] out of range", r);
+        }
+    int rc;
+    if ((rc = hf::upload(&h->blend, blend.data(), blend.size()))) return rc;
+    if ((rc = hf::upload(&h->vtemp, vt.data(), vt.size()))) return rc;
+    if ((rc = hf::upload(&h->J0, J0.data(), J0.size()))) return rc;
+    if ((rc = hf::upload(&h->Jd, Jd.data(), Jd.size()))) return rc;
+    if ((rc = hf::upload(&h->sj, sj.data(), sj.size()))) return rc;
+    if ((rc = hf::upload(&h->sw, sw.data(), sw.size()))) return rc;
+    std::vector<int> vj(vertex_joint_ids, vertex_joint_ids + nvj);
+    if (vj.empty()) vj.push_back(0);
+    if ((rc = hf::upload(&h->vj, vj.data(), vj.size()))) return rc;
+    if ((rc = hf::upload(&h->csr_ptr, ptr.data(), ptr.size()))) return rc;
+    if ((rc = hf::upload(&h->csr_col, col.data(), col.size()))) return rc;
+    if ((rc = hf::upload(&h->csr_val, val.data(), val.size()))) return rc;
+    *out = h;
+    return HF_OK;
+}
+
+extern "C" void hf_smpl_destroy(hf_smpl_t* h) {
+    if (!h) return;
+    cudaFree(h->blend); cudaFree(h->vtemp); cudaFree(h->J0); cudaFree(h->Jd); cudaFree(h->sj);
+    cudaFree(h->sw); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
+    delete h;
+}
+
+extern "C" int hf_smpl_num_joints_out(const hf_smpl_t* h) { return h->J + h->nvj + h->nextra; }
+
+extern "C" size_t hf_lbs_workspace_bytes(const hf_smpl_t* h, int M) {
+    return (size_t)M * (h->KP + h->J * 12) * sizeof(float);
+}
+
+extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats,
+                              const float* transl, float* vertices, float* joints, void* workspace,
+                              size_t workspace_bytes, int M, void* stream_) {
+    if (!h || !betas || !rotmats || !vertices || !joints) return hf::fail(HF_ERR_INVALID, "hf_lbs_forward: null argument");
+    if (M <= 0) return HF_OK;
+    if (!workspace || workspace_bytes < hf_lbs_workspace_bytes(h, M))
+        return hf::fail(HF_ERR_INVALID, "hf_lbs_forward: workspace too small (%zu < %zu)", workspace_bytes,
+                        hf_lbs_workspace_bytes(h, M));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    float* F = (float*)workspace;
+    float* A = F + (size_t)M * h->KP;
+    const int J_out = hf_smpl_num_joints_out(h);
+    Parents par;
+    for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
+    lbs_pose_kernel<<<hf::div_up(M, 128), 128, 0, stream>>>(betas, rotmats, transl, h->J0, h->Jd, par, M, h->J,
+                                                            h->nb, h->KP, J_out, F, A, joints);
+    HF_LAUNCH_CHECK();
+    constexpr int TS = kSPT * kSG;
+    size_t smem = ((size_t)h->KP * TS + (size_t)TS * h->J * 12) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        HF_CUDA(cudaFuncSetAttribute(lbs_skin_kernel<kSPT, kSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_forward: tile needs %zu B of shared memory", smem);
+    dim3 grid(h->Vp / 128, hf::div_up(M, TS));
+    lbs_skin_kernel<kSPT, kSG><<<grid, 128 * kSG, smem, stream>>>(h->blend, h->vtemp, h->sj, h->sw, F, A, transl, M,
+                                                                 h->V, h->Vp, h->KB, h->KP, h->J, h->nslots, vertices);
+    HF_LAUNCH_CHECK();
+    int per = h->nvj + h->nextra;
+    if (per > 0) {
+        lbs_extra_joints_kernel<<<hf::div_up(M * per, 256), 256, 0, stream>>>(vertices, h->vj, h->csr_ptr, h->csr_col,
+                                                                              h->csr_val, M, h->V, h->J, h->nvj,
+                                                                              h->nextra, J_out, joints);
+        HF_LAUNCH_CHECK();
+    }
+    return HF_OK;
+}
+
+extern "C" int hf_rodrigues(const float* aa, float* R, int n, void* stream) {
+    if (n <= 0) return HF_OK;
+    rodrigues_kernel<<<hf::div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(aa, R, n);
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}

@@ -1,0 +1,191 @@
+/*
+ * humaniflow_b200 — C ABI of the B200-native HuManiFlow sampling hot path.
+ *
+ * The reference (akashsengupta1997/HuManiFlow) is pure Python/PyTorch and has no FFI layer; its
+ * boundary for this path is two Python classes.  This header is the C-ABI that the
+ * Python mirrors of those classes (humaniflow_b200/humaniflow_model.py, humaniflow_b200/smpl.py)
+ * bind with ctypes.  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types in any signature;
+ *   - `*_create` functions take HOST pointers, copy + repack onto the current CUDA device and return
+ *     an opaque handle (immutable afterwards); `*_destroy` frees it;
+ *   - all other pointer arguments are DEVICE pointers borrowed for the duration of the call;
+ *     no allocation happens inside a forward call — scratch comes from the caller (`*_workspace_bytes`);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream;
+ *   - return value 0 = ok, non-zero = error (hf_last_error() gives the message, thread-local);
+ *   - tensors are dense row-major fp32 unless stated otherwise.
+ */
+#ifndef HUMANIFLOW_B200_H
+#define HUMANIFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HF_OK 0
+#define HF_ERR_INVALID 1
+#define HF_ERR_CUDA 2
+#define HF_ERR_UNSUPPORTED 3
+
+/* Library / device bookkeeping. */
+int hf_version(void);
+const char* hf_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+long long hf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * SMPL linear blend skinning.
+ * Replaces: models/smpl.py:13-41 `SMPL.__init__/forward` and, beneath it, smplx 0.1.26
+ * `SMPL.forward` -> `lbs` / `batch_rigid_transform` / `vertices2joints` / `VertexJointSelector`.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hf_smpl hf_smpl_t;
+
+/* Host arrays, smplx buffer layouts: v_template (V,3); shapedirs (V,3,num_betas); posedirs
+ * ((J-1)*9, V*3); J_regressor (J,V); lbs_weights (V,J); parents (J) with parents[0] = -1;
+ * vertex_joint_ids (num_vertex_joints) = vertices appended as joints (smplx VertexJointSelector);
+ * extra_regressors (num_extra, V) = the reference's J_regressor_extra / cocoplus / h36m stacked
+ * (models/smpl.py:16-25).  Output joint count = J + num_vertex_joints + num_extra (90 for SMPL). */
+int hf_smpl_create(hf_smpl_t** out, int num_verts, int num_betas, int num_joints,
+                   const float* v_template, const float* shapedirs, const float* posedirs,
+                   const float* J_regressor, const float* lbs_weights, const int* parents,
+                   const int* vertex_joint_ids, int num_vertex_joints,
+                   const float* extra_regressors, int num_extra);
+void hf_smpl_destroy(hf_smpl_t* h);
+int hf_smpl_num_joints_out(const hf_smpl_t* h);
+size_t hf_lbs_workspace_bytes(const hf_smpl_t* h, int M);
+
+/* betas (M,num_betas); rotmats (M,J,3,3) = [global_orient | body_pose] (the `pose2rot=False` form);
+ * transl (M,3) or NULL.  vertices (M,V,3); joints (M,J_out,3).  models/smpl.py:27-41. */
+int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats, const float* transl,
+                   float* vertices, float* joints, void* workspace, size_t workspace_bytes,
+                   int M, void* stream);
+
+/* fp32 axis-angle -> rotation matrices, n rows.  Replaces smplx `lbs.batch_rodrigues`
+ * (used by SMPL.forward when pose2rot=True and at models/humaniflow_model.py:299). */
+int hf_rodrigues(const float* axis_angle, float* rotmats, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ancestor-conditioned SO(3) normalising flow over the kinematic tree.
+ * Replaces: models/humaniflow_model.py:116-186 (context features), :286-320 (joint loop);
+ * models/norm_flows/pyro_conditional_norm_flow.py:21-129; local_diffeo_transformed_distribution.py:
+ * 72-142; transforms/{conditional_spline_coupling,scaled_radial_tanh,so3_exp,to}_transform.py;
+ * utils/rigid_transform_utils.py:142-314; pyro 1.7.0 SplineCoupling / ConditionalDenseNN / Permute.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hf_flow hf_flow_t;
+
+typedef struct hf_flow_config {
+    int num_joints;        /* body parts (23) */
+    int feats_dim;         /* INPUT_SHAPE_GLOB_CAM_FEATS_DIM (256) */
+    int context_dim;       /* NORM_FLOW.CONTEXT_DIM (64) */
+    int num_transforms;    /* NORM_FLOW.NUM_TRANSFORMS (2) */
+    int hidden[3];         /* NORM_FLOW.TRANSFORM_NN_HIDDEN_DIMS (64,32,32) */
+    int num_bins;          /* NORM_FLOW.NUM_SPLINE_SEGMENTS (8) */
+    int num_betas;         /* NUM_SMPL_BETAS (10) */
+    float radius;          /* NORM_FLOW.COMPACT_SUPPORT_RADIUS (1.5*pi) */
+    float base_std;        /* NORM_FLOW.BASE_DIST_STD (0.6) */
+} hf_flow_config;
+
+/* Host arrays.  ancestors: for joint j the list ancestors[anc_offsets[j] .. anc_offsets[j+1]) (nearest
+ * first, root excluded; models/humaniflow_model.py:16-30).  beta_weight (feats_dim, num_betas) = the beta
+ * columns of fc_input_shape_glob_cam_feats.weight.  ctx_weight[j] (context_dim, feats_dim + 9*a_j) and
+ * ctx_bias[j] = fc_flow_context[j].  coupling layer l of transform t of joint j:
+ * nn_weight[(j*num_transforms+t)*4 + l], nn_bias[...] with torch Linear layout (out,in)
+ * (= pose_so3flow_transform_modules.{j*T+t}.nn.layers.{l}). */
+int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const int* ancestors,
+                   const int* anc_offsets, const float* beta_weight,
+                   const float* const* ctx_weight, const float* const* ctx_bias,
+                   const float* const* nn_weight, const float* const* nn_bias);
+void hf_flow_destroy(hf_flow_t* h);
+
+/* Hierarchical sampling down the kinematic tree, all joints in one launch.
+ * img_base (B,feats_dim): pre-activation image-level features WITHOUT the beta term, i.e.
+ *   W[:, feats|glob|cam] . [input_feats, vec(glob_R), cam] + bias   (models/humaniflow_model.py:133-148);
+ * betas (R,num_betas) per-row shape; img_index (R) int32 row -> image;
+ * base_noise (Rn,J,3): base-distribution draws ~ N(0, base_std^2) for rows [0,Rn) ("sample rows":
+ *   fp32 flow -> fp64 exp map -> fp32 store, humaniflow_model.py:304-311);
+ * rows [Rn,R) are "point-estimate rows": zero base sample, smplx fp32 Rodrigues (humaniflow_model.py:290-301),
+ *   axis-angle written to axisangle_pe (R-Rn,J,3).
+ * rotmats (R,J,3,3) fp32. */
+int hf_flow_sample(const hf_flow_t* h, const float* img_base, const float* betas, const int* img_index,
+                   const float* base_noise, int R, int Rn, float* rotmats, float* axisangle_pe,
+                   void* stream);
+
+/* Contexts for teacher-forced log-likelihood (humaniflow_model.py:314-320): ancestors taken from
+ * given rotations anc_rotmats (R,J,3,3) fp32.  ctx_out (R,J,context_dim). */
+int hf_flow_context(const hf_flow_t* h, const float* img_base, const float* betas, const int* img_index,
+                    const float* anc_rotmats, int R, float* ctx_out, void* stream);
+
+/* log_prob on SO(3) (local_diffeo_transformed_distribution.py:84-142): for joints
+ * [joint_first, joint_first+joint_count): ctx (R, ctx_row_stride floats per row; joint j's context at
+ * offset j*context_dim), rot_f64 (R,joint_count,3,3) DOUBLE, out (R,joint_count) fp32. */
+int hf_flow_log_prob(const hf_flow_t* h, const float* ctx, int ctx_row_stride, int joint_first,
+                     int joint_count, const double* rot_f64, int R, float* out, void* stream);
+
+/* log-density on the algebra so(3) (the `conditioned_pose_so3flow_dists_for_loglik` objects):
+ * v (R,joint_count,3) fp32 -> out (R,joint_count) fp32. */
+int hf_flow_algebra_log_prob(const hf_flow_t* h, const float* ctx, int ctx_row_stride, int joint_first,
+                             int joint_count, const float* v, int R, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Heads (models/humaniflow_model.py:232-258, 116-150) and small dense layers.
+ * ---------------------------------------------------------------------------------------------- */
+/* y (M,O) = act(x (M,K; row stride ldx) . W^T (O,K; row stride ldw) + b) ; act: 0 none, 1 ELU, 2 ReLU.
+ * b may be NULL.  If accumulate != 0, y += instead of = (activation applied to the sum). */
+int hf_linear(const float* x, int ldx, const float* W, int ldw, const float* b, float* y, int ldy,
+              int M, int K, int O, int act, int accumulate, void* stream);
+
+/* Head post-processing (models/humaniflow_model.py:237-258).  heads (B, 2*nb+9) = one Linear over the
+ * concatenated [fc_shape | fc_glob | fc_cam] rows.  cam (B,3) = cam head + init_cam; glob6 (B,6) = glob head +
+ * init_glob; shape_rows (B*N + B, nb): rows [0,B*N) = shape_mode + exp(shape_log_std) * shape_eps (shape_eps
+ * (B,N,nb) ~ N(0,1); NULL = use the mode, `use_shape_mode_for_samples`), rows [B*N, B*N+B) = shape_mode. */
+int hf_heads_finish(const float* heads, const float* init_glob, const float* init_cam, const float* shape_eps,
+                    int B, int N, int nb, float* cam, float* glob6, float* shape_rows, void* stream);
+
+/* glob6 (B,6) -> rotation matrices (B,3,3): utils/rigid_transform_utils.py:86-100. */
+int hf_rot6d_to_rotmat(const float* rot6d, float* rotmats, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ResNet encoder (models/resnet.py:202-217): a small op program over bf16 NHWC activation buffers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hf_encoder hf_encoder_t;
+
+enum { HF_OP_CONV = 0, HF_OP_MAXPOOL3x3S2 = 1, HF_OP_GLOBAL_AVGPOOL = 2 };
+
+typedef struct hf_enc_op {
+    int kind;              /* HF_OP_* */
+    int src, dst, res;     /* activation buffer ids; res = -1 for none (residual added before ReLU) */
+    int cin, cout;         /* channels as stored (cin already padded for the stem) */
+    int ksize, stride, pad;
+    int relu;
+    int weight_index;      /* into the weights/bias arrays given to hf_encoder_create */
+} hf_enc_op;
+
+/* weights[i]: HOST bf16 (uint16 bit patterns) (cout, ksize, ksize, cin) with BatchNorm scale folded in;
+ * bias[i]: HOST fp32 (cout) = folded BatchNorm shift.  in_channels = channels of the fp32 NCHW input,
+ * stem_cin = padded channel count of the first conv. */
+int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int num_ops,
+                      const uint16_t* const* weights, const float* const* bias, int num_weights,
+                      int in_channels, int stem_cin, int feat_dim);
+void hf_encoder_destroy(hf_encoder_t* h);
+size_t hf_encoder_workspace_bytes(const hf_encoder_t* h, int B, int H, int W);
+/* input (B,in_channels,H,W) fp32 NCHW -> feats (B,feat_dim) fp32. */
+int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, int H, int W, float* feats,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* impl: 0 = tcgen05/TMA implicit GEMM (product path), 1 = SIMT direct convolution (debug cross-check). */
+int hf_encoder_set_impl(hf_encoder_t* h, int impl);
+
+/* Single convolution on bf16 NHWC tensors (unit-test entry point for the conv kernels).
+ * x (B,H,W,cin) bf16; w (cout,k,k,cin) bf16; bias (cout) fp32; res (B,Ho,Wo,cout) bf16 or NULL;
+ * y (B,Ho,Wo,cout) bf16. */
+int hf_conv2d_nhwc(const uint16_t* x, const uint16_t* w, const float* bias, const uint16_t* res,
+                   uint16_t* y, int B, int H, int W, int cin, int cout, int ksize, int stride, int pad,
+                   int relu, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HUMANIFLOW_B200_H */

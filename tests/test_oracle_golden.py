@@ -1,0 +1,105 @@
+"""The oracle against golden vectors produced by the REAL reference files (tests/golden/make_golden.py).
+
+This is what pins the oracle: rotation utilities, the radial tanh, ResNet, and the SO(3) log_prob plumbing
+were run from /root/reference in the build container; the committed .npz hold their outputs.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+from detweights import det_input, fill_state_dict
+from oracle import flow as oflow
+from oracle import so3
+from oracle.resnet import resnet_forward
+
+RADIUS = 1.5 * math.pi
+
+
+def _load(golden_dir, name):
+    return {k: torch.tensor(v) for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def test_so3_exp_log_xset_logdet(golden_dir):
+    g = _load(golden_dir, 'so3_golden.npz')
+    R = so3.so3_exp(g['v'])
+    assert torch.allclose(R, g['R'], atol=1e-14, rtol=0)
+    logv = so3.so3_log(g['R'].clone())
+    assert torch.allclose(logv, g['logv'], atol=1e-12, rtol=0)
+    xs = so3.so3_xset(g['logv'])
+    both_nan = torch.isnan(xs) & torch.isnan(g['xset'])
+    assert torch.allclose(torch.where(both_nan, torch.zeros_like(xs), xs),
+                          torch.where(both_nan, torch.zeros_like(xs), g['xset']), atol=1e-12, rtol=0)
+    assert torch.allclose(so3.so3_log_abs_det_jacobian(g['v']), g['lad'], atol=1e-13, rtol=0)
+    assert torch.allclose(so3.so3_log_abs_det_jacobian(g['v'].float()), g['lad32'], atol=1e-6, rtol=0)
+
+
+def test_rot6d(golden_dir):
+    g = _load(golden_dir, 'so3_golden.npz')
+    R = so3.rot6d_to_rotmat(g['r6'])
+    assert torch.allclose(R, g['R6'], atol=1e-6, rtol=0)
+    assert torch.equal(so3.rotmat_to_rot6d(g['R6']), g['back6'])
+
+
+def test_radial_tanh(golden_dir):
+    g = _load(golden_dir, 'rtanh_golden.npz')
+    y = oflow.radial_tanh_forward(g['x'], RADIUS)
+    assert torch.allclose(y, g['y'], atol=1e-6, rtol=1e-6)
+    assert torch.allclose(oflow.radial_tanh_inverse(g['y'], RADIUS), g['xinv'], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(oflow.radial_tanh_log_abs_det(g['x'], g['y'], RADIUS), g['ld'], atol=1e-5, rtol=1e-5)
+
+
+def _resnet_sd(layers):
+    import humaniflow_b200.resnet as hr
+    net = (hr.resnet18 if layers == 18 else hr.resnet50)(in_channels=18)
+    shapes = {k: v.shape for k, v in net.state_dict().items()}
+    sd = fill_state_dict(shapes, seed=100 + layers)
+    return {'image_encoder.' + k: v for k, v in sd.items()}
+
+
+def test_resnet_matches_reference_class(golden_dir):
+    g = _load(golden_dir, 'resnet_golden.npz')
+    for layers in (18, 50):
+        sd = _resnet_sd(layers)
+        x = det_input((2, 18, 64, 64), 200 + layers, kind='uniform')
+        with torch.no_grad():
+            f = resnet_forward(sd, x, layers)
+        ref = g['feats%d' % layers]
+        assert f.shape == ref.shape
+        assert torch.allclose(f, ref, atol=1e-4 * ref.abs().max().item(), rtol=1e-4)
+
+
+def _golden_flow():
+    dims = [(65, 64), (64, 32), (32, 32), (32, 62)]
+    shapes = {}
+    for t in range(2):
+        for l, (i, o) in enumerate(dims):
+            shapes['c%d.%d.weight' % (t, l)] = (o, i)
+            shapes['c%d.%d.bias' % (t, l)] = (o,)
+    sd = fill_state_dict(shapes, seed=321)
+    couplings = [[(sd['c%d.%d.weight' % (t, l)] * 0.5, sd['c%d.%d.bias' % (t, l)] * 0.5) for l in range(4)] for t in range(2)]
+    return couplings, det_input((48, 64), 322)
+
+
+def test_so3_log_prob_plumbing_matches_reference_class(golden_dir):
+    """Real LocalDiffeoTransformedDistribution / SO3ExpCompactTransform / ToTransform / ScaledRadialTanhTransform
+    over oracle-spline couplings vs oracle.flow.so3_log_prob (pre-images, masks, dtypes, logsumexp)."""
+    g = _load(golden_dir, 'logprob_golden.npz')
+    couplings, ctx = _golden_flow()
+    lp = oflow.so3_log_prob(couplings, g['Rt'], ctx, RADIUS, 0.6)
+    assert torch.allclose(lp, g['lp'], atol=2e-4, rtol=1e-4), (lp - g['lp']).abs().max()
+    lpa = oflow.algebra_log_prob(couplings, g['vt'].float() * 0.9, ctx, RADIUS, 0.6)
+    assert torch.allclose(lpa, g['lp_alg'], atol=2e-4, rtol=1e-4)
+    v = oflow.flow_forward(couplings, g['z'], ctx, RADIUS)
+    assert torch.allclose(v, g['v_alg'], atol=1e-6, rtol=1e-6)
+    R = oflow.so3_sample(couplings, g['z'], ctx, RADIUS)
+    assert torch.allclose(R, g['R_s'], atol=1e-12, rtol=0)
+    lps = oflow.so3_log_prob(couplings, g['R_s'], ctx, RADIUS, 0.6)
+    assert torch.allclose(lps, g['lp_s'], atol=2e-4, rtol=1e-4)
+
+
+def test_real_regressors_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'regressors_sparse.npz'))
+    assert tuple(g['extra_shape']) == (9, 6890) and tuple(g['cocoplus_shape']) == (19, 6890) and tuple(g['h36m_shape']) == (17, 6890)
+    assert len(g['extra_val']) == 62 and len(g['cocoplus_val']) == 86 and len(g['h36m_val']) == 107
