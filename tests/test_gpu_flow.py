@@ -1,0 +1,159 @@
+"""Ancestor-conditioned SO(3) flow: CUDA path (C-ABI via HumaniflowModel) vs the CPU oracle on identical
+weights, features and injected noise.  Tolerances (written here, from BASELINE.json north_star):
+rotation matrices <= 2e-5 abs (fp32 noise floor of the 23-joint chain is ~4e-6), log_prob rel err <= 1e-3."""
+import math
+
+import pytest
+import torch
+
+from oracle import model as om
+from util import make_model, special_rotations
+from humaniflow_b200.synthetic import SMPL_PARENTS
+
+pytestmark = pytest.mark.gpu
+ROT_TOL = 2e-5
+LP_RTOL = 1e-3
+
+
+def _noise(B, N, seed=1, positive_feats=True, feat_dim=512):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(B, feat_dim, generator=g)
+    if positive_feats:
+        feats = feats.abs()            # post-ReLU avg-pooled features are non-negative
+    z = torch.randn(B, N, 23, 3, generator=g) * 0.6
+    se = torch.randn(B, N, 10, generator=g)
+    return feats, z, se
+
+
+def _run(m, feats, z, se, **kw):
+    N = z.shape[1] if z is not None else 0
+    return m(None, input_feats=feats.cuda(), num_samples=N, base_noise=None if z is None else z.cuda(),
+             shape_eps=None if se is None else se.cuda(), **kw)
+
+
+@pytest.mark.parametrize('B,N,scale', [(3, 7, 1.0), (4, 25, 1.5), (32, 100, 1.0)])
+def test_sampling_and_point_estimate_parity(B, N, scale):
+    """(32,100) is BASELINE configs[1]: B=32, N=100, 23 joints, random-init flow + synthetic encoder features."""
+    m, sd, cfg = make_model(18, seed=0, flow_scale=scale)
+    m = m.cuda()
+    feats, z, se = _noise(B, N)
+    ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, num_samples=N, shape_eps=se, base_noise=z)
+    out = _run(m, feats, z, se)
+    assert out['pose_rotmats_samples'].shape == (B, N, 23, 3, 3) and out['pose_rotmats_samples'].dtype == torch.float32
+    assert out['shape_samples'].shape == (B, N, 10)
+    assert out['pose_rotmats_point_est'].shape == (B, 23, 3, 3) and out['pose_axisangle_point_est'].shape == (B, 23, 3)
+    for k in ('cam_wp', 'glob_rotmat', 'shape_mode', 'shape_log_std', 'shape_samples'):
+        assert torch.allclose(out[k].cpu(), ref[k], atol=2e-5, rtol=1e-5), k
+    tol = ROT_TOL * (1 if scale == 1.0 else 4)
+    assert (out['pose_rotmats_samples'].cpu() - ref['pose_rotmats_samples']).abs().max().item() <= tol
+    assert (out['pose_rotmats_point_est'].cpu() - ref['pose_rotmats_point_est']).abs().max().item() <= tol
+    assert (out['pose_axisangle_point_est'].cpu() - ref['pose_axisangle_point_est']).abs().max().item() <= tol
+    # size-independent properties: every sample is a rotation
+    R = out['pose_rotmats_samples'].double()
+    assert (R @ R.transpose(-1, -2) - torch.eye(3, device=R.device, dtype=R.dtype)).abs().max().item() <= 1e-6
+    assert (torch.linalg.det(R) - 1).abs().max().item() <= 1e-6
+
+
+def test_modes_of_forward():
+    m, sd, cfg = make_model(18, seed=2)
+    m = m.cuda()
+    feats, z, se = _noise(5, 4, seed=3)
+    # samples only
+    o = _run(m, feats, z, se, compute_point_est=False)
+    assert 'pose_rotmats_point_est' not in o and o['pose_rotmats_samples'].shape == (5, 4, 23, 3, 3)
+    ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, compute_point_est=False, num_samples=4, shape_eps=se, base_noise=z)
+    assert (o['pose_rotmats_samples'].cpu() - ref['pose_rotmats_samples']).abs().max().item() <= ROT_TOL
+    # point estimate only
+    o = m(None, input_feats=feats.cuda())
+    assert 'pose_rotmats_samples' not in o
+    ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats)
+    assert (o['pose_rotmats_point_est'].cpu() - ref['pose_rotmats_point_est']).abs().max().item() <= ROT_TOL
+    # shape mode for samples
+    o = _run(m, feats, z, None, use_shape_mode_for_samples=True)
+    ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, num_samples=4, use_shape_mode_for_samples=True, base_noise=z)
+    assert torch.allclose(o['shape_samples'].cpu(), ref['shape_samples'], atol=1e-6)
+    assert (o['pose_rotmats_samples'].cpu() - ref['pose_rotmats_samples']).abs().max().item() <= ROT_TOL
+    # own RNG path: finite rotations, different draws differ
+    a = m(None, input_feats=feats.cuda(), num_samples=3)['pose_rotmats_samples']
+    b = m(None, input_feats=feats.cuda(), num_samples=3)['pose_rotmats_samples']
+    assert torch.isfinite(a).all() and (a - b).abs().max().item() > 1e-3
+    # return_input_feats(_only)
+    assert set(m(None, input_feats=feats.cuda(), return_input_feats_only=True).keys()) == {'input_feats'}
+    assert 'input_feats' in m(None, input_feats=feats.cuda(), return_input_feats=True)
+
+
+@pytest.mark.parametrize('scale', [1.0, 1.5])
+def test_log_prob_parity(scale):
+    """Teacher-forced log-likelihood (humaniflow_model.py:314-320; losses/humaniflow_loss.py:25-35):
+    targets include theta<1e-6, theta~pi/2 and |pi-theta|<1e-2, plus the model's own samples."""
+    m, sd, cfg = make_model(18, seed=4, flow_scale=scale)
+    m = m.cuda()
+    Rt = special_rotations()                       # (40,3,3) f64
+    B = Rt.shape[0]
+    feats, z, se = _noise(B, 1, seed=6)
+    g = torch.Generator().manual_seed(7)
+    perm = torch.stack([torch.randperm(B, generator=g) for _ in range(23)], 1)       # (B,23)
+    pose_R = Rt[perm].float()                                                          # (B,23,3,3), every joint sees every case
+    own = _run(m, feats, z, se)['pose_rotmats_samples'][:, 0].cpu()
+    pose_R[: B // 2] = own[: B // 2]
+    shape = se[:, 0]
+    glob = _run(m, feats, None, None)['glob_rotmat'].cpu()
+    ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, compute_point_est=False, shape_for_loglik=shape,
+                     pose_R_for_loglik=pose_R, glob_R_for_loglik=glob)
+    out = m(None, input_feats=feats.cuda(), compute_point_est=False, compute_for_loglik=True, shape_for_loglik=shape.cuda(),
+            pose_R_for_loglik=pose_R.cuda(), glob_R_for_loglik=glob.cuda())
+    dists = out['conditioned_pose_SO3flow_dists_for_loglik']
+    assert len(dists) == 23 and len(out['conditioned_pose_so3flow_dists_for_loglik']) == 23
+    ctx_ref = torch.stack(ref['loglik_contexts'], 1)
+    assert torch.allclose(out['flow_contexts_for_loglik'].cpu(), ctx_ref, atol=2e-5, rtol=1e-5)
+    lp = torch.stack([dists[j].log_prob(pose_R[:, j].double().cuda()) for j in range(23)], 1).cpu()
+    assert lp.shape == (B, 23) and lp.dtype == torch.float32 and torch.isfinite(lp).all()
+    err = (lp - ref['pose_loglik']).abs() / ref['pose_loglik'].abs().clamp_min(1.0)
+    assert err.max().item() <= LP_RTOL, err.max()
+    # the batched entry point gives the same numbers
+    lp_all = m.pose_log_prob(out['flow_contexts_for_loglik'], pose_R.cuda()).cpu()
+    assert torch.equal(lp_all, lp)
+    # density on the algebra (the `..._so3flow_...` objects)
+    from oracle import flow as oflow
+    v = torch.randn(B, 3, generator=g) * 0.8
+    j = 11
+    ref_alg = oflow.algebra_log_prob(om.joint_couplings(sd, j, 2), v, ref['loglik_contexts'][j], cfg.NORM_FLOW.COMPACT_SUPPORT_RADIUS, 0.6)
+    got = out['conditioned_pose_so3flow_dists_for_loglik'][j].log_prob(v.cuda()).cpu()
+    assert ((got - ref_alg).abs() / ref_alg.abs().clamp_min(1.0)).max().item() <= LP_RTOL
+
+
+def test_density_consistency_property():
+    """Oracle-free: log_prob(exp(v)) of a sample equals the single-pre-image change of variables whenever the
+    other pre-images fall outside the support (|v| < pi/2): log p(v) - log|det J_exp(v)|."""
+    m, sd, cfg = make_model(18, seed=8)
+    m = m.cuda()
+    B = 64
+    feats, z, se = _noise(B, 1, seed=9)
+    o = _run(m, feats, z * 0.3, se, compute_point_est=False)
+    R = o['pose_rotmats_samples'][:, 0]
+    glob = o['glob_rotmat']
+    out = m(None, input_feats=feats.cuda(), compute_point_est=False, compute_for_loglik=True, shape_for_loglik=se[:, 0].cuda(),
+            pose_R_for_loglik=R, glob_R_for_loglik=glob)
+    lp = m.pose_log_prob(out['flow_contexts_for_loglik'], R)
+    from oracle import so3
+    v = so3.so3_log(R.double().cpu())
+    small = v.norm(dim=-1) < math.pi / 2 - 0.05
+    lp_alg = torch.stack([out['conditioned_pose_so3flow_dists_for_loglik'][j].log_prob(v[:, j].float().cuda()) for j in range(23)], 1).cpu()
+    expect = lp_alg - so3.so3_log_abs_det_jacobian(v).float()
+    assert small.float().mean() > 0.5
+    assert ((lp.cpu() - expect).abs()[small]).max().item() <= 1e-3
+
+
+def test_state_dict_roundtrip_and_repack():
+    """Reference checkpoints load with strict=True (same key names); changing weights re-packs the kernels' copies."""
+    m, sd, cfg = make_model(18, seed=10)
+    m2, sd2, _ = make_model(18, seed=11)
+    m2 = m2.cuda()
+    feats, z, se = _noise(2, 3, seed=12)
+    before = _run(m2, feats, z, se)['pose_rotmats_samples'].clone()
+    missing = m2.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    after = _run(m2, feats, z, se)['pose_rotmats_samples']
+    ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, num_samples=3, shape_eps=se, base_noise=z)
+    assert (after.cpu() - ref['pose_rotmats_samples']).abs().max().item() <= ROT_TOL
+    assert (after - before).abs().max().item() > 1e-3

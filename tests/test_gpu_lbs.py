@@ -1,0 +1,119 @@
+"""SMPL LBS: CUDA path (through the C-ABI) vs the CPU oracle.  Tolerance: vertex / joint L2 <= 1e-4 m
+(BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import smpl as osmpl
+from oracle import so3
+from util import smpl_data
+
+pytestmark = pytest.mark.gpu
+TOL_M = 1e-4
+
+
+def _smpl(batch_size=1, create_transl=True):
+    import humaniflow_b200 as hb
+    return hb.SMPL.from_arrays(smpl_data(), batch_size=batch_size, create_transl=create_transl).cuda()
+
+
+def _l2(a, b):
+    return (a.cpu() - b).norm(dim=-1).max().item()
+
+
+def _inputs(M, seed=0, pose_std=0.3):
+    g = torch.Generator().manual_seed(seed)
+    betas = torch.randn(M, 10, generator=g)
+    theta = torch.randn(M, 24, 3, generator=g) * pose_std
+    return betas, theta
+
+
+def test_config1_axis_angle_and_rotmats():
+    """BASELINE.json configs[0]: batch=4, random betas(10) / theta(24x3) -> 6890 verts, 90 joints."""
+    smpl = _smpl()
+    data = smpl_data()
+    betas, theta = _inputs(4)
+    v_ref, j_ref = osmpl.smpl_forward(data, betas, theta[:, 1:].reshape(4, 69), theta[:, 0], pose2rot=True,
+                                      transl=torch.zeros(1, 3))
+    out = smpl(betas=betas.cuda(), body_pose=theta[:, 1:].reshape(4, 69).cuda(), global_orient=theta[:, 0].cuda(), pose2rot=True)
+    assert out.vertices.shape == (4, 6890, 3) and out.joints.shape == (4, 90, 3) and out.vertices.dtype == torch.float32
+    assert _l2(out.vertices, v_ref) <= TOL_M and _l2(out.joints, j_ref) <= TOL_M
+    R = so3.batch_rodrigues(theta.reshape(-1, 3)).view(4, 24, 3, 3)
+    v2, j2 = osmpl.smpl_forward(data, betas, R[:, 1:], R[:, :1], pose2rot=False)
+    out2 = smpl(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False)
+    assert _l2(out2.vertices, v2) <= TOL_M and _l2(out2.joints, j2) <= TOL_M
+
+
+@pytest.mark.parametrize('M', [1, 63, 65, 130])
+def test_ragged_batches_and_transl(M):
+    smpl = _smpl()
+    data = smpl_data()
+    betas, theta = _inputs(M, seed=M, pose_std=0.8)
+    R = so3.batch_rodrigues(theta.reshape(-1, 3)).view(M, 24, 3, 3)
+    transl = torch.randn(M, 3, generator=torch.Generator().manual_seed(3))
+    v_ref, j_ref = osmpl.smpl_forward(data, betas, R[:, 1:], R[:, :1], pose2rot=False, transl=transl)
+    out = smpl(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), transl=transl.cuda(), pose2rot=False)
+    assert _l2(out.vertices, v_ref) <= TOL_M and _l2(out.joints, j_ref) <= TOL_M
+
+
+def test_module_defaults_tpose_and_beta_broadcast():
+    """None inputs fall back to the module's zero parameters (predict_humaniflow.py:147); betas with batch 1
+    broadcast over the pose batch ([upstream] SMPL.forward)."""
+    smpl = _smpl(batch_size=3)
+    data = smpl_data()
+    out = smpl()
+    v_ref, j_ref = osmpl.smpl_forward(data, torch.zeros(3, 10), torch.zeros(3, 69), torch.zeros(3, 3), pose2rot=True,
+                                      transl=torch.zeros(3, 3))
+    assert _l2(out.vertices, v_ref) <= TOL_M and _l2(out.joints, j_ref) <= TOL_M
+    smpl = _smpl(batch_size=1)
+    betas, theta = _inputs(5, seed=9)
+    out = smpl(betas=betas[:1].cuda(), body_pose=theta[:, 1:].reshape(5, 69).cuda(), global_orient=theta[:, 0].cuda())
+    v_ref, _ = osmpl.smpl_forward(data, betas[:1], theta[:, 1:].reshape(5, 69), theta[:, 0], transl=torch.zeros(1, 3))
+    assert _l2(out.vertices, v_ref) <= TOL_M
+
+
+def test_full_size_properties():
+    """B*N = 3200 (BASELINE configs[1..3]): oracle-free properties + oracle spot rows.
+    identity pose => vertices == v_template + shapedirs.beta; first 24 joints == chain translations;
+    a global rotation about the root joint rotates the whole mesh rigidly."""
+    M = 3200
+    smpl = _smpl(create_transl=False)
+    data = smpl_data()
+    betas, theta = _inputs(M, seed=11, pose_std=0.5)
+    eye = torch.eye(3).expand(M, 24, 3, 3).contiguous()
+    out = smpl(betas=betas.cuda(), body_pose=eye[:, 1:].cuda(), global_orient=eye[:, :1].cuda(), pose2rot=False)
+    v_shaped = data['v_template'][None] + torch.einsum('bl,mkl->bmk', betas, data['shapedirs'])
+    assert _l2(out.vertices, v_shaped) <= 2e-6
+    J = torch.einsum('bik,ji->bjk', v_shaped, data['J_regressor'])
+    assert _l2(out.joints[:, :24], J) <= 2e-6
+    R = so3.batch_rodrigues(theta.reshape(-1, 3)).view(M, 24, 3, 3)
+    outp = smpl(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False)
+    rows = [0, 1, 777, 1599, 3135, 3199]
+    v_ref, j_ref = osmpl.smpl_forward(data, betas[rows], R[rows][:, 1:], R[rows][:, :1], pose2rot=False)
+    assert _l2(outp.vertices[rows], v_ref) <= TOL_M and _l2(outp.joints[rows], j_ref) <= TOL_M
+    # rigidity: same body pose, identity global orientation, then rotate about the root joint
+    out0 = smpl(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=eye[:, :1].cuda(), pose2rot=False)
+    root = out0.joints[:, :1].cpu()
+    rotated = torch.einsum('bij,bvj->bvi', R[:, 0], out0.vertices.cpu() - root) + root
+    assert (outp.vertices.cpu() - rotated).norm(dim=-1).max().item() <= 1e-5
+    assert torch.isfinite(outp.vertices).all()
+
+
+def test_joint_layout_90():
+    """joints = 24 chain + 21 vertex picks + 9 + 19 + 17 regressed (models/smpl.py:30-34, label_conversions.py:17-21)."""
+    smpl = _smpl()
+    betas, theta = _inputs(2, seed=4)
+    out = smpl(betas=betas.cuda(), body_pose=theta[:, 1:].reshape(2, 69).cuda(), global_orient=theta[:, 0].cuda())
+    v = out.vertices.cpu()
+    from humaniflow_b200.smpl import VERTEX_JOINT_IDS
+    assert torch.allclose(out.joints[:, 24:45].cpu(), v[:, VERTEX_JOINT_IDS], atol=0, rtol=0)
+    data = smpl_data()
+    h36m = torch.einsum('bik,ji->bjk', v, data['J_regressor_h36m'])
+    assert (out.joints[:, 73:90].cpu() - h36m).norm(dim=-1).max().item() <= 1e-5
+
+
+def test_no_cpu_fallback():
+    import humaniflow_b200 as hb
+    smpl = hb.SMPL.from_arrays(smpl_data())
+    with pytest.raises(RuntimeError):
+        smpl(betas=torch.zeros(1, 10), body_pose=torch.zeros(1, 69), global_orient=torch.zeros(1, 3))
