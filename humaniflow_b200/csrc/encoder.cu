@@ -517,6 +517,7 @@ struct hf_encoder {
     std::vector<float*> bias;
     std::vector<int> w_cin;               // cin of each weight as given
     int in_channels, stem_cin, feat_dim, impl;
+    int debug_stop;                       // >= 0: forward stops after this op (layer-by-layer bring-up)
     // plan cache for one (B,H,W,workspace)
     int pB, pH, pW;
     void* pws;
@@ -528,17 +529,21 @@ constexpr int STEM_CP = 32;
 
 struct BufShape { int H, W, C; };
 
-// walk the op list to derive every buffer's shape
-int infer_shapes(const hf_encoder* h, int B, int H, int W, std::map<int, BufShape>& shp, size_t* max_act) {
-    shp.clear();
+// walk the op list to derive every op's input / output activation shape (buffer ids are reused along the way)
+struct OpShapes { std::vector<BufShape> in, out; };
+
+int infer_shapes(const hf_encoder* h, int B, int H, int W, OpShapes& os, size_t* max_act) {
+    std::map<int, BufShape> cur;
+    os.in.assign(h->ops.size(), BufShape{0, 0, 0});
+    os.out.assign(h->ops.size(), BufShape{0, 0, 0});
     size_t mx = 0;
     for (size_t i = 0; i < h->ops.size(); ++i) {
         const hf_enc_op& op = h->ops[i];
         BufShape in;
         if (i == 0) in = {H, W, h->stem_cin};
         else {
-            if (!shp.count(op.src)) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu reads unwritten buffer %d", i, op.src);
-            in = shp[op.src];
+            if (!cur.count(op.src)) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu reads unwritten buffer %d", i, op.src);
+            in = cur[op.src];
         }
         BufShape out = in;
         if (op.kind == HF_OP_CONV) {
@@ -546,12 +551,19 @@ int infer_shapes(const hf_encoder* h, int B, int H, int W, std::map<int, BufShap
             out.W = (in.W + 2 * op.pad - op.ksize) / op.stride + 1;
             out.C = op.cout;
             if (i > 0 && op.cin != in.C) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu cin %d != buffer channels %d", i, op.cin, in.C);
+            if (op.res >= 0) {
+                if (!cur.count(op.res)) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu adds unwritten buffer %d", i, op.res);
+                const BufShape r = cur[op.res];
+                if (r.H != out.H || r.W != out.W || r.C != out.C) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu residual shape mismatch", i);
+                if (op.res == op.dst) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu writes over its residual", i);
+            }
+            if (op.src == op.dst) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu is in-place", i);
         } else if (op.kind == HF_OP_MAXPOOL3x3S2) {
             out.H = (in.H + 2 - 3) / 2 + 1; out.W = (in.W + 2 - 3) / 2 + 1;
-        } else if (op.kind == HF_OP_GLOBAL_AVGPOOL) {
-            continue;
         }
-        shp[op.dst] = out;
+        os.in[i] = in; os.out[i] = out;
+        if (op.kind == HF_OP_GLOBAL_AVGPOOL) continue;
+        cur[op.dst] = out;
         mx = std::max(mx, (size_t)B * out.H * out.W * out.C * 2);
     }
     *max_act = (mx + 1023) & ~(size_t)1023;
@@ -576,7 +588,7 @@ extern "C" int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int n
         return hf::fail(HF_ERR_UNSUPPORTED, "hf_encoder_create: first op must be the 7x7/2 stem with <=32 input channels padded to 32");
     hf_encoder* h = new hf_encoder();
     h->ops.assign(ops, ops + num_ops);
-    h->in_channels = in_channels; h->stem_cin = stem_cin; h->feat_dim = feat_dim; h->impl = 0;
+    h->in_channels = in_channels; h->stem_cin = stem_cin; h->feat_dim = feat_dim; h->impl = 0; h->debug_stop = -1;
     h->pB = h->pH = h->pW = 0; h->pws = nullptr;
     h->w.resize(num_weights); h->w_plain.resize(num_weights); h->bias.resize(num_weights); h->w_cin.resize(num_weights);
     for (int i = 0; i < num_ops; ++i) {
@@ -622,7 +634,7 @@ extern "C" int hf_encoder_set_impl(hf_encoder_t* h, int impl) {
 }
 
 extern "C" size_t hf_encoder_workspace_bytes(const hf_encoder_t* h, int B, int H, int W) {
-    std::map<int, BufShape> shp;
+    OpShapes shp;
     size_t max_act = 0;
     if (infer_shapes(h, B, H, W, shp, &max_act)) return 0;
     return stem_in_bytes(B, H, W) + (size_t)num_buffers(h) * max_act + 1024;
@@ -632,7 +644,7 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
                                   size_t workspace_bytes, void* stream_) {
     if (!h || !input || !feats || !workspace) return hf::fail(HF_ERR_INVALID, "hf_encoder_forward: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
-    std::map<int, BufShape> shp;
+    OpShapes shp;
     size_t max_act = 0;
     int rc = infer_shapes(h, B, H, W, shp, &max_act);
     if (rc) return rc;
@@ -652,7 +664,7 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
             if (op.kind != HF_OP_CONV) continue;
             if (i == 0) rc = plan_conv(&h->plans[i], 1, stem_in, h->w[op.weight_index], B, H, W, STEM_CP, op.cout, 7, 2, 3, op.relu, Hp, Wp);
             else {
-                const BufShape in = shp[op.src];
+                const BufShape in = shp.in[i];
                 if (op.cin % 64 != 0) return hf::fail(HF_ERR_UNSUPPORTED, "encoder: conv %zu has cin %d (must be a multiple of 64)", i, op.cin);
                 rc = plan_conv(&h->plans[i], 0, buf(op.src), h->w[op.weight_index], B, in.H, in.W, op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, 0, 0);
             }
@@ -679,24 +691,50 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
                 rc = launch_simt(stem_in, h->w_plain[op.weight_index], h->bias[op.weight_index], res, buf(op.dst), B, Hp, Wp,
                                  STEM_CP, op.cout, 7, 2, 0, op.relu, stream, h->plans[i].g.Ho, h->plans[i].g.Wo);
             } else {
-                const BufShape in = shp[op.src];
+                const BufShape in = shp.in[i];
                 rc = launch_simt(buf(op.src), h->w_plain[op.weight_index], h->bias[op.weight_index], res, buf(op.dst), B, in.H, in.W,
                                  op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, stream);
             }
             if (rc) return rc;
         } else if (op.kind == HF_OP_MAXPOOL3x3S2) {
-            const BufShape in = shp[op.src], o = shp[op.dst];
+            const BufShape in = shp.in[i], o = shp.out[i];
             const size_t total = (size_t)B * o.H * o.W * (in.C / 8);
             int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
             maxpool_kernel<<<blocks, 256, 0, stream>>>(buf(op.src), buf(op.dst), B, in.H, in.W, in.C, o.H, o.W);
             HF_LAUNCH_CHECK();
         } else if (op.kind == HF_OP_GLOBAL_AVGPOOL) {
-            const BufShape in = shp[op.src];
+            const BufShape in = shp.in[i];
             dim3 grid(hf::div_up(in.C, 128), B);
             avgpool_kernel<<<grid, 128, 0, stream>>>(buf(op.src), feats, B, in.H * in.W, in.C);
             HF_LAUNCH_CHECK();
         }
+        if (h->debug_stop == (int)i) break;
     }
+    return HF_OK;
+}
+
+// Bring-up aid: run the program up to and including op `op_index`, then copy that op's output activation
+// (bf16 NHWC) to `out` and report its dims {H, W, C}.
+extern "C" int hf_encoder_debug_op_output(hf_encoder_t* h, int op_index, const float* input, int B, int H, int W,
+                                          void* workspace, size_t workspace_bytes, uint16_t* out, size_t out_bytes,
+                                          int* dims, float* feats, void* stream_) {
+    if (!h || op_index < 0 || op_index >= (int)h->ops.size()) return hf::fail(HF_ERR_INVALID, "debug: bad op index");
+    OpShapes shp;
+    size_t max_act = 0;
+    int rc = infer_shapes(h, B, H, W, shp, &max_act);
+    if (rc) return rc;
+    h->debug_stop = op_index;
+    rc = hf_encoder_forward(h, input, B, H, W, feats, workspace, workspace_bytes, stream_);
+    h->debug_stop = -1;
+    if (rc) return rc;
+    const hf_enc_op& op = h->ops[op_index];
+    if (op.kind == HF_OP_GLOBAL_AVGPOOL) { dims[0] = dims[1] = 1; dims[2] = h->feat_dim; return HF_OK; }
+    const BufShape o = shp.out[op_index];
+    dims[0] = o.H; dims[1] = o.W; dims[2] = o.C;
+    const size_t bytes = (size_t)B * o.H * o.W * o.C * 2;
+    if (out_bytes < bytes) return hf::fail(HF_ERR_INVALID, "debug: output buffer too small");
+    uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    HF_CUDA(cudaMemcpyAsync(out, ws + stem_in_bytes(B, H, W) + (size_t)op.dst * max_act, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
     return HF_OK;
 }
 

@@ -564,6 +564,7 @@ flow_logprob_kernel(const __grid_constant__ FlowParams P, const float* __restric
         float res = terms[0];
         if (!ALGEBRA) {
             float m = fmaxf(terms[0], fmaxf(terms[NC > 1 ? 1 : 0], terms[NC > 2 ? 2 : 0]));
+            if (isinf(m)) m = 0.f;     // torch.logsumexp: an infinite maximum is not subtracted (keeps +inf, no NaN)
             float ssum = 0.f;
             for (int c = 0; c < NC; ++c) ssum += expf(terms[c] - m);
             res = m + logf(ssum);

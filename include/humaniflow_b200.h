@@ -178,6 +178,12 @@ int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, int H, int W,
 /* impl: 0 = tcgen05/TMA implicit GEMM (product path), 1 = SIMT direct convolution (debug cross-check). */
 int hf_encoder_set_impl(hf_encoder_t* h, int impl);
 
+/* Bring-up aid: run the program up to and including op `op_index`, copy that op's bf16 NHWC output to `out`
+ * (device) and write its {H, W, C} to dims (host). */
+int hf_encoder_debug_op_output(hf_encoder_t* h, int op_index, const float* input, int B, int H, int W,
+                               void* workspace, size_t workspace_bytes, uint16_t* out, size_t out_bytes,
+                               int* dims, float* feats, void* stream);
+
 /* Single convolution on bf16 NHWC tensors (unit-test entry point for the conv kernels).
  * x (B,H,W,cin) bf16; w (cout,k,k,cin) bf16; bias (cout) fp32; res (B,Ho,Wo,cout) bf16 or NULL;
  * y (B,Ho,Wo,cout) bf16. */

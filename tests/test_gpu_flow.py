@@ -107,8 +107,14 @@ def test_log_prob_parity(scale):
     ctx_ref = torch.stack(ref['loglik_contexts'], 1)
     assert torch.allclose(out['flow_contexts_for_loglik'].cpu(), ctx_ref, atol=2e-5, rtol=1e-5)
     lp = torch.stack([dists[j].log_prob(pose_R[:, j].double().cuda()) for j in range(23)], 1).cpu()
-    assert lp.shape == (B, 23) and lp.dtype == torch.float32 and torch.isfinite(lp).all()
-    err = (lp - ref['pose_loglik']).abs() / ref['pose_loglik'].abs().clamp_min(1.0)
+    assert lp.shape == (B, 23) and lp.dtype == torch.float32
+    # Reference quirk kept on purpose: for 1e-10 < theta <~ 1e-8 the fp64 expression log((2-2cos t)/t^2) of
+    # utils/rigid_transform_utils.py:298-314 cancels to log(0), so the reference's log_prob is +inf there
+    # (special_rotations() contains theta = 1e-9).  Non-finite entries must agree exactly, finite ones to 1e-3.
+    fin = torch.isfinite(ref['pose_loglik'])
+    assert torch.equal(torch.isfinite(lp), fin) and torch.equal(lp[~fin], ref['pose_loglik'][~fin])
+    assert fin.float().mean() > 0.95
+    err = (lp - ref['pose_loglik']).abs()[fin] / ref['pose_loglik'].abs()[fin].clamp_min(1.0)
     assert err.max().item() <= LP_RTOL, err.max()
     # the batched entry point gives the same numbers
     lp_all = m.pose_log_prob(out['flow_contexts_for_loglik'], pose_R.cuda()).cpu()
@@ -119,6 +125,7 @@ def test_log_prob_parity(scale):
     j = 11
     ref_alg = oflow.algebra_log_prob(om.joint_couplings(sd, j, 2), v, ref['loglik_contexts'][j], cfg.NORM_FLOW.COMPACT_SUPPORT_RADIUS, 0.6)
     got = out['conditioned_pose_so3flow_dists_for_loglik'][j].log_prob(v.cuda()).cpu()
+    assert torch.isfinite(got).all()
     assert ((got - ref_alg).abs() / ref_alg.abs().clamp_min(1.0)).max().item() <= LP_RTOL
 
 
