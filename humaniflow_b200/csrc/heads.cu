@@ -5,9 +5,9 @@
 
 namespace {
 
-constexpr int OPW = 4;    // outputs per warp
-constexpr int MT = 16;    // rows per CTA tile
-constexpr int WARPS = 8;
+constexpr int LW = 4;      // warps per CTA
+constexpr int LO = 2;      // outputs per warp
+constexpr int KC = 256;    // K chunk staged in shared memory
 
 __device__ __forceinline__ float act_fn(float a, int act) {
     if (act == 1) return a > 0.f ? a : expm1f(a);
@@ -15,55 +15,63 @@ __device__ __forceinline__ float act_fn(float a, int act) {
     return a;
 }
 
-// y[m][o] (+)= act(sum_k x[m][k] W[o][k] + b[o]); a warp owns OPW outputs x MT rows, lanes stride K.
-__global__ void __launch_bounds__(WARPS * 32)
+// y[m][o] (+)= act(sum_k x[m][k] W[o][k] + b[o]).  Lane = batch row (32 rows per CTA tile), a warp owns LO
+// output neurons; the x tile is staged transposed in shared memory (conflict-free column reads), weights
+// are streamed with warp-broadcast (vector) loads, each element read once per row tile.  No reductions.
+template <bool VEC4>
+__global__ void __launch_bounds__(LW * 32)
 linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, int ldw,
               const float* __restrict__ b, float* __restrict__ y, int ldy, int M, int K, int O, int act,
               int accumulate) {
+    __shared__ float xs[KC][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o0 = (blockIdx.x * WARPS + warp) * OPW;
-    const int m0 = blockIdx.y * MT;
-    if (o0 >= O) return;
-    float acc[OPW][MT];
+    const int o0 = (blockIdx.x * LW + warp) * LO;
+    const int m0 = blockIdx.y * 32;
+    float acc[LO];
 #pragma unroll
-    for (int i = 0; i < OPW; ++i)
+    for (int i = 0; i < LO; ++i) acc[i] = 0.f;
+    const float* wrow[LO];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) acc[i][m] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-        float w[OPW];
+    for (int i = 0; i < LO; ++i) wrow[i] = W + (size_t)min(o0 + i, O - 1) * ldw;
+    for (int kc = 0; kc < K; kc += KC) {
+        const int kn = min(KC, K - kc);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 32 * kn; idx += LW * 32) {
+            const int r = idx / kn, k = idx - r * kn;
+            xs[k][r] = (m0 + r < M) ? __ldg(x + (size_t)(m0 + r) * ldx + kc + k) : 0.f;
+        }
+        __syncthreads();
+        if (VEC4) {
+#pragma unroll 4
+            for (int k = 0; k < kn; k += 4) {
+                const float x0 = xs[k][lane], x1 = xs[k + 1][lane], x2 = xs[k + 2][lane], x3 = xs[k + 3][lane];
 #pragma unroll
-        for (int i = 0; i < OPW; ++i) w[i] = (o0 + i < O) ? __ldg(W + (size_t)(o0 + i) * ldw + k) : 0.f;
+                for (int i = 0; i < LO; ++i) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(wrow[i] + kc + k));
+                    acc[i] = fmaf(w.x, x0, acc[i]); acc[i] = fmaf(w.y, x1, acc[i]);
+                    acc[i] = fmaf(w.z, x2, acc[i]); acc[i] = fmaf(w.w, x3, acc[i]);
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < kn; ++k) {
+                const float xv = xs[k][lane];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            const float xv = (m0 + m < M) ? __ldg(x + (size_t)(m0 + m) * ldx + k) : 0.f;
-#pragma unroll
-            for (int i = 0; i < OPW; ++i) acc[i][m] = fmaf(w[i], xv, acc[i][m]);
+                for (int i = 0; i < LO; ++i) acc[i] = fmaf(__ldg(wrow[i] + kc + k), xv, acc[i]);
+            }
         }
     }
+    const int r = m0 + lane;
+    if (r < M) {
 #pragma unroll
-    for (int i = 0; i < OPW; ++i)
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            float v = acc[i][m];
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-            acc[i][m] = v;
-        }
-    // lane l writes element (i = l / MT ... ) : spread the OPW*MT results over the lanes
-    for (int e = lane; e < OPW * MT; e += 32) {
-        const int i = e / MT, m = e - i * MT;
-        float v = 0.f;
-#pragma unroll
-        for (int ii = 0; ii < OPW; ++ii)
-#pragma unroll
-            for (int mm = 0; mm < MT; ++mm)
-                if (ii == i && mm == m) v = acc[ii][mm];
-        const int o = o0 + i, r = m0 + m;
-        if (o < O && r < M) {
-            float* dst = y + (size_t)r * ldy + o;
-            float a = v + (b ? __ldg(b + o) : 0.f);
-            if (accumulate) a += *dst;
-            *dst = act_fn(a, act);
+        for (int i = 0; i < LO; ++i) {
+            const int o = o0 + i;
+            if (o < O) {
+                float* dst = y + (size_t)r * ldy + o;
+                float a = acc[i] + (b ? __ldg(b + o) : 0.f);
+                if (accumulate) a += *dst;
+                *dst = act_fn(a, act);
+            }
         }
     }
 }
@@ -136,8 +144,12 @@ extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const
     if (!x || !W || !y) return hf::fail(HF_ERR_INVALID, "hf_linear: null argument");
     if (M <= 0 || O <= 0) return HF_OK;
     if (K < 0 || ldx < K || ldw < K || ldy < O) return hf::fail(HF_ERR_INVALID, "hf_linear: bad strides");
-    dim3 grid(hf::div_up(O, WARPS * OPW), hf::div_up(M, MT));
-    linear_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate);
+    dim3 grid(hf::div_up(O, LW * LO), hf::div_up(M, 32));
+    const bool vec4 = (K % 4 == 0) && (ldw % 4 == 0) && (((uintptr_t)W & 15) == 0);
+    if (vec4)
+        linear_kernel<true><<<grid, LW * 32, 0, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate);
+    else
+        linear_kernel<false><<<grid, LW * 32, 0, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate);
     HF_LAUNCH_CHECK();
     return HF_OK;
 }

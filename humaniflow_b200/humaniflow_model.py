@@ -202,7 +202,9 @@ class HumaniflowModel(nn.Module):
             # heads as one (2nb+9, fc1) matrix: [shape | glob | cam]
             'heads_w': dev(torch.cat([cpu(self.fc_shape.weight), cpu(self.fc_glob.weight), cpu(self.fc_cam.weight)], 0)),
             'heads_b': dev(torch.cat([cpu(self.fc_shape.bias), cpu(self.fc_glob.bias), cpu(self.fc_cam.bias)], 0)),
-            'img_w': dev(Wimg), 'img_b': dev(cpu(self.fc_input_shape_glob_cam_feats.bias)),
+            # image-level Linear split by input block (feats | beta | glob | cam) so every matrix is 16-byte aligned
+            'img_wf': dev(Wimg[:, :F]), 'img_wg': dev(Wimg[:, F + nb:F + nb + 9]), 'img_wc': dev(Wimg[:, F + nb + 9:]),
+            'img_b': dev(cpu(self.fc_input_shape_glob_cam_feats.bias)),
             'fc1_w': dev(cpu(self.fc1.weight)), 'fc1_b': dev(cpu(self.fc1.bias)),
             'init_glob': dev(cpu(self.init_glob).view(-1)), 'init_cam': dev(cpu(self.init_cam).view(-1)),
         }
@@ -221,10 +223,10 @@ class HumaniflowModel(nn.Module):
         B, F, nb = input_feats.shape[0], self.input_feats_dim, self.num_shape_params
         D = self.cfg.INPUT_SHAPE_GLOB_CAM_FEATS_DIM
         base = torch.empty(B, D, device=input_feats.device, dtype=torch.float32)
-        self._linear(input_feats, P['img_w'], P['img_b'], base, F, D)
+        self._linear(input_feats, P['img_wf'], P['img_b'], base, F, D)
         g = _lib.f32c(glob_R).reshape(B, 9)
-        self._linear(g, P['img_w'], None, base, 9, D, accumulate=1, w_offset=F + nb)
-        self._linear(cam, P['img_w'], None, base, 3, D, accumulate=1, w_offset=F + nb + 9)
+        self._linear(g, P['img_wg'], None, base, 9, D, accumulate=1)
+        self._linear(cam, P['img_wc'], None, base, 3, D, accumulate=1)
         return base
 
     def _img_index(self, B, N, with_pe, device):
