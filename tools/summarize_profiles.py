@@ -1,0 +1,102 @@
+"""Turn the ncu outputs under gpurun_out/ into the committed summaries under profiles/.
+usage: python tools/summarize_profiles.py r01"""
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+suffix = tag.replace('r0', 'r')
+G, P = 'gpurun_out', 'profiles'
+os.makedirs(P, exist_ok=True)
+out = ['# ncu summaries, round %s' % tag, '',
+       'All captured on a B200 through `gpurun` with `--clock-control none`; times under ncu are cold-cache and',
+       'serialised (compare SHARES, not absolutes — bench.py measures the live numbers with CUDA events).', '']
+
+
+def rows_of(path):
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith('==')]
+    return list(csv.DictReader(lines))
+
+
+lst = os.path.join(G, 'launches_%s.csv' % suffix)
+if os.path.exists(lst):
+    rows = rows_of(lst)
+    # one whole step = from one nchw_to_nhwc launch (first kernel of the encoder) to the next; prefer the last
+    # complete one (the capture may be truncated by -c)
+    starts = [i for i, r in enumerate(rows) if 'nchw_to_nhwc' in r['Kernel Name']]
+    has_lbs = lambda seg: any('lbs_extra' in r['Kernel Name'] for r in seg)
+    segs = [rows[a:b] for a, b in zip(starts, starts[1:] + [len(rows)])]
+    step = [seg for seg in segs if has_lbs(seg)][-1]
+    while 'lbs_extra' not in step[-1]['Kernel Name']:
+        step = step[:-1]
+    agg = collections.OrderedDict()
+    tot = 0.0
+    for r in step:
+        name = r['Kernel Name'].split('(')[0].replace('void ', '').replace('<unnamed>::', '')
+        v = float(r['Metric Value'].replace(',', ''))
+        v = v / 1000 if r['Metric Unit'] == 'ns' else (v * 1000 if r['Metric Unit'] == 'ms' else v)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+        tot += v
+    out += ['## Launch list of one step (`ncu --metrics gpu__time_duration.sum`, command: `python tools/profile_step.py 2`)', '',
+            'B=32 images, N=100 samples, ResNet-50: %d launches, %.1f us of kernel time under ncu.' % (len(step), tot), '',
+            '| kernel | launches | us | share |', '|---|---:|---:|---:|']
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append('| `%s` | %d | %.1f | %.1f%% |' % (k[:70], c, t, 100 * t / tot))
+    out.append('')
+    with open(os.path.join(P, '%s_launches.csv' % tag), 'w') as f:
+        w = csv.writer(f)
+        w.writerow(['id', 'kernel', 'grid', 'block', 'duration', 'unit'])
+        for r in step:
+            w.writerow([r['ID'], r['Kernel Name'].split('(')[0], r['Grid Size'], r['Block Size'], r['Metric Value'], r['Metric Unit']])
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'smsp__inst_executed.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'lts__t_sector_hit_rate.pct', 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio']
+for name in ('lbs', 'flow'):
+    rep = os.path.join(G, 'prof_%s_%s.ncu-rep' % (name, suffix))
+    if not os.path.exists(rep):
+        continue
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rr[0], rr[1], rr[2]
+    out += ['## `%s` (`ncu --set full --import-source on`)' % vals[hdr.index('Kernel Name')].split('(')[0].replace('void <unnamed>::', ''), '',
+            '| metric | value | unit |', '|---|---:|---|']
+    for w_ in WANT:
+        if w_ in hdr:
+            i = hdr.index(w_)
+            out.append('| %s | %s | %s |' % (w_, vals[i], units[i]))
+    out.append('')
+conv = os.path.join(G, 'prof_conv_%s_raw.csv' % suffix)
+if os.path.exists(conv):
+    rr = list(csv.reader(open(conv)))
+    hdr = rr[0]
+    c = lambda n: hdr.index(n)
+    out += ['## `conv_tcgen05_kernel`, the 53 convolutions of one ResNet-50 forward (`ncu --set full`)', '',
+            '| # | template | grid | us | tensor pipe % | DRAM % | DRAM rd MB | DRAM wr MB | L2 hit % |', '|---:|---|---|---:|---:|---:|---:|---:|---:|']
+    tot = 0.0
+    wsum = 0.0
+    for n, r in enumerate(rr[2:]):
+        t = float(r[c('gpu__time_duration.sum')])
+        tp = float(r[c('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')])
+        tot += t
+        wsum += t * tp
+        out.append('| %d | %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f |' % (
+            n, r[c('Kernel Name')].split('conv_tcgen05_kernel')[1].split('(')[0], r[c('Grid Size')], t, tp,
+            float(r[c('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')]), float(r[c('dram__bytes_read.sum')]),
+            float(r[c('dram__bytes_write.sum')]), float(r[c('lts__t_sector_hit_rate.pct')])))
+    out += ['', 'Total %.1f us; time-weighted tensor-pipe activity %.1f%%.' % (tot, wsum / tot), '']
+open(os.path.join(P, '%s_summary.md' % tag), 'w').write('\n'.join(out))
+print('\n'.join(out[:40]))
