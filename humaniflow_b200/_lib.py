@@ -36,6 +36,7 @@ SIGNATURES = {
     'hf_smpl_destroy': (None, [c_void_p]),
     'hf_smpl_num_joints_out': (c_int, [c_void_p]),
     'hf_lbs_workspace_bytes': (c_size_t, [c_void_p, c_int]),
+    'hf_lbs_set_impl': (c_int, [c_void_p, c_int]),
     'hf_lbs_forward': (c_int, [c_void_p] * 7 + [c_size_t, c_int, c_void_p]),
     'hf_rodrigues': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'hf_flow_create': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(FlowConfig)] + [c_void_p] * 7),

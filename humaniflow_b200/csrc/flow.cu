@@ -104,52 +104,50 @@ struct SplineBin {
     float in_w, in_cw, in_ch, in_h, d0, d1, lam;
 };
 
-// raw: pointer to this row's NN outputs with stride `rs` between consecutive outputs; d in {0,1}
-__device__ __forceinline__ SplineBin spline_select(const float* raw, int rs, int d, float input, float bound,
-                                                   bool inverse) {
+// Cooperative knot computation for all rows of the CTA: 8 lanes per (row, d, kind) group evaluate the softmax
+// over the 8 bins and the cumulative knot positions with warp shuffles (width 8), results to smem
+// KN[((row*2 + d)*2 + kind)*9 + i], kind 0 = widths, 1 = heights.  Ends with __syncthreads().
+template <int NR>
+__device__ __forceinline__ void spline_knots(const float* __restrict__ raw, float bound, float* __restrict__ KN) {
     const float lo = -bound, hi = bound;
-    float w[NBINS], h[NBINS];
-    {   // softmax widths / heights
-        float mw = -INFINITY, mh = -INFINITY;
-#pragma unroll
-        for (int b = 0; b < NBINS; ++b) {
-            w[b] = raw[(d * NBINS + b) * rs];
-            h[b] = raw[(2 * NBINS + d * NBINS + b) * rs];
-            mw = fmaxf(mw, w[b]); mh = fmaxf(mh, h[b]);
-        }
-        float sw = 0.f, sh = 0.f;
-#pragma unroll
-        for (int b = 0; b < NBINS; ++b) {
-            w[b] = expf(w[b] - mw); sw += w[b];
-            h[b] = expf(h[b] - mh); sh += h[b];
-        }
-#pragma unroll
-        for (int b = 0; b < NBINS; ++b) {
-            w[b] = 1e-3f + 0.992f * (w[b] / sw);
-            h[b] = 1e-3f + 0.992f * (h[b] / sh);
-        }
+    for (int t = threadIdx.x; t < NR * 32; t += HF_NT) {      // NR*4 groups of 8 lanes; HF_NT % 32 == 0 keeps groups in a warp
+        const int g = t >> 3, b = t & 7;
+        const int row = g >> 2, d = (g >> 1) & 1, kind = g & 1;
+        const float x = raw[(kind * 2 * NBINS + d * NBINS + b) * NR + row];
+        float m = x;
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4, 8));
+        const float e = expf(x - m);
+        float sum = e;
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4, 8);
+        float c = 1e-3f + 0.992f * (e / sum);
+        // inclusive scan over the 8 lanes
+        float u = __shfl_up_sync(0xffffffffu, c, 1, 8); if (b >= 1) c += u;
+        u = __shfl_up_sync(0xffffffffu, c, 2, 8); if (b >= 2) c += u;
+        u = __shfl_up_sync(0xffffffffu, c, 4, 8); if (b >= 4) c += u;
+        float* k = KN + g * 9;
+        k[b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * c + lo;
+        if (b == 0) k[0] = lo;
     }
-    float kw[NBINS + 1], kh[NBINS + 1];
-    {
-        float cw = 0.f, ch = 0.f;
-        kw[0] = lo; kh[0] = lo;
-#pragma unroll
-        for (int b = 0; b < NBINS; ++b) {
-            cw += w[b]; ch += h[b];
-            kw[b + 1] = (hi - lo) * cw + lo;
-            kh[b + 1] = (hi - lo) * ch + lo;
-        }
-        kw[NBINS] = hi; kh[NBINS] = hi;
-    }
+    __syncthreads();
+}
+
+// raw: pointer to this row's NN outputs with stride `rs` between consecutive outputs; kn: this (row, d)'s knots
+// [widths 9 | heights 9]; d in {0,1}
+__device__ __forceinline__ SplineBin spline_select(const float* raw, int rs, int d, float input, const float* kn,
+                                                   bool inverse) {
+    const float* kw = kn;
+    const float* kh = kn + 9;
+    const float* ks = inverse ? kh : kw;
     int idx = -1;
 #pragma unroll
-    for (int b = 0; b <= NBINS; ++b) idx += (input >= (inverse ? kh[b] : kw[b]) + 1e-6f) ? 1 : 0;
+    for (int b = 0; b <= NBINS; ++b) idx += (input >= ks[b] + 1e-6f) ? 1 : 0;
     idx = max(0, min(idx, NBINS - 1));
     SplineBin r;
-    r.in_w = 0.f; r.in_cw = 0.f; r.in_ch = 0.f; r.in_h = 0.f;
-#pragma unroll
-    for (int b = 0; b < NBINS; ++b)
-        if (b == idx) { r.in_w = kw[b + 1] - kw[b]; r.in_cw = kw[b]; r.in_ch = kh[b]; r.in_h = kh[b + 1] - kh[b]; }
+    r.in_w = kw[idx + 1] - kw[idx]; r.in_cw = kw[idx]; r.in_ch = kh[idx]; r.in_h = kh[idx + 1] - kh[idx];
     // derivatives: softplus + min, padded with 1 - min at both ends; lambdas: sigmoid, affine
     auto deriv = [&](int i) -> float {   // i in [0, NBINS]
         if (i == 0 || i == NBINS) return 0.999f;
@@ -165,9 +163,9 @@ __device__ __forceinline__ SplineBin spline_select(const float* raw, int rs, int
     return r;
 }
 
-__device__ __forceinline__ float spline_forward(const float* raw, int rs, int d, float x, float bound) {
+__device__ __forceinline__ float spline_forward(const float* raw, int rs, int d, float x, float bound, const float* kn) {
     if (!(x >= -bound && x <= bound)) return x;
-    SplineBin b = spline_select(raw, rs, d, x, bound, false);
+    SplineBin b = spline_select(raw, rs, d, x, kn, false);
     const float delta = b.in_h / b.in_w;
     const float wb = sqrtf(b.d0 / b.d1);
     const float wc = (b.lam * b.d0 + (1.f - b.lam) * wb * b.d1) / delta;
@@ -188,9 +186,9 @@ __device__ __forceinline__ float spline_forward(const float* raw, int rs, int d,
 // inverse spline; *fwd_logdet receives the FORWARD log|dy/dx| evaluated through the inverse formulas
 // (pyro Spline._inverse caches -logabsdet of the inverse direction).
 __device__ __forceinline__ float spline_inverse(const float* raw, int rs, int d, float y, float bound,
-                                                float* fwd_logdet) {
+                                                const float* kn, float* fwd_logdet) {
     if (!(y >= -bound && y <= bound)) { *fwd_logdet = 0.f; return y; }
-    SplineBin b = spline_select(raw, rs, d, y, bound, true);
+    SplineBin b = spline_select(raw, rs, d, y, kn, true);
     const float delta = b.in_h / b.in_w;
     const float wb = sqrtf(b.d0 / b.d1);
     const float wc = (b.lam * b.d0 + (1.f - b.lam) * wb * b.d1) / delta;
@@ -373,17 +371,18 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
         __syncthreads();
         for (int t = 0; t < P.T; ++t) {
             coupling_nn<NR>(P.pack + P.off_nn[j][t], sm);
+            spline_knots<NR>(sm + L::Raw, P.radius, sm + L::Ha);
             // spline on the two trailing coordinates, then rotate the vector for the next Permute
             // (pyro_conditional_norm_flow.py:46-62: with <=2 transforms the only non-identity Permute is [1,2,0],
             //  applied to the running vector before the second coupling).
             if (tid < 2 * NR) {
                 const int s = tid >> 1, d = tid & 1;
                 const float x = sm[L::Zs + (1 + d) * NR + s];
-                sm[L::Ha + d * NR + s] = spline_forward(sm + L::Raw + s, NR, d, x, P.radius);
+                sm[L::Hb + d * NR + s] = spline_forward(sm + L::Raw + s, NR, d, x, P.radius, sm + L::Ha + (s * 2 + d) * 18);
             }
             __syncthreads();
             if (tid < NR) {
-                const float y0 = sm[L::Zs + tid], y1 = sm[L::Ha + tid], y2 = sm[L::Ha + NR + tid];
+                const float y0 = sm[L::Zs + tid], y1 = sm[L::Hb + tid], y2 = sm[L::Hb + NR + tid];
                 if (t + 1 < P.T) {     // next permutation relative to the current order is always [1,2,0]
                     sm[L::Zs + tid] = y1; sm[L::Zs + NR + tid] = y2; sm[L::Zs + 2 * NR + tid] = y0;
                     sm[L::Cs + CTX * NR + tid] = y1;
@@ -527,17 +526,18 @@ flow_logprob_kernel(const __grid_constant__ FlowParams P, const float* __restric
     __syncthreads();
     for (int t = P.T - 1; t >= 0; --t) {
         coupling_nn<NR>(P.pack + P.off_nn[j][t], sm);
+        spline_knots<NR>(sm + L::Raw, P.radius, sm + L::Ha);
         if (tid < 2 * NR) {
             const int s = tid >> 1, d = tid & 1;
             float ld;
             const float y = sm[L::Zs + (1 + d) * NR + s];
-            sm[L::Ha + d * NR + s] = spline_inverse(sm + L::Raw + s, NR, d, y, P.radius, &ld);
-            sm[L::Hb + d * NR + s] = ld;
+            sm[L::Hb + d * NR + s] = spline_inverse(sm + L::Raw + s, NR, d, y, P.radius, sm + L::Ha + (s * 2 + d) * 18, &ld);
+            sm[L::Hc + d * NR + s] = ld;
         }
         __syncthreads();
         if (tid < NR) {
-            s_lp[tid] = s_lp[tid] - (sm[L::Hb + tid] + sm[L::Hb + NR + tid]);
-            const float x0 = sm[L::Zs + tid], x1 = sm[L::Ha + tid], x2 = sm[L::Ha + NR + tid];
+            s_lp[tid] = s_lp[tid] - (sm[L::Hc + tid] + sm[L::Hc + NR + tid]);
+            const float x0 = sm[L::Zs + tid], x1 = sm[L::Hb + tid], x2 = sm[L::Hb + NR + tid];
             if (t > 0) {   // undo Permute [1,2,0]: current = prev[[1,2,0]]  =>  prev = (cur[2], cur[0], cur[1])
                 sm[L::Zs + tid] = x2; sm[L::Zs + NR + tid] = x0; sm[L::Zs + 2 * NR + tid] = x1;
                 sm[L::Cs + CTX * NR + tid] = x2;

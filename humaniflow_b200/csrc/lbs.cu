@@ -11,11 +11,14 @@
 //   sj/sw [nslots][Vp] sparse skinning weights (SMPL: <=4 influences per vertex)
 // Per call (workspace): F [M][KP] blend coefficients (betas | vec(R_i - I)), A [M][J][3][4] relative transforms.
 #include "common.cuh"
+#include "tma.cuh"
 #include <vector>
 #include <cmath>
+#include <cstring>
 
 #define HF_MAXJ 24
 #define HF_MAXB 16
+#define LBS_KH 256          // K of one bf16 half (num_betas + 9*(J-1) <= 223, padded)
 
 struct hf_smpl {
     int V, Vp, nb, J, KB, KP, nslots, nvj, nextra, nnz;
@@ -23,6 +26,12 @@ struct hf_smpl {
     int *sj, *vj, *csr_ptr, *csr_col;
     float* csr_val;
     int parents[HF_MAXJ];
+    // tensor-core path: blend basis as split bf16 [3][Vp][KT] = [hi(256) | lo(256)] per (coordinate, vertex) row
+    __nv_bfloat16* Pbf;
+    CUtensorMap mapA;
+    int impl;                 // 0 = tcgen05 blend (product path), 1 = FP32 CUDA-core blend (debug cross-check)
+    // cached tensor map of the per-call coefficient matrix
+    const void* mapB_ptr; int mapB_M; CUtensorMap mapB;
 };
 
 namespace {
@@ -35,7 +44,7 @@ __global__ void lbs_pose_kernel(const float* __restrict__ betas, const float* __
                                 const float* __restrict__ transl, const float* __restrict__ J0,
                                 const float* __restrict__ Jd, Parents par, int M, int J, int nb, int KP,
                                 int J_out, float* __restrict__ F, float* __restrict__ A,
-                                float* __restrict__ joints) {
+                                float* __restrict__ joints, __nv_bfloat16* __restrict__ Fb) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     float beta[HF_MAXB];
@@ -52,6 +61,20 @@ __global__ void lbs_pose_kernel(const float* __restrict__ betas, const float* __
     float* Fm = F + (size_t)m * KP;
     for (int l = 0; l < nb; ++l) Fm[l] = beta[l];
     for (int k = nb + 9 * (J - 1); k < KP; ++k) Fm[k] = 0.f;
+    if (Fb) {   // split-bf16 copy of the coefficients for the tensor-core blend: [hi(KH) | lo(KH)], zero padded
+        __nv_bfloat16* fb = Fb + (size_t)m * (2 * LBS_KH);
+        for (int k = 0; k < LBS_KH; ++k) {
+            float f = 0.f;
+            if (k < nb) f = beta[k];
+            else if (k < nb + 9 * (J - 1)) {
+                const int q = k - nb, i = q / 9 + 1, e = q - (i - 1) * 9;
+                f = rotmats[((size_t)m * J + i) * 9 + e] - ((e % 4 == 0) ? 1.f : 0.f);
+            }
+            const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+            fb[k] = hi;
+            fb[LBS_KH + k] = __float2bfloat16_rn(f - __bfloat162float(hi));
+        }
+    }
     float G[HF_MAXJ][12];
     for (int i = 0; i < J; ++i) {
         float R[9];
@@ -181,6 +204,149 @@ lbs_skin_kernel(const float* __restrict__ blend, const float* __restrict__ vtemp
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core blend + CUDA-core skinning.  Tile = 128 vertices x 64 samples.
+//   D_c[v][s] = sum_k P_c[v][k] f[s][k]   for c in {x,y,z}, as split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate in
+//   TMEM): A = basis rows (vertex-major, K-major) via TMA from the L2-resident [3][Vp][512] table, B = the per-sample
+//   coefficients [M][512].  Per k-block stage: A_hi, A_lo (16 KB each), B_hi, B_lo (8 KB each); 3 products x 4 UMMA_K.
+//   Epilogue (8 warps; warp w owns TMEM lanes 32*(w%4).., samples 32*(w/4)..): v_posed = D + v_template, then
+//   v = sum_k w_k (R_k v_posed + t_k) with the 3x4 transforms of the tile's 64 samples in shared memory.
+constexpr int TC_NS = 64, TC_STAGES = 3, TC_THREADS = 320;
+constexpr int TC_STAGE_BYTES = 2 * 128 * 128 + 2 * TC_NS * 128;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+lbs_skin_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const float* __restrict__ vtemp, const int* __restrict__ sj, const float* __restrict__ sw,
+                   const float* __restrict__ A, const float* __restrict__ transl, int M, int V, int Vp, int J,
+                   int nslots, float* __restrict__ vertices) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 2];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    float* As = reinterpret_cast<float*>(smem_raw + (tile_base - smem_u32(smem_raw)) + TC_STAGES * TC_STAGE_BYTES);   // [TC_NS][J*12]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int v0 = blockIdx.x * 128, m0 = blockIdx.y * TC_NS;
+    const int J12 = J * 12;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_STAGES]), tfull = smem_u32(&bars[2 * TC_STAGES]);
+    const uint32_t abar = smem_u32(&bars[2 * TC_STAGES + 1]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(abar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    constexpr int NIT = 3 * (LBS_KH / 64);          // (coordinate, k-block) iterations
+    if (warp == 0) {
+        if (lane == 0) {
+            {   // the tile's rigid transforms: one contiguous block of the workspace -> one bulk copy
+                const int rows = min(TC_NS, M - m0);
+                const uint32_t bytes = (uint32_t)(rows * J12 * 4);
+                mbar_expect_tx(abar, bytes);
+                bulk_load_1d(tile_base + TC_STAGES * TC_STAGE_BYTES, A + (size_t)m0 * J12, bytes, abar);
+            }
+            for (int it = 0; it < NIT; ++it) {
+                const int st = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                const uint32_t sa = tile_base + st * TC_STAGE_BYTES;
+                const uint32_t fb = full0 + 8 * st;
+                mbar_expect_tx(fb, TC_STAGE_BYTES);
+                const int c = it / (LBS_KH / 64), i = it - c * (LBS_KH / 64);
+                tma_load_2d(sa, &mapA, fb, i * 64, c * Vp + v0);
+                tma_load_2d(sa + 16384, &mapA, fb, LBS_KH + i * 64, c * Vp + v0);
+                tma_load_2d(sa + 32768, &mapB, fb, i * 64, m0);
+                tma_load_2d(sa + 32768 + TC_NS * 128, &mapB, fb, LBS_KH + i * 64, m0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, TC_NS);
+            for (int it = 0; it < NIT; ++it) {
+                const int st = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(full0 + 8 * st, ph);
+                tcgen05_fence_after();
+                const uint32_t sa = tile_base + st * TC_STAGE_BYTES;
+                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + 16384);
+                const uint64_t b_hi = umma_desc_sw128(sa + 32768), b_lo = umma_desc_sw128(sa + 32768 + TC_NS * 128);
+                const int c = it / (LBS_KH / 64), i = it - c * (LBS_KH / 64);
+                const uint32_t d = tmem_base + (uint32_t)(c * TC_NS);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1u);
+                umma_commit(empty0 + 8 * st);
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int v = v0 + q * 32 + lane;                     // < Vp (tables are padded)
+        const float t0 = vtemp[v], t1 = vtemp[Vp + v], t2 = vtemp[2 * Vp + v];
+        mbar_wait(abar, 0);
+        mbar_wait(tfull, 0);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int chunk = 0; chunk < 2; ++chunk) {
+            const int s0 = half * 32 + chunk * 16;             // first sample (tile-local) of this chunk
+            uint32_t px[16], py[16], pz[16];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s0;
+            tmem_ld16(ta, px);
+            tmem_ld16(ta + TC_NS, py);
+            tmem_ld16(ta + 2 * TC_NS, pz);
+            tmem_ld_wait();
+            float o[16][3];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) o[s][0] = o[s][1] = o[s][2] = 0.f;
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int j = sj[slot * Vp + v];
+                const float w = sw[slot * Vp + v];
+                const float* a0 = As + s0 * J12 + j * 12;
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const float4* a = reinterpret_cast<const float4*>(a0 + s * J12);
+                    const float4 r0 = a[0], r1 = a[1], r2 = a[2];
+                    const float x = __uint_as_float(px[s]) + t0, y = __uint_as_float(py[s]) + t1, z = __uint_as_float(pz[s]) + t2;
+                    o[s][0] = fmaf(w, fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w))), o[s][0]);
+                    o[s][1] = fmaf(w, fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w))), o[s][1]);
+                    o[s][2] = fmaf(w, fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w))), o[s][2]);
+                }
+            }
+            if (v < V) {
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const int m = m0 + s0 + s;
+                    if (m < M) {
+                        float tx = 0.f, ty = 0.f, tz = 0.f;
+                        if (transl) { tx = transl[m * 3]; ty = transl[m * 3 + 1]; tz = transl[m * 3 + 2]; }
+                        float* out = vertices + ((size_t)m * V + v) * 3;
+                        __stcs(out + 0, o[s][0] + tx);
+                        __stcs(out + 1, o[s][1] + ty);
+                        __stcs(out + 2, o[s][2] + tz);
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
 // joints[J .. J+nvj) = picked vertices; joints[J+nvj ..) = sparse regressors applied to the final vertices.
 __global__ void lbs_extra_joints_kernel(const float* __restrict__ vertices, const int* __restrict__ vj,
                                         const int* __restrict__ csr_ptr, const int* __restrict__ csr_col,
@@ -225,6 +391,14 @@ __global__ void rodrigues_kernel(const float* __restrict__ aa, float* __restrict
 }
 
 constexpr int kSPT = 16, kSG = 4;
+
+inline uint16_t f2bf(float f) {   // round-to-nearest-even float -> bf16 bits
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
 
 }  // namespace
 
@@ -304,6 +478,26 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
             return hf::fail(HF_ERR_INVALID, "hf_smpl_create: vertex_joint_ids[%d] out of range", r);
         }
     int rc;
+    if (KB > LBS_KH) { delete h; return hf::fail(HF_ERR_UNSUPPORTED, "hf_smpl_create: %d blend coefficients exceed %d", KB, LBS_KH); }
+    {   // split-bf16 basis for the tensor-core blend: row (c, v) = [hi(256) | lo(256)]
+        std::vector<uint16_t> pb((size_t)3 * Vp * 2 * LBS_KH, 0);
+        for (int c = 0; c < 3; ++c)
+            for (int v = 0; v < V; ++v) {
+                uint16_t* row = &pb[((size_t)c * Vp + v) * 2 * LBS_KH];
+                for (int k = 0; k < KB; ++k) {
+                    const float f = blend[((size_t)k * 3 + c) * Vp + v];
+                    const uint16_t hi = f2bf(f);
+                    row[k] = hi;
+                    row[LBS_KH + k] = f2bf(f - bf2f(hi));
+                }
+            }
+        if ((rc = hf::upload((uint16_t**)&h->Pbf, pb.data(), pb.size()))) return rc;
+        const uint64_t dims[2] = {(uint64_t)2 * LBS_KH, (uint64_t)3 * Vp};
+        const uint64_t st[1] = {(uint64_t)2 * LBS_KH * 2};
+        const uint32_t box[2] = {64, 128};
+        if ((rc = encode_map(&h->mapA, h->Pbf, 2, dims, st, box))) return rc;
+        h->impl = 0; h->mapB_ptr = nullptr; h->mapB_M = 0;
+    }
     if ((rc = hf::upload(&h->blend, blend.data(), blend.size()))) return rc;
     if ((rc = hf::upload(&h->vtemp, vt.data(), vt.size()))) return rc;
     if ((rc = hf::upload(&h->J0, J0.data(), J0.size()))) return rc;
@@ -323,14 +517,20 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
 extern "C" void hf_smpl_destroy(hf_smpl_t* h) {
     if (!h) return;
     cudaFree(h->blend); cudaFree(h->vtemp); cudaFree(h->J0); cudaFree(h->Jd); cudaFree(h->sj);
-    cudaFree(h->sw); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
+    cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
     delete h;
 }
 
 extern "C" int hf_smpl_num_joints_out(const hf_smpl_t* h) { return h->J + h->nvj + h->nextra; }
 
 extern "C" size_t hf_lbs_workspace_bytes(const hf_smpl_t* h, int M) {
-    return (size_t)M * (h->KP + h->J * 12) * sizeof(float);
+    return (size_t)M * (h->KP + h->J * 12) * sizeof(float) + (size_t)M * 2 * LBS_KH * 2 + 256;
+}
+
+extern "C" int hf_lbs_set_impl(hf_smpl_t* h, int impl) {
+    if (!h || impl < 0 || impl > 1) return hf::fail(HF_ERR_INVALID, "hf_lbs_set_impl: bad argument");
+    h->impl = impl;
+    return HF_OK;
 }
 
 extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats,
@@ -344,12 +544,35 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     cudaStream_t stream = (cudaStream_t)stream_;
     float* F = (float*)workspace;
     float* A = F + (size_t)M * h->KP;
+    __nv_bfloat16* Fb = (__nv_bfloat16*)(((uintptr_t)(A + (size_t)M * h->J * 12) + 255) & ~(uintptr_t)255);
     const int J_out = hf_smpl_num_joints_out(h);
     Parents par;
     for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
     lbs_pose_kernel<<<hf::div_up(M, 128), 128, 0, stream>>>(betas, rotmats, transl, h->J0, h->Jd, par, M, h->J,
-                                                            h->nb, h->KP, J_out, F, A, joints);
+                                                            h->nb, h->KP, J_out, F, A, joints, h->impl == 0 ? Fb : nullptr);
     HF_LAUNCH_CHECK();
+    if (h->impl == 0) {
+        hf_smpl* hm = const_cast<hf_smpl*>(h);
+        if (hm->mapB_ptr != (const void*)Fb || hm->mapB_M != M) {
+            const uint64_t dims[2] = {(uint64_t)2 * LBS_KH, (uint64_t)M};
+            const uint64_t st[1] = {(uint64_t)2 * LBS_KH * 2};
+            const uint32_t box[2] = {64, (uint32_t)TC_NS};
+            int rc = encode_map(&hm->mapB, Fb, 2, dims, st, box);
+            if (rc) return rc;
+            hm->mapB_ptr = Fb; hm->mapB_M = M;
+        }
+        static bool tc_attr = false;
+        const size_t tc_smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_NS * h->J * 12 * sizeof(float) + 1024;
+        if (!tc_attr) {
+            HF_CUDA(cudaFuncSetAttribute(lbs_skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+            tc_attr = true;
+        }
+        if (tc_smem > 226 * 1024) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_forward: tile needs %zu B of shared memory", tc_smem);
+        dim3 tgrid(h->Vp / 128, hf::div_up(M, TC_NS));
+        lbs_skin_tc_kernel<<<tgrid, TC_THREADS, tc_smem, stream>>>(hm->mapA, hm->mapB, h->vtemp, h->sj, h->sw, A, transl, M, h->V,
+                                                                   h->Vp, h->J, h->nslots, vertices);
+        HF_LAUNCH_CHECK();
+    } else {
     constexpr int TS = kSPT * kSG;
     size_t smem = ((size_t)h->KP * TS + (size_t)TS * h->J * 12) * sizeof(float);
     static bool attr_set = false;
@@ -362,6 +585,7 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     lbs_skin_kernel<kSPT, kSG><<<grid, 128 * kSG, smem, stream>>>(h->blend, h->vtemp, h->sj, h->sw, F, A, transl, M,
                                                                  h->V, h->Vp, h->KB, h->KP, h->J, h->nslots, vertices);
     HF_LAUNCH_CHECK();
+    }
     int per = h->nvj + h->nextra;
     if (per > 0) {
         lbs_extra_joints_kernel<<<hf::div_up(M * per, 256), 256, 0, stream>>>(vertices, h->vj, h->csr_ptr, h->csr_col,

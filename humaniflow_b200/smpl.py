@@ -142,8 +142,16 @@ class SMPL(nn.Module):
             _lib.check(lib.hf_smpl_create(ctypes.byref(h), vt.shape[0], sd.shape[2], jr.shape[0], _lib.ptr(vt), _lib.ptr(sd),
                                           _lib.ptr(pd), _lib.ptr(jr), _lib.ptr(lw), _lib.ptr(parents), _lib.ptr(vj),
                                           len(self.vertex_joint_ids), _lib.ptr(extra), extra.shape[0]))
+        if getattr(self, '_impl', 0):
+            _lib.check(lib.hf_lbs_set_impl(h, self._impl))
         self._handles[key] = h
         return h
+
+    def set_impl(self, impl):
+        """0 = tcgen05 split-bf16 blend (product path), 1 = FP32 CUDA-core blend (debug cross-check)."""
+        self._impl = impl
+        for h in self._handles.values():
+            _lib.check(_lib.load().hf_lbs_set_impl(h, impl))
 
     def lbs(self, betas, rotmats, transl=None):
         """betas (M,nb), rotmats (M,24,3,3) fp32 CUDA -> vertices (M,V,3), joints (M,90,3)."""

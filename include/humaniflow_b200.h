@@ -58,6 +58,9 @@ void hf_smpl_destroy(hf_smpl_t* h);
 int hf_smpl_num_joints_out(const hf_smpl_t* h);
 size_t hf_lbs_workspace_bytes(const hf_smpl_t* h, int M);
 
+/* impl: 0 = tcgen05 split-bf16 blend (product path), 1 = FP32 CUDA-core blend (debug cross-check). */
+int hf_lbs_set_impl(hf_smpl_t* h, int impl);
+
 /* betas (M,num_betas); rotmats (M,J,3,3) = [global_orient | body_pose] (the `pose2rot=False` form);
  * transl (M,3) or NULL.  vertices (M,V,3); joints (M,J_out,3).  models/smpl.py:27-41. */
 int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats, const float* transl,
