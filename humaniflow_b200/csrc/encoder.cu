@@ -36,43 +36,46 @@ struct ConvGeom {
 struct ConvMaps {
     CUtensorMap a[4];   // activation maps (stride 1: [0]; stride 2: [ph*2+pw]; stem: [ph])
     CUtensorMap b;      // weights [Cout][K]
+    CUtensorMap o;      // output (B,Ho,Wo,Cout), box {64, TW, TH, TB}
+    CUtensorMap r;      // residual, same shape as the output
 };
 
-constexpr int CONV_THREADS = 192;
+constexpr int CONV_THREADS = 352;   // warp 0 operand TMA, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue, warp 10 residual TMA
 
-template <int BN, int STAGES>
+// Persistent implicit-GEMM convolution: one CTA per SM walks the output tiles (n-tile fastest, so the activation
+// tile stays hot in L2 across the Cout tiles).  Every byte that crosses the SM boundary moves by TMA:
+//   operands      global -> smem ring   (full/empty mbarriers, STAGES deep)
+//   residual      global -> staging tile (rfull), prefetched one tile ahead
+//   result        staging tile -> global (TMA store, bulk groups; sfree recycles the staging tile)
+// MMA accumulators are double-buffered in TMEM (tfull/tempty), so the epilogue of tile t (TMEM -> +bias
+// +residual -> ReLU -> bf16, in place in the 128B-swizzled staging tile) overlaps the loads/MMAs of tile t+1.
+template <int BN, int STAGES, int SR>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, const float* __restrict__ bias,
-                    const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out) {
+                    int has_res, int num_tiles, int ntn) {
     constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int SBUF_BYTES = 128 * BN * 2;     // staging tile: BN/64 boxes of [128 rows][128 B], swizzled
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
+    constexpr int HALF = BN / 2;                 // columns per epilogue warp
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 4 + 2 * SR];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bias_s[BN];
-    const uint32_t tiles = smem_u32(smem_raw);
-    const uint32_t tile_base = (tiles + 1023u) & ~1023u;
+    const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sbuf_base = tile_base + STAGES * STAGE_BYTES;
+    uint8_t* sbuf_ptr = smem_raw + (sbuf_base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile coordinates
-    int t = blockIdx.x;
-    const int tw = t % g.tiles_w; t /= g.tiles_w;
-    const int th = t % g.tiles_h; t /= g.tiles_h;
-    const int tb = t;
-    const int wo0 = tw * g.TW, ho0 = th * g.TH, b0 = tb * g.TB;
-    const int n0 = blockIdx.y * BN;
-
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
+    const uint32_t rfull0 = smem_u32(&bars[2 * STAGES + 4]), sfree0 = smem_u32(&bars[2 * STAGES + 4 + SR]);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(tfull, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 8); }
+        for (int b = 0; b < SR; ++b) { mbar_init(rfull0 + 8 * b, 1); mbar_init(sfree0 + 8 * b, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (threadIdx.x >= 64) {
-        for (int i = threadIdx.x - 64; i < BN; i += CONV_THREADS - 64) bias_s[i] = (n0 + i < g.cout) ? bias[n0 + i] : 0.f;
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -82,77 +85,132 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
     if (warp == 0) {
         if (lane == 0) {
             const int cpb = g.cin >> 6;   // 64-channel blocks per tap (generic)
-            for (int kb = 0; kb < g.nkb; ++kb) {
-                const int st = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(empty0 + 8 * st, ph ^ 1u);
-                const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
-                const uint32_t fb = full0 + 8 * st;
-                mbar_expect_tx(fb, STAGE_BYTES);
-                int mi, c0, c1, c2;
-                if (g.kind == 0) {
-                    const int tap = kb / cpb, cb = kb - tap * cpb;
-                    const int kh = tap / g.ksize, kw = tap - kh * g.ksize;
-                    const int dw = kw - g.pad, dh = kh - g.pad;
-                    c0 = cb * 64;
-                    if (g.stride == 1) { mi = 0; c1 = wo0 + dw; c2 = ho0 + dh; }
-                    else {
-                        const int pw = dw & 1, phh = dh & 1;
-                        mi = phh * 2 + pw;
-                        c1 = wo0 + ((dw - pw) >> 1);
-                        c2 = ho0 + ((dh - phh) >> 1);
+            uint32_t kbc = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % ntn;
+                int t = tile / ntn;
+                const int tw = t % g.tiles_w; t /= g.tiles_w;
+                const int th = t % g.tiles_h;
+                const int tb = t / g.tiles_h;
+                const int wo0 = tw * g.TW, ho0 = th * g.TH, b0 = tb * g.TB, n0 = nt * BN;
+                for (int kb = 0; kb < g.nkb; ++kb, ++kbc) {
+                    const uint32_t st = kbc % STAGES, ph = (kbc / STAGES) & 1u;
+                    mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                    const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint32_t fb = full0 + 8 * st;
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    int mi, c0, c1, c2;
+                    if (g.kind == 0) {
+                        const int tap = kb / cpb, cb = kb - tap * cpb;
+                        const int kh = tap / g.ksize, kw = tap - kh * g.ksize;
+                        const int dw = kw - g.pad, dh = kh - g.pad;
+                        c0 = cb * 64;
+                        if (g.stride == 1) { mi = 0; c1 = wo0 + dw; c2 = ho0 + dh; }
+                        else {
+                            const int pw = dw & 1, phh = dh & 1;
+                            mi = phh * 2 + pw;
+                            c1 = wo0 + ((dw - pw) >> 1);
+                            c2 = ho0 + ((dh - phh) >> 1);
+                        }
+                    } else {
+                        const int kh = kb >> 2, q = kb & 3;
+                        mi = kh & 1; c0 = 0; c1 = wo0 + q; c2 = ho0 + (kh >> 1);
                     }
-                } else {
-                    const int kh = kb >> 2, q = kb & 3;
-                    mi = kh & 1; c0 = 0; c1 = wo0 + q; c2 = ho0 + (kh >> 1);
+                    tma_load_4d(sa, &maps.a[mi], fb, c0, c1, c2, b0);
+                    tma_load_2d(sb, &maps.b, fb, kb * 64, n0);
                 }
-                tma_load_4d(sa, &maps.a[mi], fb, c0, c1, c2, b0);
-                tma_load_2d(sb, &maps.b, fb, kb * 64, n0);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int kb = 0; kb < g.nkb; ++kb) {
-                const int st = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(full0 + 8 * st, ph);
+            const uint32_t idesc = umma_idesc_bf16(128, BN);
+            uint32_t kbc = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const uint32_t buf = lt & 1u;
+                mbar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
-                const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
-                const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+                const uint32_t d = tmem_base + buf * BN;
+                for (int kb = 0; kb < g.nkb; ++kb, ++kbc) {
+                    const uint32_t st = kbc % STAGES, ph = (kbc / STAGES) & 1u;
+                    mbar_wait(full0 + 8 * st, ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-                umma_commit(empty0 + 8 * st);
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(empty0 + 8 * st);
+                }
+                umma_commit(tfull0 + 8 * buf);
             }
-            umma_commit(tfull);
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {
+            // staging tiles: wait until the previous store of the buffer has left smem, then fetch the residual
+            uint32_t lt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const int nt = tile % ntn;
+                int t = tile / ntn;
+                const int tw = t % g.tiles_w; t /= g.tiles_w;
+                const int th = t % g.tiles_h;
+                const int tb = t / g.tiles_h;
+                const uint32_t sb = lt % SR, k = lt / SR;
+                mbar_wait(sfree0 + 8 * sb, (k & 1u) ^ 1u);
+                const uint32_t rb = rfull0 + 8 * sb;
+                if (has_res) {
+                    mbar_expect_tx(rb, SBUF_BYTES);
+#pragma unroll
+                    for (int x = 0; x < BN / 64; ++x)
+                        tma_load_4d(sbuf_base + sb * SBUF_BYTES + x * 16384, &maps.r, rb, nt * BN + x * 64, tw * g.TW, th * g.TH, tb * g.TB);
+                } else {
+                    mbar_arrive(rb);
+                }
+            }
         }
     } else {
-        // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
-        const int q = warp & 3;
-        const int row = q * 32 + lane;                   // tile row = output pixel
-        const int ltw = row % g.TW, lth = (row / g.TW) % g.TH, ltb = row / (g.TW * g.TH);
-        const int wo = wo0 + ltw, ho = ho0 + lth, b = b0 + ltb;
-        const bool valid = (wo < g.Wo) && (ho < g.Ho) && (b < g.B);
-        const size_t pix = ((size_t)b * g.Ho + ho) * g.Wo + wo;
-        mbar_wait(tfull, 0);
-        tcgen05_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld_wait();
-            if (valid && n0 + c0 < g.cout) {
-                float f[16];
+        // epilogue: warp e owns TMEM lanes [32*(warp%4), +32) (= tile rows) and the column half e/4
+        const int e = warp - 2;
+        const int q = warp & 3, colhalf = e >> 2;
+        const int row = q * 32 + lane;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int nt = tile % ntn;
+            int t = tile / ntn;
+            const int tw = t % g.tiles_w; t /= g.tiles_w;
+            const int th = t % g.tiles_h;
+            const int tb = t / g.tiles_h;
+            const int n0 = nt * BN;
+            const uint32_t buf = lt & 1u, par = (lt >> 1) & 1u;
+            const uint32_t sb = lt % SR;
+            mbar_wait(rfull0 + 8 * sb, (lt / SR) & 1u);  // staging tile free (+ residual landed)
+            mbar_wait(tfull0 + 8 * buf, par);            // accumulator complete
+            tcgen05_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(colhalf * HALF);
+            uint8_t* srow = sbuf_ptr + sb * SBUF_BYTES + row * 128;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_s[c0 + i];
-                if (res) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res + pix * g.cout + n0 + c0);
-                    uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            for (int c0 = 0; c0 < HALF; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                tmem_ld_wait();
+                const int col = colhalf * HALF + c0;                       // column within the BN tile
+                uint8_t* sbox = srow + (col >> 6) * 16384;                 // 64-channel box
+                const int j0 = (col & 63) >> 3;                            // 16-byte piece within the 128-byte row
+                uint4* p0 = reinterpret_cast<uint4*>(sbox + (((j0) ^ (row & 7)) << 4));
+                uint4* p1 = reinterpret_cast<uint4*>(sbox + (((j0 + 1) ^ (row & 7)) << 4));
+                float f[16];
+                const float4* bp = reinterpret_cast<const float4*>(bias + n0 + col);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 bb = __ldg(bp + i);
+                    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
+                    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
+                }
+                if (has_res) {
+                    const uint4 ra = *p0, rb = *p1;
+                    const uint32_t r8[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+                        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&r8[i]);
                         f[2 * i] += __bfloat162float(h.x);
                         f[2 * i + 1] += __bfloat162float(h.y);
                     }
@@ -167,17 +225,31 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                     __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                     o[i] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                uint4* op = reinterpret_cast<uint4*>(out + pix * g.cout + n0 + c0);
-                op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                *p0 = make_uint4(o[0], o[1], o[2], o[3]);
+                *p1 = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+            // accumulator buffer can be refilled; staging tile goes out by TMA
+            tcgen05_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+#pragma unroll
+                for (int x = 0; x < BN / 64; ++x)
+                    tma_store_4d(&maps.o, sbuf_base + sb * SBUF_BYTES + x * 16384, n0 + x * 64, tw * g.TW, th * g.TH, tb * g.TB);
+                bulk_commit();
+                bulk_wait_read<1>();                      // every group but the newest has finished reading smem
+                if (lt >= 1) mbar_arrive(sfree0 + 8 * ((lt - 1) % SR));
             }
         }
+        if (threadIdx.x == 64) bulk_wait<0>();
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -292,12 +364,23 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __res
 }
 
 // ------------------------------------------------------------------ host side
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 struct ConvPlan {
     ConvGeom g;
     ConvMaps maps;
-    int bn;
+    int bn, ntn, num_tiles, has_res, sr;
     dim3 grid;
     size_t smem;
     int stages;
@@ -307,7 +390,7 @@ struct ConvPlan {
 // Generic: x (B,H,W,cin), cin % 64 == 0.  Stem (kind 1): x is (B,Hp,Wp,32) with 3 zero rows/cols before the
 // image, ksize 7, stride 2, pad 3; H, W are the UNPADDED sizes.
 int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H, int W, int cin, int cout, int ks,
-              int stride, int pad, int relu, int Hp, int Wp) {
+              int stride, int pad, int relu, int Hp, int Wp, const void* out, const void* res) {
     ConvGeom& g = p->g;
     g.kind = kind; g.ksize = ks; g.stride = stride; g.pad = pad; g.cin = cin; g.B = B; g.cout = cout; g.relu = relu;
     g.Ho = (H + 2 * pad - ks) / stride + 1;
@@ -353,7 +436,17 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
             if (rc) return rc;
         }
     }
+    const int tiles_m = g.tiles_w * g.tiles_h * g.tiles_b;
     p->bn = (cout % 128 == 0) ? 128 : 64;
+    {
+        const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)B};
+        const uint64_t st[3] = {(uint64_t)cout * 2, (uint64_t)g.Wo * cout * 2, (uint64_t)g.Ho * g.Wo * cout * 2};
+        int rc = encode_map(&p->maps.o, out, 4, dims, st, box);
+        if (rc) return rc;
+        p->has_res = res != nullptr;
+        rc = encode_map(&p->maps.r, res ? res : out, 4, dims, st, box);
+        if (rc) return rc;
+    }
     {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout};
         const uint64_t st[1] = {(uint64_t)ktot * 2};
@@ -361,25 +454,32 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
         int rc = encode_map(&p->maps.b, w, 2, dims, st, bx);
         if (rc) return rc;
     }
-    p->stages = (p->bn == 128) ? 3 : 4;
-    p->smem = (size_t)p->stages * (128 * 128 + p->bn * 128) + 1024;
-    p->grid = dim3(g.tiles_w * g.tiles_h * g.tiles_b, cout / p->bn);
+    // operand ring depth vs staging tiles: residual layers prefetch the residual several tiles ahead (DRAM latency),
+    // layers without residual spend the shared memory on a deeper operand ring
+    if (p->bn == 128) { p->stages = p->has_res ? 3 : 4; p->sr = p->has_res ? 3 : 2; }
+    else              { p->stages = p->has_res ? 5 : 6; p->sr = p->has_res ? 4 : 2; }
+    p->smem = (size_t)p->stages * (128 * 128 + p->bn * 128) + (size_t)p->sr * 128 * p->bn * 2 + 1024;
+    p->ntn = cout / p->bn;
+    p->num_tiles = tiles_m * p->ntn;
+    p->grid = dim3(std::min(p->num_tiles, num_sms()));
     return HF_OK;
 }
 
-int launch_conv(const ConvPlan& p, const float* bias, const __nv_bfloat16* res, __nv_bfloat16* out, cudaStream_t s) {
+template <int BN, int STAGES, int SR>
+int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    if (p.bn == 128)
-        conv_tcgen05_kernel<128, 3><<<p.grid, CONV_THREADS, p.smem, s>>>(p.maps, p.g, bias, res, out);
-    else
-        conv_tcgen05_kernel<64, 4><<<p.grid, CONV_THREADS, p.smem, s>>>(p.maps, p.g, bias, res, out);
+    conv_tcgen05_kernel<BN, STAGES, SR><<<p.grid, CONV_THREADS, p.smem, s>>>(p.maps, p.g, bias, p.has_res, p.num_tiles, p.ntn);
     HF_LAUNCH_CHECK();
     return HF_OK;
+}
+
+int launch_conv(const ConvPlan& p, const float* bias, cudaStream_t s) {
+    if (p.bn == 128) return p.has_res ? launch_conv_t<128, 3, 3>(p, bias, s) : launch_conv_t<128, 4, 2>(p, bias, s);
+    return p.has_res ? launch_conv_t<64, 5, 4>(p, bias, s) : launch_conv_t<64, 6, 2>(p, bias, s);
 }
 
 int launch_simt(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, const __nv_bfloat16* res,
@@ -548,11 +648,12 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
         for (size_t i = 0; i < h->ops.size(); ++i) {
             const hf_enc_op& op = h->ops[i];
             if (op.kind != HF_OP_CONV) continue;
-            if (i == 0) rc = plan_conv(&h->plans[i], 1, stem_in, h->w[op.weight_index], B, H, W, STEM_CP, op.cout, 7, 2, 3, op.relu, Hp, Wp);
+            if (i == 0) rc = plan_conv(&h->plans[i], 1, stem_in, h->w[op.weight_index], B, H, W, STEM_CP, op.cout, 7, 2, 3, op.relu, Hp, Wp, buf(op.dst), nullptr);
             else {
                 const BufShape in = shp.in[i];
                 if (op.cin % 64 != 0) return hf::fail(HF_ERR_UNSUPPORTED, "encoder: conv %zu has cin %d (must be a multiple of 64)", i, op.cin);
-                rc = plan_conv(&h->plans[i], 0, buf(op.src), h->w[op.weight_index], B, in.H, in.W, op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, 0, 0);
+                rc = plan_conv(&h->plans[i], 0, buf(op.src), h->w[op.weight_index], B, in.H, in.W, op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, 0, 0,
+                               buf(op.dst), op.res >= 0 ? buf(op.res) : nullptr);
             }
             if (rc) return rc;
         }
@@ -571,7 +672,7 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
         if (op.kind == HF_OP_CONV) {
             const __nv_bfloat16* res = op.res >= 0 ? buf(op.res) : nullptr;
             if (h->impl == 0) {
-                rc = launch_conv(h->plans[i], h->bias[op.weight_index], res, buf(op.dst), stream);
+                rc = launch_conv(h->plans[i], h->bias[op.weight_index], stream);
             } else if (i == 0) {
                 // SIMT path reads the physically padded input as a pad-0 convolution with the true output size
                 rc = launch_simt(stem_in, h->w_plain[op.weight_index], h->bias[op.weight_index], res, buf(op.dst), B, Hp, Wp,
@@ -632,7 +733,7 @@ extern "C" int hf_conv2d_nhwc(const uint16_t* x, const uint16_t* w, const float*
         return launch_simt((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (const __nv_bfloat16*)res,
                            (__nv_bfloat16*)y, B, H, W, cin, cout, ksize, stride, pad, relu, (cudaStream_t)stream);
     ConvPlan p;
-    int rc = plan_conv(&p, 0, x, w, B, H, W, cin, cout, ksize, stride, pad, relu, 0, 0);
+    int rc = plan_conv(&p, 0, x, w, B, H, W, cin, cout, ksize, stride, pad, relu, 0, 0, y, res);
     if (rc) return rc;
-    return launch_conv(p, bias, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, (cudaStream_t)stream);
+    return launch_conv(p, bias, (cudaStream_t)stream);
 }
