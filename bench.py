@@ -306,6 +306,18 @@ def run_ours(args):
         s_main.wait_stream(s_out)
         s_main.wait_stream(s_in)
 
+    # PCIe sanity numbers for the e2e line (plain pinned copies of the same buffers, not part of any timed region)
+    def copy_gbs(dst, src, iters=3):
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        c0, c1 = ev(), ev()
+        c0.record()
+        for _ in range(iters):
+            dst.copy_(src, non_blocking=True)
+        c1.record(); torch.cuda.synchronize()
+        return src.numel() * src.element_size() * iters / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    v_dev_tmp = torch.empty(B * N, V, 3, device=dev)
+    pcie = {'h2d_gbs': copy_gbs(x_stage[0], x_host), 'd2h_gbs': copy_gbs(v_host[0], v_dev_tmp)}
+    del v_dev_tmp
     e2e_steps(3)
     sync_all()
     a, b_ev = ev(), ev()
@@ -327,7 +339,7 @@ def run_ours(args):
             'data': 'synthetic (random-init weights, SMPL-shaped synthetic body model)', 'config': workload_config(args),
             'e2e': {'value': world * B * N / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': (v_host[0].numel() + j_host[0].numel()) * 4,
-                    'pipelining': 'H2D | kernels | D2H on three streams, double-buffered'},
+                    'pipelining': 'H2D | kernels | D2H on three streams, double-buffered', 'pcie_measured': pcie},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'stages': stages,
             'step_breakdown_ms': {'model_forward': ms_model, 'lbs': ms_lbs},
         }

@@ -5,9 +5,8 @@
 
 namespace {
 
-constexpr int LW = 4;      // warps per CTA
-constexpr int LO = 2;      // outputs per warp
-constexpr int KC = 256;    // K chunk staged in shared memory
+constexpr int LW = 8;        // warps per CTA, one output neuron each
+constexpr int KC = 512;      // K chunk of the activations staged in shared memory (32 rows x KC fp32 = 64 KB)
 
 __device__ __forceinline__ float act_fn(float a, int act) {
     if (act == 1) return a > 0.f ? a : expm1f(a);
@@ -15,65 +14,87 @@ __device__ __forceinline__ float act_fn(float a, int act) {
     return a;
 }
 
-// y[m][o] (+)= act(sum_k x[m][k] W[o][k] + b[o]).  Lane = batch row (32 rows per CTA tile), a warp owns LO
-// output neurons; the x tile is staged transposed in shared memory (conflict-free column reads), weights
-// are streamed with warp-broadcast (vector) loads, each element read once per row tile.  No reductions.
-template <bool VEC4>
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// y[m][o] (+)= act(sum_k x[m][k] W[o][k] + b[o]) for a tile of 32 batch rows.  K % 4 == 0, 16-byte aligned rows.
+// A warp owns one output neuron; lanes split K (coalesced 128-bit weight loads, each weight read once per row
+// tile); the 32 x KC activation chunk is staged in shared memory with cp.async, double buffered, and shared by the
+// 8 warps of the CTA; per-row partial sums are reduced with shuffles at the end.
 __global__ void __launch_bounds__(LW * 32)
-linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, int ldw,
-              const float* __restrict__ b, float* __restrict__ y, int ldy, int M, int K, int O, int act,
-              int accumulate) {
-    __shared__ float xs[KC][33];
+linear_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, int ldw,
+                  const float* __restrict__ b, float* __restrict__ y, int ldy, int M, int K, int O, int act,
+                  int accumulate) {
+    extern __shared__ __align__(16) float xs[];           // [2][32][KC]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o0 = (blockIdx.x * LW + warp) * LO;
+    const int o = blockIdx.x * LW + warp;
     const int m0 = blockIdx.y * 32;
-    float acc[LO];
-#pragma unroll
-    for (int i = 0; i < LO; ++i) acc[i] = 0.f;
-    const float* wrow[LO];
-#pragma unroll
-    for (int i = 0; i < LO; ++i) wrow[i] = W + (size_t)min(o0 + i, O - 1) * ldw;
-    for (int kc = 0; kc < K; kc += KC) {
-        const int kn = min(KC, K - kc);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < 32 * kn; idx += LW * 32) {
-            const int r = idx / kn, k = idx - r * kn;
-            xs[k][r] = (m0 + r < M) ? __ldg(x + (size_t)(m0 + r) * ldx + kc + k) : 0.f;
+    const int oc = min(o, O - 1);
+    const float4* wrow = reinterpret_cast<const float4*>(W + (size_t)oc * ldw);
+    auto stage = [&](int buf, int kc) {
+        const int kn4 = min(KC, K - kc) >> 2;              // float4 per row in this chunk
+        for (int idx = threadIdx.x; idx < 32 * kn4; idx += LW * 32) {
+            const int r = idx / kn4, c4 = idx - r * kn4;
+            const int m = min(m0 + r, M - 1);               // rows past M duplicate the last row (never stored)
+            cp_async16(xs + ((size_t)buf * 32 + r) * KC + c4 * 4, x + (size_t)m * ldx + kc + c4 * 4);
         }
+        cp_async_commit();
+    };
+    float acc[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) acc[m] = 0.f;
+    const int nchunks = (K + KC - 1) / KC;
+    stage(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        const int kc = c * KC, kn4 = min(KC, K - kc) >> 2;
+        if (c + 1 < nchunks) { stage((c + 1) & 1, kc + KC); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
-        if (VEC4) {
-#pragma unroll 4
-            for (int k = 0; k < kn; k += 4) {
-                const float x0 = xs[k][lane], x1 = xs[k + 1][lane], x2 = xs[k + 2][lane], x3 = xs[k + 3][lane];
+        const float* xb = xs + (size_t)(c & 1) * 32 * KC;
+        for (int k4 = lane; k4 < kn4; k4 += 32) {
+            const float4 w = __ldg(wrow + (kc >> 2) + k4);
 #pragma unroll
-                for (int i = 0; i < LO; ++i) {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(wrow[i] + kc + k));
-                    acc[i] = fmaf(w.x, x0, acc[i]); acc[i] = fmaf(w.y, x1, acc[i]);
-                    acc[i] = fmaf(w.z, x2, acc[i]); acc[i] = fmaf(w.w, x3, acc[i]);
-                }
-            }
-        } else {
-#pragma unroll 4
-            for (int k = 0; k < kn; ++k) {
-                const float xv = xs[k][lane];
-#pragma unroll
-                for (int i = 0; i < LO; ++i) acc[i] = fmaf(__ldg(wrow[i] + kc + k), xv, acc[i]);
+            for (int m = 0; m < 32; ++m) {
+                const float4 xv = *reinterpret_cast<const float4*>(xb + m * KC + k4 * 4);
+                acc[m] = fmaf(w.x, xv.x, fmaf(w.y, xv.y, fmaf(w.z, xv.z, fmaf(w.w, xv.w, acc[m]))));
             }
         }
+        __syncthreads();
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+        float v = acc[m];
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+        if (lane == m) mine = v;
     }
     const int r = m0 + lane;
-    if (r < M) {
-#pragma unroll
-        for (int i = 0; i < LO; ++i) {
-            const int o = o0 + i;
-            if (o < O) {
-                float* dst = y + (size_t)r * ldy + o;
-                float a = acc[i] + (b ? __ldg(b + o) : 0.f);
-                if (accumulate) a += *dst;
-                *dst = act_fn(a, act);
-            }
-        }
+    if (o < O && r < M) {
+        float* dst = y + (size_t)r * ldy + o;
+        float a = mine + (b ? __ldg(b + o) : 0.f);
+        if (accumulate) a += *dst;
+        *dst = act_fn(a, act);
     }
+}
+
+// Generic small-K fallback (K not a multiple of 4 or unaligned rows): lane = batch row, broadcast weight loads.
+__global__ void __launch_bounds__(128)
+linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, int ldw,
+                    const float* __restrict__ b, float* __restrict__ y, int ldy, int M, int K, int O, int act,
+                    int accumulate) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 4 + warp;
+    const int r = blockIdx.y * 32 + lane;
+    if (o >= O || r >= M) return;
+    float a = b ? __ldg(b + o) : 0.f;
+    for (int k = 0; k < K; ++k) a = fmaf(__ldg(W + (size_t)o * ldw + k), __ldg(x + (size_t)r * ldx + k), a);
+    float* dst = y + (size_t)r * ldy + o;
+    if (accumulate) a += *dst;
+    *dst = act_fn(a, act);
 }
 
 __global__ void rot6d_kernel(const float* __restrict__ x6, float* __restrict__ R, int n) {
@@ -144,12 +165,20 @@ extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const
     if (!x || !W || !y) return hf::fail(HF_ERR_INVALID, "hf_linear: null argument");
     if (M <= 0 || O <= 0) return HF_OK;
     if (K < 0 || ldx < K || ldw < K || ldy < O) return hf::fail(HF_ERR_INVALID, "hf_linear: bad strides");
-    dim3 grid(hf::div_up(O, LW * LO), hf::div_up(M, 32));
-    const bool vec4 = (K % 4 == 0) && (ldw % 4 == 0) && (((uintptr_t)W & 15) == 0);
-    if (vec4)
-        linear_kernel<true><<<grid, LW * 32, 0, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate);
-    else
-        linear_kernel<false><<<grid, LW * 32, 0, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate);
+    const bool vec4 = (K % 4 == 0) && (K >= 64) && (ldw % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)W & 15) == 0) && (((uintptr_t)x & 15) == 0);
+    if (vec4) {
+        static bool attr = false;
+        const int smem = 2 * 32 * KC * (int)sizeof(float);
+        if (!attr) {
+            HF_CUDA(cudaFuncSetAttribute(linear_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr = true;
+        }
+        dim3 grid(hf::div_up(O, LW), hf::div_up(M, 32));
+        linear_vec_kernel<<<grid, LW * 32, smem, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate);
+    } else {
+        dim3 grid(hf::div_up(O, 4), hf::div_up(M, 32));
+        linear_small_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate);
+    }
     HF_LAUNCH_CHECK();
     return HF_OK;
 }

@@ -44,7 +44,7 @@ __global__ void lbs_pose_kernel(const float* __restrict__ betas, const float* __
                                 const float* __restrict__ transl, const float* __restrict__ J0,
                                 const float* __restrict__ Jd, Parents par, int M, int J, int nb, int KP,
                                 int J_out, float* __restrict__ F, float* __restrict__ A,
-                                float* __restrict__ joints, __nv_bfloat16* __restrict__ Fb) {
+                                float* __restrict__ joints) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     float beta[HF_MAXB];
@@ -58,29 +58,17 @@ __global__ void lbs_pose_kernel(const float* __restrict__ betas, const float* __
         }
     float tr[3] = {0.f, 0.f, 0.f};
     if (transl) { tr[0] = transl[m * 3]; tr[1] = transl[m * 3 + 1]; tr[2] = transl[m * 3 + 2]; }
-    float* Fm = F + (size_t)m * KP;
-    for (int l = 0; l < nb; ++l) Fm[l] = beta[l];
-    for (int k = nb + 9 * (J - 1); k < KP; ++k) Fm[k] = 0.f;
-    if (Fb) {   // split-bf16 copy of the coefficients for the tensor-core blend: [hi(KH) | lo(KH)], zero padded
-        __nv_bfloat16* fb = Fb + (size_t)m * (2 * LBS_KH);
-        for (int k = 0; k < LBS_KH; ++k) {
-            float f = 0.f;
-            if (k < nb) f = beta[k];
-            else if (k < nb + 9 * (J - 1)) {
-                const int q = k - nb, i = q / 9 + 1, e = q - (i - 1) * 9;
-                f = rotmats[((size_t)m * J + i) * 9 + e] - ((e % 4 == 0) ? 1.f : 0.f);
-            }
-            const __nv_bfloat16 hi = __float2bfloat16_rn(f);
-            fb[k] = hi;
-            fb[LBS_KH + k] = __float2bfloat16_rn(f - __bfloat162float(hi));
-        }
+    float* Fm = F ? F + (size_t)m * KP : nullptr;     // fp32 coefficients are only needed by the CUDA-core blend
+    if (Fm) {
+        for (int l = 0; l < nb; ++l) Fm[l] = beta[l];
+        for (int k = nb + 9 * (J - 1); k < KP; ++k) Fm[k] = 0.f;
     }
     float G[HF_MAXJ][12];
     for (int i = 0; i < J; ++i) {
         float R[9];
         const float* Rm = rotmats + ((size_t)m * J + i) * 9;
         for (int e = 0; e < 9; ++e) R[e] = Rm[e];
-        if (i > 0)
+        if (i > 0 && Fm)
             for (int e = 0; e < 9; ++e) Fm[nb + (i - 1) * 9 + e] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
         float t[3];
         int p = par.p[i];
@@ -108,6 +96,25 @@ __global__ void lbs_pose_kernel(const float* __restrict__ betas, const float* __
             Am[r * 4 + 3] = g[r * 4 + 3] - (g[r * 4 + 0] * Jl[i][0] + g[r * 4 + 1] * Jl[i][1] + g[r * 4 + 2] * Jl[i][2]);
             jo[r] = g[r * 4 + 3] + tr[r];
         }
+    }
+}
+
+// Split-bf16 blend coefficients for the tensor-core path: Fb[m] = [hi(KH) | lo(KH)] of (beta | vec(R_i - I)),
+// zero padded; one thread per element, coalesced bf16 writes.
+__global__ void lbs_coef_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats, int M, int J, int nb,
+                                __nv_bfloat16* __restrict__ Fb) {
+    const size_t total = (size_t)M * LBS_KH;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(e / LBS_KH), k = (int)(e - (size_t)m * LBS_KH);
+        float f = 0.f;
+        if (k < nb) f = __ldg(betas + (size_t)m * nb + k);
+        else if (k < nb + 9 * (J - 1)) {
+            const int q = k - nb, i = q / 9 + 1, el = q - (i - 1) * 9;
+            f = __ldg(rotmats + ((size_t)m * J + i) * 9 + el) - ((el % 4 == 0) ? 1.f : 0.f);
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+        Fb[(size_t)m * 2 * LBS_KH + k] = hi;
+        Fb[(size_t)m * 2 * LBS_KH + LBS_KH + k] = __float2bfloat16_rn(f - __bfloat162float(hi));
     }
 }
 
@@ -549,9 +556,11 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     Parents par;
     for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
     lbs_pose_kernel<<<hf::div_up(M, 128), 128, 0, stream>>>(betas, rotmats, transl, h->J0, h->Jd, par, M, h->J,
-                                                            h->nb, h->KP, J_out, F, A, joints, h->impl == 0 ? Fb : nullptr);
+                                                            h->nb, h->KP, J_out, h->impl == 0 ? nullptr : F, A, joints);
     HF_LAUNCH_CHECK();
     if (h->impl == 0) {
+        lbs_coef_kernel<<<std::min(hf::div_up(M * LBS_KH, 256), 148 * 16), 256, 0, stream>>>(betas, rotmats, M, h->J, h->nb, Fb);
+        HF_LAUNCH_CHECK();
         hf_smpl* hm = const_cast<hf_smpl*>(h);
         if (hm->mapB_ptr != (const void*)Fb || hm->mapB_M != M) {
             const uint64_t dims[2] = {(uint64_t)2 * LBS_KH, (uint64_t)M};
