@@ -41,7 +41,8 @@ SIGNATURES = {
     'hf_rodrigues': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'hf_flow_create': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(FlowConfig)] + [c_void_p] * 7),
     'hf_flow_destroy': (None, [c_void_p]),
-    'hf_flow_sample': (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'hf_flow_workspace_bytes': (c_size_t, [c_void_p, c_int]),
+    'hf_flow_sample': (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'hf_flow_context': (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_void_p]),
     'hf_flow_log_prob': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'hf_flow_algebra_log_prob': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),

@@ -12,6 +12,7 @@
 // streamed with 128-bit read-only loads, each element exactly once per CTA.  fp32 everywhere the
 // reference is fp32, fp64 for the exp/log maps and the radial-tanh inverse, as in the reference.
 #include "common.cuh"
+#include "tma.cuh"
 #include <vector>
 #include <cmath>
 
@@ -36,12 +37,17 @@ struct FlowParams {
     int off_ctxW[HF_FJ], off_ctxB[HF_FJ], off_nn[HF_FJ][2];
     int anc_cnt[HF_FJ];
     signed char anc[HF_FJ][HF_FANC];
+    // sampling kernel: feature part of every context Linear as one K-major matrix [FEATS][J*CTX]; per joint one
+    // contiguous block [ancW (9a x CTX) | ctxB (CTX) | coupling 0 | coupling 1] streamed into shared memory
+    const float* wfeat;
+    const float* jpack;
+    int off_jb[HF_FJ];
 };
 
 __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expm1f(x); }
 
 // ---- register-tiled partial GEMM of one warp: part[32][NR] = sum_{k in [k0,k1)} W[k][ob*32 + :] x X[k][:] ----
-template <int NR, typename XRow>
+template <int NR, bool SMEMW = false, int UNR = 4, bool PART_T = false, typename XRow>
 __device__ __forceinline__ void warp_gemm(const float* __restrict__ W, int ldw, int ob, int k0, int k1, XRow xrow,
                                           float* __restrict__ part, int lane) {
     constexpr int SPL = NR / 4;
@@ -52,9 +58,10 @@ __device__ __forceinline__ void warp_gemm(const float* __restrict__ W, int ldw, 
 #pragma unroll
         for (int s = 0; s < SPL; ++s) acc[i][s] = 0.f;
     const float* wp = W + ob * 32 + oi * 4;
-#pragma unroll 4
+#pragma unroll UNR
     for (int k = k0; k < k1; ++k) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * ldw));
+        const float4 w = SMEMW ? *reinterpret_cast<const float4*>(wp + (size_t)k * ldw)
+                               : __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * ldw));
         const float2* xp = reinterpret_cast<const float2*>(xrow(k) + sq * SPL);
 #pragma unroll
         for (int q = 0; q < SPL / 2; ++q) {
@@ -65,31 +72,39 @@ __device__ __forceinline__ void warp_gemm(const float* __restrict__ W, int ldw, 
             acc[3][2 * q] = fmaf(w.w, x.x, acc[3][2 * q]); acc[3][2 * q + 1] = fmaf(w.w, x.y, acc[3][2 * q + 1]);
         }
     }
+    if (PART_T) {   // partial tile transposed [row][32 outputs]: one 128-bit store per row, bank-conflict free
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float2* pp = reinterpret_cast<float2*>(part + (oi * 4 + i) * NR + sq * SPL);
+        for (int r = 0; r < SPL; ++r)
+            *reinterpret_cast<float4*>(part + (sq * SPL + r) * 32 + oi * 4) = make_float4(acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
+    } else {
 #pragma unroll
-        for (int q = 0; q < SPL / 2; ++q) pp[q] = make_float2(acc[i][2 * q], acc[i][2 * q + 1]);
+        for (int i = 0; i < 4; ++i) {
+            float2* pp = reinterpret_cast<float2*>(part + (oi * 4 + i) * NR + sq * SPL);
+#pragma unroll
+            for (int q = 0; q < SPL / 2; ++q) pp[q] = make_float2(acc[i][2 * q], acc[i][2 * q + 1]);
+        }
     }
 }
 
 // A dense layer over the CTA: OT output tiles of 32, K split over HF_NW/OT warps, partials in scratch,
 // then bias + activation into dst[O][NR].  ACT: 0 none, 1 ELU, 2 ReLU.  Ends with __syncthreads().
-template <int NR, int OT, int ACT, typename XRow>
+template <int NR, int OT, int ACT, bool SMEMW = false, typename XRow>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias, int K,
-                                            XRow xrow, float* scratch, float* dst) {
+                                            XRow xrow, float* scratch, float* dst, const float* add = nullptr) {
     constexpr int NS = HF_NW / OT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ob = warp / NS, sp = warp - ob * NS;
     const int chunk = (K + NS - 1) / NS;
     const int k0 = min(sp * chunk, K), k1 = min(k0 + chunk, K);
-    warp_gemm<NR>(W, OT * 32, ob, k0, k1, xrow, scratch + warp * 32 * NR, lane);
+    warp_gemm<NR, SMEMW, 4, true>(W, OT * 32, ob, k0, k1, xrow, scratch + warp * 32 * NR, lane);
     __syncthreads();
     for (int e = threadIdx.x; e < OT * 32 * NR; e += HF_NT) {
-        const int o = e / NR, s = e - o * NR;
-        const int ob2 = o >> 5, ol = o & 31;
-        float a = __ldg(bias + o);
-        const float* p = scratch + ((ob2 * NS) * 32 + ol) * NR + s;
+        // consecutive threads -> consecutive outputs of one row: conflict-free reads of the transposed partial tiles
+        const int ol = e & 31, s = (e >> 5) % NR, ob2 = e / (32 * NR);
+        const int o = ob2 * 32 + ol;
+        float a = SMEMW ? bias[o] : __ldg(bias + o);
+        if (add) a += add[o * NR + s];
+        const float* p = scratch + (ob2 * NS) * 32 * NR + s * 32 + ol;
 #pragma unroll
         for (int q = 0; q < NS; ++q) a += p[q * 32 * NR];
         if (ACT == 1) a = elu(a);
@@ -341,22 +356,109 @@ __device__ __forceinline__ void coupling_nn(const float* __restrict__ cw, float*
     dense_layer<NR, 2, 0>(cw + OFF_W3, cw + OFF_B3, H3, PlainRow{sm + L::Hc, NR}, sm + L::Scratch, sm + L::Raw);
 }
 
+template <int NR>
+__device__ __forceinline__ void coupling_nn_smem(const float* cw, float* sm) {
+    using L = SmemLayout<NR>;
+    dense_layer<NR, 2, 2, true>(cw + OFF_W0, cw + OFF_B0, CTX + 1, PlainRow{sm + L::Cs, NR}, sm + L::Scratch, sm + L::Ha);
+    dense_layer<NR, 1, 2, true>(cw + OFF_W1, cw + OFF_B1, H1, PlainRow{sm + L::Ha, NR}, sm + L::Scratch, sm + L::Hb);
+    dense_layer<NR, 1, 2, true>(cw + OFF_W2, cw + OFF_B2, H2, PlainRow{sm + L::Hb, NR}, sm + L::Scratch, sm + L::Hc);
+    dense_layer<NR, 2, 0, true>(cw + OFF_W3, cw + OFF_B3, H3, PlainRow{sm + L::Hc, NR}, sm + L::Scratch, sm + L::Raw);
+}
+
+// ancestors' rotation rows only (the feature part of the context Linear is precomputed)
+struct AncRow {
+    const float* Ps; const signed char* anc; int NR;
+    __device__ __forceinline__ const float* operator()(int k) const {
+        const int a = k / 9;
+        return Ps + (anc[a] * 9 + (k - a * 9)) * NR;
+    }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// shared-memory layout of the sampling kernel (floats)
+template <int NR>
+struct SampleSmem {
+    static constexpr int ANC_MAX = 7 * 9 * CTX + CTX;     // deepest SMPL joint has 7 ancestors; checked on the host
+    static constexpr int Wanc = 0;
+    static constexpr int Wc0 = Wanc + ANC_MAX;
+    static constexpr int Wc1 = Wc0 + COUPLING_FLOATS;
+    static constexpr int Us = Wc1 + COUPLING_FLOATS;       // [2][CTX*NR]
+    static constexpr int Act = Us + 2 * CTX * NR;           // SmemLayout<NR> minus its Fs (aliased onto Scratch)
+    static constexpr int Total = Act + (SmemLayout<NR>::Total - SmemLayout<NR>::Ps);
+};
+
 // =====================================  sampling  =====================================
+// One CTA owns NR rows for the whole tree.
+//  prologue : image features -> U[j] = Wfeat_j . feats for all joints (one long fp32 GEMM with no dependency chain,
+//             parked in an L2-resident scratch, laid out so that a joint's 64 x NR block is contiguous)
+//  chain    : per joint, weights arrive in shared memory by 1-D bulk copies issued one joint ahead (mbarrier
+//             complete_tx), U(j) by cp.async; every dense layer then runs on low-latency LDS operands.
 template <int NR>
 __global__ void __launch_bounds__(HF_NT, 1)
 flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict__ img_base, const float* __restrict__ betas,
                    const int* __restrict__ img_index, const float* __restrict__ base_noise, int R, int Rn,
-                   float* __restrict__ rotmats, float* __restrict__ axisangle_pe) {
+                   float* __restrict__ rotmats, float* __restrict__ axisangle_pe, float* __restrict__ Uscratch) {
     using L = SmemLayout<NR>;
-    extern __shared__ __align__(16) float sm[];
+    using S = SampleSmem<NR>;
+    extern __shared__ __align__(16) float smraw[];
+    __shared__ __align__(8) uint64_t wbar[3];
+    float* sm = smraw + S::Act - L::Ps;              // so that sm + L::Ps, sm + L::Cs ... address the activation block
+    float* Fs = sm + L::Scratch;                      // image features live in the scratch area during the prologue
+    float* Us = smraw + S::Us;
     const int r0 = blockIdx.x * NR;
-    const int tid = threadIdx.x;
-    image_feats<NR>(P, img_base, betas, img_index, r0, R, sm + L::Fs);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(&wbar[0]);
+    float* Ucta = Uscratch + (size_t)blockIdx.x * P.J * CTX * NR;
+    auto joint_bytes_anc = [&](int j) { return (uint32_t)((9 * P.anc_cnt[j] * CTX + CTX) * 4); };
+    auto issue_anc = [&](int j) {
+        mbar_expect_tx(bar0, joint_bytes_anc(j));
+        bulk_load_1d(smem_u32(smraw + S::Wanc), P.jpack + P.off_jb[j], joint_bytes_anc(j), bar0);
+    };
+    auto issue_cpl = [&](int j, int t) {
+        mbar_expect_tx(bar0 + 8 * (1 + t), COUPLING_FLOATS * 4);
+        bulk_load_1d(smem_u32(smraw + (t ? S::Wc1 : S::Wc0)),
+                     P.jpack + P.off_jb[j] + 9 * P.anc_cnt[j] * CTX + CTX + t * COUPLING_FLOATS, COUPLING_FLOATS * 4,
+                     bar0 + 8 * (1 + t));
+    };
+    auto fetch_U = [&](int j) {   // 64 x NR floats, contiguous in the scratch
+        const float* src = Ucta + (size_t)j * CTX * NR;
+        float* dst = Us + (j & 1) * CTX * NR;
+        for (int i = tid; i < CTX * NR / 4; i += HF_NT) cp_async16(dst + i * 4, src + i * 4);
+        cp_async_commit();
+    };
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(bar0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    image_feats<NR>(P, img_base, betas, img_index, r0, R, Fs);
     __syncthreads();
+    if (tid == 0) { issue_anc(0); issue_cpl(0, 0); if (P.T > 1) issue_cpl(0, 1); }
+    // prologue GEMM: 2*J output tiles of 32, full K = FEATS per warp (no split, no barrier)
+    for (int t = warp; t < 2 * P.J; t += HF_NW)
+        warp_gemm<NR, false, 8>(P.wfeat + t * 32, P.J * CTX, 0, 0, FEATS, PlainRow{Fs, NR},
+                                Ucta + (size_t)(t >> 1) * CTX * NR + (t & 1) * 32 * NR, lane);
+    __threadfence();
+    __syncthreads();
+    fetch_U(0);
+
     for (int j = 0; j < P.J; ++j) {
-        const int Kc = FEATS + 9 * P.anc_cnt[j];
-        dense_layer<NR, 2, 1>(P.pack + P.off_ctxW[j], P.pack + P.off_ctxB[j], Kc,
-                              CtxRow{sm + L::Fs, sm + L::Ps, P.anc[j], NR}, sm + L::Scratch, sm + L::Cs);
+        const uint32_t par = (uint32_t)j & 1u;
+        const int Ka = 9 * P.anc_cnt[j];
+        cp_async_wait_all();
+        mbar_wait(bar0, par);
+        __syncthreads();
+        // context = ELU(U_j + b + Wanc . vec(ancestor rotations))
+        dense_layer<NR, 2, 1, true>(smraw + S::Wanc, smraw + S::Wanc + Ka * CTX, Ka, AncRow{sm + L::Ps, P.anc[j], NR},
+                                    sm + L::Scratch, sm + L::Cs, Us + (j & 1) * CTX * NR);
+        if (j + 1 < P.J) {
+            if (tid == 0) issue_anc(j + 1);
+            fetch_U(j + 1);
+        }
         // base sample (zero for point-estimate rows); first permutation is the identity
         if (tid < NR) {
             const int r = r0 + tid;
@@ -370,7 +472,9 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
         }
         __syncthreads();
         for (int t = 0; t < P.T; ++t) {
-            coupling_nn<NR>(P.pack + P.off_nn[j][t], sm);
+            mbar_wait(bar0 + 8 * (1 + t), par);
+            coupling_nn_smem<NR>(smraw + (t ? S::Wc1 : S::Wc0), sm);
+            if (tid == 0 && j + 1 < P.J) issue_cpl(j + 1, t);
             spline_knots<NR>(sm + L::Raw, P.radius, sm + L::Ha);
             // spline on the two trailing coordinates, then rotate the vector for the next Permute
             // (pyro_conditional_norm_flow.py:46-62: with <=2 transforms the only non-identity Permute is [1,2,0],
@@ -580,6 +684,8 @@ struct hf_flow {
     FlowParams P;
     float* pack;
     float* betaW;
+    float* wfeat;
+    float* jpack;
 };
 
 namespace {
@@ -593,8 +699,7 @@ int set_smem(K kernel, size_t bytes) {
 int pick_rows(int R) {
     if (R <= 148 * 8) return 8;
     if (R <= 148 * 16) return 16;
-    if (R <= 148 * 24) return 24;
-    return 32;
+    return 24;     // larger batches run as several waves of 24-row CTAs (shared memory is full at 24 rows)
 }
 
 }  // namespace
@@ -649,20 +754,38 @@ extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const 
             }
         }
     }
+    // sampling-kernel packing: Wfeat [FEATS][J*CTX] and per-joint blocks [ancW | ctxB | coupling 0 | coupling 1]
+    std::vector<float> wfeat((size_t)FEATS * P.J * CTX), jpack;
+    for (int j = 0; j < P.J; ++j) {
+        const int a = P.anc_cnt[j], Kc = FEATS + 9 * a;
+        if (a > 7) { delete h; return hf::fail(HF_ERR_UNSUPPORTED, "hf_flow_create: joint %d has %d ancestors (sampling kernel stages at most 7)", j, a); }
+        for (int k = 0; k < FEATS; ++k)
+            for (int o = 0; o < CTX; ++o) wfeat[(size_t)k * P.J * CTX + j * CTX + o] = ctx_weight[j][(size_t)o * Kc + k];
+        P.off_jb[j] = (int)jpack.size();
+        for (int k = 0; k < 9 * a; ++k)
+            for (int o = 0; o < CTX; ++o) jpack.push_back(ctx_weight[j][(size_t)o * Kc + FEATS + k]);
+        jpack.insert(jpack.end(), ctx_bias[j], ctx_bias[j] + CTX);
+        for (int t = 0; t < 2; ++t) {
+            if (t < P.T) jpack.insert(jpack.end(), pack.begin() + P.off_nn[j][t], pack.begin() + P.off_nn[j][t] + COUPLING_FLOATS);
+            else jpack.resize(jpack.size() + COUPLING_FLOATS, 0.f);
+        }
+    }
     std::vector<float> bw((size_t)P.nb * FEATS);
     for (int l = 0; l < P.nb; ++l)
         for (int o = 0; o < FEATS; ++o) bw[l * FEATS + o] = beta_weight[(size_t)o * P.nb + l];
     int rc;
     if ((rc = hf::upload(&h->pack, pack.data(), pack.size()))) return rc;
     if ((rc = hf::upload(&h->betaW, bw.data(), bw.size()))) return rc;
-    P.pack = h->pack; P.betaW = h->betaW;
+    if ((rc = hf::upload(&h->wfeat, wfeat.data(), wfeat.size()))) return rc;
+    if ((rc = hf::upload(&h->jpack, jpack.data(), jpack.size()))) return rc;
+    P.pack = h->pack; P.betaW = h->betaW; P.wfeat = h->wfeat; P.jpack = h->jpack;
     *out = h;
     return HF_OK;
 }
 
 extern "C" void hf_flow_destroy(hf_flow_t* h) {
     if (!h) return;
-    cudaFree(h->pack); cudaFree(h->betaW);
+    cudaFree(h->pack); cudaFree(h->betaW); cudaFree(h->wfeat); cudaFree(h->jpack);
     delete h;
 }
 
@@ -670,23 +793,30 @@ extern "C" void hf_flow_destroy(hf_flow_t* h) {
     switch (NRv) {                                            \
         case 8:  { constexpr int NR = 8;  __VA_ARGS__; } break; \
         case 16: { constexpr int NR = 16; __VA_ARGS__; } break; \
-        case 24: { constexpr int NR = 24; __VA_ARGS__; } break; \
-        default: { constexpr int NR = 32; __VA_ARGS__; } break; \
+        default: { constexpr int NR = 24; __VA_ARGS__; } break; \
     }
+
+extern "C" size_t hf_flow_workspace_bytes(const hf_flow_t* h, int R) {
+    if (!h || R <= 0) return 0;
+    const int nr = pick_rows(R);
+    return (size_t)hf::div_up(R, nr) * h->P.J * CTX * nr * sizeof(float);
+}
 
 extern "C" int hf_flow_sample(const hf_flow_t* h, const float* img_base, const float* betas, const int* img_index,
                               const float* base_noise, int R, int Rn, float* rotmats, float* axisangle_pe,
-                              void* stream) {
+                              void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !img_base || !betas || !img_index || !rotmats) return hf::fail(HF_ERR_INVALID, "hf_flow_sample: null argument");
     if (Rn < 0 || Rn > R || (Rn > 0 && !base_noise)) return hf::fail(HF_ERR_INVALID, "hf_flow_sample: bad row split R=%d Rn=%d", R, Rn);
     if (R <= 0) return HF_OK;
+    if (!workspace || workspace_bytes < hf_flow_workspace_bytes(h, R) || ((uintptr_t)workspace & 15))
+        return hf::fail(HF_ERR_INVALID, "hf_flow_sample: workspace too small or unaligned (%zu < %zu)", workspace_bytes, hf_flow_workspace_bytes(h, R));
     const int nr = pick_rows(R);
     HF_DISPATCH_ROWS(nr, {
-        const size_t smem = SmemLayout<NR>::Total * sizeof(float);
+        const size_t smem = SampleSmem<NR>::Total * sizeof(float);
         int rc = set_smem(flow_sample_kernel<NR>, smem);
         if (rc) return rc;
         flow_sample_kernel<NR><<<hf::div_up(R, NR), HF_NT, smem, (cudaStream_t)stream>>>(
-            h->P, img_base, betas, img_index, base_noise, R, Rn, rotmats, axisangle_pe);
+            h->P, img_base, betas, img_index, base_noise, R, Rn, rotmats, axisangle_pe, (float*)workspace);
     });
     HF_LAUNCH_CHECK();
     return HF_OK;

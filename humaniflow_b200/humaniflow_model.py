@@ -135,6 +135,7 @@ class HumaniflowModel(nn.Module):
         self._packed = None
         self._packed_version = None
         self._index_cache = {}
+        self._flow_ws = None
 
     # ------------------------------------------------------------------ packing
     def _apply(self, fn, *a, **k):
@@ -300,8 +301,11 @@ class HumaniflowModel(nn.Module):
                     assert noise.shape == (B, N, J, 3)
                 rot = torch.empty(R, J, 3, 3, device=dev, dtype=torch.float32)
                 aa = torch.empty(B, J, 3, device=dev, dtype=torch.float32) if compute_point_est else None
+                nbytes = lib.hf_flow_workspace_bytes(self._flow, R)
+                if self._flow_ws is None or self._flow_ws.numel() < nbytes or self._flow_ws.device != dev:
+                    self._flow_ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
                 _lib.check(lib.hf_flow_sample(self._flow, _lib.ptr(base), _lib.ptr(rows), _lib.ptr(idx), _lib.ptr(noise), R, Rn,
-                                              _lib.ptr(rot), _lib.ptr(aa), st))
+                                              _lib.ptr(rot), _lib.ptr(aa), _lib.ptr(self._flow_ws), self._flow_ws.numel(), st))
                 if compute_point_est:
                     out['pose_axisangle_point_est'] = aa
                     out['pose_rotmats_point_est'] = rot[Rn:]

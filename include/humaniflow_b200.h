@@ -112,10 +112,11 @@ void hf_flow_destroy(hf_flow_t* h);
  *   fp32 flow -> fp64 exp map -> fp32 store, humaniflow_model.py:304-311);
  * rows [Rn,R) are "point-estimate rows": zero base sample, smplx fp32 Rodrigues (humaniflow_model.py:290-301),
  *   axis-angle written to axisangle_pe (R-Rn,J,3).
- * rotmats (R,J,3,3) fp32. */
+ * rotmats (R,J,3,3) fp32.  workspace: hf_flow_workspace_bytes(h, R) bytes of 16-byte aligned device scratch. */
+size_t hf_flow_workspace_bytes(const hf_flow_t* h, int R);
 int hf_flow_sample(const hf_flow_t* h, const float* img_base, const float* betas, const int* img_index,
                    const float* base_noise, int R, int Rn, float* rotmats, float* axisangle_pe,
-                   void* stream);
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* Contexts for teacher-forced log-likelihood (humaniflow_model.py:314-320): ancestors taken from
  * given rotations anc_rotmats (R,J,3,3) fp32.  ctx_out (R,J,context_dim). */
