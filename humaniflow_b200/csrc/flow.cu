@@ -229,7 +229,7 @@ __device__ __forceinline__ void so3_exp_f64(double x, double y, double z, float*
     // utils/rigid_transform_utils.py:182-201
     double th = sqrt(x * x + y * y + z * z);
     double alpha, beta;
-    if (th > 1e-10) { alpha = sin(th) / th; beta = (1.0 - cos(th)) / (th * th); }
+    if (th > 1e-10) { double sn, cs; sincos(th, &sn, &cs); alpha = sn / th; beta = (1.0 - cs) / (th * th); }
     else { alpha = 1.0 - 1.0 / 6.0; beta = 0.5 - 1.0 / 24.0; }   // reference substitutes theta=1 in the Taylor terms
     double xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
     R[0] = (float)(1.0 + beta * (-(yy + zz))); R[1] = (float)(-alpha * z + beta * xy); R[2] = (float)(alpha * y + beta * xz);
@@ -452,14 +452,8 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
         cp_async_wait_all();
         mbar_wait(bar0, par);
         __syncthreads();
-        // context = ELU(U_j + b + Wanc . vec(ancestor rotations))
-        dense_layer<NR, 2, 1, true>(smraw + S::Wanc, smraw + S::Wanc + Ka * CTX, Ka, AncRow{sm + L::Ps, P.anc[j], NR},
-                                    sm + L::Scratch, sm + L::Cs, Us + (j & 1) * CTX * NR);
-        if (j + 1 < P.J) {
-            if (tid == 0) issue_anc(j + 1);
-            fetch_U(j + 1);
-        }
-        // base sample (zero for point-estimate rows); first permutation is the identity
+        // base sample (zero for point-estimate rows); first permutation is the identity.  Written here (row CTX of
+        // Cs and Zs are not touched by the context layer), ordered by the layer's own barriers.
         if (tid < NR) {
             const int r = r0 + tid;
             float z0 = 0.f, z1 = 0.f, z2 = 0.f;
@@ -470,7 +464,13 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
             sm[L::Zs + tid] = z0; sm[L::Zs + NR + tid] = z1; sm[L::Zs + 2 * NR + tid] = z2;
             sm[L::Cs + CTX * NR + tid] = z0;
         }
-        __syncthreads();
+        // context = ELU(U_j + b + Wanc . vec(ancestor rotations))
+        dense_layer<NR, 2, 1, true>(smraw + S::Wanc, smraw + S::Wanc + Ka * CTX, Ka, AncRow{sm + L::Ps, P.anc[j], NR},
+                                    sm + L::Scratch, sm + L::Cs, Us + (j & 1) * CTX * NR);
+        if (j + 1 < P.J) {
+            if (tid == 0) issue_anc(j + 1);
+            fetch_U(j + 1);
+        }
         for (int t = 0; t < P.T; ++t) {
             mbar_wait(bar0 + 8 * (1 + t), par);
             coupling_nn_smem<NR>(smraw + (t ? S::Wc1 : S::Wc0), sm);
@@ -479,19 +479,21 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
             // spline on the two trailing coordinates, then rotate the vector for the next Permute
             // (pyro_conditional_norm_flow.py:46-62: with <=2 transforms the only non-identity Permute is [1,2,0],
             //  applied to the running vector before the second coupling).
-            if (tid < 2 * NR) {
+            if (tid < 2 * NR) {        // 2*NR <= 64: whole warps (NR in {8,16,24} -> 16/32/48 threads: lanes come in (d=0,d=1) pairs)
                 const int s = tid >> 1, d = tid & 1;
                 const float x = sm[L::Zs + (1 + d) * NR + s];
-                sm[L::Hb + d * NR + s] = spline_forward(sm + L::Raw + s, NR, d, x, P.radius, sm + L::Ha + (s * 2 + d) * 18);
-            }
-            __syncthreads();
-            if (tid < NR) {
-                const float y0 = sm[L::Zs + tid], y1 = sm[L::Hb + tid], y2 = sm[L::Hb + NR + tid];
-                if (t + 1 < P.T) {     // next permutation relative to the current order is always [1,2,0]
-                    sm[L::Zs + tid] = y1; sm[L::Zs + NR + tid] = y2; sm[L::Zs + 2 * NR + tid] = y0;
-                    sm[L::Cs + CTX * NR + tid] = y1;
-                } else {
-                    sm[L::Zs + tid] = y0; sm[L::Zs + NR + tid] = y1; sm[L::Zs + 2 * NR + tid] = y2;
+                const float y0 = sm[L::Zs + s];
+                const float mine = spline_forward(sm + L::Raw + s, NR, d, x, P.radius, sm + L::Ha + (s * 2 + d) * 18);
+                const unsigned act = __activemask();
+                const float other = __shfl_xor_sync(act, mine, 1);
+                if (d == 0) {
+                    const float y1 = mine, y2 = other;
+                    if (t + 1 < P.T) {     // next permutation relative to the current order is always [1,2,0]
+                        sm[L::Zs + s] = y1; sm[L::Zs + NR + s] = y2; sm[L::Zs + 2 * NR + s] = y0;
+                        sm[L::Cs + CTX * NR + s] = y1;
+                    } else {
+                        sm[L::Zs + NR + s] = y1; sm[L::Zs + 2 * NR + s] = y2;
+                    }
                 }
             }
             __syncthreads();
