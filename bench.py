@@ -131,7 +131,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     B_ref = min(args.B, args.ref_images)
     val, sec = time_cpu(B_ref, args.N, args.layers, args.steps, args.warmup)
@@ -157,6 +157,27 @@ def workload_config(args, images_per_step=None):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+_FULL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU before any pinned host buffer is allocated, so
+    first-touch places the staging buffers on the GPU's own NUMA node (matters for the H2D/D2H legs at N > 1)."""
+    global _FULL_AFFINITY
+    try:
+        _FULL_AFFINITY = os.sched_getaffinity(0)
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
+
+
 def run_ours(args):
     import humaniflow_b200 as hb
     from humaniflow_b200 import _lib
@@ -169,6 +190,7 @@ def run_ours(args):
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -263,9 +285,13 @@ def run_ours(args):
     for s in ('encoder', 'lbs'):
         stages[s]['frac'] = stages[s]['achieved'] / stages[s]['peak']
     dom = 'encoder' if ms_enc >= ms_lbs_k else 'lbs'
-    roofline = {'kernel': 'conv_tcgen05_kernel (ResNet-%d trunk, 53 launches)' % args.layers if dom == 'encoder' else 'lbs_skin_kernel (+ pose / extra-joint kernels, <3%)',
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if dom == 'encoder' and args.layers == 50 and B == 32 and os.path.exists(tpath):
+        traffic = json.load(open(tpath))['dram_bytes_per_step']     # ncu dram bytes of the 53 conv launches of one forward
+    roofline = {'kernel': 'conv_tcgen05_kernel (ResNet-%d trunk, 53 launches per step)' % args.layers if dom == 'encoder' else 'lbs_skin_tc_kernel (+ pose / coefficient / extra-joint kernels)',
                 'bound': stages[dom]['bound'], 'achieved': stages[dom]['achieved'], 'peak': stages[dom]['peak'],
-                'unit': stages[dom]['unit'], 'frac': stages[dom]['frac'], 'traffic': None,
+                'unit': stages[dom]['unit'], 'frac': stages[dom]['frac'], 'traffic': traffic,
                 'peak_source': pk['source'] + (' (sustained bf16)' if dom == 'encoder' else ' (copy bandwidth)')}
 
     # ---------------- end to end through the public API with HOST buffers (H2D of the images, D2H of the meshes)
@@ -344,7 +370,9 @@ def run_ours(args):
             'step_breakdown_ms': {'model_forward': ms_model, 'lbs': ms_lbs},
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            if _FULL_AFFINITY:
+                os.sched_setaffinity(0, _FULL_AFFINITY)      # the CPU baseline may use every host core again
+            cores = len(os.sched_getaffinity(0))
             torch.set_num_threads(cores)
             Bc = min(B, args.ref_images)
             val, sec = time_cpu(Bc, N, args.layers, steps=2, warmup=1)

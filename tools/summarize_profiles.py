@@ -6,8 +6,8 @@ import os
 import subprocess
 import sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
-suffix = tag.replace('r0', 'r')
+tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'          # name of the committed summary (round)
+suffix = sys.argv[2] if len(sys.argv) > 2 else tag.replace('r0', 'r')   # suffix of the gpurun_out files
 G, P = 'gpurun_out', 'profiles'
 os.makedirs(P, exist_ok=True)
 out = ['# ncu summaries, round %s' % tag, '',
@@ -79,24 +79,43 @@ for name in ('lbs', 'flow'):
             i = hdr.index(w_)
             out.append('| %s | %s | %s |' % (w_, vals[i], units[i]))
     out.append('')
-conv = os.path.join(G, 'prof_conv_%s_raw.csv' % suffix)
+conv = os.path.join(G, 'prof_conv_%s.csv' % suffix)
 if os.path.exists(conv):
-    rr = list(csv.reader(open(conv)))
-    hdr = rr[0]
-    c = lambda n: hdr.index(n)
-    out += ['## `conv_tcgen05_kernel`, the 53 convolutions of one ResNet-50 forward (`ncu --set full`)', '',
-            '| # | template | grid | us | tensor pipe % | DRAM % | DRAM rd MB | DRAM wr MB | L2 hit % |', '|---:|---|---|---:|---:|---:|---:|---:|---:|']
-    tot = 0.0
-    wsum = 0.0
-    for n, r in enumerate(rr[2:]):
-        t = float(r[c('gpu__time_duration.sum')])
-        tp = float(r[c('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')])
+    import json
+    rows = rows_of(conv)
+    by = collections.OrderedDict()
+    for r in rows:
+        d = by.setdefault(r['ID'], {'name': r['Kernel Name'].split('conv_tcgen05_kernel')[1].split('(')[0], 'grid': r['Grid Size']})
+        d[r['Metric Name']] = (float(r['Metric Value'].replace(',', '')), r['Metric Unit'])
+
+    def us(d):
+        v, u = d['gpu__time_duration.sum']
+        return v / 1000 if u == 'ns' else (v if u == 'us' else v * 1000)
+
+    def mb(d, k):
+        v, u = d[k]
+        return {'byte': v / 1e6, 'Kbyte': v / 1e3, 'Mbyte': v, 'Gbyte': v * 1e3}[u]
+    out += ['## `conv_tcgen05_kernel`, the 53 convolutions of one ResNet-50 forward at B=32 (`ncu --metrics ...`)', '',
+            '| # | template <BN,STAGES,SR> | CTAs | us | tensor pipe % | DRAM rd MB | DRAM wr MB | L2->SM MB | L2 hit % |',
+            '|---:|---|---:|---:|---:|---:|---:|---:|---:|']
+    tot = wsum = traffic = 0.0
+    for n, d in enumerate(by.values()):
+        t = us(d)
+        tp = d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'][0]
         tot += t
         wsum += t * tp
+        traffic += mb(d, 'dram__bytes_read.sum') + mb(d, 'dram__bytes_write.sum')
         out.append('| %d | %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f |' % (
-            n, r[c('Kernel Name')].split('conv_tcgen05_kernel')[1].split('(')[0], r[c('Grid Size')], t, tp,
-            float(r[c('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')]), float(r[c('dram__bytes_read.sum')]),
-            float(r[c('dram__bytes_write.sum')]), float(r[c('lts__t_sector_hit_rate.pct')])))
-    out += ['', 'Total %.1f us; time-weighted tensor-pipe activity %.1f%%.' % (tot, wsum / tot), '']
+            n, d['name'], d['grid'].strip('()').split(',')[0], t, tp, mb(d, 'dram__bytes_read.sum'), mb(d, 'dram__bytes_write.sum'),
+            mb(d, 'l1tex__m_xbar2l1tex_read_bytes.sum'), d['lts__t_sector_hit_rate.pct'][0]))
+    out += ['', 'Total %.1f us under ncu; time-weighted tensor-pipe activity %.1f%%; DRAM traffic of the 53 launches %.1f MB.'
+            % (tot, wsum / tot, traffic), '']
+    json.dump({'kernel': 'conv_tcgen05_kernel x53 (one ResNet-50 forward, B=32, 18ch, 256x256)', 'dram_bytes_per_step': traffic * 1e6,
+               'source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/%s_summary.md' % tag},
+              open(os.path.join(P, '%s_traffic.json' % tag), 'w'))
+sass = os.path.join(G, 'sass_mnemonics_%s.txt' % suffix)
+if os.path.exists(sass):
+    out += ['## Blackwell-native evidence: SASS mnemonics in libhumaniflow_b200.so (`cuobjdump -sass | grep`)', '', '```'] + \
+           [l.rstrip() for l in open(sass)] + ['```', '']
 open(os.path.join(P, '%s_summary.md' % tag), 'w').write('\n'.join(out))
 print('\n'.join(out[:40]))
