@@ -23,7 +23,7 @@ namespace {
 
 // ------------------------------------------------------------------ tcgen05 implicit-GEMM conv
 struct ConvGeom {
-    int kind;        // 0 = generic (Cin % 64 == 0), 1 = stem pixel-pair layout
+    int kind;        // 0 = generic (Cin % 64 == 0), 1 = stem pixel-pair layout (32 ch), 2 = compact stem (24 ch, sliding window map)
     int ksize, stride, pad;
     int cin;         // channels per pixel in the A tensor
     int Ho, Wo, B, cout;
@@ -55,7 +55,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                     int has_res, int num_tiles, int ntn) {
     constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int SBUF_BYTES = 128 * BN * 2;     // staging tile: BN/64 boxes of [128 rows][128 B], swizzled
-    constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
     constexpr int HALF = BN / 2;                 // columns per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 4 + 2 * SR];
@@ -112,9 +112,12 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                             c1 = wo0 + ((dw - pw) >> 1);
                             c2 = ho0 + ((dh - phh) >> 1);
                         }
-                    } else {
+                    } else if (g.kind == 1) {
                         const int kh = kb >> 2, q = kb & 3;
                         mi = kh & 1; c0 = 0; c1 = wo0 + q; c2 = ho0 + (kh >> 1);
+                    } else {   // compact stem: 8 taps x 24 ch = 192 contiguous elements per (pixel, kh), 3 k-blocks
+                        const int kh = kb / 3, q = kb - kh * 3;
+                        mi = kh & 1; c0 = q * 64; c1 = wo0; c2 = ho0 + (kh >> 1);
                     }
                     tma_load_4d(sa, &maps.a[mi], fb, c0, c1, c2, b0);
                     tma_load_2d(sb, &maps.b, fb, kb * 64, n0);
@@ -239,8 +242,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                 for (int x = 0; x < BN / 64; ++x)
                     tma_store_4d(&maps.o, sbuf_base + sb * SBUF_BYTES + x * 16384, n0 + x * 64, tw * g.TW, th * g.TH, tb * g.TB);
                 bulk_commit();
-                bulk_wait_read<1>();                      // every group but the newest has finished reading smem
-                if (lt >= 1) mbar_arrive(sfree0 + 8 * ((lt - 1) % SR));
+                if (SR == 1) {                            // single staging tile: recycle it as soon as this store has read it
+                    bulk_wait_read<0>();
+                    mbar_arrive(sfree0);
+                } else {
+                    bulk_wait_read<1>();                  // every group but the newest has finished reading smem
+                    if (lt >= 1) mbar_arrive(sfree0 + 8 * ((lt - 1) % SR));
+                }
             }
         }
         if (threadIdx.x == 64) bulk_wait<0>();
@@ -424,6 +432,20 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
                     if (rc) return rc;
                 }
         }
+    } else if (kind == 2) {
+        // Compact stem: the 7 horizontal taps x 24 channels of one output pixel are 168 contiguous bf16 of the padded NHWC
+        // row (padded to 192 = three 64-wide k-blocks, the 8th tap has zero weights).  Consecutive output pixels start
+        // 2 pixels = 96 bytes apart, so dimension 1 of the map is a SLIDING WINDOW over dimension 0 (stride 96 B < 384 B).
+        if (ks != 7 || stride != 2 || pad != 3 || cin != 24 || (Wp & 1)) return hf::fail(HF_ERR_UNSUPPORTED, "stem conv: unsupported geometry");
+        g.nkb = 7 * 3;
+        ktot = 7 * 8 * 24;
+        for (int ph = 0; ph < 2; ++ph) {
+            const uint64_t dims[4] = {192, (uint64_t)g.Wo, (uint64_t)((Hp - ph + 1) / 2), (uint64_t)B};
+            const uint64_t st[3] = {96, 2 * (uint64_t)Wp * 48, (uint64_t)Hp * Wp * 48};
+            const uint8_t* base = (const uint8_t*)x + (size_t)ph * Wp * 48;
+            int rc = encode_map(&p->maps.a[ph], base, 4, dims, st, box);
+            if (rc) return rc;
+        }
     } else {
         if (ks != 7 || stride != 2 || pad != 3 || cin != 32 || (Wp & 1)) return hf::fail(HF_ERR_UNSUPPORTED, "stem conv: unsupported geometry");
         g.nkb = 7 * 4;
@@ -438,6 +460,8 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
     }
     const int tiles_m = g.tiles_w * g.tiles_h * g.tiles_b;
     p->bn = (cout % 128 == 0) ? 128 : 64;
+    // 256-wide tiles for wide layers without residual: a third fewer operand bytes per FLOP through the L2->SM fabric
+    if (res == nullptr && cout % 256 == 0 && tiles_m * (cout / 256) >= num_sms()) p->bn = 256;
     {
         const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)B};
         const uint64_t st[3] = {(uint64_t)cout * 2, (uint64_t)g.Wo * cout * 2, (uint64_t)g.Ho * g.Wo * cout * 2};
@@ -456,8 +480,9 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
     }
     // operand ring depth vs staging tiles: residual layers prefetch the residual several tiles ahead (DRAM latency),
     // layers without residual spend the shared memory on a deeper operand ring
-    if (p->bn == 128) { p->stages = p->has_res ? 3 : 4; p->sr = p->has_res ? 3 : 2; }
-    else              { p->stages = p->has_res ? 5 : 6; p->sr = p->has_res ? 4 : 2; }
+    if (p->bn == 256)      { p->stages = 3; p->sr = 1; }
+    else if (p->bn == 128) { p->stages = p->has_res ? 3 : 5; p->sr = p->has_res ? 3 : 1; }
+    else                   { p->stages = p->has_res ? 5 : 7; p->sr = p->has_res ? 4 : 1; }
     p->smem = (size_t)p->stages * (128 * 128 + p->bn * 128) + (size_t)p->sr * 128 * p->bn * 2 + 1024;
     p->ntn = cout / p->bn;
     p->num_tiles = tiles_m * p->ntn;
@@ -469,7 +494,7 @@ template <int BN, int STAGES, int SR>
 int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
         attr = true;
     }
     conv_tcgen05_kernel<BN, STAGES, SR><<<p.grid, CONV_THREADS, p.smem, s>>>(p.maps, p.g, bias, p.has_res, p.num_tiles, p.ntn);
@@ -478,8 +503,9 @@ int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
 }
 
 int launch_conv(const ConvPlan& p, const float* bias, cudaStream_t s) {
-    if (p.bn == 128) return p.has_res ? launch_conv_t<128, 3, 3>(p, bias, s) : launch_conv_t<128, 4, 2>(p, bias, s);
-    return p.has_res ? launch_conv_t<64, 5, 4>(p, bias, s) : launch_conv_t<64, 6, 2>(p, bias, s);
+    if (p.bn == 256) return launch_conv_t<256, 3, 1>(p, bias, s);
+    if (p.bn == 128) return p.has_res ? launch_conv_t<128, 3, 3>(p, bias, s) : launch_conv_t<128, 5, 1>(p, bias, s);
+    return p.has_res ? launch_conv_t<64, 5, 4>(p, bias, s) : launch_conv_t<64, 7, 1>(p, bias, s);
 }
 
 int launch_simt(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, const __nv_bfloat16* res,
@@ -503,6 +529,8 @@ struct hf_encoder {
     std::vector<float*> bias;
     std::vector<int> w_cin;               // cin of each weight as given
     int in_channels, stem_cin, feat_dim, impl;
+    int stem_cp;                          // channels per pixel of the staged stem input actually in use (24 or 32)
+    __nv_bfloat16 *w_stem24, *w_plain24;  // compact-stem weight packings (cout,7,8,24) / (cout,7,7,24)
     int debug_stop;                       // >= 0: forward stops after this op (layer-by-layer bring-up)
     // plan cache for one (B,H,W,workspace)
     int pB, pH, pW;
@@ -575,6 +603,7 @@ extern "C" int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int n
     hf_encoder* h = new hf_encoder();
     h->ops.assign(ops, ops + num_ops);
     h->in_channels = in_channels; h->stem_cin = stem_cin; h->feat_dim = feat_dim; h->impl = 0; h->debug_stop = -1;
+    h->stem_cp = STEM_CP; h->w_stem24 = nullptr; h->w_plain24 = nullptr;
     h->pB = h->pH = h->pW = 0; h->pws = nullptr;
     h->w.resize(num_weights); h->w_plain.resize(num_weights); h->bias.resize(num_weights); h->w_cin.resize(num_weights);
     for (int i = 0; i < num_ops; ++i) {
@@ -595,6 +624,18 @@ extern "C" int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int n
                     for (int kw = 0; kw < 7; ++kw)
                         memcpy(&pk[(((size_t)co * 7 + kh) * 8 + kw) * STEM_CP], &weights[wi][(((size_t)co * 7 + kh) * 7 + kw) * STEM_CP], STEM_CP * 2);
             if ((rc = hf::upload((uint16_t**)&h->w[wi], pk.data(), pk.size()))) return rc;
+            if (in_channels <= 24) {   // compact variants: drop the (all-zero) channels 24..31
+                std::vector<uint16_t> p24((size_t)op.cout * 7 * 8 * 24, 0), q24((size_t)op.cout * 7 * 7 * 24, 0);
+                for (int co = 0; co < op.cout; ++co)
+                    for (int kh = 0; kh < 7; ++kh)
+                        for (int kw = 0; kw < 7; ++kw) {
+                            const uint16_t* src = &weights[wi][(((size_t)co * 7 + kh) * 7 + kw) * STEM_CP];
+                            memcpy(&p24[(((size_t)co * 7 + kh) * 8 + kw) * 24], src, 24 * 2);
+                            memcpy(&q24[(((size_t)co * 7 + kh) * 7 + kw) * 24], src, 24 * 2);
+                        }
+                if ((rc = hf::upload((uint16_t**)&h->w_stem24, p24.data(), p24.size()))) return rc;
+                if ((rc = hf::upload((uint16_t**)&h->w_plain24, q24.data(), q24.size()))) return rc;
+            }
         } else {
             h->w[wi] = h->w_plain[wi];
         }
@@ -605,6 +646,7 @@ extern "C" int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int n
 
 extern "C" void hf_encoder_destroy(hf_encoder_t* h) {
     if (!h) return;
+    cudaFree(h->w_stem24); cudaFree(h->w_plain24);
     for (size_t i = 0; i < h->w.size(); ++i) {
         if (h->w[i] && h->w[i] != h->w_plain[i]) cudaFree(h->w[i]);
         if (h->w_plain[i]) cudaFree(h->w_plain[i]);
@@ -612,6 +654,8 @@ extern "C" void hf_encoder_destroy(hf_encoder_t* h) {
     }
     delete h;
 }
+
+extern "C" int hf_encoder_stem_channels(const hf_encoder_t* h) { return h ? h->stem_cp : 0; }
 
 extern "C" int hf_encoder_set_impl(hf_encoder_t* h, int impl) {
     if (!h || impl < 0 || impl > 1) return hf::fail(HF_ERR_INVALID, "hf_encoder_set_impl: bad argument");
@@ -648,8 +692,17 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
         for (size_t i = 0; i < h->ops.size(); ++i) {
             const hf_enc_op& op = h->ops[i];
             if (op.kind != HF_OP_CONV) continue;
-            if (i == 0) rc = plan_conv(&h->plans[i], 1, stem_in, h->w[op.weight_index], B, H, W, STEM_CP, op.cout, 7, 2, 3, op.relu, Hp, Wp, buf(op.dst), nullptr);
-            else {
+            if (i == 0) {
+                rc = HF_ERR_UNSUPPORTED;
+                if (h->w_stem24) {   // compact stem first; its sliding-window tensor map may be refused by the driver
+                    rc = plan_conv(&h->plans[i], 2, stem_in, h->w_stem24, B, H, W, 24, op.cout, 7, 2, 3, op.relu, Hp, Wp, buf(op.dst), nullptr);
+                    if (rc == HF_OK) h->stem_cp = 24;
+                }
+                if (rc != HF_OK) {
+                    rc = plan_conv(&h->plans[i], 1, stem_in, h->w[op.weight_index], B, H, W, STEM_CP, op.cout, 7, 2, 3, op.relu, Hp, Wp, buf(op.dst), nullptr);
+                    h->stem_cp = STEM_CP;
+                }
+            } else {
                 const BufShape in = shp.in[i];
                 if (op.cin % 64 != 0) return hf::fail(HF_ERR_UNSUPPORTED, "encoder: conv %zu has cin %d (must be a multiple of 64)", i, op.cin);
                 rc = plan_conv(&h->plans[i], 0, buf(op.src), h->w[op.weight_index], B, in.H, in.W, op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, 0, 0,
@@ -664,7 +717,7 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
     {
         const size_t total = (size_t)B * H * W;
         int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
-        nchw_to_nhwc_pad_kernel<<<blocks, 256, 0, stream>>>(input, stem_in, B, h->in_channels, H, W, STEM_CP, Hp, Wp, 3, 3);
+        nchw_to_nhwc_pad_kernel<<<blocks, 256, 0, stream>>>(input, stem_in, B, h->in_channels, H, W, h->stem_cp, Hp, Wp, 3, 3);
         HF_LAUNCH_CHECK();
     }
     for (size_t i = 0; i < h->ops.size(); ++i) {
@@ -675,8 +728,8 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
                 rc = launch_conv(h->plans[i], h->bias[op.weight_index], stream);
             } else if (i == 0) {
                 // SIMT path reads the physically padded input as a pad-0 convolution with the true output size
-                rc = launch_simt(stem_in, h->w_plain[op.weight_index], h->bias[op.weight_index], res, buf(op.dst), B, Hp, Wp,
-                                 STEM_CP, op.cout, 7, 2, 0, op.relu, stream, h->plans[i].g.Ho, h->plans[i].g.Wo);
+                rc = launch_simt(stem_in, h->stem_cp == 24 ? h->w_plain24 : h->w_plain[op.weight_index], h->bias[op.weight_index], res,
+                                 buf(op.dst), B, Hp, Wp, h->stem_cp, op.cout, 7, 2, 0, op.relu, stream, h->plans[i].g.Ho, h->plans[i].g.Wo);
             } else {
                 const BufShape in = shp.in[i];
                 rc = launch_simt(buf(op.src), h->w_plain[op.weight_index], h->bias[op.weight_index], res, buf(op.dst), B, in.H, in.W,

@@ -179,6 +179,9 @@ size_t hf_encoder_workspace_bytes(const hf_encoder_t* h, int B, int H, int W);
 /* input (B,in_channels,H,W) fp32 NCHW -> feats (B,feat_dim) fp32. */
 int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, int H, int W, float* feats,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* Channels per pixel of the staged stem input chosen at the first forward: 24 (compact stem, sliding-window
+ * tensor map) or 32 (pixel-pair layout, used when the driver refuses the overlapping map or in_channels > 24). */
+int hf_encoder_stem_channels(const hf_encoder_t* h);
 /* impl: 0 = tcgen05/TMA implicit GEMM (product path), 1 = SIMT direct convolution (debug cross-check). */
 int hf_encoder_set_impl(hf_encoder_t* h, int impl);
 

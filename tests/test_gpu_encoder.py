@@ -47,6 +47,9 @@ CASES = [
     (5, 4, 4, 128, 64, 3, 1, 1, False, False),       # 4x4 maps: 8 images per tile, ragged
     (1, 64, 64, 64, 128, 3, 1, 1, False, True),      # many tiles, BN=128
     (1, 14, 14, 64, 64, 3, 1, 1, False, True),       # non power-of-two maps: partial tiles in w and h
+    (8, 64, 64, 64, 256, 1, 1, 0, False, True),      # >= 148 wide tiles: the BN=256 kernel variant, persistent loop > 1 tile/CTA
+    (5, 64, 64, 64, 256, 1, 1, 0, True, True),       # residual ring (3 staging tiles) over many tiles per CTA
+    (6, 32, 32, 128, 512, 3, 2, 1, False, False),    # BN=256 with a K-heavy strided 3x3
 ]
 
 
@@ -78,6 +81,7 @@ def test_trunk(layers, size, B):
         f32 = resnet_forward(sd, x, layers)
         emu = resnet_bf16emu(sd, x, layers)
     got = enc(x.cuda()).cpu()
+    print('stem channels per pixel:', _lib.load().hf_encoder_stem_channels(enc._enc))
     assert got.shape == f32.shape and got.dtype == torch.float32
     rel = lambda a, b: ((a - b).norm() / b.norm()).item()
     assert rel(got, emu) <= 5e-3, rel(got, emu)
