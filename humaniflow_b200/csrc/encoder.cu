@@ -497,7 +497,13 @@ int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
         HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
         attr = true;
     }
-    conv_tcgen05_kernel<BN, STAGES, SR><<<p.grid, CONV_THREADS, p.smem, s>>>(p.maps, p.g, bias, p.has_res, p.num_tiles, p.ntn);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = p.grid; cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    HF_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, STAGES, SR>, p.maps, p.g, bias, p.has_res, p.num_tiles, p.ntn));
     HF_LAUNCH_CHECK();
     return HF_OK;
 }
