@@ -254,7 +254,12 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
         if (threadIdx.x == 64) bulk_wait<0>();
     }
     tcgen05_fence_before();
+    __threadfence();
     __syncthreads();
+    // Every thread of this CTA is past its last global write (thread 64 has waited for the TMA stores): only now may
+    // the next kernel of the stream be released (measured on B200: griddepcontrol.wait in the dependent returns once all
+    // CTAs of this grid have triggered, NOT when the grid has completed; an earlier trigger races).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -297,6 +302,7 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv
 __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
                                         int H, int W, int Cp, int Hp, int Wp, int top, int left) {
     // one thread per (b, h, w): reads C strided planes (coalesced over w), writes Cp contiguous bf16
+    HF_PDL_SYNC();
     const size_t total = (size_t)B * H * W;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int w = (int)(e % W);
@@ -323,6 +329,7 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __nv_bfloat
 // 3x3 stride-2 pad-1 max pooling on bf16 NHWC, 8 channels per thread.
 __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                                int C, int Ho, int Wo) {
+    HF_PDL_SYNC();
     const int C8 = C / 8;
     const size_t total = (size_t)B * Ho * Wo * C8;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -362,6 +369,7 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 
 // global average pool bf16 NHWC -> fp32 (B, C)
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+    HF_PDL_SYNC();
     const int b = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -502,7 +510,8 @@ int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("HF_NO_PDL") != nullptr;
+    cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
     HF_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, STAGES, SR>, p.maps, p.g, bias, p.has_res, p.num_tiles, p.ntn));
     HF_LAUNCH_CHECK();
     return HF_OK;
@@ -723,7 +732,7 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
     {
         const size_t total = (size_t)B * H * W;
         int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
-        nchw_to_nhwc_pad_kernel<<<blocks, 256, 0, stream>>>(input, stem_in, B, h->in_channels, H, W, h->stem_cp, Hp, Wp, 3, 3);
+        nchw_to_nhwc_pad_kernel<<<blocks, 256, 0, stream>>>(input, stem_in, B, h->in_channels, H, W, h->stem_cp, Hp, Wp, 3, 3);   // follows a memset: plain launch
         HF_LAUNCH_CHECK();
     }
     for (size_t i = 0; i < h->ops.size(); ++i) {

@@ -435,6 +435,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
         for (int i = 0; i < 3; ++i) mbar_init(bar0 + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    HF_PDL_SYNC();
     image_feats<NR>(P, img_base, betas, img_index, r0, R, Fs);
     __syncthreads();
     if (tid == 0) { issue_anc(0); issue_cpl(0, 0); if (P.T > 1) issue_cpl(0, 1); }
@@ -817,8 +818,8 @@ extern "C" int hf_flow_sample(const hf_flow_t* h, const float* img_base, const f
         const size_t smem = SampleSmem<NR>::Total * sizeof(float);
         int rc = set_smem(flow_sample_kernel<NR>, smem);
         if (rc) return rc;
-        flow_sample_kernel<NR><<<hf::div_up(R, NR), HF_NT, smem, (cudaStream_t)stream>>>(
-            h->P, img_base, betas, img_index, base_noise, R, Rn, rotmats, axisangle_pe, (float*)workspace);
+        HF_CUDA(hf::launch_pdl(flow_sample_kernel<NR>, dim3(hf::div_up(R, NR)), dim3(HF_NT), smem, (cudaStream_t)stream, h->P, img_base, betas,
+                               img_index, base_noise, R, Rn, rotmats, axisangle_pe, (float*)workspace));
     });
     HF_LAUNCH_CHECK();
     return HF_OK;

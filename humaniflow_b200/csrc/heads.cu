@@ -30,6 +30,7 @@ linear_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
                   const float* __restrict__ b, float* __restrict__ y, int ldy, int M, int K, int O, int act,
                   int accumulate) {
     extern __shared__ __align__(16) float xs[];           // [2][32][KC]
+    HF_PDL_SYNC();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int o = blockIdx.x * LW + warp;
     const int m0 = blockIdx.y * 32;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(128)
 linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, int ldw,
                     const float* __restrict__ b, float* __restrict__ y, int ldy, int M, int K, int O, int act,
                     int accumulate) {
+    HF_PDL_SYNC();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int o = blockIdx.x * 4 + warp;
     const int r = blockIdx.y * 32 + lane;
@@ -98,6 +100,7 @@ linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restric
 }
 
 __global__ void rot6d_kernel(const float* __restrict__ x6, float* __restrict__ R, int n) {
+    HF_PDL_SYNC();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     // x.view(-1,3,2): a1 = (x0,x2,x4), a2 = (x1,x3,x5); F.normalize eps 1e-12; columns b1,b2,b3
@@ -121,6 +124,7 @@ __global__ void heads_finish_kernel(const float* __restrict__ heads, const float
                                     const float* __restrict__ init_cam, const float* __restrict__ shape_eps,
                                     int B, int N, int nb, float* __restrict__ cam, float* __restrict__ glob6,
                                     float* __restrict__ shape_rows) {
+    HF_PDL_SYNC();
     const int ld = 2 * nb + 9;
     const int total = B * N * nb + B * nb;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -154,8 +158,8 @@ extern "C" int hf_heads_finish(const float* heads, const float* init_glob, const
     int blocks = hf::div_up(total > B * 6 ? total : B * 6, 256);
     if (blocks > 1024) blocks = 1024;
     if (blocks * 256 < B * 6) return hf::fail(HF_ERR_UNSUPPORTED, "hf_heads_finish: batch too large");
-    heads_finish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(heads, init_glob, init_cam, shape_eps, B, N, nb, cam,
-                                                                 glob6, shape_rows);
+    HF_CUDA(hf::launch_pdl(heads_finish_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, heads, init_glob, init_cam, shape_eps, B, N,
+                           nb, cam, glob6, shape_rows));
     HF_LAUNCH_CHECK();
     return HF_OK;
 }
@@ -174,10 +178,10 @@ extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const
             attr = true;
         }
         dim3 grid(hf::div_up(O, LW), hf::div_up(M, 32));
-        linear_vec_kernel<<<grid, LW * 32, smem, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate);
+        HF_CUDA(hf::launch_pdl(linear_vec_kernel, grid, dim3(LW * 32), (size_t)smem, (cudaStream_t)stream, x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate));
     } else {
         dim3 grid(hf::div_up(O, 4), hf::div_up(M, 32));
-        linear_small_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate);
+        HF_CUDA(hf::launch_pdl(linear_small_kernel, grid, dim3(128), 0, (cudaStream_t)stream, x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate));
     }
     HF_LAUNCH_CHECK();
     return HF_OK;
@@ -185,7 +189,7 @@ extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const
 
 extern "C" int hf_rot6d_to_rotmat(const float* rot6d, float* rotmats, int n, void* stream) {
     if (n <= 0) return HF_OK;
-    rot6d_kernel<<<hf::div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(rot6d, rotmats, n);
+    HF_CUDA(hf::launch_pdl(rot6d_kernel, dim3(hf::div_up(n, 128)), dim3(128), 0, (cudaStream_t)stream, rot6d, rotmats, n));
     HF_LAUNCH_CHECK();
     return HF_OK;
 }

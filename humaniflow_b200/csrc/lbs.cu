@@ -45,6 +45,7 @@ __global__ void lbs_pose_kernel(const float* __restrict__ betas, const float* __
                                 const float* __restrict__ Jd, Parents par, int M, int J, int nb, int KP,
                                 int J_out, float* __restrict__ F, float* __restrict__ A,
                                 float* __restrict__ joints) {
+    HF_PDL_SYNC();
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     float beta[HF_MAXB];
@@ -103,6 +104,7 @@ __global__ void lbs_pose_kernel(const float* __restrict__ betas, const float* __
 // zero padded; one thread per element, coalesced bf16 writes.
 __global__ void lbs_coef_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats, int M, int J, int nb,
                                 __nv_bfloat16* __restrict__ Fb) {
+    HF_PDL_SYNC();
     const size_t total = (size_t)M * LBS_KH;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(e / LBS_KH), k = (int)(e - (size_t)m * LBS_KH);
@@ -249,6 +251,7 @@ lbs_skin_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
 
     constexpr int NIT = 3 * (LBS_KH / 64);          // (coordinate, k-block) iterations
@@ -359,6 +362,7 @@ __global__ void lbs_extra_joints_kernel(const float* __restrict__ vertices, cons
                                         const int* __restrict__ csr_ptr, const int* __restrict__ csr_col,
                                         const float* __restrict__ csr_val, int M, int V, int J, int nvj,
                                         int nextra, int J_out, float* __restrict__ joints) {
+    HF_PDL_SYNC();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int per = nvj + nextra;
     if (idx >= M * per) return;
@@ -555,11 +559,12 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     const int J_out = hf_smpl_num_joints_out(h);
     Parents par;
     for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
-    lbs_pose_kernel<<<hf::div_up(M, 128), 128, 0, stream>>>(betas, rotmats, transl, h->J0, h->Jd, par, M, h->J,
-                                                            h->nb, h->KP, J_out, h->impl == 0 ? nullptr : F, A, joints);
+    HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, 128)), dim3(128), 0, stream, betas, rotmats, transl, h->J0, h->Jd, par, M,
+                           h->J, h->nb, h->KP, J_out, h->impl == 0 ? (float*)nullptr : F, A, joints));
     HF_LAUNCH_CHECK();
     if (h->impl == 0) {
-        lbs_coef_kernel<<<std::min(hf::div_up(M * LBS_KH, 256), 148 * 16), 256, 0, stream>>>(betas, rotmats, M, h->J, h->nb, Fb);
+        HF_CUDA(hf::launch_pdl(lbs_coef_kernel, dim3(std::min(hf::div_up(M * LBS_KH, 256), 148 * 16)), dim3(256), 0, stream, betas, rotmats,
+                               M, h->J, h->nb, Fb));
         HF_LAUNCH_CHECK();
         hf_smpl* hm = const_cast<hf_smpl*>(h);
         if (hm->mapB_ptr != (const void*)Fb || hm->mapB_M != M) {
@@ -578,8 +583,8 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
         }
         if (tc_smem > 226 * 1024) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_forward: tile needs %zu B of shared memory", tc_smem);
         dim3 tgrid(h->Vp / 128, hf::div_up(M, TC_NS));
-        lbs_skin_tc_kernel<<<tgrid, TC_THREADS, tc_smem, stream>>>(hm->mapA, hm->mapB, h->vtemp, h->sj, h->sw, A, transl, M, h->V,
-                                                                   h->Vp, h->J, h->nslots, vertices);
+        HF_CUDA(hf::launch_pdl(lbs_skin_tc_kernel, tgrid, dim3(TC_THREADS), tc_smem, stream, hm->mapA, hm->mapB, h->vtemp, h->sj, h->sw,
+                               A, transl, M, h->V, h->Vp, h->J, h->nslots, vertices));
         HF_LAUNCH_CHECK();
     } else {
     constexpr int TS = kSPT * kSG;
@@ -597,9 +602,8 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     }
     int per = h->nvj + h->nextra;
     if (per > 0) {
-        lbs_extra_joints_kernel<<<hf::div_up(M * per, 256), 256, 0, stream>>>(vertices, h->vj, h->csr_ptr, h->csr_col,
-                                                                              h->csr_val, M, h->V, h->J, h->nvj,
-                                                                              h->nextra, J_out, joints);
+        HF_CUDA(hf::launch_pdl(lbs_extra_joints_kernel, dim3(hf::div_up(M * per, 256)), dim3(256), 0, stream, vertices, h->vj, h->csr_ptr,
+                               h->csr_col, h->csr_val, M, h->V, h->J, h->nvj, h->nextra, J_out, joints));
         HF_LAUNCH_CHECK();
     }
     return HF_OK;

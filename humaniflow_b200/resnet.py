@@ -8,6 +8,7 @@ Training-mode BatchNorm (batch statistics) and backward are out of scope of this
 """
 import ctypes
 import math
+import os
 
 import torch
 from torch import nn
@@ -193,6 +194,8 @@ class ResNet(nn.Module):
             nbytes = lib.hf_encoder_workspace_bytes(self._enc, B, H, W)
             if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
                 self._ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+                if os.environ.get('HF_POISON_WS'):      # debugging aid: make any read of uninitialised scratch visible
+                    self._ws.fill_(0x7f)
             feats = torch.empty(B, self.feat_dim, device=dev, dtype=torch.float32)
             _lib.check(lib.hf_encoder_forward(self._enc, _lib.ptr(x), B, H, W, _lib.ptr(feats), _lib.ptr(self._ws),
                                               self._ws.numel(), _lib.stream()))

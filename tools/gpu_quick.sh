@@ -2,7 +2,7 @@
 # usage: tools/gpu_quick.sh "<pytest -k expr or empty>" : run gpu tests + short bench
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 900 python -m pytest tests -q -m gpu --timeout 600 -x -s > gpurun_out/t_all.log 2>&1; echo "tests rc=$?"
+timeout 900 python -m pytest tests -q -m gpu --timeout 600 -s > gpurun_out/t_all.log 2>&1; echo "tests rc=$?"
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
 tail -n 6 gpurun_out/t_all.log
 python - <<'PY'
