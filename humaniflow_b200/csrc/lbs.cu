@@ -38,64 +38,78 @@ namespace {
 
 struct Parents { int p[HF_MAXJ]; };
 
-// One thread per sample: joints from betas, 24-step chain of rigid transforms, relative transforms,
-// blend coefficients.  Tiny (M threads); layouts chosen for the skinning kernel that follows.
-__global__ void lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats,
+// One WARP per sample: lane j < J regresses joint j from the betas; the 24-step chain of rigid transforms runs
+// with lanes 0..11 each owning one entry of the 3x4 matrix (G_i = G_parent . [R_i | t_i]), parents read back from
+// shared memory; relative transforms A_i, posed joints and (for the CUDA-core blend) fp32 coefficients are written
+// coalesced.  PW warps per block.
+constexpr int PW = 8;
+__global__ void __launch_bounds__(PW * 32)
+lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats,
                                 const float* __restrict__ transl, const float* __restrict__ J0,
                                 const float* __restrict__ Jd, Parents par, int M, int J, int nb, int KP,
                                 int J_out, float* __restrict__ F, float* __restrict__ A,
                                 float* __restrict__ joints) {
     HF_PDL_SYNC();
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float Gs[PW][HF_MAXJ][12];
+    __shared__ float Js[PW][HF_MAXJ][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * PW + warp;
     if (m >= M) return;
-    float beta[HF_MAXB];
-    for (int l = 0; l < nb; ++l) beta[l] = betas[(size_t)m * nb + l];
-    float Jl[HF_MAXJ][3];
-    for (int i = 0; i < J; ++i)
-        for (int c = 0; c < 3; ++c) {
-            float a = J0[i * 3 + c];
-            for (int l = 0; l < nb; ++l) a = fmaf(Jd[(i * 3 + c) * nb + l], beta[l], a);
-            Jl[i][c] = a;
+    // joints of the shaped template: lane j handles joint j
+    if (lane < J) {
+        float acc[3] = {J0[lane * 3], J0[lane * 3 + 1], J0[lane * 3 + 2]};
+        for (int l = 0; l < nb; ++l) {
+            const float bl = __ldg(betas + (size_t)m * nb + l);
+            acc[0] = fmaf(Jd[(lane * 3 + 0) * nb + l], bl, acc[0]);
+            acc[1] = fmaf(Jd[(lane * 3 + 1) * nb + l], bl, acc[1]);
+            acc[2] = fmaf(Jd[(lane * 3 + 2) * nb + l], bl, acc[2]);
         }
-    float tr[3] = {0.f, 0.f, 0.f};
-    if (transl) { tr[0] = transl[m * 3]; tr[1] = transl[m * 3 + 1]; tr[2] = transl[m * 3 + 2]; }
-    float* Fm = F ? F + (size_t)m * KP : nullptr;     // fp32 coefficients are only needed by the CUDA-core blend
-    if (Fm) {
-        for (int l = 0; l < nb; ++l) Fm[l] = beta[l];
-        for (int k = nb + 9 * (J - 1); k < KP; ++k) Fm[k] = 0.f;
+        Js[warp][lane][0] = acc[0]; Js[warp][lane][1] = acc[1]; Js[warp][lane][2] = acc[2];
     }
-    float G[HF_MAXJ][12];
-    for (int i = 0; i < J; ++i) {
-        float R[9];
-        const float* Rm = rotmats + ((size_t)m * J + i) * 9;
-        for (int e = 0; e < 9; ++e) R[e] = Rm[e];
-        if (i > 0 && Fm)
-            for (int e = 0; e < 9; ++e) Fm[nb + (i - 1) * 9 + e] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
-        float t[3];
-        int p = par.p[i];
-        for (int c = 0; c < 3; ++c) t[c] = (i == 0) ? Jl[0][c] : Jl[i][c] - Jl[p][c];
-        float* g = G[i];
-        if (i == 0) {
-            for (int r = 0; r < 3; ++r) {
-                g[r * 4 + 0] = R[r * 3 + 0]; g[r * 4 + 1] = R[r * 3 + 1]; g[r * 4 + 2] = R[r * 3 + 2];
-                g[r * 4 + 3] = t[r];
+    if (F) {   // fp32 blend coefficients (beta | vec(R_i - I)), only for the CUDA-core blend
+        float* Fm = F + (size_t)m * KP;
+        for (int k = lane; k < KP; k += 32) {
+            float f = 0.f;
+            if (k < nb) f = __ldg(betas + (size_t)m * nb + k);
+            else if (k < nb + 9 * (J - 1)) {
+                const int q = k - nb, i = q / 9 + 1, e = q - (i - 1) * 9;
+                f = __ldg(rotmats + ((size_t)m * J + i) * 9 + e) - ((e % 4 == 0) ? 1.f : 0.f);
             }
-        } else {
-            const float* gp = G[p];
-            for (int r = 0; r < 3; ++r) {
-                float a0 = gp[r * 4 + 0], a1 = gp[r * 4 + 1], a2 = gp[r * 4 + 2];
-                g[r * 4 + 0] = a0 * R[0] + a1 * R[3] + a2 * R[6];
-                g[r * 4 + 1] = a0 * R[1] + a1 * R[4] + a2 * R[7];
-                g[r * 4 + 2] = a0 * R[2] + a1 * R[5] + a2 * R[8];
-                g[r * 4 + 3] = a0 * t[0] + a1 * t[1] + a2 * t[2] + gp[r * 4 + 3];
-            }
+            Fm[k] = f;
         }
-        float* Am = A + ((size_t)m * J + i) * 12;
-        float* jo = joints + ((size_t)m * J_out + i) * 3;
-        for (int r = 0; r < 3; ++r) {
-            Am[r * 4 + 0] = g[r * 4 + 0]; Am[r * 4 + 1] = g[r * 4 + 1]; Am[r * 4 + 2] = g[r * 4 + 2];
-            Am[r * 4 + 3] = g[r * 4 + 3] - (g[r * 4 + 0] * Jl[i][0] + g[r * 4 + 1] * Jl[i][1] + g[r * 4 + 2] * Jl[i][2]);
-            jo[r] = g[r * 4 + 3] + tr[r];
+    }
+    __syncwarp();
+    const int r = lane >> 2, c = lane & 3;        // entry (r, c) of the 3x4 matrix for lanes 0..11
+    float trc = 0.f;                              // lanes 16..18 write the posed joints (x, y, z)
+    if (transl && lane >= 16 && lane < 19) trc = transl[m * 3 + lane - 16];
+    const float* Rm = rotmats + (size_t)m * J * 9;
+    for (int i = 0; i < J; ++i) {
+        const int p = par.p[i];
+        if (lane < 12) {
+            // local transform [R_i | t_i], t_i = J_i - J_parent (root: J_0)
+            float l0, l1, l2;        // column c of [R|t]
+            if (c < 3) { l0 = __ldg(Rm + i * 9 + c); l1 = __ldg(Rm + i * 9 + 3 + c); l2 = __ldg(Rm + i * 9 + 6 + c); }
+            else {
+                l0 = Js[warp][i][0]; l1 = Js[warp][i][1]; l2 = Js[warp][i][2];
+                if (i > 0) { l0 -= Js[warp][p][0]; l1 -= Js[warp][p][1]; l2 -= Js[warp][p][2]; }
+            }
+            float gv;
+            if (i == 0) gv = (r == 0) ? l0 : ((r == 1) ? l1 : l2);
+            else {
+                const float* gp = Gs[warp][p];
+                gv = gp[r * 4 + 0] * l0 + gp[r * 4 + 1] * l1 + gp[r * 4 + 2] * l2 + ((c == 3) ? gp[r * 4 + 3] : 0.f);
+            }
+            Gs[warp][i][lane] = gv;
+        }
+        __syncwarp();
+        if (lane < 12) {
+            const float* g = Gs[warp][i];
+            float av = g[lane];
+            if (c == 3) av -= g[r * 4 + 0] * Js[warp][i][0] + g[r * 4 + 1] * Js[warp][i][1] + g[r * 4 + 2] * Js[warp][i][2];
+            A[((size_t)m * J + i) * 12 + lane] = av;
+        } else if (lane >= 16 && lane < 19) {
+            const int cc = lane - 16;
+            joints[((size_t)m * J_out + i) * 3 + cc] = Gs[warp][i][cc * 4 + 3] + trc;
         }
     }
 }
@@ -559,7 +573,7 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     const int J_out = hf_smpl_num_joints_out(h);
     Parents par;
     for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
-    HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, 128)), dim3(128), 0, stream, betas, rotmats, transl, h->J0, h->Jd, par, M,
+    HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, PW)), dim3(PW * 32), 0, stream, betas, rotmats, transl, h->J0, h->Jd, par, M,
                            h->J, h->nb, h->KP, J_out, h->impl == 0 ? (float*)nullptr : F, A, joints));
     HF_LAUNCH_CHECK();
     if (h->impl == 0) {
