@@ -153,8 +153,9 @@ class SMPL(nn.Module):
         for h in self._handles.values():
             _lib.check(_lib.load().hf_lbs_set_impl(h, impl))
 
-    def lbs(self, betas, rotmats, transl=None):
-        """betas (M,nb), rotmats (M,24,3,3) fp32 CUDA -> vertices (M,V,3), joints (M,90,3)."""
+    def lbs(self, betas, rotmats, transl=None, out_vertices=None, out_joints=None):
+        """betas (M,nb), rotmats (M,24,3,3) fp32 CUDA -> vertices (M,V,3), joints (M,90,3).
+        ``out_vertices`` / ``out_joints``: optional preallocated fp32 CUDA outputs (serving loops that double-buffer)."""
         _lib.require_cuda('SMPL.forward')
         if not betas.is_cuda:
             raise RuntimeError('humaniflow_b200.SMPL: inputs must be CUDA tensors (no CPU fallback)')
@@ -168,8 +169,10 @@ class SMPL(nn.Module):
         transl = None if transl is None else _lib.f32c(transl).expand(M, 3).contiguous()
         h = self._handle(dev)
         V = self.v_template.shape[0]
-        verts = torch.empty(M, V, 3, device=dev, dtype=torch.float32)
-        joints = torch.empty(M, self.num_joints_out, 3, device=dev, dtype=torch.float32)
+        verts = torch.empty(M, V, 3, device=dev, dtype=torch.float32) if out_vertices is None else out_vertices
+        joints = torch.empty(M, self.num_joints_out, 3, device=dev, dtype=torch.float32) if out_joints is None else out_joints
+        assert verts.shape == (M, V, 3) and verts.is_contiguous() and verts.dtype == torch.float32 and verts.device == dev
+        assert joints.shape == (M, self.num_joints_out, 3) and joints.is_contiguous() and joints.dtype == torch.float32
         with torch.cuda.device(dev):
             nbytes = lib.hf_lbs_workspace_bytes(h, M)
             ws = self._ws.get(dev)
@@ -181,7 +184,7 @@ class SMPL(nn.Module):
         return verts, joints
 
     def forward(self, betas=None, body_pose=None, global_orient=None, transl=None, return_verts=True,
-                return_full_pose=False, pose2rot=True, **kwargs):
+                return_full_pose=False, pose2rot=True, out_vertices=None, out_joints=None, **kwargs):
         """models/smpl.py:27-41 + [upstream] smplx SMPL.forward.  ``None`` inputs fall back to the module's
         parameters; ``pose2rot=False`` takes rotation matrices (M,23,3,3)/(M,1,3,3), ``True`` axis-angle."""
         global_orient = global_orient if global_orient is not None else self.global_orient
@@ -209,7 +212,7 @@ class SMPL(nn.Module):
             rotmats = rotmats.expand(M, -1, -1, -1)
         if transl is not None and transl.shape[0] not in (1, M):
             raise ValueError('transl batch %d does not match %d' % (transl.shape[0], M))
-        verts, joints = self.lbs(betas.to(rotmats.device), rotmats, transl)
+        verts, joints = self.lbs(betas.to(rotmats.device), rotmats, transl, out_vertices, out_joints)
         return SMPLOutput(vertices=verts if return_verts else None, joints=joints,
                           full_pose=full_pose if return_full_pose else None, betas=betas,
                           global_orient=global_orient, body_pose=body_pose)
