@@ -12,6 +12,7 @@
 // Per call (workspace): F [M][KP] blend coefficients (betas | vec(R_i - I)), A [M][J][3][4] relative transforms.
 #include "common.cuh"
 #include "tma.cuh"
+#include <cuda_fp16.h>
 #include <vector>
 #include <cmath>
 #include <cstring>
@@ -19,6 +20,12 @@
 #define HF_MAXJ 24
 #define HF_MAXB 16
 #define LBS_KH 256          // K of one bf16 half (num_betas + 9*(J-1) <= 223, padded)
+// fp16 single-pass layout (product path): K = 256 = [pose 0..207 | beta_hi 208..223 | beta_lo 224..239 | beta_hi 240..255]
+// against basis columns              [posedirs        | shape_hi        | shape_hi        | shape_lo        ]
+// i.e. the 207 pose terms take one fp16 x fp16 product each (fp32 accumulation; measured <= 5e-5 m at pose std 0.8)
+// and the 10 shape terms, which carry ten times the magnitude, the three-product split (error ~1e-7 m).
+#define LBS_K2 256
+#define LBS_K2_POSE 208
 
 struct hf_smpl {
     int V, Vp, nb, J, KB, KP, nslots, nvj, nextra, nnz;
@@ -29,7 +36,13 @@ struct hf_smpl {
     // tensor-core path: blend basis as split bf16 [3][Vp][KT] = [hi(256) | lo(256)] per (coordinate, vertex) row
     __nv_bfloat16* Pbf;
     CUtensorMap mapA;
-    int impl;                 // 0 = tcgen05 blend (product path), 1 = FP32 CUDA-core blend (debug cross-check)
+    int impl;                 // 0 = persistent fp16 tcgen05 blend (product path), 1 = FP32 CUDA-core blend (debug
+                              // cross-check), 2 = split-bf16 three-pass tcgen05 blend (high-precision cross-check)
+    // product path: fp16 basis [3][Vp][LBS_K2] scaled by 2^k = pose block | shape hi | shape hi | shape lo
+    __half* Pf16;
+    float inv_scale;
+    CUtensorMap mapA2;
+    const void* mapB2_ptr; int mapB2_M; CUtensorMap mapB2;
     // cached tensor map of the per-call coefficient matrix
     const void* mapB_ptr; int mapB_M; CUtensorMap mapB;
 };
@@ -371,6 +384,222 @@ lbs_skin_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Product path: persistent fp16 tensor-core blend + CUDA-core skinning.
+//   unit = 128 vertices x 64 samples; units are numbered sample-tile major and every CTA (one per SM) walks a
+//   contiguous range of them, so the 64 samples' coefficients (B operand, 32 KB) and 3x4 transforms (72 KB) stay
+//   resident in shared memory while the basis tiles (A operand, 3 coordinates x 4 k-blocks of 16 KB) stream through a
+//   TMA ring.  D_c[v][s] = sum_k P_c[v][k] f[s][k] accumulates in TMEM, double-buffered (2 x 3 x 64 columns), so the
+//   skinning epilogue of unit u (16 warps) overlaps the loads and MMAs of unit u+1.
+//   warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..17: epilogue; warp w reads TMEM lanes 32*(w%4)..
+//   (= vertices) and 16 of the 64 samples.
+constexpr int T2_NS = 64, T2_STAGES = 6, T2_EPI_WARPS = 16, T2_THREADS = (2 + T2_EPI_WARPS) * 32;
+constexpr int T2_KBLK = LBS_K2 / 64, T2_NIT = 3 * T2_KBLK;
+constexpr int T2_BRES_BYTES = T2_KBLK * T2_NS * 128;
+
+// fp16 blend coefficients for the product path (layout: see LBS_K2), one thread per element.
+__global__ void lbs_coef16_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats, int M, int J, int nb,
+                                  __half* __restrict__ Fh) {
+    HF_PDL_SYNC();
+    const size_t total = (size_t)M * LBS_K2;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(e / LBS_K2), k = (int)(e - (size_t)m * LBS_K2);
+        __half h = __float2half_rn(0.f);
+        if (k < LBS_K2_POSE) {
+            if (k < 9 * (J - 1)) {
+                const int i = k / 9 + 1, el = k - (i - 1) * 9;
+                h = __float2half_rn(__ldg(rotmats + ((size_t)m * J + i) * 9 + el) - ((el % 4 == 0) ? 1.f : 0.f));
+            }
+        } else {
+            const int blk = (k - LBS_K2_POSE) >> 4, l = (k - LBS_K2_POSE) & 15;   // blk 0: hi, 1: lo, 2: hi
+            if (l < nb) {
+                const float b = __ldg(betas + (size_t)m * nb + l);
+                const __half hi = __float2half_rn(b);
+                h = (blk == 1) ? __float2half_rn(b - __half2float(hi)) : hi;
+            }
+        }
+        Fh[e] = h;
+    }
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);   // same instruction (kind::f16); the operand formats live in idesc
+}
+// instruction descriptor: fp16 x fp16 -> fp32, both operands K-major
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const float* __restrict__ vtemp, const int* __restrict__ sj, const float* __restrict__ sw,
+                    const float* __restrict__ A, const float* __restrict__ transl, int M, int V, int Vp, int J,
+                    int nslots, float inv_scale, int nvt, int num_units, float* __restrict__ vertices) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * T2_STAGES + 6];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bres = tile_base + T2_STAGES * 16384;                    // resident B operand: 4 k-blocks [64 rows][128 B]
+    const uint32_t as_addr = bres + T2_BRES_BYTES;                          // transforms [64][J*12] fp32
+    const float* As = reinterpret_cast<const float*>(smem_raw + (as_addr - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int J12 = J * 12;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[T2_STAGES]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * T2_STAGES]), tempty0 = smem_u32(&bars[2 * T2_STAGES + 2]);
+    const uint32_t bfull = smem_u32(&bars[2 * T2_STAGES + 4]), sdone = smem_u32(&bars[2 * T2_STAGES + 5]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, T2_EPI_WARPS); }
+        mbar_init(bfull, 1);
+        mbar_init(sdone, T2_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const int u0 = (int)((long long)blockIdx.x * num_units / gridDim.x);
+    const int u1 = (int)((long long)(blockIdx.x + 1) * num_units / gridDim.x);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t kbc = 0, sc = 0;
+            int cur_st = -1;
+            for (int u = u0; u < u1; ++u) {
+                const int st = u / nvt, vt = u - st * nvt;
+                const bool new_tile = st != cur_st;
+                for (int it = 0; it < T2_NIT; ++it, ++kbc) {
+                    const uint32_t sg = kbc % T2_STAGES, ph = (kbc / T2_STAGES) & 1u;
+                    mbar_wait(empty0 + 8 * sg, ph ^ 1u);
+                    const uint32_t fb = full0 + 8 * sg;
+                    mbar_expect_tx(fb, 16384);
+                    const int c = it / T2_KBLK, kb = it - c * T2_KBLK;
+                    tma_load_2d(tile_base + sg * 16384, &mapA, fb, kb * 64, c * Vp + vt * 128);
+                    // switch the resident sample tile once the ring is primed with the new unit's first blocks: the old
+                    // tile's coefficients / transforms are free when every epilogue warp has finished its last unit
+                    if (new_tile && it == (T2_STAGES < T2_NIT ? T2_STAGES : T2_NIT) - 1) {
+                        if (cur_st >= 0) mbar_wait(sdone, (sc - 1) & 1u);
+                        const int m0 = st * T2_NS;
+                        const int rows = min(T2_NS, M - m0);
+                        const uint32_t abytes = (uint32_t)(rows * J12 * 4);
+                        mbar_expect_tx(bfull, (uint32_t)T2_BRES_BYTES + abytes);
+#pragma unroll
+                        for (int k = 0; k < T2_KBLK; ++k) tma_load_2d(bres + k * (T2_NS * 128), &mapB, bfull, k * 64, m0);
+                        bulk_load_1d(as_addr, A + (size_t)m0 * J12, abytes, bfull);
+                        cur_st = st; ++sc;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, T2_NS);
+            uint32_t kbc = 0, lt = 0, sc = 0;
+            int cur_st = -1;
+            for (int u = u0; u < u1; ++u, ++lt) {
+                const int st = u / nvt;
+                if (st != cur_st) { mbar_wait(bfull, sc & 1u); ++sc; cur_st = st; }
+                const uint32_t buf = lt & 1u;
+                mbar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                for (int it = 0; it < T2_NIT; ++it, ++kbc) {
+                    const uint32_t sg = kbc % T2_STAGES, ph = (kbc / T2_STAGES) & 1u;
+                    mbar_wait(full0 + 8 * sg, ph);
+                    tcgen05_fence_after();
+                    const int c = it / T2_KBLK, kb = it - c * T2_KBLK;
+                    const uint64_t da = umma_desc_sw128(tile_base + sg * 16384), db = umma_desc_sw128(bres + kb * (T2_NS * 128));
+                    const uint32_t d = tmem_base + buf * (3 * T2_NS) + (uint32_t)(c * T2_NS);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(empty0 + 8 * sg);
+                }
+                umma_commit(tfull0 + 8 * buf);
+            }
+        }
+    } else {
+        const int q = warp & 3, sgrp = (warp - 2) >> 2;     // TMEM lane quarter (= vertex group), 16-sample group
+        uint32_t lt = 0, sc = 0;
+        int cur_st = -1;
+        for (int u = u0; u < u1; ++u, ++lt) {
+            const int st = u / nvt, vt = u - st * nvt;
+            if (st != cur_st) { mbar_wait(bfull, sc & 1u); ++sc; cur_st = st; }
+            const uint32_t buf = lt & 1u;
+            const int v = vt * 128 + q * 32 + lane;                 // < Vp (tables are padded)
+            const int m0 = st * T2_NS;
+            const float t0 = vtemp[v], t1 = vtemp[Vp + v], t2 = vtemp[2 * Vp + v];
+            mbar_wait(tfull0 + 8 * buf, (lt >> 1) & 1u);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int chunk = 0; chunk < 2; ++chunk) {
+                const int s0 = sgrp * 16 + chunk * 8;               // first sample (tile-local) of this chunk
+                uint32_t px[8], py[8], pz[8];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (3 * T2_NS) + (uint32_t)s0;
+                tmem_ld8(ta, px);
+                tmem_ld8(ta + T2_NS, py);
+                tmem_ld8(ta + 2 * T2_NS, pz);
+                tmem_ld_wait();
+                float o[8][3];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) o[s][0] = o[s][1] = o[s][2] = 0.f;
+                for (int slot = 0; slot < nslots; ++slot) {
+                    const float w = __ldg(sw + slot * Vp + v);
+                    if (__all_sync(0xffffffffu, w == 0.f)) continue;
+                    const int j = __ldg(sj + slot * Vp + v);
+                    const float* a0 = As + s0 * J12 + j * 12;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const float4* a = reinterpret_cast<const float4*>(a0 + s * J12);
+                        const float4 r0 = a[0], r1 = a[1], r2 = a[2];
+                        const float x = fmaf(__uint_as_float(px[s]), inv_scale, t0), y = fmaf(__uint_as_float(py[s]), inv_scale, t1),
+                                    z = fmaf(__uint_as_float(pz[s]), inv_scale, t2);
+                        o[s][0] = fmaf(w, fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w))), o[s][0]);
+                        o[s][1] = fmaf(w, fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w))), o[s][1]);
+                        o[s][2] = fmaf(w, fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w))), o[s][2]);
+                    }
+                }
+                if (v < V) {
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int m = m0 + s0 + s;
+                        if (m < M) {
+                            float tx = 0.f, ty = 0.f, tz = 0.f;
+                            if (transl) { tx = __ldg(transl + m * 3); ty = __ldg(transl + m * 3 + 1); tz = __ldg(transl + m * 3 + 2); }
+                            float* out = vertices + ((size_t)m * V + v) * 3;
+                            __stcs(out + 0, o[s][0] + tx);
+                            __stcs(out + 1, o[s][1] + ty);
+                            __stcs(out + 2, o[s][2] + tz);
+                        }
+                    }
+                }
+            }
+            // accumulator buffer may be refilled; on the last unit of a sample tile the resident tile may be replaced
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(tempty0 + 8 * buf);
+                if (u + 1 < u1 && (u + 1) / nvt != st) mbar_arrive(sdone);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // joints[J .. J+nvj) = picked vertices; joints[J+nvj ..) = sparse regressors applied to the final vertices.
 __global__ void lbs_extra_joints_kernel(const float* __restrict__ vertices, const int* __restrict__ vj,
                                         const int* __restrict__ csr_ptr, const int* __restrict__ csr_col,
@@ -523,6 +752,34 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
         if ((rc = encode_map(&h->mapA, h->Pbf, 2, dims, st, box))) return rc;
         h->impl = 0; h->mapB_ptr = nullptr; h->mapB_M = 0;
     }
+    {   // fp16 basis for the product path: row (c, v) = [posedirs (208) | shape hi (16) | shape hi (16) | shape lo (16)] * 2^k
+        if (9 * (J - 1) > LBS_K2_POSE || nb > 16) { delete h; return hf::fail(HF_ERR_UNSUPPORTED, "hf_smpl_create: J=%d nb=%d exceed the fp16 blend layout", J, nb); }
+        float mx = 0.f;
+        for (size_t i = 0; i < blend.size(); ++i) mx = std::max(mx, std::fabs(blend[i]));
+        int ex = 0;
+        if (mx > 0.f) { std::frexp(mx, &ex); }            // mx = m * 2^ex, 0.5 <= m < 1
+        const float scale = std::ldexp(1.f, 10 - ex);       // max |entry| * scale in [512, 1024): far from fp16 overflow and subnormals
+        h->inv_scale = 1.f / scale;
+        std::vector<__half> pf((size_t)3 * Vp * LBS_K2, __float2half(0.f));
+        for (int c = 0; c < 3; ++c)
+            for (int v = 0; v < V; ++v) {
+                __half* row = &pf[((size_t)c * Vp + v) * LBS_K2];
+                for (int k = 0; k < 9 * (J - 1); ++k) row[k] = __float2half_rn(blend[((size_t)(nb + k) * 3 + c) * Vp + v] * scale);
+                for (int l = 0; l < nb; ++l) {
+                    const float f = blend[((size_t)l * 3 + c) * Vp + v] * scale;
+                    const __half hi = __float2half_rn(f);
+                    row[LBS_K2_POSE + l] = hi;
+                    row[LBS_K2_POSE + 16 + l] = hi;
+                    row[LBS_K2_POSE + 32 + l] = __float2half_rn(f - __half2float(hi));
+                }
+            }
+        if ((rc = hf::upload(&h->Pf16, pf.data(), pf.size()))) return rc;
+        const uint64_t dims[2] = {(uint64_t)LBS_K2, (uint64_t)3 * Vp};
+        const uint64_t st[1] = {(uint64_t)LBS_K2 * 2};
+        const uint32_t box[2] = {64, 128};
+        if ((rc = encode_map(&h->mapA2, h->Pf16, 2, dims, st, box))) return rc;
+        h->mapB2_ptr = nullptr; h->mapB2_M = 0;
+    }
     if ((rc = hf::upload(&h->blend, blend.data(), blend.size()))) return rc;
     if ((rc = hf::upload(&h->vtemp, vt.data(), vt.size()))) return rc;
     if ((rc = hf::upload(&h->J0, J0.data(), J0.size()))) return rc;
@@ -542,7 +799,7 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
 extern "C" void hf_smpl_destroy(hf_smpl_t* h) {
     if (!h) return;
     cudaFree(h->blend); cudaFree(h->vtemp); cudaFree(h->J0); cudaFree(h->Jd); cudaFree(h->sj);
-    cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
+    cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->Pf16); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
     delete h;
 }
 
@@ -553,7 +810,7 @@ extern "C" size_t hf_lbs_workspace_bytes(const hf_smpl_t* h, int M) {
 }
 
 extern "C" int hf_lbs_set_impl(hf_smpl_t* h, int impl) {
-    if (!h || impl < 0 || impl > 1) return hf::fail(HF_ERR_INVALID, "hf_lbs_set_impl: bad argument");
+    if (!h || impl < 0 || impl > 2) return hf::fail(HF_ERR_INVALID, "hf_lbs_set_impl: bad argument");
     h->impl = impl;
     return HF_OK;
 }
@@ -574,9 +831,37 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     Parents par;
     for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
     HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, PW)), dim3(PW * 32), 0, stream, betas, rotmats, transl, h->J0, h->Jd, par, M,
-                           h->J, h->nb, h->KP, J_out, h->impl == 0 ? (float*)nullptr : F, A, joints));
+                           h->J, h->nb, h->KP, J_out, h->impl != 1 ? (float*)nullptr : F, A, joints));
     HF_LAUNCH_CHECK();
     if (h->impl == 0) {
+        __half* Fh = (__half*)Fb;
+        HF_CUDA(hf::launch_pdl(lbs_coef16_kernel, dim3(std::min(hf::div_up(M * LBS_K2, 256), 148 * 16)), dim3(256), 0, stream, betas, rotmats,
+                               M, h->J, h->nb, Fh));
+        HF_LAUNCH_CHECK();
+        hf_smpl* hm = const_cast<hf_smpl*>(h);
+        if (hm->mapB2_ptr != (const void*)Fh || hm->mapB2_M != M) {
+            const uint64_t dims[2] = {(uint64_t)LBS_K2, (uint64_t)M};
+            const uint64_t st[1] = {(uint64_t)LBS_K2 * 2};
+            const uint32_t box[2] = {64, (uint32_t)T2_NS};
+            int rc = encode_map(&hm->mapB2, Fh, 2, dims, st, box);
+            if (rc) return rc;
+            hm->mapB2_ptr = Fh; hm->mapB2_M = M;
+        }
+        static bool t2_attr = false;
+        const size_t t2_smem = (size_t)T2_STAGES * 16384 + T2_BRES_BYTES + (size_t)T2_NS * h->J * 12 * sizeof(float) + 1024;
+        if (t2_smem > 226 * 1024) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_forward: tile needs %zu B of shared memory", t2_smem);
+        if (!t2_attr) {
+            HF_CUDA(cudaFuncSetAttribute(lbs_skin_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            t2_attr = true;
+        }
+        const int nvt = h->Vp / 128, num_units = nvt * hf::div_up(M, T2_NS);
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        HF_CUDA(hf::launch_pdl(lbs_skin_tc2_kernel, dim3(std::min(num_units, sms)), dim3(T2_THREADS), t2_smem, stream, hm->mapA2, hm->mapB2,
+                               h->vtemp, h->sj, h->sw, A, transl, M, h->V, h->Vp, h->J, h->nslots, h->inv_scale, nvt, num_units, vertices));
+        HF_LAUNCH_CHECK();
+    } else if (h->impl == 2) {
         HF_CUDA(hf::launch_pdl(lbs_coef_kernel, dim3(std::min(hf::div_up(M * LBS_KH, 256), 148 * 16)), dim3(256), 0, stream, betas, rotmats,
                                M, h->J, h->nb, Fb));
         HF_LAUNCH_CHECK();

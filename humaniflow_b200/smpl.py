@@ -148,7 +148,8 @@ class SMPL(nn.Module):
         return h
 
     def set_impl(self, impl):
-        """0 = tcgen05 split-bf16 blend (product path), 1 = FP32 CUDA-core blend (debug cross-check)."""
+        """0 = persistent fp16 tcgen05 blend (product path), 1 = FP32 CUDA-core blend, 2 = split-bf16 three-pass tcgen05
+        blend (both cross-checks)."""
         self._impl = impl
         for h in self._handles.values():
             _lib.check(_lib.load().hf_lbs_set_impl(h, impl))

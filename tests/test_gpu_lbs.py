@@ -83,7 +83,7 @@ def test_full_size_properties():
     eye = torch.eye(3).expand(M, 24, 3, 3).contiguous()
     out = smpl(betas=betas.cuda(), body_pose=eye[:, 1:].cuda(), global_orient=eye[:, :1].cuda(), pose2rot=False)
     v_shaped = data['v_template'][None] + torch.einsum('bl,mkl->bmk', betas, data['shapedirs'])
-    assert _l2(out.vertices, v_shaped) <= 1e-5      # split-bf16 blend: ~3e-6 m
+    assert _l2(out.vertices, v_shaped) <= 1e-5      # shape terms: three-product fp16 split, ~1e-7 m
     J = torch.einsum('bik,ji->bjk', v_shaped, data['J_regressor'])
     assert _l2(out.joints[:, :24], J) <= 2e-6
     R = so3.batch_rodrigues(theta.reshape(-1, 3)).view(M, 24, 3, 3)
@@ -119,19 +119,43 @@ def test_no_cpu_fallback():
         smpl(betas=torch.zeros(1, 10), body_pose=torch.zeros(1, 69), global_orient=torch.zeros(1, 3))
 
 
-def test_fp32_cuda_core_blend_cross_check():
-    """The debug implementation (FP32 blend on CUDA cores) and the product path (split-bf16 blend on tcgen05)
-    agree with each other and with the oracle."""
+def test_blend_implementations_cross_check():
+    """The product path (persistent fp16 tcgen05 blend: one fp16 product per pose term, three-product split for the
+    shape terms), the FP32 CUDA-core blend (impl 1) and the split-bf16 three-pass tcgen05 blend (impl 2) agree with
+    each other and with the oracle."""
     smpl = _smpl(create_transl=False)
     data = smpl_data()
     M = 200
     betas, theta = _inputs(M, seed=21, pose_std=0.7)
     R = so3.batch_rodrigues(theta.reshape(-1, 3)).view(M, 24, 3, 3)
     v_ref, j_ref = osmpl.smpl_forward(data, betas, R[:, 1:], R[:, :1], pose2rot=False)
-    tc = smpl(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False)
+    args = dict(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False)
+    tc = smpl(**args)
+    smpl.set_impl(1)
+    cc = smpl(**args)
+    smpl.set_impl(2)
+    t3 = smpl(**args)
+    smpl.set_impl(0)
+    print('fp16-tc err %.2e  fp32-cc err %.2e  bf16x3-tc err %.2e' % (_l2(tc.vertices, v_ref), _l2(cc.vertices, v_ref), _l2(t3.vertices, v_ref)))
+    assert _l2(tc.vertices, v_ref) <= TOL_M and _l2(cc.vertices, v_ref) <= TOL_M and _l2(t3.vertices, v_ref) <= TOL_M
+    assert _l2(tc.joints, j_ref) <= TOL_M
+    assert (t3.vertices - cc.vertices).norm(dim=-1).max().item() <= 2e-5
+    assert (tc.vertices - cc.vertices).norm(dim=-1).max().item() <= TOL_M
+
+
+@pytest.mark.parametrize('M', [64, 192, 1000])
+def test_sample_tile_switches(M):
+    """The persistent kernel replaces its resident sample tile (coefficients + transforms) mid-range: cover batch sizes
+    where CTAs own whole tiles, fractions of a tile and ranges spanning two tiles."""
+    smpl = _smpl(create_transl=False)
+    data = smpl_data()
+    betas, theta = _inputs(M, seed=100 + M, pose_std=0.4)
+    R = so3.batch_rodrigues(theta.reshape(-1, 3)).view(M, 24, 3, 3)
+    out = smpl(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False)
+    rows = sorted(set([0, 1, 63, M // 2, M - 65 if M > 65 else 0, M - 2, M - 1]))
+    v_ref, j_ref = osmpl.smpl_forward(data, betas[rows], R[rows][:, 1:], R[rows][:, :1], pose2rot=False)
+    assert _l2(out.vertices[rows], v_ref) <= TOL_M and _l2(out.joints[rows], j_ref) <= TOL_M
     smpl.set_impl(1)
     cc = smpl(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False)
     smpl.set_impl(0)
-    assert _l2(tc.vertices, v_ref) <= TOL_M and _l2(cc.vertices, v_ref) <= TOL_M
-    assert (tc.vertices - cc.vertices).norm(dim=-1).max().item() <= 2e-5
-    print('tc err %.2e cc err %.2e' % (_l2(tc.vertices, v_ref), _l2(cc.vertices, v_ref)))
+    assert (out.vertices - cc.vertices).norm(dim=-1).max().item() <= TOL_M      # every row, against the FP32 CUDA-core path
