@@ -94,7 +94,7 @@ def build_cpu_problem(B, N, layers, seed=0):
     cfg.NUM_RESNET_LAYERS = layers
     m = hb.HumaniflowModel('cpu', cfg, SMPL_PARENTS).eval()
     sd = {k: v.detach() for k, v in m.state_dict().items()}
-    data = synthetic_smpl_data(seed=0)
+    data = synthetic_smpl_data(seed=0, skinning='body_parts')
     x = synthetic_proxy_input(B, 18, 256, seed=1)
     g = torch.Generator().manual_seed(2)
     z = torch.randn(B, N, 23, 3, generator=g) * 0.6
@@ -138,7 +138,7 @@ def run_reference(args):
     line = {
         'metric': METRIC, 'value': val, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic (random-init weights, SMPL-shaped synthetic body model)',
+        'dtype': 'f32', 'data': 'synthetic (random-init weights; SMPL-shaped synthetic body model, skinning weights grouped by body part like the real SMPL)',
         'config': workload_config(args, images_per_step=B_ref),
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                          'sample': '%d images x %d samples per step (of the %d-image batch), oracle/ = CPU restatement of the '
@@ -200,7 +200,7 @@ def run_ours(args):
     cfg = hb.get_model_cfg_defaults()
     cfg.NUM_RESNET_LAYERS = args.layers
     model = hb.HumaniflowModel(dev, cfg, SMPL_PARENTS).eval().to(dev)
-    smpl = hb.SMPL.from_arrays(synthetic_smpl_data(seed=0), create_transl=False).to(dev)
+    smpl = hb.SMPL.from_arrays(synthetic_smpl_data(seed=0, skinning='body_parts'), create_transl=False).to(dev)
     x_host = synthetic_proxy_input(B, 18, 256, seed=1 + rank).pin_memory()
     x_dev = x_host.to(dev)
     g = torch.Generator().manual_seed(2 + rank)
@@ -366,7 +366,7 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16 (encoder) / f32 (flow, LBS; f64 exp/log maps)',
-            'data': 'synthetic (random-init weights, SMPL-shaped synthetic body model)', 'config': workload_config(args),
+            'data': 'synthetic (random-init weights; SMPL-shaped synthetic body model, skinning weights grouped by body part like the real SMPL)', 'config': workload_config(args),
             'e2e': {'value': world * B * N / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': (v_host[0].numel() + j_host[0].numel()) * 4,
                     'pipelining': 'H2D | kernels | D2H on three streams, double-buffered', 'pcie_measured': pcie},

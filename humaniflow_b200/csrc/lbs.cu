@@ -41,6 +41,9 @@ struct hf_smpl {
     // product path: fp16 basis [3][Vp][LBS_K2] scaled by 2^k = pose block | shape hi | shape hi | shape lo
     __half* Pf16;
     float inv_scale;
+    // vertices read by the joint picks / extra regressors (~4 %) are flagged: the product skinning kernel stores them with an
+    // L2 evict_last policy (everything else streams evict_first), so the extra-joint kernel's gathers hit L2 instead of DRAM
+    int* vflag;
     CUtensorMap mapA2;
     const void* mapB2_ptr; int mapB2_M; CUtensorMap mapB2;
     // cached tensor map of the per-call coefficient matrix
@@ -51,79 +54,124 @@ namespace {
 
 struct Parents { int p[HF_MAXJ]; };
 
-// One WARP per sample: lane j < J regresses joint j from the betas; the 24-step chain of rigid transforms runs
-// with lanes 0..11 each owning one entry of the 3x4 matrix (G_i = G_parent . [R_i | t_i]), parents read back from
-// shared memory; relative transforms A_i, posed joints and (for the CUDA-core blend) fp32 coefficients are written
-// coalesced.  PW warps per block.
-constexpr int PW = 8;
-__global__ void __launch_bounds__(PW * 32)
+// Kinematic chain, joint regression and blend coefficients.  FOUR LANES per sample (8 samples per warp): lane r < 3 owns
+// row r of every 3x4 global transform, G_i[r][:] = G_parent[r][0..2] . [R_i | t_i] (+ G_parent[r][3]), which depends on
+// row r of the parent only, so the 24-step chain needs no cross-lane traffic and every lane keeps its own rows in
+// shared memory (dynamic parent index).  The samples' rotation matrices are staged into shared memory with coalesced
+// loads first, so the chain runs on shared-memory operands only.  Outputs: relative transforms A_i (one 16-byte store
+// per lane and joint), posed joints, and the blend coefficients (fp16 layout LBS_K2 for the product path -> Fh, or
+// fp32 -> F for the CUDA-core blend).
+// One block = PS samples, 4 warps: all warps stage the inputs and regress the joints, then warp 0 walks the chain while
+// warps 1..3 write the blend coefficients.
+constexpr int PS = 8, PTHREADS = 128, PR = HF_MAXJ * 9 + 1;
+__global__ void __launch_bounds__(PTHREADS)
 lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats,
                                 const float* __restrict__ transl, const float* __restrict__ J0,
                                 const float* __restrict__ Jd, Parents par, int M, int J, int nb, int KP,
-                                int J_out, float* __restrict__ F, float* __restrict__ A,
+                                int J_out, float* __restrict__ F, __half* __restrict__ Fh, float* __restrict__ A,
                                 float* __restrict__ joints) {
+    __shared__ __align__(16) float Gs[HF_MAXJ][PS][12];
+    __shared__ float Js[HF_MAXJ][PS][3];
+    __shared__ float Rs[PS][PR];
+    __shared__ float Bs[PS][HF_MAXB];
+    __shared__ float Jds[HF_MAXJ * 3 * HF_MAXB], J0s[HF_MAXJ * 3];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mb = blockIdx.x * PS;                              // first sample of this block
+    const int ns = min(PS, M - mb);
+    const int J9 = J * 9, J3 = J * 3;
+    for (int k = tid; k < J3 * nb; k += PTHREADS) Jds[k] = Jd[k];       // model constants: no dependency on the predecessor
+    for (int k = tid; k < J3; k += PTHREADS) J0s[k] = J0[k];
     HF_PDL_SYNC();
-    __shared__ float Gs[PW][HF_MAXJ][12];
-    __shared__ float Js[PW][HF_MAXJ][3];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = blockIdx.x * PW + warp;
-    if (m >= M) return;
-    // joints of the shaped template: lane j handles joint j
-    if (lane < J) {
-        float acc[3] = {J0[lane * 3], J0[lane * 3 + 1], J0[lane * 3 + 2]};
-        for (int l = 0; l < nb; ++l) {
-            const float bl = __ldg(betas + (size_t)m * nb + l);
-            acc[0] = fmaf(Jd[(lane * 3 + 0) * nb + l], bl, acc[0]);
-            acc[1] = fmaf(Jd[(lane * 3 + 1) * nb + l], bl, acc[1]);
-            acc[2] = fmaf(Jd[(lane * 3 + 2) * nb + l], bl, acc[2]);
+    {
+        const float* Rm = rotmats + (size_t)mb * J9;
+        for (int e = tid; e < ns * J9; e += PTHREADS) {
+            const int s2 = e / J9;
+            Rs[s2][e - s2 * J9] = __ldg(Rm + e);
         }
-        Js[warp][lane][0] = acc[0]; Js[warp][lane][1] = acc[1]; Js[warp][lane][2] = acc[2];
+        for (int e = tid; e < ns * nb; e += PTHREADS) {
+            const int s2 = e / nb;
+            Bs[s2][e - s2 * nb] = __ldg(betas + (size_t)mb * nb + e);
+        }
     }
-    if (F) {   // fp32 blend coefficients (beta | vec(R_i - I)), only for the CUDA-core blend
-        float* Fm = F + (size_t)m * KP;
-        for (int k = lane; k < KP; k += 32) {
-            float f = 0.f;
-            if (k < nb) f = __ldg(betas + (size_t)m * nb + k);
-            else if (k < nb + 9 * (J - 1)) {
-                const int q = k - nb, i = q / 9 + 1, e = q - (i - 1) * 9;
-                f = __ldg(rotmats + ((size_t)m * J + i) * 9 + e) - ((e % 4 == 0) ? 1.f : 0.f);
+    __syncthreads();
+    // joints of the shaped template
+    for (int o = tid; o < ns * J3; o += PTHREADS) {
+        const int s2 = o / J3, jr = o - s2 * J3;
+        float acc = J0s[jr];
+        const float* jd = Jds + jr * nb;
+        for (int l = 0; l < nb; ++l) acc = fmaf(jd[l], Bs[s2][l], acc);
+        Js[jr / 3][s2][jr % 3] = acc;
+    }
+    __syncthreads();
+    if (warp > 0) {
+        const int t = tid - 32, nt = PTHREADS - 32;
+        if (F) {   // fp32 blend coefficients (beta | vec(R_i - I)), only for the CUDA-core blend
+            for (int e = t; e < ns * KP; e += nt) {
+                const int s2 = e / KP, k = e - s2 * KP;
+                float f = 0.f;
+                if (k < nb) f = Bs[s2][k];
+                else if (k < nb + 9 * (J - 1)) {
+                    const int q = k - nb;
+                    f = Rs[s2][9 + q] - (((q % 9) % 4 == 0) ? 1.f : 0.f);
+                }
+                F[(size_t)mb * KP + e] = f;
             }
-            Fm[k] = f;
         }
+        if (Fh) {  // fp16 blend coefficients, layout LBS_K2: [vec(R_i - I) (208) | beta_hi (16) | beta_lo (16) | beta_hi (16)]
+            __half2* Fm = reinterpret_cast<__half2*>(Fh + (size_t)mb * LBS_K2);
+            for (int e = t; e < ns * (LBS_K2 / 2); e += nt) {
+                const int s2 = e / (LBS_K2 / 2), k2 = e - s2 * (LBS_K2 / 2);
+                float f[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int k = 2 * k2 + u;
+                    float v = 0.f;
+                    if (k < LBS_K2_POSE) {
+                        if (k < 9 * (J - 1)) v = Rs[s2][9 + k] - (((k % 9) % 4 == 0) ? 1.f : 0.f);
+                    } else {
+                        const int blk = (k - LBS_K2_POSE) >> 4, l = (k - LBS_K2_POSE) & 15;   // blk 0: hi, 1: lo, 2: hi
+                        if (l < nb) {
+                            const float b = Bs[s2][l];
+                            const float hi = __half2float(__float2half_rn(b));
+                            v = (blk == 1) ? b - hi : hi;
+                        }
+                    }
+                    f[u] = v;
+                }
+                Fm[e] = __floats2half2_rn(f[0], f[1]);
+            }
+        }
+        return;
     }
-    __syncwarp();
-    const int r = lane >> 2, c = lane & 3;        // entry (r, c) of the 3x4 matrix for lanes 0..11
-    float trc = 0.f;                              // lanes 16..18 write the posed joints (x, y, z)
-    if (transl && lane >= 16 && lane < 19) trc = transl[m * 3 + lane - 16];
-    const float* Rm = rotmats + (size_t)m * J * 9;
+    // warp 0: FOUR LANES per sample; lane r < 3 owns row r of every 3x4 global transform,
+    // G_i[r][:] = G_parent[r][0..2] . [R_i | t_i] (+ G_parent[r][3]), which depends on row r of the parent only: the
+    // 24-step chain needs no cross-lane traffic, every lane keeps its own rows in shared memory (dynamic parent index)
+    const int sl = lane >> 2, r = lane & 3;
+    const int m = mb + sl;
+    if (sl >= ns || r == 3) return;
+    float tr = 0.f;
+    if (transl) tr = __ldg(transl + m * 3 + r);
+    const float* Rm = Rs[sl];
+    float* Am = A + (size_t)m * J * 12 + r * 4;
+    float* jm = joints + (size_t)m * J_out * 3 + r;
     for (int i = 0; i < J; ++i) {
         const int p = par.p[i];
-        if (lane < 12) {
-            // local transform [R_i | t_i], t_i = J_i - J_parent (root: J_0)
-            float l0, l1, l2;        // column c of [R|t]
-            if (c < 3) { l0 = __ldg(Rm + i * 9 + c); l1 = __ldg(Rm + i * 9 + 3 + c); l2 = __ldg(Rm + i * 9 + 6 + c); }
-            else {
-                l0 = Js[warp][i][0]; l1 = Js[warp][i][1]; l2 = Js[warp][i][2];
-                if (i > 0) { l0 -= Js[warp][p][0]; l1 -= Js[warp][p][1]; l2 -= Js[warp][p][2]; }
-            }
-            float gv;
-            if (i == 0) gv = (r == 0) ? l0 : ((r == 1) ? l1 : l2);
-            else {
-                const float* gp = Gs[warp][p];
-                gv = gp[r * 4 + 0] * l0 + gp[r * 4 + 1] * l1 + gp[r * 4 + 2] * l2 + ((c == 3) ? gp[r * 4 + 3] : 0.f);
-            }
-            Gs[warp][i][lane] = gv;
+        const float* Ri = Rm + i * 9;
+        const float jx = Js[i][sl][0], jy = Js[i][sl][1], jz = Js[i][sl][2];
+        float4 g;
+        if (i == 0) {
+            g = make_float4(Ri[r * 3], Ri[r * 3 + 1], Ri[r * 3 + 2], r == 0 ? jx : (r == 1 ? jy : jz));
+        } else {
+            const float4 gp = *reinterpret_cast<const float4*>(&Gs[p][sl][r * 4]);
+            const float tx = jx - Js[p][sl][0], ty = jy - Js[p][sl][1], tz = jz - Js[p][sl][2];
+            g.x = gp.x * Ri[0] + gp.y * Ri[3] + gp.z * Ri[6];
+            g.y = gp.x * Ri[1] + gp.y * Ri[4] + gp.z * Ri[7];
+            g.z = gp.x * Ri[2] + gp.y * Ri[5] + gp.z * Ri[8];
+            g.w = gp.x * tx + gp.y * ty + gp.z * tz + gp.w;
         }
-        __syncwarp();
-        if (lane < 12) {
-            const float* g = Gs[warp][i];
-            float av = g[lane];
-            if (c == 3) av -= g[r * 4 + 0] * Js[warp][i][0] + g[r * 4 + 1] * Js[warp][i][1] + g[r * 4 + 2] * Js[warp][i][2];
-            A[((size_t)m * J + i) * 12 + lane] = av;
-        } else if (lane >= 16 && lane < 19) {
-            const int cc = lane - 16;
-            joints[((size_t)m * J_out + i) * 3 + cc] = Gs[warp][i][cc * 4 + 3] + trc;
-        }
+        *reinterpret_cast<float4*>(&Gs[i][sl][r * 4]) = g;
+        *reinterpret_cast<float4*>(Am + i * 12) = make_float4(g.x, g.y, g.z, g.w - (g.x * jx + g.y * jy + g.z * jz));
+        jm[i * 3] = g.w + tr;
     }
 }
 
@@ -397,31 +445,6 @@ constexpr int T2_NS = 64, T2_STAGES = 6, T2_EPI_WARPS = 16, T2_THREADS = (2 + T2
 constexpr int T2_KBLK = LBS_K2 / 64, T2_NIT = 3 * T2_KBLK;
 constexpr int T2_BRES_BYTES = T2_KBLK * T2_NS * 128;
 
-// fp16 blend coefficients for the product path (layout: see LBS_K2), one thread per element.
-__global__ void lbs_coef16_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats, int M, int J, int nb,
-                                  __half* __restrict__ Fh) {
-    HF_PDL_SYNC();
-    const size_t total = (size_t)M * LBS_K2;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int m = (int)(e / LBS_K2), k = (int)(e - (size_t)m * LBS_K2);
-        __half h = __float2half_rn(0.f);
-        if (k < LBS_K2_POSE) {
-            if (k < 9 * (J - 1)) {
-                const int i = k / 9 + 1, el = k - (i - 1) * 9;
-                h = __float2half_rn(__ldg(rotmats + ((size_t)m * J + i) * 9 + el) - ((el % 4 == 0) ? 1.f : 0.f));
-            }
-        } else {
-            const int blk = (k - LBS_K2_POSE) >> 4, l = (k - LBS_K2_POSE) & 15;   // blk 0: hi, 1: lo, 2: hi
-            if (l < nb) {
-                const float b = __ldg(betas + (size_t)m * nb + l);
-                const __half hi = __float2half_rn(b);
-                h = (blk == 1) ? __float2half_rn(b - __half2float(hi)) : hi;
-            }
-        }
-        Fh[e] = h;
-    }
-}
-
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);   // same instruction (kind::f16); the operand formats live in idesc
 }
@@ -429,17 +452,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ void st_hint(float* p, float v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
 }
 
+// NSLOT: skinning slots kept in registers (1..4; 0 = any number, read per chunk); TRANSL: add the per-sample translation
+template <int NSLOT, bool TRANSL>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const float* __restrict__ vtemp, const int* __restrict__ sj, const float* __restrict__ sw,
                     const float* __restrict__ A, const float* __restrict__ transl, int M, int V, int Vp, int J,
-                    int nslots, float inv_scale, int nvt, int num_units, float* __restrict__ vertices) {
+                    int nslots, float inv_scale, int nvt, int num_units, float* __restrict__ vertices,
+                    const int* __restrict__ vflag) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * T2_STAGES + 6];
     __shared__ uint32_t tmem_base_s;
@@ -528,17 +557,37 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
     } else {
         const int q = warp & 3, sgrp = (warp - 2) >> 2;     // TMEM lane quarter (= vertex group), 16-sample group
+        const size_t vstride = (size_t)V * 3;
+        uint64_t pol_first, pol_last;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
         uint32_t lt = 0, sc = 0;
         int cur_st = -1;
         for (int u = u0; u < u1; ++u, ++lt) {
             const int st = u / nvt, vt = u - st * nvt;
-            if (st != cur_st) { mbar_wait(bfull, sc & 1u); ++sc; cur_st = st; }
             const uint32_t buf = lt & 1u;
             const int v = vt * 128 + q * 32 + lane;                 // < Vp (tables are padded)
             const int m0 = st * T2_NS;
-            const float t0 = vtemp[v], t1 = vtemp[Vp + v], t2 = vtemp[2 * Vp + v];
+            // per-vertex constants first (global loads in flight while the accumulator is still being produced)
+            const float t0 = __ldg(vtemp + v), t1 = __ldg(vtemp + Vp + v), t2 = __ldg(vtemp + 2 * Vp + v);
+            const uint64_t pol = __ldg(vflag + v) ? pol_last : pol_first;   // vertices that feed a joint pick / regressor stay in L2
+            float wgt[NSLOT > 0 ? NSLOT : 1];
+            int jo[NSLOT > 0 ? NSLOT : 1];
+            uint32_t live = 0;                                       // slots with a non-zero weight somewhere in this warp
+            if (NSLOT > 0) {
+#pragma unroll
+                for (int k = 0; k < NSLOT; ++k) {
+                    wgt[k] = __ldg(sw + k * Vp + v);
+                    jo[k] = __ldg(sj + k * Vp + v) * 12;
+                }
+#pragma unroll
+                for (int k = 0; k < NSLOT; ++k) live |= (__any_sync(0xffffffffu, wgt[k] != 0.f) ? 1u : 0u) << k;
+            }
+            if (st != cur_st) { mbar_wait(bfull, sc & 1u); ++sc; cur_st = st; }
             mbar_wait(tfull0 + 8 * buf, (lt >> 1) & 1u);
             tcgen05_fence_after();
+            const int rows = min(T2_NS, M - m0);
+            const bool store_v = v < V;
 #pragma unroll 1
             for (int chunk = 0; chunk < 2; ++chunk) {
                 const int s0 = sgrp * 16 + chunk * 8;               // first sample (tile-local) of this chunk
@@ -548,36 +597,61 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 tmem_ld8(ta + T2_NS, py);
                 tmem_ld8(ta + 2 * T2_NS, pz);
                 tmem_ld_wait();
-                float o[8][3];
+                float x[8], y[8], z[8], o[8][3];
 #pragma unroll
-                for (int s = 0; s < 8; ++s) o[s][0] = o[s][1] = o[s][2] = 0.f;
-                for (int slot = 0; slot < nslots; ++slot) {
-                    const float w = __ldg(sw + slot * Vp + v);
-                    if (__all_sync(0xffffffffu, w == 0.f)) continue;
-                    const int j = __ldg(sj + slot * Vp + v);
-                    const float* a0 = As + s0 * J12 + j * 12;
+                for (int s = 0; s < 8; ++s) {
+                    x[s] = fmaf(__uint_as_float(px[s]), inv_scale, t0);
+                    y[s] = fmaf(__uint_as_float(py[s]), inv_scale, t1);
+                    z[s] = fmaf(__uint_as_float(pz[s]), inv_scale, t2);
+                    o[s][0] = o[s][1] = o[s][2] = 0.f;
+                }
+                const float* ab = As + s0 * J12;
+                if (NSLOT > 0) {
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        const float4* a = reinterpret_cast<const float4*>(a0 + s * J12);
-                        const float4 r0 = a[0], r1 = a[1], r2 = a[2];
-                        const float x = fmaf(__uint_as_float(px[s]), inv_scale, t0), y = fmaf(__uint_as_float(py[s]), inv_scale, t1),
-                                    z = fmaf(__uint_as_float(pz[s]), inv_scale, t2);
-                        o[s][0] = fmaf(w, fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w))), o[s][0]);
-                        o[s][1] = fmaf(w, fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w))), o[s][1]);
-                        o[s][2] = fmaf(w, fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w))), o[s][2]);
+                    for (int k = 0; k < NSLOT; ++k) {
+                        if (!((live >> k) & 1u)) continue;          // warp-uniform
+                        const float w = wgt[k];
+                        const float* a0 = ab + jo[k];
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            const float4* a = reinterpret_cast<const float4*>(a0 + s * J12);
+                            const float4 r0 = a[0], r1 = a[1], r2 = a[2];
+                            o[s][0] = fmaf(w, fmaf(r0.x, x[s], fmaf(r0.y, y[s], fmaf(r0.z, z[s], r0.w))), o[s][0]);
+                            o[s][1] = fmaf(w, fmaf(r1.x, x[s], fmaf(r1.y, y[s], fmaf(r1.z, z[s], r1.w))), o[s][1]);
+                            o[s][2] = fmaf(w, fmaf(r2.x, x[s], fmaf(r2.y, y[s], fmaf(r2.z, z[s], r2.w))), o[s][2]);
+                        }
+                    }
+                } else {
+                    for (int slot = 0; slot < nslots; ++slot) {
+                        const float w = __ldg(sw + slot * Vp + v);
+                        const float* a0 = ab + __ldg(sj + slot * Vp + v) * 12;
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            const float4* a = reinterpret_cast<const float4*>(a0 + s * J12);
+                            const float4 r0 = a[0], r1 = a[1], r2 = a[2];
+                            o[s][0] = fmaf(w, fmaf(r0.x, x[s], fmaf(r0.y, y[s], fmaf(r0.z, z[s], r0.w))), o[s][0]);
+                            o[s][1] = fmaf(w, fmaf(r1.x, x[s], fmaf(r1.y, y[s], fmaf(r1.z, z[s], r1.w))), o[s][1]);
+                            o[s][2] = fmaf(w, fmaf(r2.x, x[s], fmaf(r2.y, y[s], fmaf(r2.z, z[s], r2.w))), o[s][2]);
+                        }
                     }
                 }
-                if (v < V) {
+                if (store_v) {
+                    float* out = vertices + ((size_t)(m0 + s0) * V + v) * 3;
+                    if (!TRANSL && s0 + 8 <= rows) {                // full chunk, no translation: straight-line stores
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        const int m = m0 + s0 + s;
-                        if (m < M) {
-                            float tx = 0.f, ty = 0.f, tz = 0.f;
-                            if (transl) { tx = __ldg(transl + m * 3); ty = __ldg(transl + m * 3 + 1); tz = __ldg(transl + m * 3 + 2); }
-                            float* out = vertices + ((size_t)m * V + v) * 3;
-                            __stcs(out + 0, o[s][0] + tx);
-                            __stcs(out + 1, o[s][1] + ty);
-                            __stcs(out + 2, o[s][2] + tz);
+                        for (int s = 0; s < 8; ++s) {
+                            st_hint(out + 0, o[s][0], pol); st_hint(out + 1, o[s][1], pol); st_hint(out + 2, o[s][2], pol);
+                            out += vstride;
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            const int m = m0 + s0 + s;
+                            if (s0 + s < rows) {
+                                if (TRANSL) { o[s][0] += __ldg(transl + m * 3); o[s][1] += __ldg(transl + m * 3 + 1); o[s][2] += __ldg(transl + m * 3 + 2); }
+                                st_hint(out + 0, o[s][0], pol); st_hint(out + 1, o[s][1], pol); st_hint(out + 2, o[s][2], pol);
+                            }
+                            out += vstride;
                         }
                     }
                 }
@@ -601,7 +675,42 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 }
 
 // joints[J .. J+nvj) = picked vertices; joints[J+nvj ..) = sparse regressors applied to the final vertices.
-__global__ void lbs_extra_joints_kernel(const float* __restrict__ vertices, const int* __restrict__ vj,
+// One block per sample: every (row, vertex) entry of the picks + CSR regressors is fetched by its own thread (all
+// gathers of a sample in flight at once), then one thread per output row sums its entries in CSR order.
+constexpr int XJ_THREADS = 256, XJ_MAXE = 1024;
+__global__ void __launch_bounds__(XJ_THREADS)
+lbs_extra_joints_kernel(const float* __restrict__ vertices, const int* __restrict__ vj,
+                                        const int* __restrict__ csr_ptr, const int* __restrict__ csr_col,
+                                        const float* __restrict__ csr_val, int M, int V, int J, int nvj,
+                                        int nextra, int J_out, float* __restrict__ joints) {
+    __shared__ float ps[XJ_MAXE][3];
+    const int m = blockIdx.x;
+    const int nnz = csr_ptr[nextra], E = nvj + nnz;
+    HF_PDL_SYNC();
+    const float* vm = vertices + (size_t)m * V * 3;
+    for (int e = threadIdx.x; e < E; e += XJ_THREADS) {
+        const int col = e < nvj ? vj[e] : csr_col[e - nvj];
+        const float* p = vm + (size_t)col * 3;
+        ps[e][0] = __ldg(p); ps[e][1] = __ldg(p + 1); ps[e][2] = __ldg(p + 2);
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < nvj + nextra; r += XJ_THREADS) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (r < nvj) { x = ps[r][0]; y = ps[r][1]; z = ps[r][2]; }
+        else {
+            const int row = r - nvj;
+            for (int e = csr_ptr[row]; e < csr_ptr[row + 1]; ++e) {
+                const float w = csr_val[e];
+                x = fmaf(w, ps[nvj + e][0], x); y = fmaf(w, ps[nvj + e][1], y); z = fmaf(w, ps[nvj + e][2], z);
+            }
+        }
+        float* o = joints + ((size_t)m * J_out + J + r) * 3;
+        o[0] = x; o[1] = y; o[2] = z;
+    }
+}
+
+// Fallback for regressors with more than XJ_MAXE - nvj non-zeros: one thread per output row.
+__global__ void lbs_extra_joints_rows_kernel(const float* __restrict__ vertices, const int* __restrict__ vj,
                                         const int* __restrict__ csr_ptr, const int* __restrict__ csr_col,
                                         const float* __restrict__ csr_val, int M, int V, int J, int nvj,
                                         int nextra, int J_out, float* __restrict__ joints) {
@@ -789,6 +898,12 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
     std::vector<int> vj(vertex_joint_ids, vertex_joint_ids + nvj);
     if (vj.empty()) vj.push_back(0);
     if ((rc = hf::upload(&h->vj, vj.data(), vj.size()))) return rc;
+    {
+        std::vector<int> vflag((size_t)Vp, 0);
+        for (int r = 0; r < nvj; ++r) vflag[vj[r]] = 1;
+        for (int e = 0; e < h->nnz; ++e) vflag[col[e]] = 1;
+        if ((rc = hf::upload(&h->vflag, vflag.data(), vflag.size()))) return rc;
+    }
     if ((rc = hf::upload(&h->csr_ptr, ptr.data(), ptr.size()))) return rc;
     if ((rc = hf::upload(&h->csr_col, col.data(), col.size()))) return rc;
     if ((rc = hf::upload(&h->csr_val, val.data(), val.size()))) return rc;
@@ -799,7 +914,7 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
 extern "C" void hf_smpl_destroy(hf_smpl_t* h) {
     if (!h) return;
     cudaFree(h->blend); cudaFree(h->vtemp); cudaFree(h->J0); cudaFree(h->Jd); cudaFree(h->sj);
-    cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->Pf16); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
+    cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->Pf16); cudaFree(h->vflag); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
     delete h;
 }
 
@@ -830,14 +945,14 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     const int J_out = hf_smpl_num_joints_out(h);
     Parents par;
     for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
-    HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, PW)), dim3(PW * 32), 0, stream, betas, rotmats, transl, h->J0, h->Jd, par, M,
-                           h->J, h->nb, h->KP, J_out, h->impl != 1 ? (float*)nullptr : F, A, joints));
+    static const int stage_mask = getenv("HF_LBS_STAGES") ? atoi(getenv("HF_LBS_STAGES")) : 7;   // profiling aid: bit 0 pose, 1 skin, 2 extra joints
+    if (stage_mask & 1)
+    HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, PS)), dim3(PTHREADS), 0, stream, betas, rotmats, transl, h->J0, h->Jd, par, M,
+                           h->J, h->nb, h->KP, J_out, h->impl != 1 ? (float*)nullptr : F, h->impl == 0 ? (__half*)Fb : (__half*)nullptr, A, joints));
     HF_LAUNCH_CHECK();
-    if (h->impl == 0) {
+    if (!(stage_mask & 2)) {
+    } else if (h->impl == 0) {
         __half* Fh = (__half*)Fb;
-        HF_CUDA(hf::launch_pdl(lbs_coef16_kernel, dim3(std::min(hf::div_up(M * LBS_K2, 256), 148 * 16)), dim3(256), 0, stream, betas, rotmats,
-                               M, h->J, h->nb, Fh));
-        HF_LAUNCH_CHECK();
         hf_smpl* hm = const_cast<hf_smpl*>(h);
         if (hm->mapB2_ptr != (const void*)Fh || hm->mapB2_M != M) {
             const uint64_t dims[2] = {(uint64_t)LBS_K2, (uint64_t)M};
@@ -847,19 +962,28 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
             if (rc) return rc;
             hm->mapB2_ptr = Fh; hm->mapB2_M = M;
         }
-        static bool t2_attr = false;
         const size_t t2_smem = (size_t)T2_STAGES * 16384 + T2_BRES_BYTES + (size_t)T2_NS * h->J * 12 * sizeof(float) + 1024;
         if (t2_smem > 226 * 1024) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_forward: tile needs %zu B of shared memory", t2_smem);
-        if (!t2_attr) {
-            HF_CUDA(cudaFuncSetAttribute(lbs_skin_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            t2_attr = true;
-        }
         const int nvt = h->Vp / 128, num_units = nvt * hf::div_up(M, T2_NS);
         int sms = 148, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        HF_CUDA(hf::launch_pdl(lbs_skin_tc2_kernel, dim3(std::min(num_units, sms)), dim3(T2_THREADS), t2_smem, stream, hm->mapA2, hm->mapB2,
-                               h->vtemp, h->sj, h->sw, A, transl, M, h->V, h->Vp, h->J, h->nslots, h->inv_scale, nvt, num_units, vertices));
+        auto launch = [&](auto kern) -> int {
+            HF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            HF_CUDA(hf::launch_pdl(kern, dim3(std::min(num_units, sms)), dim3(T2_THREADS), t2_smem, stream, hm->mapA2, hm->mapB2,
+                                   h->vtemp, h->sj, h->sw, A, transl, M, h->V, h->Vp, h->J, h->nslots, h->inv_scale, nvt, num_units, vertices, h->vflag));
+            return HF_OK;
+        };
+        int rc;
+        const bool tr = transl != nullptr;
+        switch (h->nslots <= 4 ? h->nslots : 0) {
+            case 1: rc = tr ? launch(lbs_skin_tc2_kernel<1, true>) : launch(lbs_skin_tc2_kernel<1, false>); break;
+            case 2: rc = tr ? launch(lbs_skin_tc2_kernel<2, true>) : launch(lbs_skin_tc2_kernel<2, false>); break;
+            case 3: rc = tr ? launch(lbs_skin_tc2_kernel<3, true>) : launch(lbs_skin_tc2_kernel<3, false>); break;
+            case 4: rc = tr ? launch(lbs_skin_tc2_kernel<4, true>) : launch(lbs_skin_tc2_kernel<4, false>); break;
+            default: rc = tr ? launch(lbs_skin_tc2_kernel<0, true>) : launch(lbs_skin_tc2_kernel<0, false>); break;
+        }
+        if (rc) return rc;
         HF_LAUNCH_CHECK();
     } else if (h->impl == 2) {
         HF_CUDA(hf::launch_pdl(lbs_coef_kernel, dim3(std::min(hf::div_up(M * LBS_KH, 256), 148 * 16)), dim3(256), 0, stream, betas, rotmats,
@@ -900,9 +1024,13 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     HF_LAUNCH_CHECK();
     }
     int per = h->nvj + h->nextra;
-    if (per > 0) {
-        HF_CUDA(hf::launch_pdl(lbs_extra_joints_kernel, dim3(hf::div_up(M * per, 256)), dim3(256), 0, stream, vertices, h->vj, h->csr_ptr,
-                               h->csr_col, h->csr_val, M, h->V, h->J, h->nvj, h->nextra, J_out, joints));
+    if (per > 0 && (stage_mask & 4)) {
+        if (h->nvj + h->nnz <= XJ_MAXE)
+            HF_CUDA(hf::launch_pdl(lbs_extra_joints_kernel, dim3(M), dim3(XJ_THREADS), 0, stream, vertices, h->vj, h->csr_ptr,
+                                   h->csr_col, h->csr_val, M, h->V, h->J, h->nvj, h->nextra, J_out, joints));
+        else
+            HF_CUDA(hf::launch_pdl(lbs_extra_joints_rows_kernel, dim3(hf::div_up(M * per, 256)), dim3(256), 0, stream, vertices, h->vj, h->csr_ptr,
+                                   h->csr_col, h->csr_val, M, h->V, h->J, h->nvj, h->nextra, J_out, joints));
         HF_LAUNCH_CHECK();
     }
     return HF_OK;

@@ -21,10 +21,38 @@ def _sparse_rows(rs, rows, cols, nnz_per_row):
     return a
 
 
-def synthetic_smpl_data(seed=0, num_verts=NUM_VERTS, num_betas=10, regressors=None):
+def _body_part_weights(rs, V):
+    """Skinning weights with the structure of the real SMPL model: vertex ids fall into contiguous runs that belong to
+    one body part (a primary joint); inside a run, patches of neighbouring vertices are bound to the same 1..4 joints
+    taken from the primary joint and its kinematic neighbours (parent, grandparent, children), with per-vertex
+    weights.  (The real SMPL_*.pkl are licence-gated and absent; their vertex numbering groups body parts in runs.)"""
+    children = {j: [c for c, p in enumerate(SMPL_PARENTS) if p == j] for j in range(24)}
+    W = np.zeros((V, 24))
+    v = 0
+    while v < V:
+        run = min(V - v, int(rs.randint(60, 500)))
+        prim = int(rs.randint(0, 24))
+        nbrs = [SMPL_PARENTS[prim]] + children[prim] + ([SMPL_PARENTS[SMPL_PARENTS[prim]]] if SMPL_PARENTS[prim] > 0 else [])
+        nbrs = [j for j in nbrs if j >= 0]
+        end = v + run
+        while v < end:
+            patch = min(end - v, int(rs.randint(16, 120)))
+            k = int(rs.randint(1, 5))
+            others = list(rs.permutation(nbrs))[:k - 1]
+            idx = [prim] + [int(j) for j in others]
+            for u in range(v, v + patch):
+                w = rs.uniform(0.05, 1.0, size=len(idx))
+                W[u, idx] = w / w.sum()
+            v += patch
+    return W
+
+
+def synthetic_smpl_data(seed=0, num_verts=NUM_VERTS, num_betas=10, regressors=None, skinning='random'):
     """Returns a dict of fp32 torch tensors with the smplx buffer names/shapes
     (v_template, shapedirs, posedirs, J_regressor, lbs_weights, parents) plus the three extra regressors
-    of models/smpl.py:16-25 (synthetic sparse rows unless ``regressors`` supplies the real ones)."""
+    of models/smpl.py:16-25 (synthetic sparse rows unless ``regressors`` supplies the real ones).
+    ``skinning``: 'random' = every vertex bound to 1..4 joints drawn uniformly from the 24 (adversarial: no two
+    neighbouring vertices share a joint set); 'body_parts' = SMPL-like structure (see _body_part_weights)."""
     rs = np.random.RandomState(seed)
     V = num_verts
     d = {}
@@ -38,7 +66,7 @@ def synthetic_smpl_data(seed=0, num_verts=NUM_VERTS, num_betas=10, regressors=No
         idx = rs.choice(24, size=k, replace=False)
         w = rs.uniform(0.05, 1.0, size=k)
         W[v, idx] = w / w.sum()
-    d['lbs_weights'] = W
+    d['lbs_weights'] = W if skinning == 'random' else _body_part_weights(np.random.RandomState(seed + 1000), V)
     d['J_regressor_extra'] = _sparse_rows(rs, 9, V, 7)
     d['J_regressor_cocoplus'] = _sparse_rows(rs, 19, V, 5)
     d['J_regressor_h36m'] = _sparse_rows(rs, 17, V, 6)

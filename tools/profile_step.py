@@ -15,7 +15,7 @@ torch.manual_seed(0)
 cfg = hb.get_model_cfg_defaults()
 cfg.NUM_RESNET_LAYERS = 50
 model = hb.HumaniflowModel('cuda', cfg, SMPL_PARENTS).eval().cuda()
-smpl = hb.SMPL.from_arrays(synthetic_smpl_data(seed=0), create_transl=False).cuda()
+smpl = hb.SMPL.from_arrays(synthetic_smpl_data(seed=0, skinning='body_parts'), create_transl=False).cuda()
 x = synthetic_proxy_input(B, 18, 256, seed=1).cuda()
 g = torch.Generator().manual_seed(2)
 z = (torch.randn(B, N, 23, 3, generator=g) * 0.6).cuda()
