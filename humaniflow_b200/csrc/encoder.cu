@@ -52,7 +52,7 @@ constexpr int CONV_THREADS = 352;   // warp 0 operand TMA, warp 1 MMA issuer + T
 template <int BN, int STAGES, int SR>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, const float* __restrict__ bias,
-                    int has_res, int num_tiles, int ntn) {
+                    int has_res, int num_tiles, int ntn, int pdl_early) {
     constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int SBUF_BYTES = 128 * BN * 2;     // staging tile: BN/64 boxes of [128 rows][128 B], swizzled
     constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
@@ -81,6 +81,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    if (pdl_early) {
+        // Programmatic dependent launch: release the next kernel of the stream now (its CTAs take over each SM as soon as this
+        // grid's CTA leaves it and run their own prologue up to this point), then wait until the predecessor grid has
+        // completed and its writes are visible before touching any activation buffer.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -190,46 +197,57 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
             tcgen05_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(colhalf * HALF);
             uint8_t* srow = sbuf_ptr + sb * SBUF_BYTES + row * 128;
+            // 32-column chunks, double-buffered in registers: the TMEM load of chunk c+1 is in flight while chunk c is
+            // converted (tcgen05.wait::ld waits for every outstanding load, so the next one is issued right after it)
+            constexpr int NCH = HALF / 32;
+            uint32_t v[2][32];
+            tmem_ld32(trow, v[0]);
 #pragma unroll
-            for (int c0 = 0; c0 < HALF; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + (uint32_t)c0, v);
-                tmem_ld_wait();
-                const int col = colhalf * HALF + c0;                       // column within the BN tile
-                uint8_t* sbox = srow + (col >> 6) * 16384;                 // 64-channel box
-                const int j0 = (col & 63) >> 3;                            // 16-byte piece within the 128-byte row
-                uint4* p0 = reinterpret_cast<uint4*>(sbox + (((j0) ^ (row & 7)) << 4));
-                uint4* p1 = reinterpret_cast<uint4*>(sbox + (((j0 + 1) ^ (row & 7)) << 4));
-                float f[16];
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int col = colhalf * HALF + ch * 32;                  // first column (within the BN tile) of this chunk
+                float4 bb[8];
                 const float4* bp = reinterpret_cast<const float4*>(bias + n0 + col);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 bb = __ldg(bp + i);
-                    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
-                    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
-                }
+                for (int i = 0; i < 8; ++i) bb[i] = __ldg(bp + i);
+                uint8_t* sbox = srow + (col >> 6) * 16384;                 // 64-channel box
+                const int j0 = (col & 63) >> 3;                            // first 16-byte piece within the 128-byte row
+                uint4 rr[4];
                 if (has_res) {
-                    const uint4 ra = *p0, rb = *p1;
-                    const uint32_t r8[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&r8[i]);
-                        f[2 * i] += __bfloat162float(h.x);
-                        f[2 * i + 1] += __bfloat162float(h.y);
+                    for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(sbox + (((j0 + i) ^ (row & 7)) << 4));
+                }
+                tmem_ld_wait();
+                if (ch + 1 < NCH) tmem_ld32(trow + (uint32_t)((ch + 1) * 32), v[(ch + 1) & 1]);
+                const uint32_t* vv = v[ch & 1];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                              // one 16-byte piece = 8 channels
+                    float f[8];
+                    const float4 b0 = bb[2 * i], b1 = bb[2 * i + 1];
+                    f[0] = __uint_as_float(vv[8 * i + 0]) + b0.x; f[1] = __uint_as_float(vv[8 * i + 1]) + b0.y;
+                    f[2] = __uint_as_float(vv[8 * i + 2]) + b0.z; f[3] = __uint_as_float(vv[8 * i + 3]) + b0.w;
+                    f[4] = __uint_as_float(vv[8 * i + 4]) + b1.x; f[5] = __uint_as_float(vv[8 * i + 5]) + b1.y;
+                    f[6] = __uint_as_float(vv[8 * i + 6]) + b1.z; f[7] = __uint_as_float(vv[8 * i + 7]) + b1.w;
+                    if (has_res) {
+                        const uint32_t r4[4] = {rr[i].x, rr[i].y, rr[i].z, rr[i].w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&r4[t]);
+                            f[2 * t] += __bfloat162float(h.x);
+                            f[2 * t + 1] += __bfloat162float(h.y);
+                        }
                     }
-                }
-                if (g.relu) {
+                    if (g.relu) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-                }
-                uint32_t o[8];
+                        for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], 0.f);
+                    }
+                    uint32_t o[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                    o[i] = *reinterpret_cast<uint32_t*>(&h);
+                    for (int t = 0; t < 4; ++t) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
+                        o[t] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(sbox + (((j0 + i) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
-                *p0 = make_uint4(o[0], o[1], o[2], o[3]);
-                *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
             // accumulator buffer can be refilled; staging tile goes out by TMA
             tcgen05_fence_before();
@@ -254,12 +272,10 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
         if (threadIdx.x == 64) bulk_wait<0>();
     }
     tcgen05_fence_before();
-    __threadfence();
+    if (!pdl_early) __threadfence();
     __syncthreads();
-    // Every thread of this CTA is past its last global write (thread 64 has waited for the TMA stores): only now may
-    // the next kernel of the stream be released (measured on B200: griddepcontrol.wait in the dependent returns once all
-    // CTAs of this grid have triggered, NOT when the grid has completed; an earlier trigger races).
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // late-trigger mode: every thread of this CTA is past its last global write (thread 64 has waited for the TMA stores)
+    if (!pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -488,9 +504,10 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
     }
     // operand ring depth vs staging tiles: residual layers prefetch the residual several tiles ahead (DRAM latency),
     // layers without residual spend the shared memory on a deeper operand ring
+    // (one staging tile serialises the epilogue of tile t+1 behind the TMA store of tile t: only the 64 KB tiles of BN = 256)
     if (p->bn == 256)      { p->stages = 3; p->sr = 1; }
-    else if (p->bn == 128) { p->stages = p->has_res ? 3 : 5; p->sr = p->has_res ? 3 : 1; }
-    else                   { p->stages = p->has_res ? 5 : 7; p->sr = p->has_res ? 4 : 1; }
+    else if (p->bn == 128) { p->stages = p->has_res ? 3 : 4; p->sr = p->has_res ? 3 : 2; }
+    else                   { p->stages = p->has_res ? 5 : 6; p->sr = p->has_res ? 4 : 2; }
     p->smem = (size_t)p->stages * (128 * 128 + p->bn * 128) + (size_t)p->sr * 128 * p->bn * 2 + 1024;
     p->ntn = cout / p->bn;
     p->num_tiles = tiles_m * p->ntn;
@@ -512,15 +529,18 @@ int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     static const bool no_pdl = getenv("HF_NO_PDL") != nullptr;
     cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
-    HF_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, STAGES, SR>, p.maps, p.g, bias, p.has_res, p.num_tiles, p.ntn));
+    // early trigger + griddepcontrol.wait is the default (digest-identical to serialized launches, tools/enc_pdl_check.py);
+    // HF_PDL_EARLY=0 falls back to triggering at the end of the kernel
+    static const int pdl_early = no_pdl ? 0 : (getenv("HF_PDL_EARLY") ? atoi(getenv("HF_PDL_EARLY")) : 1);
+    HF_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, STAGES, SR>, p.maps, p.g, bias, p.has_res, p.num_tiles, p.ntn, pdl_early));
     HF_LAUNCH_CHECK();
     return HF_OK;
 }
 
 int launch_conv(const ConvPlan& p, const float* bias, cudaStream_t s) {
     if (p.bn == 256) return launch_conv_t<256, 3, 1>(p, bias, s);
-    if (p.bn == 128) return p.has_res ? launch_conv_t<128, 3, 3>(p, bias, s) : launch_conv_t<128, 5, 1>(p, bias, s);
-    return p.has_res ? launch_conv_t<64, 5, 4>(p, bias, s) : launch_conv_t<64, 7, 1>(p, bias, s);
+    if (p.bn == 128) return p.has_res ? launch_conv_t<128, 3, 3>(p, bias, s) : launch_conv_t<128, 4, 2>(p, bias, s);
+    return p.has_res ? launch_conv_t<64, 5, 4>(p, bias, s) : launch_conv_t<64, 6, 2>(p, bias, s);
 }
 
 int launch_simt(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, const __nv_bfloat16* res,
