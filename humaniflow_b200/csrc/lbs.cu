@@ -50,6 +50,8 @@ struct hf_smpl {
     const void* mapB_ptr; int mapB_M; CUtensorMap mapB;
 };
 
+int hf_lbs_extra_joints(const hf_smpl* h, const float* vertices, float* joints, int M, cudaStream_t stream);
+
 namespace {
 
 struct Parents { int p[HF_MAXJ]; };
@@ -930,6 +932,31 @@ extern "C" int hf_lbs_set_impl(hf_smpl_t* h, int impl) {
     return HF_OK;
 }
 
+// joints[J ..) from finished vertices: 21 vertex picks + the sparse extra regressors (shared with hf_lbs_tpose)
+int hf_lbs_extra_joints(const hf_smpl* h, const float* vertices, float* joints, int M, cudaStream_t stream) {
+    const int per = h->nvj + h->nextra, J_out = hf_smpl_num_joints_out(h);
+    if (per <= 0) return HF_OK;
+    if (h->nvj + h->nnz <= XJ_MAXE)
+        HF_CUDA(hf::launch_pdl(lbs_extra_joints_kernel, dim3(M), dim3(XJ_THREADS), 0, stream, vertices, h->vj, h->csr_ptr,
+                               h->csr_col, h->csr_val, M, h->V, h->J, h->nvj, h->nextra, J_out, joints));
+    else
+        HF_CUDA(hf::launch_pdl(lbs_extra_joints_rows_kernel, dim3(hf::div_up(M * per, 256)), dim3(256), 0, stream, vertices, h->vj, h->csr_ptr,
+                               h->csr_col, h->csr_val, M, h->V, h->J, h->nvj, h->nextra, J_out, joints));
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
+
+extern "C" int hf_smpl_dims(const hf_smpl* h, int* V, int* Vp, int* nb, int* J, int* J_out) {
+    if (!h) return hf::fail(HF_ERR_INVALID, "hf_smpl_dims: null handle");
+    if (V) *V = h->V; if (Vp) *Vp = h->Vp; if (nb) *nb = h->nb; if (J) *J = h->J; if (J_out) *J_out = hf_smpl_num_joints_out(h);
+    return HF_OK;
+}
+
+int hf_smpl_tpose_tables(const hf_smpl* h, const float** blend, const float** vtemp, const float** J0, const float** Jd) {
+    *blend = h->blend; *vtemp = h->vtemp; *J0 = h->J0; *Jd = h->Jd;
+    return HF_OK;
+}
+
 extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats,
                               const float* transl, float* vertices, float* joints, void* workspace,
                               size_t workspace_bytes, int M, void* stream_) {
@@ -1023,15 +1050,9 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
                                                                  h->V, h->Vp, h->KB, h->KP, h->J, h->nslots, vertices);
     HF_LAUNCH_CHECK();
     }
-    int per = h->nvj + h->nextra;
-    if (per > 0 && (stage_mask & 4)) {
-        if (h->nvj + h->nnz <= XJ_MAXE)
-            HF_CUDA(hf::launch_pdl(lbs_extra_joints_kernel, dim3(M), dim3(XJ_THREADS), 0, stream, vertices, h->vj, h->csr_ptr,
-                                   h->csr_col, h->csr_val, M, h->V, h->J, h->nvj, h->nextra, J_out, joints));
-        else
-            HF_CUDA(hf::launch_pdl(lbs_extra_joints_rows_kernel, dim3(hf::div_up(M * per, 256)), dim3(256), 0, stream, vertices, h->vj, h->csr_ptr,
-                                   h->csr_col, h->csr_val, M, h->V, h->J, h->nvj, h->nextra, J_out, joints));
-        HF_LAUNCH_CHECK();
+    if (stage_mask & 4) {
+        int rc = hf_lbs_extra_joints(h, vertices, joints, M, stream);
+        if (rc) return rc;
     }
     return HF_OK;
 }

@@ -184,6 +184,24 @@ class SMPL(nn.Module):
                                           _lib.ptr(joints), _lib.ptr(ws), ws.numel(), M, _lib.stream()))
         return verts, joints
 
+    def tpose(self, betas=None, transl=None):
+        """T-pose meshes: what ``forward(betas=...)`` returns with the default zero pose (predict_humaniflow.py:147,
+        evaluate_humaniflow.py:131-133), computed without pose blend and skinning.  betas (M,nb) CUDA fp32."""
+        _lib.require_cuda('SMPL.tpose')
+        betas = betas if betas is not None else self.betas
+        if not betas.is_cuda:
+            raise RuntimeError('humaniflow_b200.SMPL: inputs must be CUDA tensors (no CPU fallback)')
+        lib = _lib.load()
+        betas = _lib.f32c(betas)
+        M, dev = betas.shape[0], betas.device
+        transl = None if transl is None else _lib.f32c(transl).expand(M, 3).contiguous()
+        h = self._handle(dev)
+        verts = torch.empty(M, self.v_template.shape[0], 3, device=dev, dtype=torch.float32)
+        joints = torch.empty(M, self.num_joints_out, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hf_lbs_tpose(h, _lib.ptr(betas), _lib.ptr(transl), _lib.ptr(verts), _lib.ptr(joints), M, _lib.stream()))
+        return SMPLOutput(vertices=verts, joints=joints, full_pose=None, betas=betas, global_orient=None, body_pose=None)
+
     def forward(self, betas=None, body_pose=None, global_orient=None, transl=None, return_verts=True,
                 return_full_pose=False, pose2rot=True, out_vertices=None, out_joints=None, **kwargs):
         """models/smpl.py:27-41 + [upstream] smplx SMPL.forward.  ``None`` inputs fall back to the module's

@@ -68,6 +68,28 @@ int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats,
                    float* vertices, float* joints, void* workspace, size_t workspace_bytes,
                    int M, void* stream);
 
+/* T-pose forward (zero pose): vertices = v_template + shapedirs.betas (+ transl), joints as hf_lbs_forward would give for
+ * identity rotations.  Replaces models/smpl.py:27-41 called with the default pose (predict_humaniflow.py:147,
+ * evaluate_humaniflow.py:131-133); skips pose blend and skinning. */
+int hf_lbs_tpose(const hf_smpl_t* h, const float* betas, const float* transl, float* vertices, float* joints, int M,
+                 void* stream);
+int hf_smpl_dims(const hf_smpl_t* h, int* V, int* Vp, int* num_betas, int* J, int* J_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-image reductions / projections of the sampled meshes.
+ * ---------------------------------------------------------------------------------------------- */
+/* vertices (B,N,V,3) -> avg_dist (B,V) = mean over the N samples of ||x - mean||, dir_std (B,V,3) =
+ * sqrt(mean((x - mean)^2)).  Replaces utils/sampling_utils.py:22-33 compute_vertex_variance_from_samples, batched over
+ * images (predict_humaniflow.py:168).  N <= 532. */
+int hf_vertex_variance(const float* vertices, int B, int N, int V, float* avg_dist, float* dir_std, void* stream);
+
+/* joints (M,J_in,3) -> out (M,n_ids,2): select joint_ids (NULL = first n_ids), optional rotation by pi about the x axis
+ * (utils/rigid_transform_utils.py:67-83 with axes=x, angles=pi), weak-perspective projection with cam_wp[m / per_cam]
+ * = (s, tx, ty) (utils/cam_utils.py:9-16), and, if img_wh > 0, un-normalisation to pixels (utils/joints2d_utils.py:5-10).
+ * Replaces utils/sampling_utils.py:50-58 and evaluate_humaniflow.py:186-206. */
+int hf_project_joints2d(const float* joints, const float* cam_wp, const int* joint_ids, int M, int per_cam, int J_in,
+                        int n_ids, int flip_x, float img_wh, float* out, void* stream);
+
 /* fp32 axis-angle -> rotation matrices, n rows.  Replaces smplx `lbs.batch_rodrigues`
  * (used by SMPL.forward when pose2rot=True and at models/humaniflow_model.py:299). */
 int hf_rodrigues(const float* axis_angle, float* rotmats, int n, void* stream);

@@ -103,3 +103,17 @@ def test_real_regressors_fixture(golden_dir):
     g = np.load(os.path.join(golden_dir, 'regressors_sparse.npz'))
     assert tuple(g['extra_shape']) == (9, 6890) and tuple(g['cocoplus_shape']) == (19, 6890) and tuple(g['h36m_shape']) == (17, 6890)
     assert len(g['extra_val']) == 62 and len(g['cocoplus_val']) == 86 and len(g['h36m_val']) == 107
+
+
+def test_sampling_helpers(golden_dir):
+    """oracle/sampling.py against the real utils/sampling_utils.py / cam_utils.py / joints2d_utils.py outputs."""
+    from oracle import sampling as osamp
+    g = _load(golden_dir, 'sampling_golden.npz')
+    avg, std = osamp.compute_vertex_variance_from_samples(g['verts'])
+    assert torch.equal(avg, g['avg']) and torch.equal(std, g['std'])
+    assert list(g['coco'].tolist()) == osamp.ALL_JOINTS_TO_COCO_MAP
+    proj = osamp.project_joints2d(g['joints'], g['cam'], flip_x=False)
+    assert torch.equal(proj, g['proj'])
+    assert torch.equal(osamp.project_joints2d(g['joints'], g['cam'], flip_x=False, img_wh=256), g['pix'])
+    flipped = osamp.project_joints2d(g['joints'], g['cam'], flip_x=True)
+    assert torch.equal(flipped[..., 0], g['proj'][..., 0])      # rotation by pi about x leaves x alone, negates y
