@@ -60,6 +60,7 @@ SIGNATURES = {
     'hf_encoder_stem_channels': (c_int, [c_void_p]),
     'hf_encoder_set_impl': (c_int, [c_void_p, c_int]),
     'hf_encoder_debug_op_output': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    'hf_debug_conv_stamps': (c_int, [c_void_p]),
     'hf_conv2d_nhwc': (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p]),
 }
 

@@ -40,6 +40,16 @@ struct ConvMaps {
     CUtensorMap r;      // residual, same shape as the output
 };
 
+// timing aid (HF_CONV_DBG bit 3): %globaltimer stamps of CTA 0 at the milestones of one launch, fetched by hf_debug_conv_stamps
+__device__ unsigned long long g_conv_ts[16];
+__device__ __forceinline__ void conv_stamp(int dbg, int slot) {
+    if ((dbg & 8) && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_conv_ts[slot] = t;
+    }
+}
+
 constexpr int CONV_THREADS = 352;   // warp 0 operand TMA, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue, warp 10 residual TMA
 
 // Persistent implicit-GEMM convolution: one CTA per SM walks the output tiles (n-tile fastest, so the activation
@@ -49,11 +59,23 @@ constexpr int CONV_THREADS = 352;   // warp 0 operand TMA, warp 1 MMA issuer + T
 //   result        staging tile -> global (TMA store, bulk groups; sfree recycles the staging tile)
 // MMA accumulators are double-buffered in TMEM (tfull/tempty), so the epilogue of tile t (TMEM -> +bias
 // +residual -> ReLU -> bf16, in place in the 128B-swizzled staging tile) overlaps the loads/MMAs of tile t+1.
-template <int BN, int STAGES, int SR>
+// PAIR: the two CTAs of a (2,1,1) cluster work on two vertically adjacent M-tiles of the same N-tile as ONE 256 x BN
+// tcgen05.mma.cta_group::2 issued by the leader (rank 0): each CTA stages its own 128 activation rows but only HALF of the
+// weight tile (BN/2 rows), which cuts the operand bytes every SM pulls through the L2->SM fabric (the measured limiter)
+// by a quarter (BN = 128) to a third (BN = 256).  num_tiles then counts pair tiles.
+template <int BN, int STAGES, int SR, bool PAIR>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, const float* __restrict__ bias,
-                    int has_res, int num_tiles, int ntn, int pdl_early) {
-    constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+                    int has_res, int num_tiles, int ntn, int pdl_early, int dbg) {
+    // dbg (HF_CONV_DBG, timing experiments only, results are garbage): bit 0 skip the MMAs, bit 1 skip the activation loads,
+    // bit 2 skip the weight loads
+    constexpr int BROWS = PAIR ? BN / 2 : BN;     // weight rows staged by this CTA
+    constexpr int A_BYTES = 128 * 128, B_BYTES = BROWS * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;           // persistent worker id (a CTA or a CTA pair)
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    if (threadIdx.x == 0) conv_stamp(dbg, 0);                       // kernel entry
     constexpr int SBUF_BYTES = 128 * BN * 2;     // staging tile: BN/64 boxes of [128 rows][128 B], swizzled
     constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
     constexpr int HALF = BN / 2;                 // columns per epilogue warp
@@ -69,18 +91,24 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
     const uint32_t rfull0 = smem_u32(&bars[2 * STAGES + 4]), sfree0 = smem_u32(&bars[2 * STAGES + 4 + SR]);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, PAIR ? 16 : 8); }
         for (int b = 0; b < SR; ++b) { mbar_init(rfull0 + 8 * b, 1); mbar_init(sfree0 + 8 * b, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();       // barrier inits + TMEM base visible (pair: in both CTAs)
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    if (threadIdx.x == 0) conv_stamp(dbg, 1);                       // barriers + TMEM ready
     if (pdl_early) {
         // Programmatic dependent launch: release the next kernel of the stream now (its CTAs take over each SM as soon as this
         // grid's CTA leaves it and run their own prologue up to this point), then wait until the predecessor grid has
@@ -88,79 +116,109 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
+    if (threadIdx.x == 0) conv_stamp(dbg, 2);                       // dependency wait over
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // the WHOLE warp walks the loop (converged waits; a lone lane of a diverged warp pays for every YIELD of its
+            // polling loop with a switch to the parked lanes); lane 0 alone issues the barrier arrive and the TMA loads
+            // loop on the critical path of every k-block: all index arithmetic is incremental (no integer divisions)
             const int cpb = g.cin >> 6;   // 64-channel blocks per tap (generic)
-            uint32_t kbc = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nt = tile % ntn;
-                int t = tile / ntn;
+            const uint32_t full_lead = PAIR ? mapa_rank(full0, 0) : full0;   // pair: both CTAs' loads complete on the leader's barrier
+            const uint32_t my_bytes = ((dbg & 2) ? 0u : (uint32_t)A_BYTES) + ((dbg & 4) ? 0u : (uint32_t)B_BYTES);
+            const uint32_t tx_bytes = PAIR ? 2 * my_bytes : my_bytes;
+            const int kind = g.kind, ksize = g.ksize, pad = g.pad, stride = g.stride, nkb = g.nkb;
+            uint32_t st = 0, ph = 0;
+            int nt = cta % ntn, mt = cta / ntn;                      // tile = mt * ntn + nt, advanced by nworkers per step
+            const int step_nt = nworkers % ntn, step_mt = nworkers / ntn;
+            for (int tile = cta; tile < num_tiles; tile += nworkers) {
+                int t = PAIR ? 2 * mt + (int)rank : mt;              // this CTA's M-tile (past the end: all-zero boxes)
                 const int tw = t % g.tiles_w; t /= g.tiles_w;
                 const int th = t % g.tiles_h;
                 const int tb = t / g.tiles_h;
-                const int wo0 = tw * g.TW, ho0 = th * g.TH, b0 = tb * g.TB, n0 = nt * BN;
-                for (int kb = 0; kb < g.nkb; ++kb, ++kbc) {
-                    const uint32_t st = kbc % STAGES, ph = (kbc / STAGES) & 1u;
+                const int wo0 = tw * g.TW, ho0 = th * g.TH, b0 = tb * g.TB, n0 = nt * BN + (int)rank * BROWS;
+                int cb = 0, kw = 0, kh = 0;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(empty0 + 8 * st, ph ^ 1u);
                     const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
-                    const uint32_t fb = full0 + 8 * st;
-                    mbar_expect_tx(fb, STAGE_BYTES);
+                    const uint32_t fb = full_lead + 8 * st;
+                    if (leader && lane == 0) mbar_expect_tx(full0 + 8 * st, tx_bytes);
                     int mi, c0, c1, c2;
-                    if (g.kind == 0) {
-                        const int tap = kb / cpb, cb = kb - tap * cpb;
-                        const int kh = tap / g.ksize, kw = tap - kh * g.ksize;
-                        const int dw = kw - g.pad, dh = kh - g.pad;
+                    if (kind == 0) {            // (kh, kw) = filter tap, cb = 64-channel block within the tap
+                        const int dw = kw - pad, dh = kh - pad;
                         c0 = cb * 64;
-                        if (g.stride == 1) { mi = 0; c1 = wo0 + dw; c2 = ho0 + dh; }
+                        if (stride == 1) { mi = 0; c1 = wo0 + dw; c2 = ho0 + dh; }
                         else {
                             const int pw = dw & 1, phh = dh & 1;
                             mi = phh * 2 + pw;
                             c1 = wo0 + ((dw - pw) >> 1);
                             c2 = ho0 + ((dh - phh) >> 1);
                         }
-                    } else if (g.kind == 1) {
-                        const int kh = kb >> 2, q = kb & 3;
-                        mi = kh & 1; c0 = 0; c1 = wo0 + q; c2 = ho0 + (kh >> 1);
-                    } else {   // compact stem: 8 taps x 24 ch = 192 contiguous elements per (pixel, kh), 3 k-blocks
-                        const int kh = kb / 3, q = kb - kh * 3;
-                        mi = kh & 1; c0 = q * 64; c1 = wo0; c2 = ho0 + (kh >> 1);
+                        if (++cb == cpb) { cb = 0; if (++kw == ksize) { kw = 0; ++kh; } }
+                    } else if (kind == 1) {
+                        const int kh1 = kb >> 2, q = kb & 3;
+                        mi = kh1 & 1; c0 = 0; c1 = wo0 + q; c2 = ho0 + (kh1 >> 1);
+                    } else {   // compact stem: 8 taps x 24 ch = 192 contiguous elements per (pixel, kh), 3 k-blocks (cb counts them)
+                        mi = kh & 1; c0 = cb * 64; c1 = wo0; c2 = ho0 + (kh >> 1);
+                        if (++cb == 3) { cb = 0; ++kh; }
                     }
-                    tma_load_4d(sa, &maps.a[mi], fb, c0, c1, c2, b0);
-                    tma_load_2d(sb, &maps.b, fb, kb * 64, n0);
+                    if (lane == 0) {
+                        if (PAIR) {
+                            if (!(dbg & 2)) tma_load_4d_2cta(sa, &maps.a[mi], fb, c0, c1, c2, b0);
+                            if (!(dbg & 4)) tma_load_2d_2cta(sb, &maps.b, fb, kb * 64, n0);
+                        } else {
+                            if (!(dbg & 2)) tma_load_4d(sa, &maps.a[mi], fb, c0, c1, c2, b0);
+                            if (!(dbg & 4)) tma_load_2d(sb, &maps.b, fb, kb * 64, n0);
+                        }
+                    }
+                    __syncwarp();
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
+                nt += step_nt; mt += step_mt;
+                if (nt >= ntn) { nt -= ntn; ++mt; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, BN);
-            uint32_t kbc = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        if (leader) {           // whole warp converged on the waits, lane 0 issues the MMAs and commits
+            const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN);
+            uint32_t lt = 0, st = 0, ph = 0;
+            const int nkb = g.nkb;
+            for (int tile = cta; tile < num_tiles; tile += nworkers, ++lt) {
                 const uint32_t buf = lt & 1u;
                 mbar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t d = tmem_base + buf * BN;
-                for (int kb = 0; kb < g.nkb; ++kb, ++kbc) {
-                    const uint32_t st = kbc % STAGES, ph = (kbc / STAGES) & 1u;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(full0 + 8 * st, ph);
                     tcgen05_fence_after();
+                    if (lt == 0 && kb == 0 && lane == 0) conv_stamp(dbg, 3);     // first operand stage landed
                     const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+                    if (lane == 0) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-                    umma_commit(empty0 + 8 * st);
+                    for (int k = 0; k < 4; ++k) {
+                        if (dbg & 1) continue;
+                        if (PAIR) umma_bf16_2cta(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        else umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    if (PAIR) umma_commit_2cta(empty0 + 8 * st); else umma_commit(empty0 + 8 * st);
+                    }
+                    __syncwarp();
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
-                umma_commit(tfull0 + 8 * buf);
+                if (lane == 0) {
+                    if (PAIR) umma_commit_2cta(tfull0 + 8 * buf); else umma_commit(tfull0 + 8 * buf);
+                    if (lt == 0) conv_stamp(dbg, 4);                // all MMAs of the first tile issued
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 10) {
         if (lane == 0) {
             // staging tiles: wait until the previous store of the buffer has left smem, then fetch the residual
             uint32_t lt = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            for (int tile = cta; tile < num_tiles; tile += nworkers, ++lt) {
                 const int nt = tile % ntn;
-                int t = tile / ntn;
+                int t = PAIR ? 2 * (tile / ntn) + (int)rank : tile / ntn;
                 const int tw = t % g.tiles_w; t /= g.tiles_w;
                 const int th = t % g.tiles_h;
                 const int tb = t / g.tiles_h;
@@ -183,18 +241,19 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
         const int q = warp & 3, colhalf = e >> 2;
         const int row = q * 32 + lane;
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = cta; tile < num_tiles; tile += nworkers, ++lt) {
             const int nt = tile % ntn;
-            int t = tile / ntn;
+            int t = PAIR ? 2 * (tile / ntn) + (int)rank : tile / ntn;
             const int tw = t % g.tiles_w; t /= g.tiles_w;
             const int th = t % g.tiles_h;
             const int tb = t / g.tiles_h;
             const int n0 = nt * BN;
             const uint32_t buf = lt & 1u, par = (lt >> 1) & 1u;
             const uint32_t sb = lt % SR;
-            mbar_wait(rfull0 + 8 * sb, (lt / SR) & 1u);  // staging tile free (+ residual landed)
-            mbar_wait(tfull0 + 8 * buf, par);            // accumulator complete
+            mbar_wait_warp(rfull0 + 8 * sb, (lt / SR) & 1u);  // staging tile free (+ residual landed)
+            mbar_wait_warp(tfull0 + 8 * buf, par);            // accumulator complete
             tcgen05_fence_after();
+            if (lt == 0 && threadIdx.x == 64) conv_stamp(dbg, 5);   // first accumulator complete
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(colhalf * HALF);
             uint8_t* srow = sbuf_ptr + sb * SBUF_BYTES + row * 128;
             // 32-column chunks, double-buffered in registers: the TMEM load of chunk c+1 is in flight while chunk c is
@@ -253,9 +312,12 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
             tcgen05_fence_before();
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            if (lane == 0) {                                   // the accumulator buffer of BOTH CTAs is released to the leader's MMA thread
+                if (PAIR && !leader) mbar_arrive_cluster(mapa_rank(tempty0 + 8 * buf, 0)); else mbar_arrive(tempty0 + 8 * buf);
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x == 64) {
+                if (lt == 0) conv_stamp(dbg, 6);                    // first tile converted into the staging buffer
 #pragma unroll
                 for (int x = 0; x < BN / 64; ++x)
                     tma_store_4d(&maps.o, sbuf_base + sb * SBUF_BYTES + x * 16384, n0 + x * 64, tw * g.TW, th * g.TH, tb * g.TB);
@@ -269,16 +331,19 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                 }
             }
         }
-        if (threadIdx.x == 64) bulk_wait<0>();
+        if (threadIdx.x == 64) { conv_stamp(dbg, 7); bulk_wait<0>(); conv_stamp(dbg, 8); }   // last store issued / landed
     }
     tcgen05_fence_before();
     if (!pdl_early) __threadfence();
     __syncthreads();
     // late-trigger mode: every thread of this CTA is past its last global write (thread 64 has waited for the TMA stores)
     if (!pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) conv_stamp(dbg, 9);                       // all roles done
+    if (PAIR) cluster_sync_all();       // neither CTA may leave (or free TMEM) while its peer can still signal it
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -412,7 +477,7 @@ int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 struct ConvPlan {
     ConvGeom g;
     ConvMaps maps;
-    int bn, ntn, num_tiles, has_res, sr;
+    int bn, ntn, num_tiles, has_res, sr, pair;
     dim3 grid;
     size_t smem;
     int stages;
@@ -495,52 +560,89 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
         rc = encode_map(&p->maps.r, res ? res : out, 4, dims, st, box);
         if (rc) return rc;
     }
+    // CTA pairs (one 256-row cta_group::2 MMA per two M-tiles, each CTA staging half of the weight tile): bit-identical
+    // results and 25 % fewer operand bytes per SM, but measured 6-10 % SLOWER on this network (the k-block loop is bound by
+    // the ~700 cycles of issue latency of its barrier / TMA / MMA / commit instructions, not by operand bytes),
+    // so it is opt-in: HF_CONV_PAIR=1
+    static const int pair_env = getenv("HF_CONV_PAIR") ? atoi(getenv("HF_CONV_PAIR")) : 0;
+    p->pair = (pair_env && tiles_m >= 2) ? 1 : 0;
     {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout};
         const uint64_t st[1] = {(uint64_t)ktot * 2};
-        const uint32_t bx[2] = {64, (uint32_t)p->bn};
+        const uint32_t bx[2] = {64, (uint32_t)(p->pair ? p->bn / 2 : p->bn)};
         int rc = encode_map(&p->maps.b, w, 2, dims, st, bx);
         if (rc) return rc;
     }
     // operand ring depth vs staging tiles: residual layers prefetch the residual several tiles ahead (DRAM latency),
     // layers without residual spend the shared memory on a deeper operand ring
     // (one staging tile serialises the epilogue of tile t+1 behind the TMA store of tile t: only the 64 KB tiles of BN = 256)
-    if (p->bn == 256)      { p->stages = 3; p->sr = 1; }
-    else if (p->bn == 128) { p->stages = p->has_res ? 3 : 4; p->sr = p->has_res ? 3 : 2; }
-    else                   { p->stages = p->has_res ? 5 : 6; p->sr = p->has_res ? 4 : 2; }
-    p->smem = (size_t)p->stages * (128 * 128 + p->bn * 128) + (size_t)p->sr * 128 * p->bn * 2 + 1024;
+    if (p->pair) {      // stage = 16 KB of activations + bn/2 weight rows
+        if (p->bn == 256)      { p->stages = 4; p->sr = 1; }
+        else if (p->bn == 128) { p->stages = p->has_res ? 4 : 5; p->sr = p->has_res ? 3 : 2; }
+        else                   { p->stages = p->has_res ? 6 : 7; p->sr = p->has_res ? 4 : 2; }
+    } else {
+        if (p->bn == 256)      { p->stages = 3; p->sr = 1; }
+        else if (p->bn == 128) { p->stages = p->has_res ? 3 : 4; p->sr = p->has_res ? 3 : 2; }
+        else                   { p->stages = p->has_res ? 5 : 6; p->sr = p->has_res ? 4 : 2; }
+    }
+    static const int stages_env = getenv("HF_CONV_STAGES") ? atoi(getenv("HF_CONV_STAGES")) : 0;     // timing experiment: BN = 128 without residual
+    if (stages_env && !p->pair && p->bn == 128 && !p->has_res) { p->stages = stages_env; p->sr = stages_env >= 5 ? 1 : 2; }
+    p->smem = (size_t)p->stages * (128 * 128 + (p->pair ? p->bn / 2 : p->bn) * 128) + (size_t)p->sr * 128 * p->bn * 2 + 1024;
     p->ntn = cout / p->bn;
-    p->num_tiles = tiles_m * p->ntn;
-    p->grid = dim3(std::min(p->num_tiles, num_sms()));
+    if (p->pair) {
+        p->num_tiles = hf::div_up(tiles_m, 2) * p->ntn;                      // pair tiles
+        p->grid = dim3(2 * std::min(p->num_tiles, num_sms() / 2));
+    } else {
+        p->num_tiles = tiles_m * p->ntn;
+        p->grid = dim3(std::min(p->num_tiles, num_sms()));
+    }
     return HF_OK;
 }
 
-template <int BN, int STAGES, int SR>
+template <int BN, int STAGES, int SR, bool PAIR>
 int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
+        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = p.grid; cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
     static const bool no_pdl = getenv("HF_NO_PDL") != nullptr;
-    cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+    if (!no_pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (PAIR) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
     // early trigger + griddepcontrol.wait is the default (digest-identical to serialized launches, tools/enc_pdl_check.py);
     // HF_PDL_EARLY=0 falls back to triggering at the end of the kernel
     static const int pdl_early = no_pdl ? 0 : (getenv("HF_PDL_EARLY") ? atoi(getenv("HF_PDL_EARLY")) : 1);
-    HF_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, STAGES, SR>, p.maps, p.g, bias, p.has_res, p.num_tiles, p.ntn, pdl_early));
+    static const int dbg = getenv("HF_CONV_DBG") ? atoi(getenv("HF_CONV_DBG")) : 0;
+    HF_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<BN, STAGES, SR, PAIR>, p.maps, p.g, bias, p.has_res, p.num_tiles, p.ntn, pdl_early, dbg));
     HF_LAUNCH_CHECK();
     return HF_OK;
 }
 
 int launch_conv(const ConvPlan& p, const float* bias, cudaStream_t s) {
-    if (p.bn == 256) return launch_conv_t<256, 3, 1>(p, bias, s);
-    if (p.bn == 128) return p.has_res ? launch_conv_t<128, 3, 3>(p, bias, s) : launch_conv_t<128, 4, 2>(p, bias, s);
-    return p.has_res ? launch_conv_t<64, 5, 4>(p, bias, s) : launch_conv_t<64, 6, 2>(p, bias, s);
+    if (p.pair) {
+        if (p.bn == 256) return launch_conv_t<256, 4, 1, true>(p, bias, s);
+        if (p.bn == 128) return p.has_res ? launch_conv_t<128, 4, 3, true>(p, bias, s) : launch_conv_t<128, 5, 2, true>(p, bias, s);
+        return p.has_res ? launch_conv_t<64, 6, 4, true>(p, bias, s) : launch_conv_t<64, 7, 2, true>(p, bias, s);
+    }
+    if (p.bn == 256) return launch_conv_t<256, 3, 1, false>(p, bias, s);
+    if (p.bn == 128 && !p.has_res && p.stages == 2) return launch_conv_t<128, 2, 2, false>(p, bias, s);
+    if (p.bn == 128 && !p.has_res && p.stages == 3) return launch_conv_t<128, 3, 2, false>(p, bias, s);
+    if (p.bn == 128 && !p.has_res && p.stages == 5) return launch_conv_t<128, 5, 1, false>(p, bias, s);
+    if (p.bn == 128) return p.has_res ? launch_conv_t<128, 3, 3, false>(p, bias, s) : launch_conv_t<128, 4, 2, false>(p, bias, s);
+    return p.has_res ? launch_conv_t<64, 5, 4, false>(p, bias, s) : launch_conv_t<64, 6, 2, false>(p, bias, s);
 }
 
 int launch_simt(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, const __nv_bfloat16* res,
@@ -810,6 +912,12 @@ extern "C" int hf_encoder_debug_op_output(hf_encoder_t* h, int op_index, const f
     if (out_bytes < bytes) return hf::fail(HF_ERR_INVALID, "debug: output buffer too small");
     uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
     HF_CUDA(cudaMemcpyAsync(out, ws + stem_in_bytes(B, H, W) + (size_t)op.dst * max_act, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+    return HF_OK;
+}
+
+extern "C" int hf_debug_conv_stamps(unsigned long long* out16) {
+    HF_CUDA(cudaDeviceSynchronize());
+    HF_CUDA(cudaMemcpyFromSymbol(out16, g_conv_ts, sizeof(unsigned long long) * 16));
     return HF_OK;
 }
 

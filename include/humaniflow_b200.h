@@ -214,6 +214,10 @@ int hf_encoder_debug_op_output(hf_encoder_t* h, int op_index, const float* input
                                void* workspace, size_t workspace_bytes, uint16_t* out, size_t out_bytes,
                                int* dims, float* feats, void* stream);
 
+/* Timing aid: with HF_CONV_DBG bit 3 set, CTA 0 of every conv launch records %globaltimer at ten milestones; this
+ * synchronises the device and returns the stamps of the most recent launch (16 values, ns). */
+int hf_debug_conv_stamps(unsigned long long* out16);
+
 /* Single convolution on bf16 NHWC tensors (unit-test entry point for the conv kernels).
  * x (B,H,W,cin) bf16; w (cout,k,k,cin) bf16; bias (cout) fp32; res (B,Ho,Wo,cout) bf16 or NULL;
  * y (B,Ho,Wo,cout) bf16. */
