@@ -208,6 +208,8 @@ def run_ours(args):
     se = torch.randn(B, N, 10, generator=g).to(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
+    pending, last_metric = [None], [None]
+
     def step(x, marks=None, outs=None):
         out = model(x, num_samples=N, base_noise=z, shape_eps=se)
         if marks is not None:
@@ -218,11 +220,18 @@ def run_ours(args):
                   out_vertices=None if outs is None else outs[0], out_joints=None if outs is None else outs[1])
         if marks is not None:
             marks[1].record()
-        # per-image metric row (sample diversity: mean over joints of the std over samples), gathered across ranks
-        metric = gather_rows(sample_diversity_rows(so.joints, B, N), num_images=world * B)
-        return so, metric
+        # per-image metric row (sample diversity: mean over joints of the std over samples), gathered across ranks;
+        # the collective is asynchronous: its result is read when the NEXT step issues its own gather, so the cross-rank
+        # rendezvous never stalls the following step's kernels
+        if pending[0] is not None:
+            last_metric[0] = pending[0].result()
+        pending[0] = gather_rows(sample_diversity_rows(so.joints, B, N), num_images=world * B, async_op=True)
+        return so, pending[0]
 
     def sync_all():
+        if pending[0] is not None:
+            last_metric[0] = pending[0].result()
+            pending[0] = None
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()

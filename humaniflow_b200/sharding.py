@@ -23,11 +23,30 @@ def shard(t, world_size, rank, dim=0):
     return t.narrow(dim, a, b - a)
 
 
-def gather_rows(local_rows, num_images=None, group=None):
-    """all_gather of per-image rows (B_local, n) -> (B_global, n) in image order on every rank.
-    Handles ragged shards (B_global not divisible by the world size) by padding to the largest shard."""
+class _Gathered:
+    """Handle of an in-flight gather_rows: ``result()`` waits for the collective (on the current stream for NCCL) and
+    returns the (B_global, n) rows in image order."""
+
+    def __init__(self, flat, work, sizes, width, tail):
+        self._flat, self._work, self._sizes, self._width, self._tail = flat, work, sizes, width, tail
+
+    def result(self):
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        out = self._flat.view((len(self._sizes), self._width) + self._tail)
+        if all(b - a == self._width for a, b in self._sizes):
+            return out.reshape((-1,) + self._tail)
+        return torch.cat([out[r, :b - a] for r, (a, b) in enumerate(self._sizes)], dim=0)
+
+
+def gather_rows(local_rows, num_images=None, group=None, async_op=False):
+    """all_gather of per-image rows (B_local, n) -> (B_global, n) in image order on every rank (one collective kernel,
+    ``all_gather_into_tensor``).  Handles ragged shards (B_global not divisible by the world size) by padding to the
+    largest shard.  ``async_op=True`` returns a handle whose ``result()`` waits for the collective, so the next step's
+    kernels need not queue behind the cross-rank rendezvous."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return local_rows
+        return _Gathered(local_rows, None, [(0, local_rows.shape[0])], local_rows.shape[0], tuple(local_rows.shape[1:])) if async_op else local_rows
     world = dist.get_world_size(group)
     if num_images is None:
         n = torch.tensor([local_rows.shape[0]], device=local_rows.device)
@@ -35,11 +54,16 @@ def gather_rows(local_rows, num_images=None, group=None):
         num_images = int(n.item())
     sizes = [shard_range(num_images, world, r) for r in range(world)]
     width = max(b - a for a, b in sizes)
-    pad = local_rows.new_zeros((width,) + tuple(local_rows.shape[1:]))
-    pad[:local_rows.shape[0]] = local_rows
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad, group=group)
-    return torch.cat([o[:b - a] for o, (a, b) in zip(out, sizes)], dim=0)
+    tail = tuple(local_rows.shape[1:])
+    if local_rows.shape[0] == width:
+        pad = local_rows.contiguous()
+    else:
+        pad = local_rows.new_zeros((width,) + tail)
+        pad[:local_rows.shape[0]] = local_rows
+    flat = torch.empty((world * width,) + tail, dtype=pad.dtype, device=pad.device)
+    work = dist.all_gather_into_tensor(flat, pad, group=group, async_op=async_op)
+    h = _Gathered(flat, work if async_op else None, sizes, width, tail)
+    return h if async_op else h.result()
 
 
 def sample_diversity_rows(joints, batch, num_samples):

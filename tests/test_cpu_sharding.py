@@ -53,6 +53,8 @@ def _worker(rank, world, port, B, N, q):
     sd, cfg, data, feats, z, se = _problem(B, N)
     local = _rows(sd, cfg, data, shard(feats, world, rank), shard(z, world, rank), shard(se, world, rank))
     allrows = gather_rows(local, num_images=B)
+    pending = gather_rows(local, num_images=B, async_op=True)      # the handle form bench.py uses
+    assert torch.equal(pending.result(), allrows)
     if rank == 0:
         q.put(allrows.clone())
     dist.barrier()
