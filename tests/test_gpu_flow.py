@@ -164,3 +164,24 @@ def test_state_dict_roundtrip_and_repack():
     ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, num_samples=3, shape_eps=se, base_noise=z)
     assert (after.cpu() - ref['pose_rotmats_samples']).abs().max().item() <= ROT_TOL
     assert (after - before).abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize('M,K,O,act,acc', [(32, 2048, 512, 1, 0), (32, 2048, 256, 0, 0), (5, 512, 29, 0, 0), (33, 128, 7, 2, 1),
+                                            (1, 64, 4, 0, 0), (32, 9, 256, 0, 1)])
+def test_linear_layers(M, K, O, act, acc):
+    """hf_linear (humaniflow_model.py:232-258 fc1 / heads / image-level features) against torch fp32 on the CPU:
+    ragged row tiles, neuron counts that are not a multiple of the CTA tile, ELU / ReLU, accumulate-into-output."""
+    import torch.nn.functional as F
+    from humaniflow_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 7 + K)
+    x = torch.randn(M, K, generator=g)
+    W = torch.randn(O, K, generator=g) / K ** 0.5
+    b = torch.randn(O, generator=g)
+    y0 = torch.randn(M, O, generator=g)
+    ref = x.double() @ W.double().T + b.double() + (y0.double() if acc else 0)
+    ref = F.elu(ref) if act == 1 else (F.relu(ref) if act == 2 else ref)
+    xd, Wd, bd, yd = x.cuda(), W.cuda(), b.cuda(), y0.clone().cuda()
+    _lib.check(lib.hf_linear(_lib.ptr(xd), K, _lib.ptr(Wd), K, _lib.ptr(bd), _lib.ptr(yd), O, M, K, O, act, acc, _lib.stream()))
+    torch.cuda.synchronize()
+    assert (yd.cpu().double() - ref).abs().max().item() <= 2e-5
