@@ -1,0 +1,206 @@
+// Per-sample 3-D error metrics of the evaluation path on the device.
+//
+// For every predicted point set (a sampled mesh: P = 6890 vertices, or a joint set: P = 14 / 17) and its image's target:
+//   plain  mean_i || p_i - t_i ||                                   metrics/eval_metrics_tracker.py:119-125, 169-174, 201-206
+//   SC     after scale_and_translation_transform_batch(p, t)        utils/eval_utils.py:105-125  (tracker :128-136, 209-217)
+//   PA     after procrustes_analysis_batch(p, t)                    utils/eval_utils.py:62-102   (tracker :139-147, 220-229)
+// These per-sample means are what every PVE / PVE-SC / PVE-PA / PVE-T(-SC) / MPJPE(-SC/-PA) variant and their
+// "samples_min" forms reduce (sum = mean * P, minimum over the samples of an image).  The reference copies all meshes to
+// the host (2 x 265 MB per batch) and runs numpy incl. one 3x3 SVD per mesh; here a block per sample reads the mesh twice
+// from HBM and nothing but 3 floats per sample leaves the GPU.
+#include "common.cuh"
+
+namespace {
+
+constexpr int ME_THREADS = 256;
+
+// Jacobi eigen-decomposition of a symmetric 3x3 matrix (fp64): A = V diag(w) V^T, columns of V orthonormal.
+__device__ void eig_sym3(double A[3][3], double V[3][3], double w[3]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (fabs(A[p][q]) < 1e-300) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) {          // A <- A J
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {          // A <- J^T A
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {          // V <- V J
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// block-wide sums of NV doubles per thread -> every thread gets the totals (through shared memory)
+template <int NV>
+__device__ void block_sum(double* v, double* scratch /* [ME_THREADS/32][NV] + [NV] */) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) scratch[warp * NV + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < ME_THREADS / 32; ++w) s += scratch[w * NV + threadIdx.x];
+        scratch[(ME_THREADS / 32) * NV + threadIdx.x] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = scratch[(ME_THREADS / 32) * NV + i];
+    __syncthreads();
+}
+
+// pred (B*N, P, 3), target (B, P, 3) -> out (B*N, 3) = [plain, SC, PA] mean point errors
+__global__ void __launch_bounds__(ME_THREADS)
+pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__ target, int N, int P, float* __restrict__ out) {
+    HF_PDL_SYNC();
+    __shared__ double scratch[(ME_THREADS / 32 + 1) * 18];
+    __shared__ float xf[16];                                   // SC: s, mu1, mu2;  PA: scale*R (9), t (3)
+    const int m = blockIdx.x, b = m / N;
+    const float* p = pred + (size_t)m * P * 3;
+    const float* t = target + (size_t)b * P * 3;
+    // pass 1: raw moments + the plain error
+    const float p0x = __ldg(p), p0y = __ldg(p + 1), p0z = __ldg(p + 2), t0x = __ldg(t), t0y = __ldg(t + 1), t0z = __ldg(t + 2);
+    double v[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) v[i] = 0.0;
+    {
+        float sp[3] = {0.f, 0.f, 0.f}, st[3] = {0.f, 0.f, 0.f}, spp = 0.f, stt = 0.f, k[9], e = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) k[i] = 0.f;
+        for (int i = threadIdx.x; i < P; i += ME_THREADS) {
+            // moments are taken about the first point of each set (shift invariance of the centred quantities): no
+            // cancellation when the sets sit far from the origin (camera-space meshes)
+            const float dx = __ldg(p + i * 3) - __ldg(t + i * 3), dy = __ldg(p + i * 3 + 1) - __ldg(t + i * 3 + 1),
+                        dz = __ldg(p + i * 3 + 2) - __ldg(t + i * 3 + 2);
+            const float px = __ldg(p + i * 3) - p0x, py = __ldg(p + i * 3 + 1) - p0y, pz = __ldg(p + i * 3 + 2) - p0z;
+            const float tx = __ldg(t + i * 3) - t0x, ty = __ldg(t + i * 3 + 1) - t0y, tz = __ldg(t + i * 3 + 2) - t0z;
+            sp[0] += px; sp[1] += py; sp[2] += pz;
+            st[0] += tx; st[1] += ty; st[2] += tz;
+            spp += px * px + py * py + pz * pz;
+            stt += tx * tx + ty * ty + tz * tz;
+            k[0] += px * tx; k[1] += px * ty; k[2] += px * tz;
+            k[3] += py * tx; k[4] += py * ty; k[5] += py * tz;
+            k[6] += pz * tx; k[7] += pz * ty; k[8] += pz * tz;
+            e += sqrtf(dx * dx + dy * dy + dz * dz);
+        }
+        for (int i = 0; i < 3; ++i) { v[i] = sp[i]; v[3 + i] = st[i]; }
+        v[6] = spp; v[7] = stt;
+        for (int i = 0; i < 9; ++i) v[8 + i] = k[i];
+        v[17] = e;
+    }
+    block_sum<18>(v, scratch);
+    if (threadIdx.x == 0) {
+        const double n = (double)P;
+        double mu1[3], mu2[3];
+        for (int i = 0; i < 3; ++i) { mu1[i] = v[i] / n; mu2[i] = v[3 + i] / n; }        // means of the SHIFTED sets
+        const double var1 = v[6] - n * (mu1[0] * mu1[0] + mu1[1] * mu1[1] + mu1[2] * mu1[2]);      // sum |p - mu1|^2
+        const double var2 = v[7] - n * (mu2[0] * mu2[0] + mu2[1] * mu2[1] + mu2[2] * mu2[2]);
+        const double o1[3] = {(double)p0x, (double)p0y, (double)p0z}, o2[3] = {(double)t0x, (double)t0y, (double)t0z};
+        // SC (eval_utils.py:105-125): (p - mu1) / sqrt(var1 / n) * sqrt(var2 / n) + mu2   (absolute means = shifted + origin)
+        xf[0] = (float)sqrt(var2 / var1);
+        for (int i = 0; i < 3; ++i) { xf[1 + i] = (float)(mu1[i] + o1[i]); xf[4 + i] = (float)(mu2[i] + o2[i]); }
+        // PA (eval_utils.py:62-102): K = X1 X2^T; R = V Z U^T for K = U S V^T = V diag(1/s1, 1/s2, d/s3) V^T K^T, d = sign det K
+        double K[3][3], KtK[3][3], V[3][3], w[3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) K[i][j] = v[8 + i * 3 + j] - n * mu1[i] * mu2[j];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) KtK[i][j] = K[0][i] * K[0][j] + K[1][i] * K[1][j] + K[2][i] * K[2][j];
+        eig_sym3(KtK, V, w);
+        int order[3] = {0, 1, 2};                                  // singular values in descending order, as numpy returns them
+        for (int a = 0; a < 2; ++a)
+            for (int c = a + 1; c < 3; ++c)
+                if (w[order[c]] > w[order[a]]) { const int tmp = order[a]; order[a] = order[c]; order[c] = tmp; }
+        const double detK = K[0][0] * (K[1][1] * K[2][2] - K[1][2] * K[2][1]) - K[0][1] * (K[1][0] * K[2][2] - K[1][2] * K[2][0]) +
+                            K[0][2] * (K[1][0] * K[2][1] - K[1][1] * K[2][0]);
+        const double d = detK < 0.0 ? -1.0 : 1.0;
+        double sv[3], g[3];
+        for (int a = 0; a < 3; ++a) sv[a] = sqrt(fmax(w[order[a]], 0.0));
+        const double tiny = 1e-30;
+        g[0] = 1.0 / fmax(sv[0], tiny); g[1] = 1.0 / fmax(sv[1], tiny); g[2] = d / fmax(sv[2], tiny);
+        double M[3][3];                                            // V diag(g) V^T
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0.0;
+                for (int a = 0; a < 3; ++a) s += V[i][order[a]] * g[a] * V[j][order[a]];
+                M[i][j] = s;
+            }
+        double R[3][3];                                            // M K^T
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) R[i][j] = M[i][0] * K[j][0] + M[i][1] * K[j][1] + M[i][2] * K[j][2];
+        const double scale = (sv[0] + sv[1] + d * sv[2]) / var1;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) xf[7 + i * 3 + j] = (float)(scale * R[i][j]);
+        }
+        // translation folded with the means in fp64: t = mu2 - scale R mu1
+        double tt[3];
+        for (int i = 0; i < 3; ++i)
+            tt[i] = (mu2[i] + o2[i]) - scale * (R[i][0] * (mu1[0] + o1[0]) + R[i][1] * (mu1[1] + o1[1]) + R[i][2] * (mu1[2] + o1[2]));
+        scratch[0] = tt[0]; scratch[1] = tt[1]; scratch[2] = tt[2];
+        scratch[3] = v[17] / n;
+    }
+    __syncthreads();
+    const float s_sc = xf[0];
+    const float m1x = xf[1], m1y = xf[2], m1z = xf[3], m2x = xf[4], m2y = xf[5], m2z = xf[6];
+    const float r0 = xf[7], r1 = xf[8], r2 = xf[9], r3 = xf[10], r4 = xf[11], r5 = xf[12], r6 = xf[13], r7 = xf[14], r8 = xf[15];
+    const float t0 = (float)scratch[0], t1 = (float)scratch[1], t2 = (float)scratch[2];
+    const double plain = scratch[3];
+    __syncthreads();
+    // pass 2: errors after the two alignments
+    double e2[2];
+    {
+        float esc = 0.f, epa = 0.f;
+        for (int i = threadIdx.x; i < P; i += ME_THREADS) {
+            const float px = __ldg(p + i * 3), py = __ldg(p + i * 3 + 1), pz = __ldg(p + i * 3 + 2);
+            const float tx = __ldg(t + i * 3), ty = __ldg(t + i * 3 + 1), tz = __ldg(t + i * 3 + 2);
+            float dx = (px - m1x) * s_sc + m2x - tx, dy = (py - m1y) * s_sc + m2y - ty, dz = (pz - m1z) * s_sc + m2z - tz;
+            esc += sqrtf(dx * dx + dy * dy + dz * dz);
+            dx = r0 * px + r1 * py + r2 * pz + t0 - tx;
+            dy = r3 * px + r4 * py + r5 * pz + t1 - ty;
+            dz = r6 * px + r7 * py + r8 * pz + t2 - tz;
+            epa += sqrtf(dx * dx + dy * dy + dz * dz);
+        }
+        e2[0] = esc; e2[1] = epa;
+    }
+    block_sum<2>(e2, scratch);
+    if (threadIdx.x == 0) {
+        out[(size_t)m * 3 + 0] = (float)plain;
+        out[(size_t)m * 3 + 1] = (float)(e2[0] / (double)P);
+        out[(size_t)m * 3 + 2] = (float)(e2[1] / (double)P);
+    }
+}
+
+}  // namespace
+
+extern "C" int hf_pointset_errors(const float* pred, const float* target, int B, int N, int P, float* out, void* stream) {
+    if (!pred || !target || !out) return hf::fail(HF_ERR_INVALID, "hf_pointset_errors: null argument");
+    if (B <= 0 || N <= 0) return HF_OK;
+    if (P < 3) return hf::fail(HF_ERR_INVALID, "hf_pointset_errors: at least 3 points per set are needed (got %d)", P);
+    HF_CUDA(hf::launch_pdl(pointset_errors_kernel, dim3(B * N), dim3(ME_THREADS), 0, (cudaStream_t)stream, pred, target, N, P, out));
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}

@@ -1,0 +1,38 @@
+"""On-device 3-D error metrics of the evaluation path.
+
+`pointset_errors` returns, per predicted point set, the mean point error against its image's target, plain and after the
+reference's two alignments (utils/eval_utils.py:105-125 scale + translation, :62-102 Procrustes).  Everything
+metrics/eval_metrics_tracker.py:119-280 accumulates for PVE / PVE-SC / PVE-PA / PVE-T(-SC) / MPJPE(-SC/-PA) and the
+"samples_min" variants is a sum or a minimum of these values; `samples_min` is that minimum.  No CPU fallback.
+"""
+import torch
+
+from . import _lib
+
+
+def pointset_errors(pred, target):
+    """pred (B,N,P,3) or (B,P,3) CUDA fp32; target (B,P,3) -> dict of (B,N) (or (B,)) tensors 'plain', 'sc', 'pa':
+    mean over the P points of ||pred - target|| without alignment, after scale-and-translation correction and after
+    Procrustes alignment."""
+    _lib.require_cuda('pointset_errors')
+    if not pred.is_cuda:
+        raise RuntimeError('humaniflow_b200.metrics: inputs must be CUDA tensors (no CPU fallback)')
+    p = _lib.f32c(pred)
+    t = _lib.f32c(target).to(p.device)
+    squeeze = p.dim() == 3
+    if squeeze:
+        p = p[:, None]
+    B, N, P, _ = p.shape
+    if t.shape != (B, P, 3):
+        raise ValueError('target shape %s does not match predictions %s' % (tuple(t.shape), tuple(p.shape)))
+    out = torch.empty(B, N, 3, device=p.device, dtype=torch.float32)
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.load().hf_pointset_errors(_lib.ptr(p), _lib.ptr(t), B, N, P, _lib.ptr(out), _lib.stream()))
+    res = {'plain': out[..., 0], 'sc': out[..., 1], 'pa': out[..., 2]}
+    return {k: v[:, 0] for k, v in res.items()} if squeeze else res
+
+
+def samples_min(per_sample_errors):
+    """(B,N) per-sample mean errors -> (B,) error of the best sample of every image
+    (eval_metrics_tracker.py:201-280: argmin over the samples of the mean error)."""
+    return per_sample_errors.min(dim=1).values

@@ -90,6 +90,15 @@ int hf_vertex_variance(const float* vertices, int B, int N, int V, float* avg_di
 int hf_project_joints2d(const float* joints, const float* cam_wp, const int* joint_ids, int M, int per_cam, int J_in,
                         int n_ids, int flip_x, float img_wh, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Per-sample 3-D error metrics of the evaluation path.
+ * pred (B*N, P, 3) point sets (sampled meshes or joint sets), target (B, P, 3), out (B*N, 3) =
+ * [mean_i ||p_i - t_i||, the same after scale_and_translation_transform_batch, the same after procrustes_analysis_batch].
+ * Replaces utils/eval_utils.py:62-125 + the norm / mean reductions of metrics/eval_metrics_tracker.py:119-280
+ * (PVE, PVE-SC, PVE-PA, PVE-T(-SC), MPJPE(-SC/-PA) and their samples_min forms are sums / minima of these values).
+ * ---------------------------------------------------------------------------------------------- */
+int hf_pointset_errors(const float* pred, const float* target, int B, int N, int P, float* out, void* stream);
+
 /* fp32 axis-angle -> rotation matrices, n rows.  Replaces smplx `lbs.batch_rodrigues`
  * (used by SMPL.forward when pose2rot=True and at models/humaniflow_model.py:299). */
 int hf_rodrigues(const float* axis_angle, float* rotmats, int n, void* stream);

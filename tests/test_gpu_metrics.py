@@ -1,0 +1,61 @@
+"""3-D error metrics: CUDA path through the C-ABI vs the oracle and the golden vectors of the real
+utils/eval_utils.py.  Tolerance 1e-5 relative + 1e-6 m absolute (the reference runs numpy fp32 incl. an fp32 SVD; the
+kernel accumulates moments in fp32 per thread / fp64 across the block and solves the 3x3 problem in fp64)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as omet
+from util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.all(np.abs(a - b) <= 1e-5 * np.abs(b) + 1e-6)
+
+
+def test_golden():
+    from humaniflow_b200.metrics import pointset_errors, samples_min
+    g = np.load(os.path.join(GOLDEN, 'metrics_golden.npz'))
+    e = pointset_errors(torch.tensor(g['pred']).cuda(), torch.tensor(g['target']).cuda())
+    for k in ('plain', 'sc', 'pa'):
+        assert e[k].shape == (3, 4) and _close(e[k].cpu().numpy(), g[k]), (k, e[k].cpu().numpy(), g[k])
+    assert _close(samples_min(e['pa']).cpu().numpy(), g['pa'].min(1))
+    one = pointset_errors(torch.tensor(g['pred'][:, 0]).cuda(), torch.tensor(g['target']).cuda())       # point-estimate form (B,P,3)
+    assert one['sc'].shape == (3,) and _close(one['sc'].cpu().numpy(), g['sc'][:, 0])
+
+
+@pytest.mark.parametrize('B,N,P', [(2, 3, 14), (1, 1, 17), (4, 25, 6890), (32, 100, 6890)])
+def test_against_oracle(B, N, P):
+    """Joint sets (MPJPE family), meshes, and the full BASELINE size (spot-checked images)."""
+    from humaniflow_b200.metrics import pointset_errors
+    g = torch.Generator().manual_seed(B * 100 + N)
+    target = torch.randn(B, P, 3, generator=g) * 0.3 + torch.tensor([0.1, -0.2, 2.5])
+    pred = target[:, None] * (1 + 0.1 * torch.randn(B, N, 1, 1, generator=g)) + 0.05 * torch.randn(B, N, P, 3, generator=g) \
+        + 0.1 * torch.randn(B, N, 1, 3, generator=g)
+    e = pointset_errors(pred.cuda(), target.cuda())
+    rows = list(range(B)) if B <= 4 else [0, 13, 31]
+    ref = omet.pointset_errors(pred[rows].numpy(), target[rows].numpy())
+    for k in ('plain', 'sc', 'pa'):
+        assert _close(e[k][rows].cpu().numpy(), ref[k]), k
+
+
+def test_exact_similarity_is_zero_after_procrustes():
+    from humaniflow_b200.metrics import pointset_errors
+    g = torch.Generator().manual_seed(5)
+    target = torch.randn(2, 300, 3, generator=g)
+    from oracle import so3
+    R = so3.batch_rodrigues(torch.tensor([[0.3, -1.2, 0.4], [2.0, 0.1, -0.5]])).float()
+    pred = 1.7 * torch.einsum('bij,bpj->bpi', R, target) + torch.tensor([0.5, -1.0, 2.0])
+    e = pointset_errors(pred.cuda(), target.cuda())
+    assert e['pa'].abs().max().item() <= 2e-6 and e['plain'].min().item() > 0.5
+
+
+def test_no_cpu_fallback():
+    from humaniflow_b200.metrics import pointset_errors
+    with pytest.raises(RuntimeError):
+        pointset_errors(torch.zeros(1, 2, 5, 3), torch.zeros(1, 5, 3))

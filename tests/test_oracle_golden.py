@@ -117,3 +117,12 @@ def test_sampling_helpers(golden_dir):
     assert torch.equal(osamp.project_joints2d(g['joints'], g['cam'], flip_x=False, img_wh=256), g['pix'])
     flipped = osamp.project_joints2d(g['joints'], g['cam'], flip_x=True)
     assert torch.equal(flipped[..., 0], g['proj'][..., 0])      # rotation by pi about x leaves x alone, negates y
+
+
+def test_metrics(golden_dir):
+    """oracle/metrics.py against the real utils/eval_utils.py outputs (incl. a mirrored and a near-planar prediction)."""
+    from oracle import metrics as omet
+    g = np.load(os.path.join(golden_dir, 'metrics_golden.npz'))
+    e = omet.pointset_errors(g['pred'], g['target'])
+    for k in ('plain', 'sc', 'pa'):
+        assert np.array_equal(e[k], g[k]), k
