@@ -43,6 +43,7 @@ SIGNATURES = {
     'hf_smpl_dims': (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 5),
     'hf_vertex_variance': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'hf_pointset_errors': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'hf_proxy_rep': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_float, c_int, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'hf_project_joints2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float, c_void_p, c_void_p]),
     'hf_flow_create': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(FlowConfig)] + [c_void_p] * 7),
     'hf_flow_destroy': (None, [c_void_p]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libhumaniflow_b200.so')
-SOURCES = ['api.cu', 'lbs.cu', 'sampling.cu', 'metrics.cu', 'flow.cu', 'heads.cu', 'encoder.cu']
+SOURCES = ['api.cu', 'lbs.cu', 'sampling.cu', 'metrics.cu', 'proxy_rep.cu', 'flow.cu', 'heads.cu', 'encoder.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
 

@@ -99,6 +99,17 @@ int hf_project_joints2d(const float* joints, const float* cam_wp, const int* joi
  * ---------------------------------------------------------------------------------------------- */
 int hf_pointset_errors(const float* pred, const float* target, int B, int N, int P, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input proxy representation: rgb (B,C,H,W) fp32 + joints2D (B,J,2) = (column, row) pixel
+ * coordinates [+ joints_vis (B,J) or NULL] -> out (B,1+J,H,W): channel 0 = edge map, channels 1..J = Gaussian heatmaps.
+ * Replaces models/canny_edge_detector.py:104-166 (gauss5 = the five normalised Gaussian taps, threshold, nms = EDGE_NMS)
+ * and utils/label_conversions.py:106-125 times the visibility flags (predict_humaniflow.py:96-110).
+ * dbg_mag / dbg_ori: optional (B,H,W) outputs of the gradient magnitude / binned orientation (tests), else NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int hf_proxy_rep(const float* rgb, const float* joints2D, const float* joints_vis, int B, int C, int H, int W, int J,
+                 const float* gauss5, float threshold, int nms, float heat_std, float* out, float* dbg_mag, float* dbg_ori,
+                 void* stream);
+
 /* fp32 axis-angle -> rotation matrices, n rows.  Replaces smplx `lbs.batch_rodrigues`
  * (used by SMPL.forward when pose2rot=True and at models/humaniflow_model.py:299). */
 int hf_rodrigues(const float* axis_angle, float* rotmats, int n, void* stream);

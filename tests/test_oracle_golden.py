@@ -126,3 +126,16 @@ def test_metrics(golden_dir):
     e = omet.pointset_errors(g['pred'], g['target'])
     for k in ('plain', 'sc', 'pa'):
         assert np.array_equal(e[k], g[k]), k
+
+
+def test_proxy_representation(golden_dir):
+    """oracle/proxy_rep.py against the real models/canny_edge_detector.py and utils/label_conversions.py outputs."""
+    from oracle import proxy_rep as opr
+    g = np.load(os.path.join(golden_dir, 'proxy_golden.npz'))
+    img = torch.tensor(g['img'])
+    for thr, nms in ((0.0, True), (0.2, True), (0.1, False)):
+        r = opr.canny(img, threshold=thr, nms=nms)
+        key = 'thresholded_thin_edges' if nms else 'thresholded_grad_magnitude'
+        assert torch.equal(r[key], torch.tensor(g['edge_%g_%d' % (thr, int(nms))])), (thr, nms)
+    assert torch.equal(r['grad_magnitude'], torch.tensor(g['mag'])) and torch.equal(r['grad_orientation'], torch.tensor(g['ori']))
+    assert torch.equal(opr.heatmaps(torch.tensor(g['j2d']), img.shape[-1]), torch.tensor(g['heat']))
