@@ -377,6 +377,40 @@ def run_ours(args):
         s_main.wait_stream(s_out)
         s_main.wait_stream(s_in)
 
+    # image-to-metrics end to end (SURVEY 8f N4 + N1 around the hot path): the host sends the RGB crops and 2-D joints, the
+    # proxy representation is built on the device (hf_proxy_rep), and only the per-image metric rows come back
+    from humaniflow_b200.proxy_rep import build_proxy_representation
+    rgb_host = torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+    j2d_host = (torch.rand(B, 17, 2, generator=torch.Generator().manual_seed(8 + rank)) * 256).pin_memory()
+    rgb_stage = [torch.empty(B, 3, 256, 256, device=dev) for _ in range(2)]
+    j2d_stage = [torch.empty(B, 17, 2, device=dev) for _ in range(2)]
+
+    def rgb_steps(n):
+        for b in range(2):
+            ev_used[b].record(s_main)
+            ev_rows[b].record(s_out)
+        for i in range(n):
+            b = i & 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_used[b])
+                rgb_stage[b].copy_(rgb_host, non_blocking=True)
+                j2d_stage[b].copy_(j2d_host, non_blocking=True)
+                ev_in[b].record(s_in)
+            s_main.wait_event(ev_in[b])
+            s_main.wait_event(ev_rows[b])
+            so, metric = step(build_proxy_representation(rgb_stage[b], j2d_stage[b]), outs=out_dev[b])
+            err = pointset_errors(so.vertices.view(B, N, V, 3), tgt)
+            rows = torch.stack([samples_min(err['plain']), samples_min(err['sc']), samples_min(err['pa']), err['plain'].mean(1)], 1)
+            ev_used[b].record(s_main)
+            ev_done[b].record(s_main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[b])
+                rows_host[b].copy_(rows, non_blocking=True)
+                ev_rows[b].record(s_out)
+            keep[b] = (so, rows)
+        s_main.wait_stream(s_out)
+        s_main.wait_stream(s_in)
+
     # PCIe sanity numbers for the e2e line (plain pinned copies of the same buffers, not part of any timed region)
     def copy_gbs(dst, src, iters=3):
         dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
@@ -411,6 +445,17 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     eval_ms = t.item() / args.steps
+    rgb_steps(5)
+    sync_all()
+    a3, b3 = ev(), ev()
+    a3.record()
+    rgb_steps(args.steps)
+    b3.record()
+    sync_all()
+    t = torch.tensor([a3.elapsed_time(b3)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    rgb_ms = t.item() / args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     line = None
@@ -426,6 +471,10 @@ def run_ours(args):
                              'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': rows_host[0].numel() * 4,
                              'what': 'same step + per-sample PVE / PVE-SC / PVE-PA against one target mesh per image reduced on the '
                                      'device (hf_pointset_errors); only the (B,4) per-image rows are copied back'},
+            'e2e_from_rgb': {'value': world * B * N / (rgb_ms * 1e-3), 'unit': UNIT, 'ms_per_step': rgb_ms,
+                             'h2d_bytes_per_step': (rgb_host.numel() + j2d_host.numel()) * 4, 'd2h_bytes_per_step': rows_host[0].numel() * 4,
+                             'what': 'RGB crops + 2-D joints from the host -> proxy representation on the device (hf_proxy_rep) -> the '
+                                     'step -> on-device PVE / PVE-SC / PVE-PA rows back to the host'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'stages': stages,
             'step_breakdown_ms': {'model_forward': ms_model, 'lbs': ms_lbs},
         }
