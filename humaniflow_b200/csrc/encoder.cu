@@ -50,7 +50,8 @@ __device__ __forceinline__ void conv_stamp(int dbg, int slot) {
     }
 }
 
-constexpr int CONV_THREADS = 352;   // warp 0 operand TMA, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue, warp 10 residual TMA
+constexpr int CONV_THREADS = 416;   // warp 0 operand TMA, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue, warp 10 residual TMA,
+                                    // warps 11 / 12: second operand-TMA / MMA issuer (odd k-blocks)
 
 // Persistent implicit-GEMM convolution: one CTA per SM walks the output tiles (n-tile fastest, so the activation
 // tile stays hot in L2 across the Cout tiles).  Every byte that crosses the SM boundary moves by TMA:
@@ -77,7 +78,17 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
     const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     if (threadIdx.x == 0) conv_stamp(dbg, 0);                       // kernel entry
     constexpr int SBUF_BYTES = 128 * BN * 2;     // staging tile: BN/64 boxes of [128 rows][128 B], swizzled
-    constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
+    // DUAL: two producer warps (0, 11) and two MMA issuers (1, 12) take alternate k-blocks; the issuers accumulate into
+    // SEPARATE TMEM accumulators that the epilogue adds.  Each single-thread role spends ~700 cycles per k-block on the issue
+    // latencies of its barrier / TMA / MMA / commit instructions against 256 cycles of tensor-pipe work; two
+    // interleaved instances of each role halve that.  Needs 2 x 2 x BN TMEM columns (BN <= 128) and at least two k-blocks.
+    // The split is by the parity of the GLOBAL k-block counter and the ring has an even number of slots, so every slot (and
+    // its two mbarriers) is always handled by the same producer and the same issuer: an mbarrier wait only tells phases
+    // apart by parity, which is safe only for a waiter that has observed every earlier phase of that barrier.
+    constexpr bool DUAL_OK = !PAIR && BN <= 128 && (STAGES % 2 == 0);
+    constexpr int NACC = DUAL_OK ? 2 : 1;
+    constexpr uint32_t TMEM_COLS = (2 * NACC * BN <= 128) ? 128 : ((2 * NACC * BN <= 256) ? 256 : 512);
+    const bool dual = DUAL_OK && g.nkb >= 2 && !(dbg & 16);
     constexpr int HALF = BN / 2;                 // columns per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 4 + 2 * SR];
@@ -91,7 +102,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
     const uint32_t rfull0 = smem_u32(&bars[2 * STAGES + 4]), sfree0 = smem_u32(&bars[2 * STAGES + 4 + SR]);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, PAIR ? 16 : 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, dual ? 2 : 1); mbar_init(tempty0 + 8 * b, PAIR ? 16 : 8); }
         for (int b = 0; b < SR; ++b) { mbar_init(rfull0 + 8 * b, 1); mbar_init(sfree0 + 8 * b, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -118,32 +129,36 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
     }
     if (threadIdx.x == 0) conv_stamp(dbg, 2);                       // dependency wait over
 
-    if (warp == 0) {
-        {   // the WHOLE warp walks the loop (converged waits; a lone lane of a diverged warp pays for every YIELD of its
-            // polling loop with a switch to the parked lanes); lane 0 alone issues the barrier arrive and the TMA loads
-            // loop on the critical path of every k-block: all index arithmetic is incremental (no integer divisions)
+    if (warp == 0 || warp == 11) {
+        const int t = warp == 0 ? 0 : 1;                             // producer id = parity of the k-blocks it loads
+        if ((t == 0 || dual) && lane == 0) {
+            // ONE thread walks the loop: an mbarrier parity wait is only safe for a waiter that goes on to the next use of
+            // the barrier itself (31 more lanes polling would race with the phases lane 0 starts), and a lane-0 poll with the
+            // other lanes parked at a warp barrier inside the loop measured 2x slower than leaving them out altogether
             const int cpb = g.cin >> 6;   // 64-channel blocks per tap (generic)
             const uint32_t full_lead = PAIR ? mapa_rank(full0, 0) : full0;   // pair: both CTAs' loads complete on the leader's barrier
             const uint32_t my_bytes = ((dbg & 2) ? 0u : (uint32_t)A_BYTES) + ((dbg & 4) ? 0u : (uint32_t)B_BYTES);
             const uint32_t tx_bytes = PAIR ? 2 * my_bytes : my_bytes;
-            const int kind = g.kind, ksize = g.ksize, pad = g.pad, stride = g.stride, nkb = g.nkb;
-            uint32_t st = 0, ph = 0;
+            const int kind = g.kind, ksize = g.ksize, pad = g.pad, stride = g.stride, nkb = g.nkb, kstep = dual ? 2 : 1;
+            uint32_t base = 0;                                        // k-blocks of all previous tiles (ring position)
             int nt = cta % ntn, mt = cta / ntn;                      // tile = mt * ntn + nt, advanced by nworkers per step
             const int step_nt = nworkers % ntn, step_mt = nworkers / ntn;
             for (int tile = cta; tile < num_tiles; tile += nworkers) {
-                int t = PAIR ? 2 * mt + (int)rank : mt;              // this CTA's M-tile (past the end: all-zero boxes)
-                const int tw = t % g.tiles_w; t /= g.tiles_w;
-                const int th = t % g.tiles_h;
-                const int tb = t / g.tiles_h;
+                int tt = PAIR ? 2 * mt + (int)rank : mt;             // this CTA's M-tile (past the end: all-zero boxes)
+                const int tw = tt % g.tiles_w; tt /= g.tiles_w;
+                const int th = tt % g.tiles_h;
+                const int tb = tt / g.tiles_h;
                 const int wo0 = tw * g.TW, ho0 = th * g.TH, b0 = tb * g.TB, n0 = nt * BN + (int)rank * BROWS;
-                int cb = 0, kw = 0, kh = 0;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = dual ? (int)((base ^ (uint32_t)t) & 1u) : 0; kb < nkb; kb += kstep) {
+                    const uint32_t kbc = base + (uint32_t)kb, st = kbc % STAGES, ph = (kbc / STAGES) & 1u;
                     mbar_wait(empty0 + 8 * st, ph ^ 1u);
                     const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
                     const uint32_t fb = full_lead + 8 * st;
-                    if (leader && lane == 0) mbar_expect_tx(full0 + 8 * st, tx_bytes);
+                    if (leader) mbar_expect_tx(full0 + 8 * st, tx_bytes);
                     int mi, c0, c1, c2;
                     if (kind == 0) {            // (kh, kw) = filter tap, cb = 64-channel block within the tap
+                        const int tap = kb / cpb, cb = kb - tap * cpb;
+                        const int kh = tap / ksize, kw = tap - kh * ksize;
                         const int dw = kw - pad, dh = kh - pad;
                         c0 = cb * 64;
                         if (stride == 1) { mi = 0; c1 = wo0 + dw; c2 = ho0 + dh; }
@@ -153,63 +168,57 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                             c1 = wo0 + ((dw - pw) >> 1);
                             c2 = ho0 + ((dh - phh) >> 1);
                         }
-                        if (++cb == cpb) { cb = 0; if (++kw == ksize) { kw = 0; ++kh; } }
                     } else if (kind == 1) {
                         const int kh1 = kb >> 2, q = kb & 3;
                         mi = kh1 & 1; c0 = 0; c1 = wo0 + q; c2 = ho0 + (kh1 >> 1);
-                    } else {   // compact stem: 8 taps x 24 ch = 192 contiguous elements per (pixel, kh), 3 k-blocks (cb counts them)
+                    } else {   // compact stem: 8 taps x 24 ch = 192 contiguous elements per (pixel, kh), 3 k-blocks
+                        const int kh = kb / 3, cb = kb - kh * 3;
                         mi = kh & 1; c0 = cb * 64; c1 = wo0; c2 = ho0 + (kh >> 1);
-                        if (++cb == 3) { cb = 0; ++kh; }
                     }
-                    if (lane == 0) {
-                        if (PAIR) {
-                            if (!(dbg & 2)) tma_load_4d_2cta(sa, &maps.a[mi], fb, c0, c1, c2, b0);
-                            if (!(dbg & 4)) tma_load_2d_2cta(sb, &maps.b, fb, kb * 64, n0);
-                        } else {
-                            if (!(dbg & 2)) tma_load_4d(sa, &maps.a[mi], fb, c0, c1, c2, b0);
-                            if (!(dbg & 4)) tma_load_2d(sb, &maps.b, fb, kb * 64, n0);
-                        }
+                    if (PAIR) {
+                        if (!(dbg & 2)) tma_load_4d_2cta(sa, &maps.a[mi], fb, c0, c1, c2, b0);
+                        if (!(dbg & 4)) tma_load_2d_2cta(sb, &maps.b, fb, kb * 64, n0);
+                    } else {
+                        if (!(dbg & 2)) tma_load_4d(sa, &maps.a[mi], fb, c0, c1, c2, b0);
+                        if (!(dbg & 4)) tma_load_2d(sb, &maps.b, fb, kb * 64, n0);
                     }
-                    __syncwarp();
-                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
+                base += (uint32_t)nkb;
                 nt += step_nt; mt += step_mt;
                 if (nt >= ntn) { nt -= ntn; ++mt; }
             }
         }
-    } else if (warp == 1) {
-        if (leader) {           // whole warp converged on the waits, lane 0 issues the MMAs and commits
+    } else if (warp == 1 || warp == 12) {
+        const int t = warp == 1 ? 0 : 1;                             // issuer id = parity of the k-blocks it takes
+        if (leader && (t == 0 || dual) && lane == 0) {              // one thread (see the producer)
             const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN);
-            uint32_t lt = 0, st = 0, ph = 0;
-            const int nkb = g.nkb;
+            const int nkb = g.nkb, kstep = dual ? 2 : 1;
+            uint32_t lt = 0, base = 0;                               // base = k-blocks of all previous tiles (ring position)
             for (int tile = cta; tile < num_tiles; tile += nworkers, ++lt) {
                 const uint32_t buf = lt & 1u;
                 mbar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
-                const uint32_t d = tmem_base + buf * BN;
-                for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t d = tmem_base + (buf * NACC + (uint32_t)t) * BN;
+                const int kb0 = dual ? (int)((base ^ (uint32_t)t) & 1u) : 0;     // this issuer's first k-block of the tile
+                for (int kb = kb0; kb < nkb; kb += kstep) {
+                    const uint32_t kbc = base + (uint32_t)kb, st = kbc % STAGES, ph = (kbc / STAGES) & 1u;
                     mbar_wait(full0 + 8 * st, ph);
                     tcgen05_fence_after();
-                    if (lt == 0 && kb == 0 && lane == 0) conv_stamp(dbg, 3);     // first operand stage landed
+                    if (lt == 0 && kb == 0) conv_stamp(dbg, 3);                  // first operand stage landed
                     const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
-                    if (lane == 0) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (dbg & 1) continue;
-                        if (PAIR) umma_bf16_2cta(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-                        else umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        const uint32_t acc = (uint32_t)((kb > kb0) | (k != 0));        // this issuer's first MMA of the tile overwrites
+                        if (PAIR) umma_bf16_2cta(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                        else umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
                     }
                     if (PAIR) umma_commit_2cta(empty0 + 8 * st); else umma_commit(empty0 + 8 * st);
-                    }
-                    __syncwarp();
-                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
-                if (lane == 0) {
-                    if (PAIR) umma_commit_2cta(tfull0 + 8 * buf); else umma_commit(tfull0 + 8 * buf);
-                    if (lt == 0) conv_stamp(dbg, 4);                // all MMAs of the first tile issued
-                }
-                __syncwarp();
+                if (PAIR) umma_commit_2cta(tfull0 + 8 * buf); else umma_commit(tfull0 + 8 * buf);
+                if (lt == 0 && t == 0) conv_stamp(dbg, 4);          // all MMAs of the first tile issued
+                base += (uint32_t)nkb;
             }
         }
     } else if (warp == 10) {
@@ -254,13 +263,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
             mbar_wait_warp(tfull0 + 8 * buf, par);            // accumulator complete
             tcgen05_fence_after();
             if (lt == 0 && threadIdx.x == 64) conv_stamp(dbg, 5);   // first accumulator complete
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(colhalf * HALF);
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (NACC * BN) + (uint32_t)(colhalf * HALF);
             uint8_t* srow = sbuf_ptr + sb * SBUF_BYTES + row * 128;
             // 32-column chunks, double-buffered in registers: the TMEM load of chunk c+1 is in flight while chunk c is
             // converted (tcgen05.wait::ld waits for every outstanding load, so the next one is issued right after it)
             constexpr int NCH = HALF / 32;
             uint32_t v[2][32];
-            tmem_ld32(trow, v[0]);
+            if (!dual) tmem_ld32(trow, v[0]);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int col = colhalf * HALF + ch * 32;                  // first column (within the BN tile) of this chunk
@@ -275,8 +284,16 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
 #pragma unroll
                     for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(sbox + (((j0 + i) ^ (row & 7)) << 4));
                 }
-                tmem_ld_wait();
-                if (ch + 1 < NCH) tmem_ld32(trow + (uint32_t)((ch + 1) * 32), v[(ch + 1) & 1]);
+                if (dual) {          // the two issuers' partial sums (even / odd k-blocks) are added here
+                    tmem_ld32(trow + (uint32_t)(ch * 32), v[ch & 1]);
+                    tmem_ld32(trow + (uint32_t)(BN + ch * 32), v[(ch & 1) ^ 1]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[ch & 1][i] = __float_as_uint(__uint_as_float(v[ch & 1][i]) + __uint_as_float(v[(ch & 1) ^ 1][i]));
+                } else {
+                    tmem_ld_wait();
+                    if (ch + 1 < NCH) tmem_ld32(trow + (uint32_t)((ch + 1) * 32), v[(ch + 1) & 1]);
+                }
                 const uint32_t* vv = v[ch & 1];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {                              // one 16-byte piece = 8 channels
@@ -581,6 +598,8 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
         else if (p->bn == 128) { p->stages = p->has_res ? 4 : 5; p->sr = p->has_res ? 3 : 2; }
         else                   { p->stages = p->has_res ? 6 : 7; p->sr = p->has_res ? 4 : 2; }
     } else {
+        // layers without residual: even ring -> dual producers / issuers; residual layers (short K, epilogue-bound) keep the
+        // deeper residual prefetch (three / four staging tiles) and an odd ring, i.e. one producer and one issuer
         if (p->bn == 256)      { p->stages = 3; p->sr = 1; }
         else if (p->bn == 128) { p->stages = p->has_res ? 3 : 4; p->sr = p->has_res ? 3 : 2; }
         else                   { p->stages = p->has_res ? 5 : 6; p->sr = p->has_res ? 4 : 2; }

@@ -35,7 +35,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (;;) {
         if (mbar_try_wait(bar, parity)) return;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+#ifdef HF_DEBUG_BARRIERS
+        if (t1 - t0 > 2000000000ull) {              // 2 s: report who is stuck, then abort the launch (debug builds only:
+            // a device printf in this inlined wait costs a stack frame and ~2x in every tensor-core kernel)
+            printf("humaniflow_b200: mbarrier wait timed out: block %d warp %d barrier smem 0x%x parity %u\n", (int)blockIdx.x,
+                   (int)(threadIdx.x >> 5), bar, parity);
+            __trap();
+        }
+#else
         if (t1 - t0 > 2000000000ull) __trap();     // 2 s
+#endif
     }
 }
 // Warp-collective wait: ONE lane polls, the other 31 sleep at the warp barrier and then observe the completed phase with

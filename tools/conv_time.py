@@ -18,6 +18,11 @@ SHAPES = {   # name: B, H, W, Cin, Cout, k, stride, pad, res
     'l3c2': (32, 16, 16, 256, 256, 3, 1, 1, 0),
     'l3c3': (32, 16, 16, 256, 1024, 1, 1, 0, 1),
     'l4c2': (32, 8, 8, 512, 512, 3, 1, 1, 0),
+    'e64': (32, 64, 64, 128, 64, 3, 1, 1, 0),         # BN=64, even k-block count, many tiles per CTA
+    'so64': (2, 32, 32, 64, 64, 3, 1, 1, 0),          # BN=64, odd k-block count, one tile per CTA
+    'se64': (2, 32, 32, 128, 64, 3, 1, 1, 0),
+    'o128': (32, 32, 32, 64, 128, 3, 1, 1, 0),        # BN=128, odd k-block count (9), two tiles per CTA
+    'l1c1': (32, 64, 64, 256, 64, 1, 1, 0, 0),
 }
 names = sys.argv[1:] or list(SHAPES)
 for name in names:

@@ -2,7 +2,8 @@
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 timeout 900 python -m pytest tests/test_gpu_encoder.py -q -x --timeout 600 > gpurun_out/t_enc.log 2>&1; echo "enc tests rc=$?"
-tail -n 3 gpurun_out/t_enc.log
+tail -n 5 gpurun_out/t_enc.log
+bash tools/gpu_pdl.sh 2>&1 | tail -7
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
 python - <<'PY'
 import json
