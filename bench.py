@@ -298,8 +298,8 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
     if dom == 'encoder' and args.layers == 50 and B == 32 and os.path.exists(tpath):
-        traffic = json.load(open(tpath))['dram_bytes_per_step']     # ncu dram bytes of the 53 conv launches of one forward
-    roofline = {'kernel': 'conv_tcgen05_kernel (ResNet-%d trunk, 53 launches per step)' % args.layers if dom == 'encoder' else 'lbs_skin_tc_kernel (+ pose / coefficient / extra-joint kernels)',
+        traffic = json.load(open(tpath))['dram_bytes_per_step']     # ncu dram bytes of the 49 conv launches of one forward
+    roofline = {'kernel': 'conv_tcgen05_kernel (ResNet-%d trunk, 49 launches per step)' % args.layers if dom == 'encoder' else 'lbs_skin_tc2_kernel (+ pose / extra-joint kernels)',
                 'bound': stages[dom]['bound'], 'achieved': stages[dom]['achieved'], 'peak': stages[dom]['peak'],
                 'unit': stages[dom]['unit'], 'frac': stages[dom]['frac'], 'traffic': traffic,
                 'peak_source': pk['source'] + (' (sustained bf16)' if dom == 'encoder' else ' (copy bandwidth)')}

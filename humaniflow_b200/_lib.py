@@ -22,7 +22,11 @@ class FlowConfig(ctypes.Structure):
 
 class EncOp(ctypes.Structure):
     _fields_ = [('kind', c_int), ('src', c_int), ('dst', c_int), ('res', c_int), ('cin', c_int), ('cout', c_int),
-                ('ksize', c_int), ('stride', c_int), ('pad', c_int), ('relu', c_int), ('weight_index', c_int)]
+                ('ksize', c_int), ('stride', c_int), ('pad', c_int), ('relu', c_int), ('weight_index', c_int),
+                ('src2', c_int), ('cin2', c_int), ('stride2', c_int)]
+
+    def __init__(self, kind, src, dst, res, cin, cout, ksize, stride, pad, relu, weight_index, src2=-1, cin2=0, stride2=1):
+        super().__init__(kind, src, dst, res, cin, cout, ksize, stride, pad, relu, weight_index, src2, cin2, stride2)
 
 
 OP_CONV, OP_MAXPOOL, OP_AVGPOOL = 0, 1, 2

@@ -29,12 +29,14 @@ struct ConvGeom {
     int Ho, Wo, B, cout;
     int TW, TH, TB;  // output tile (TW*TH*TB == 128)
     int tiles_w, tiles_h, tiles_b;
-    int nkb;         // number of 64-wide k-blocks
+    int nkb;         // number of 64-wide k-blocks (primary convolution + fused 1x1 branch)
+    int nkb1;        // k-blocks of the primary convolution; k-blocks >= nkb1 read the second input (1x1, own stride)
     int relu;
 };
 
 struct ConvMaps {
     CUtensorMap a[4];   // activation maps (stride 1: [0]; stride 2: [ph*2+pw]; stem: [ph])
+    CUtensorMap a2;     // second input of a fused op (the block's 1x1 downsample branch): strided 1x1 view of its NHWC tensor
     CUtensorMap b;      // weights [Cout][K]
     CUtensorMap o;      // output (B,Ho,Wo,Cout), box {64, TW, TH, TB}
     CUtensorMap r;      // residual, same shape as the output
@@ -156,6 +158,10 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                     const uint32_t fb = full_lead + 8 * st;
                     if (leader) mbar_expect_tx(full0 + 8 * st, tx_bytes);
                     int mi, c0, c1, c2;
+                    const CUtensorMap* amap;
+                    if (kb >= g.nkb1) {         // fused 1x1 branch: channel block of the second input at the output pixel
+                        mi = -1; c0 = (kb - g.nkb1) * 64; c1 = wo0; c2 = ho0;
+                    } else
                     if (kind == 0) {            // (kh, kw) = filter tap, cb = 64-channel block within the tap
                         const int tap = kb / cpb, cb = kb - tap * cpb;
                         const int kh = tap / ksize, kw = tap - kh * ksize;
@@ -175,11 +181,12 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                         const int kh = kb / 3, cb = kb - kh * 3;
                         mi = kh & 1; c0 = cb * 64; c1 = wo0; c2 = ho0 + (kh >> 1);
                     }
+                    amap = mi < 0 ? &maps.a2 : &maps.a[mi];
                     if (PAIR) {
-                        if (!(dbg & 2)) tma_load_4d_2cta(sa, &maps.a[mi], fb, c0, c1, c2, b0);
+                        if (!(dbg & 2)) tma_load_4d_2cta(sa, amap, fb, c0, c1, c2, b0);
                         if (!(dbg & 4)) tma_load_2d_2cta(sb, &maps.b, fb, kb * 64, n0);
                     } else {
-                        if (!(dbg & 2)) tma_load_4d(sa, &maps.a[mi], fb, c0, c1, c2, b0);
+                        if (!(dbg & 2)) tma_load_4d(sa, amap, fb, c0, c1, c2, b0);
                         if (!(dbg & 4)) tma_load_2d(sb, &maps.b, fb, kb * 64, n0);
                     }
                 }
@@ -368,7 +375,9 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
 __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                  const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res,
                                  __nv_bfloat16* __restrict__ y, int B, int H, int W, int cin, int cout, int ks,
-                                 int stride, int pad, int Ho, int Wo, int relu) {
+                                 int stride, int pad, int Ho, int Wo, int relu, const __nv_bfloat16* __restrict__ x2,
+                                 int H2, int W2, int cin2, int stride2) {
+    const int ldw = ks * ks * cin + (x2 ? cin2 : 0);      // weight row = [primary taps | fused 1x1 branch]
     const size_t total = (size_t)B * Ho * Wo * cout;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int co = (int)(e % cout);
@@ -384,9 +393,14 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv
                 const int iw = wo * stride + kw - pad;
                 if (iw < 0 || iw >= W) continue;
                 const __nv_bfloat16* xp = x + (((size_t)b * H + ih) * W + iw) * cin;
-                const __nv_bfloat16* wp = w + (((size_t)co * ks + kh) * ks + kw) * cin;
+                const __nv_bfloat16* wp = w + (size_t)co * ldw + ((size_t)kh * ks + kw) * cin;
                 for (int c = 0; c < cin; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
             }
+        }
+        if (x2) {
+            const __nv_bfloat16* xp = x2 + (((size_t)b * H2 + (size_t)ho * stride2) * W2 + (size_t)wo * stride2) * cin2;
+            const __nv_bfloat16* wp = w + (size_t)co * ldw + (size_t)ks * ks * cin;
+            for (int c = 0; c < cin2; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
         }
         acc += bias[co];
         if (res) acc += __bfloat162float(res[e]);
@@ -504,7 +518,8 @@ struct ConvPlan {
 // Generic: x (B,H,W,cin), cin % 64 == 0.  Stem (kind 1): x is (B,Hp,Wp,32) with 3 zero rows/cols before the
 // image, ksize 7, stride 2, pad 3; H, W are the UNPADDED sizes.
 int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H, int W, int cin, int cout, int ks,
-              int stride, int pad, int relu, int Hp, int Wp, const void* out, const void* res) {
+              int stride, int pad, int relu, int Hp, int Wp, const void* out, const void* res,
+              const void* x2 = nullptr, int H2 = 0, int W2 = 0, int cin2 = 0, int stride2 = 1) {
     ConvGeom& g = p->g;
     g.kind = kind; g.ksize = ks; g.stride = stride; g.pad = pad; g.cin = cin; g.B = B; g.cout = cout; g.relu = relu;
     g.Ho = (H + 2 * pad - ks) / stride + 1;
@@ -563,6 +578,19 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
             int rc = encode_map(&p->maps.a[ph], base, 4, dims, st, box);
             if (rc) return rc;
         }
+    }
+    g.nkb1 = g.nkb;
+    if (x2) {   // fused 1x1 branch: second input (B,H2,W2,cin2) sampled with stride2 at the output pixels, K appended
+        if (kind != 0 || cin2 % 64 || stride2 < 1 || (H2 - 1) / stride2 + 1 != g.Ho || (W2 - 1) / stride2 + 1 != g.Wo)
+            return hf::fail(HF_ERR_UNSUPPORTED, "conv: fused 1x1 branch does not match the output geometry");
+        const uint64_t dims[4] = {(uint64_t)cin2, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)B};
+        const uint64_t st[3] = {(uint64_t)stride2 * cin2 * 2, (uint64_t)stride2 * W2 * cin2 * 2, (uint64_t)H2 * W2 * cin2 * 2};
+        int rc = encode_map(&p->maps.a2, x2, 4, dims, st, box);
+        if (rc) return rc;
+        g.nkb += cin2 / 64;
+        ktot += cin2;
+    } else {
+        p->maps.a2 = p->maps.a[0];
     }
     const int tiles_m = g.tiles_w * g.tiles_h * g.tiles_b;
     p->bn = (cout % 128 == 0) ? 128 : 64;
@@ -666,12 +694,13 @@ int launch_conv(const ConvPlan& p, const float* bias, cudaStream_t s) {
 
 int launch_simt(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, const __nv_bfloat16* res,
                 __nv_bfloat16* y, int B, int H, int W, int cin, int cout, int ks, int stride, int pad, int relu,
-                cudaStream_t s, int Ho_override = 0, int Wo_override = 0) {
+                cudaStream_t s, int Ho_override = 0, int Wo_override = 0, const __nv_bfloat16* x2 = nullptr, int H2 = 0, int W2 = 0,
+                int cin2 = 0, int stride2 = 1) {
     const int Ho = Ho_override ? Ho_override : (H + 2 * pad - ks) / stride + 1;
     const int Wo = Wo_override ? Wo_override : (W + 2 * pad - ks) / stride + 1;
     const size_t total = (size_t)B * Ho * Wo * cout;
     int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 64);
-    conv_simt_kernel<<<blocks, 256, 0, s>>>(x, w, bias, res, y, B, H, W, cin, cout, ks, stride, pad, Ho, Wo, relu);
+    conv_simt_kernel<<<blocks, 256, 0, s>>>(x, w, bias, res, y, B, H, W, cin, cout, ks, stride, pad, Ho, Wo, relu, x2, H2, W2, cin2, stride2);
     HF_LAUNCH_CHECK();
     return HF_OK;
 }
@@ -700,12 +729,13 @@ constexpr int STEM_CP = 32;
 struct BufShape { int H, W, C; };
 
 // walk the op list to derive every op's input / output activation shape (buffer ids are reused along the way)
-struct OpShapes { std::vector<BufShape> in, out; };
+struct OpShapes { std::vector<BufShape> in, out, in2; };
 
 int infer_shapes(const hf_encoder* h, int B, int H, int W, OpShapes& os, size_t* max_act) {
     std::map<int, BufShape> cur;
     os.in.assign(h->ops.size(), BufShape{0, 0, 0});
     os.out.assign(h->ops.size(), BufShape{0, 0, 0});
+    os.in2.assign(h->ops.size(), BufShape{0, 0, 0});
     size_t mx = 0;
     for (size_t i = 0; i < h->ops.size(); ++i) {
         const hf_enc_op& op = h->ops[i];
@@ -728,6 +758,14 @@ int infer_shapes(const hf_encoder* h, int B, int H, int W, OpShapes& os, size_t*
                 if (op.res == op.dst) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu writes over its residual", i);
             }
             if (op.src == op.dst) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu is in-place", i);
+            if (op.src2 >= 0) {
+                if (!cur.count(op.src2)) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu reads unwritten buffer %d", i, op.src2);
+                const BufShape s2 = cur[op.src2];
+                if (op.stride2 < 1 || s2.C != op.cin2 || (s2.H - 1) / op.stride2 + 1 != out.H || (s2.W - 1) / op.stride2 + 1 != out.W)
+                    return hf::fail(HF_ERR_INVALID, "encoder program: op %zu fused 1x1 branch shape mismatch", i);
+                if (op.src2 == op.dst) return hf::fail(HF_ERR_INVALID, "encoder program: op %zu writes over its second input", i);
+                os.in2[i] = s2;
+            }
         } else if (op.kind == HF_OP_MAXPOOL3x3S2) {
             out.H = (in.H + 2 - 3) / 2 + 1; out.W = (in.W + 2 - 3) / 2 + 1;
         }
@@ -742,7 +780,7 @@ int infer_shapes(const hf_encoder* h, int B, int H, int W, OpShapes& os, size_t*
 
 int num_buffers(const hf_encoder* h) {
     int n = 0;
-    for (auto& op : h->ops) { n = std::max(n, op.dst + 1); n = std::max(n, op.src + 1); n = std::max(n, op.res + 1); }
+    for (auto& op : h->ops) { n = std::max(n, op.dst + 1); n = std::max(n, op.src + 1); n = std::max(n, op.res + 1); n = std::max(n, op.src2 + 1); }
     return n;
 }
 
@@ -767,7 +805,7 @@ extern "C" int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int n
         if (op.kind != HF_OP_CONV) continue;
         const int wi = op.weight_index;
         if (wi < 0 || wi >= num_weights) { delete h; return hf::fail(HF_ERR_INVALID, "hf_encoder_create: weight index %d", wi); }
-        const size_t n = (size_t)op.cout * op.ksize * op.ksize * op.cin;
+        const size_t n = (size_t)op.cout * ((size_t)op.ksize * op.ksize * op.cin + (op.src2 >= 0 ? op.cin2 : 0));
         int rc;
         if ((rc = hf::upload((uint16_t**)&h->w_plain[wi], weights[wi], n))) return rc;
         if ((rc = hf::upload(&h->bias[wi], bias[wi], (size_t)op.cout))) return rc;
@@ -861,8 +899,9 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
             } else {
                 const BufShape in = shp.in[i];
                 if (op.cin % 64 != 0) return hf::fail(HF_ERR_UNSUPPORTED, "encoder: conv %zu has cin %d (must be a multiple of 64)", i, op.cin);
+                const BufShape in2 = shp.in2[i];
                 rc = plan_conv(&h->plans[i], 0, buf(op.src), h->w[op.weight_index], B, in.H, in.W, op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, 0, 0,
-                               buf(op.dst), op.res >= 0 ? buf(op.res) : nullptr);
+                               buf(op.dst), op.res >= 0 ? buf(op.res) : nullptr, op.src2 >= 0 ? buf(op.src2) : nullptr, in2.H, in2.W, op.cin2, op.stride2);
             }
             if (rc) return rc;
         }
@@ -888,8 +927,10 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
                                  buf(op.dst), B, Hp, Wp, h->stem_cp, op.cout, 7, 2, 0, op.relu, stream, h->plans[i].g.Ho, h->plans[i].g.Wo);
             } else {
                 const BufShape in = shp.in[i];
+                const BufShape in2 = shp.in2[i];
                 rc = launch_simt(buf(op.src), h->w_plain[op.weight_index], h->bias[op.weight_index], res, buf(op.dst), B, in.H, in.W,
-                                 op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, stream);
+                                 op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, stream, 0, 0, op.src2 >= 0 ? buf(op.src2) : nullptr, in2.H,
+                                 in2.W, op.cin2, op.stride2);
             }
             if (rc) return rc;
         } else if (op.kind == HF_OP_MAXPOOL3x3S2) {

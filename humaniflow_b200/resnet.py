@@ -100,12 +100,21 @@ class ResNet(nn.Module):
             nbuf[0] += 1
             return nbuf[0] - 1
 
-        def conv_op(conv, bn, src, dst, res, relu, cin_pad=None):
+        def conv_op(conv, bn, src, dst, res, relu, cin_pad=None, branch=None):
+            """branch = (conv1x1, bn, src2): the block's downsample path fused into this op (one launch, fp32 accumulation of
+            both convolutions in the same accumulator, no bf16 round trip of the branch output)."""
             w, b = self._fold(conv, bn, cin_pad)
+            cin = w.shape[3]
+            src2, cin2, stride2 = -1, 0, 1
+            if branch is not None:
+                w2, b2 = self._fold(branch[0], branch[1])
+                src2, cin2, stride2 = branch[2], w2.shape[3], branch[0].stride[0]
+                w = torch.cat([w.reshape(w.shape[0], -1), w2.reshape(w2.shape[0], -1)], dim=1).contiguous()   # rows [K1 | K2]
+                b = (b + b2).contiguous()
             weights.append(w)
             biases.append(b)
-            ops.append(_lib.EncOp(_lib.OP_CONV, src, dst, res, w.shape[3], w.shape[0], conv.kernel_size[0],
-                                  conv.stride[0], conv.padding[0], int(relu), len(weights) - 1))
+            ops.append(_lib.EncOp(_lib.OP_CONV, src, dst, res, cin, w.shape[0], conv.kernel_size[0],
+                                  conv.stride[0], conv.padding[0], int(relu), len(weights) - 1, src2, cin2, stride2))
 
         x = alloc()
         conv_op(self.conv1, self.bn1, -1, x, -1, True, cin_pad=STEM_CIN)
@@ -123,21 +132,16 @@ class ResNet(nn.Module):
                     conv_op(blk.conv2, blk.bn2, t1, t2, -1, True)
                     free.append(t1)
                     last_in = t2
-                res = x
-                idb = None
-                if hasattr(blk, 'downsample'):
-                    idb = alloc()
-                    conv_op(blk.downsample[0], blk.downsample[1], x, idb, -1, False)
-                    res = idb
+                # identity blocks add the input as residual; blocks with a downsample path fuse its 1x1 conv into the last op
+                branch = (blk.downsample[0], blk.downsample[1], x) if hasattr(blk, 'downsample') else None
+                res = x if branch is None else -1
                 out = alloc()
                 if blk.kind == 'basic':
-                    conv_op(blk.conv2, blk.bn2, last_in, out, res, True)
+                    conv_op(blk.conv2, blk.bn2, last_in, out, res, True, branch=branch)
                 else:
-                    conv_op(blk.conv3, blk.bn3, last_in, out, res, True)
+                    conv_op(blk.conv3, blk.bn3, last_in, out, res, True, branch=branch)
                 free.append(last_in)
                 free.append(x)
-                if idb is not None:
-                    free.append(idb)
                 x = out
         ops.append(_lib.EncOp(_lib.OP_AVGPOOL, x, x, -1, self.feat_dim, self.feat_dim, 0, 1, 0, 0, -1))
         op_arr = (_lib.EncOp * len(ops))(*ops)

@@ -209,6 +209,10 @@ typedef struct hf_enc_op {
     int ksize, stride, pad;
     int relu;
     int weight_index;      /* into the weights/bias arrays given to hf_encoder_create */
+    /* optional fused 1x1 branch (a residual block's downsample path, models/resnet.py:70-74,108-119): a second input buffer
+     * src2 (-1 = none) with cin2 channels, sampled with stride2 at the output pixels; its weights are appended along K to
+     * every weight row ([ksize*ksize*cin | cin2]) and its folded BatchNorm shift is added into the bias */
+    int src2, cin2, stride2;
 } hf_enc_op;
 
 /* weights[i]: HOST bf16 (uint16 bit patterns) (cout, ksize, ksize, cin) with BatchNorm scale folded in;

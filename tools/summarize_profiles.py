@@ -95,7 +95,7 @@ if os.path.exists(conv):
     def mb(d, k):
         v, u = d[k]
         return {'byte': v / 1e6, 'Kbyte': v / 1e3, 'Mbyte': v, 'Gbyte': v * 1e3}[u]
-    out += ['## `conv_tcgen05_kernel`, the 53 convolutions of one ResNet-50 forward at B=32 (`ncu --metrics ...`)', '',
+    out += ['## `conv_tcgen05_kernel`, the 49 convolution launches (53 convolutions, the four downsample branches fused) of one ResNet-50 forward at B=32 (`ncu --metrics ...`)', '',
             '| # | template <BN,STAGES,SR> | CTAs | us | tensor pipe % | DRAM rd MB | DRAM wr MB | L2->SM MB | L2 hit % |',
             '|---:|---|---:|---:|---:|---:|---:|---:|---:|']
     tot = wsum = traffic = 0.0
@@ -108,9 +108,9 @@ if os.path.exists(conv):
         out.append('| %d | %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f |' % (
             n, d['name'], d['grid'].strip('()').split(',')[0], t, tp, mb(d, 'dram__bytes_read.sum'), mb(d, 'dram__bytes_write.sum'),
             mb(d, 'l1tex__m_xbar2l1tex_read_bytes.sum'), d['lts__t_sector_hit_rate.pct'][0]))
-    out += ['', 'Total %.1f us under ncu; time-weighted tensor-pipe activity %.1f%%; DRAM traffic of the 53 launches %.1f MB.'
+    out += ['', 'Total %.1f us under ncu; time-weighted tensor-pipe activity %.1f%%; DRAM traffic of the 49 launches %.1f MB.'
             % (tot, wsum / tot, traffic), '']
-    json.dump({'kernel': 'conv_tcgen05_kernel x53 (one ResNet-50 forward, B=32, 18ch, 256x256)', 'dram_bytes_per_step': traffic * 1e6,
+    json.dump({'kernel': 'conv_tcgen05_kernel x49 (one ResNet-50 forward, B=32, 18ch, 256x256)', 'dram_bytes_per_step': traffic * 1e6,
                'source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/%s_summary.md' % tag},
               open(os.path.join(P, '%s_traffic.json' % tag), 'w'))
 sass = os.path.join(G, 'sass_mnemonics_%s.txt' % suffix)
