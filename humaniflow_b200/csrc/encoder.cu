@@ -628,14 +628,22 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
     } else {
         // layers without residual: even ring -> dual producers / issuers; residual layers (short K, epilogue-bound) keep the
         // deeper residual prefetch (three / four staging tiles) and an odd ring, i.e. one producer and one issuer
+        // HF_CONV_CFG bits (A/B switches, default all on): 1 = four-slot ring for residual layers, 2 = eight stages for the
+        // 64-wide layers, 4 = six stages + one staging tile also for layers with two tiles per CTA
+        static const int cfg_env = getenv("HF_CONV_CFG") ? atoi(getenv("HF_CONV_CFG")) : 7;
         if (p->bn == 256)      { p->stages = 3; p->sr = 1; }
-        else if (p->bn == 128) { p->stages = p->has_res ? 3 : 4; p->sr = p->has_res ? 3 : 2; }
-        else                   { p->stages = p->has_res ? 5 : 6; p->sr = p->has_res ? 4 : 2; }
+        else if (p->bn == 128) { p->stages = p->has_res ? ((cfg_env & 1) ? 4 : 3) : 4; p->sr = p->has_res ? 3 : 2; }
+        else                   { p->stages = p->has_res ? 5 : ((cfg_env & 2) ? 8 : 6); p->sr = p->has_res ? 4 : 2; }
     }
     static const int stages_env = getenv("HF_CONV_STAGES") ? atoi(getenv("HF_CONV_STAGES")) : 0;     // timing experiment: BN = 128 without residual
     if (stages_env && !p->pair && p->bn == 128 && !p->has_res) { p->stages = stages_env; p->sr = stages_env >= 5 ? 1 : 2; }
-    p->smem = (size_t)p->stages * (128 * 128 + (p->pair ? p->bn / 2 : p->bn) * 128) + (size_t)p->sr * 128 * p->bn * 2 + 1024;
     p->ntn = cout / p->bn;
+    // one tile per CTA (the 16x16 and 8x8 layers at B = 32): a second staging tile is useless, and in the network these
+    // layers are bound by operand latency (weights and activations arrive from HBM / a cold L2), i.e. by the bytes the
+    // ring keeps in flight -> six 32 KB stages + one staging tile = 224 KB
+    static const int cfg_env2 = getenv("HF_CONV_CFG") ? atoi(getenv("HF_CONV_CFG")) : 7;
+    if (!p->pair && p->bn == 128 && !p->has_res && tiles_m * p->ntn <= ((cfg_env2 & 4) ? 2 : 1) * num_sms() && stages_env == 0) { p->stages = 6; p->sr = 1; }
+    p->smem = (size_t)p->stages * (128 * 128 + (p->pair ? p->bn / 2 : p->bn) * 128) + (size_t)p->sr * 128 * p->bn * 2 + 1024;
     if (p->pair) {
         p->num_tiles = hf::div_up(tiles_m, 2) * p->ntn;                      // pair tiles
         p->grid = dim3(2 * std::min(p->num_tiles, num_sms() / 2));
@@ -650,7 +658,7 @@ template <int BN, int STAGES, int SR, bool PAIR>
 int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
+        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -685,10 +693,13 @@ int launch_conv(const ConvPlan& p, const float* bias, cudaStream_t s) {
         return p.has_res ? launch_conv_t<64, 6, 4, true>(p, bias, s) : launch_conv_t<64, 7, 2, true>(p, bias, s);
     }
     if (p.bn == 256) return launch_conv_t<256, 3, 1, false>(p, bias, s);
+    if (p.bn == 128 && !p.has_res && p.stages == 6) return launch_conv_t<128, 6, 1, false>(p, bias, s);
     if (p.bn == 128 && !p.has_res && p.stages == 2) return launch_conv_t<128, 2, 2, false>(p, bias, s);
     if (p.bn == 128 && !p.has_res && p.stages == 3) return launch_conv_t<128, 3, 2, false>(p, bias, s);
     if (p.bn == 128 && !p.has_res && p.stages == 5) return launch_conv_t<128, 5, 1, false>(p, bias, s);
+    if (p.bn == 128 && p.has_res && p.stages == 4) return launch_conv_t<128, 4, 3, false>(p, bias, s);
     if (p.bn == 128) return p.has_res ? launch_conv_t<128, 3, 3, false>(p, bias, s) : launch_conv_t<128, 4, 2, false>(p, bias, s);
+    if (p.bn == 64 && !p.has_res && p.stages == 8) return launch_conv_t<64, 8, 2, false>(p, bias, s);
     return p.has_res ? launch_conv_t<64, 5, 4, false>(p, bias, s) : launch_conv_t<64, 6, 2, false>(p, bias, s);
 }
 
