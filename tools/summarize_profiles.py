@@ -65,7 +65,7 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio']
-for name in ('lbs', 'flow'):
+for name in ('lbs', 'flow', 'conv3x3'):      # conv3x3 = one representative launch: a layer3 3x3 convolution (256 -> 256 at 16x16)
     rep = os.path.join(G, 'prof_%s_%s.ncu-rep' % (name, suffix))
     if not os.path.exists(rep):
         continue
