@@ -450,23 +450,28 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
         const int wo = (int)(p % Wo); p /= Wo;
         const int ho = (int)(p % Ho);
         const int b = (int)(p / Ho);
+        // all nine taps are requested before any is used (out-of-range taps re-read the centre, which is always in range)
+        uint4 tap[9];
+        const int ihc = ho * 2, iwc = wo * 2;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                int ih = ihc + kh - 1, iw = iwc + kw - 1;
+                if (ih < 0 || ih >= H || iw < 0 || iw >= W) { ih = ihc; iw = iwc; }
+                tap[kh * 3 + kw] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + c8 * 8));
+            }
         float m[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
-        for (int kh = 0; kh < 3; ++kh) {
-            const int ih = ho * 2 + kh - 1;
-            if (ih < 0 || ih >= H) continue;
-            for (int kw = 0; kw < 3; ++kw) {
-                const int iw = wo * 2 + kw - 1;
-                if (iw < 0 || iw >= W) continue;
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + c8 * 8));
-                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&vv[i]);
-                    m[2 * i] = fmaxf(m[2 * i], __bfloat162float(h.x));
-                    m[2 * i + 1] = fmaxf(m[2 * i + 1], __bfloat162float(h.y));
-                }
+        for (int t = 0; t < 9; ++t) {
+            const uint32_t vv[4] = {tap[t].x, tap[t].y, tap[t].z, tap[t].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&vv[i]);
+                m[2 * i] = fmaxf(m[2 * i], __bfloat162float(h.x));
+                m[2 * i + 1] = fmaxf(m[2 * i + 1], __bfloat162float(h.y));
             }
         }
         uint32_t o[4];
