@@ -1,52 +1,47 @@
 """Oracle (test infrastructure): CPU restatement of the reference's 3-D error metrics.
 
 PINNED by tests/golden/metrics_golden.npz, produced by the real utils/eval_utils.py functions in the build container
-(tests/golden/make_golden_metrics.py).  numpy, like the reference.
+(tests/golden/make_golden_metrics.py).  numpy float64 internally, written from the definitions:
+
+  scale + translation correction (utils/eval_utils.py:105-125): centre the prediction, rescale it so that its RMS
+      distance from its centroid equals the target's, move it to the target's centroid;
+  Procrustes alignment (utils/eval_utils.py:62-102): the similarity transform (s, R, t), det R = +1, minimising
+      sum_i || s R p_i + t - q_i ||^2  (Umeyama / Kabsch with the reflection fix on the smallest singular direction);
+  error = mean over the points of the Euclidean distance (metrics/eval_metrics_tracker.py:119-280).
 """
 import numpy as np
 
 
-def scale_and_translation_transform_batch(P, T):
-    """utils/eval_utils.py:105-125."""
-    P_mean = np.mean(P, axis=-2, keepdims=True)
-    P_trans = P - P_mean
-    P_scale = np.sqrt(np.sum(P_trans ** 2, axis=(-2, -1), keepdims=True) / P.shape[-2])
-    P_normalised = P_trans / P_scale
-    T_mean = np.mean(T, axis=-2, keepdims=True)
-    T_scale = np.sqrt(np.sum((T - T_mean) ** 2, axis=(-2, -1), keepdims=True) / T.shape[-2])
-    return P_normalised * T_scale + T_mean
+def _centroid(x):
+    return x.mean(axis=-2, keepdims=True)
 
 
-def procrustes_analysis_batch(S1, S2):
-    """utils/eval_utils.py:62-102 (similarity transform of S1 onto S2, det(R) = +1)."""
-    batch_size = S1.shape[0]
-    S1 = S1.transpose(0, 2, 1)
-    S2 = S2.transpose(0, 2, 1)
-    mu1 = S1.mean(axis=2, keepdims=True)
-    mu2 = S2.mean(axis=2, keepdims=True)
-    X1 = S1 - mu1
-    X2 = S2 - mu2
-    var1 = (X1 ** 2).sum(axis=(1, 2))
-    K = np.matmul(X1, X2.transpose(0, 2, 1))
-    U, s, Vh = np.linalg.svd(K)
-    V = Vh.transpose(0, 2, 1)
-    Z = np.tile(np.eye(U.shape[1])[None, :, :], (batch_size, 1, 1))
-    Z[:, -1, -1] *= np.sign(np.linalg.det(np.matmul(U, Vh)))
-    R = np.matmul(np.matmul(V, Z), U.transpose(0, 2, 1))
-    trace = np.matmul(R, K).diagonal(offset=0, axis1=-1, axis2=-2).sum(axis=-1)
-    scale = (trace / var1)[..., None, None]
-    t = mu2 - scale * np.matmul(R, mu1)
-    S1_hat = scale * np.matmul(R, S1) + t
-    return S1_hat.transpose(0, 2, 1)
+def align_scale_translation(pred, target):
+    """(..., P, 3) x2 -> pred moved onto the target's centroid and RMS radius (utils/eval_utils.py:105-125)."""
+    pc, tc = pred - _centroid(pred), target - _centroid(target)
+    radius = lambda c: np.sqrt((c * c).sum(axis=(-2, -1), keepdims=True) / c.shape[-2])
+    return pc * (radius(tc) / radius(pc)) + _centroid(target)
+
+
+def align_procrustes(pred, target):
+    """(n, P, 3) x2 -> s R pred + t with the optimal similarity transform per set (utils/eval_utils.py:62-102)."""
+    mu_p, mu_t = _centroid(pred), _centroid(target)
+    pc, tc = pred - mu_p, target - mu_t
+    cov = np.einsum('npi,npj->nij', pc, tc)                       # sum_p pc_p tc_p^T  (3x3 per set)
+    u, sing, vt = np.linalg.svd(cov)
+    flip = np.sign(np.linalg.det(u @ vt))                         # -1 where the best orthogonal map is a reflection
+    fix = np.ones_like(sing)
+    fix[:, -1] = flip
+    rot = np.einsum('nji,nj,nkj->nik', vt, fix, u)                # V diag(fix) U^T
+    scale = (sing * fix).sum(-1) / (pc * pc).sum(axis=(-2, -1))   # trace(R cov) / ||pc||^2
+    return scale[:, None, None] * np.einsum('nij,npj->npi', rot, pc) + mu_t
 
 
 def pointset_errors(pred, target):
-    """pred (B,N,P,3), target (B,P,3) numpy -> dict of (B,N): the per-sample means that
-    metrics/eval_metrics_tracker.py:119-280 sums (np.linalg.norm(..., axis=-1) then mean over the points)."""
+    """pred (B,N,P,3), target (B,P,3) -> dict of (B,N) mean point errors: plain, scale-corrected, Procrustes-aligned."""
     B, N, P, _ = pred.shape
-    tgt = np.tile(target[:, None], (1, N, 1, 1))
-    plain = np.linalg.norm(pred - tgt, axis=-1).mean(-1)
-    sc = np.linalg.norm(scale_and_translation_transform_batch(pred, tgt) - tgt, axis=-1).mean(-1)
-    pa = procrustes_analysis_batch(pred.reshape(B * N, P, 3), tgt.reshape(B * N, P, 3)).reshape(B, N, P, 3)
-    pa = np.linalg.norm(pa - tgt, axis=-1).mean(-1)
-    return {'plain': plain, 'sc': sc, 'pa': pa}
+    p = pred.astype(np.float64)
+    t = np.broadcast_to(target.astype(np.float64)[:, None], p.shape)
+    dist = lambda a: np.linalg.norm(a - t, axis=-1).mean(-1)
+    pa = align_procrustes(p.reshape(B * N, P, 3), t.reshape(B * N, P, 3)).reshape(p.shape)
+    return {'plain': dist(p), 'sc': dist(align_scale_translation(p, t)), 'pa': dist(pa)}

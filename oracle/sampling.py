@@ -12,12 +12,12 @@ ALL_JOINTS_TO_COCO_MAP = [24, 26, 25, 28, 27, 16, 17, 18, 19, 20, 21, 1, 2, 4, 5
 
 
 def compute_vertex_variance_from_samples(vertices_samples):
-    """utils/sampling_utils.py:22-33.  (N,V,3) -> ((V,), (V,3))."""
-    mean_vertices = torch.mean(vertices_samples, dim=0)
-    diff_from_mean = vertices_samples - mean_vertices
-    directional_vertex_variances = torch.sqrt(torch.mean(diff_from_mean ** 2, dim=0))
-    avg_vertex_l2_distance_from_mean = torch.norm(diff_from_mean, dim=-1).mean(dim=0)
-    return avg_vertex_l2_distance_from_mean, directional_vertex_variances
+    """utils/sampling_utils.py:22-33.  (N,V,3) samples of one image -> (mean distance of a vertex from its sample mean (V,),
+    per-coordinate RMS deviation (V,3))."""
+    dev = vertices_samples - vertices_samples.mean(dim=0)
+    rms_per_coordinate = (dev ** 2).mean(dim=0).sqrt()
+    mean_distance = dev.norm(dim=-1).mean(dim=0)
+    return mean_distance, rms_per_coordinate
 
 
 def orthographic_project(points3D, cam_params):

@@ -124,8 +124,8 @@ def test_metrics(golden_dir):
     from oracle import metrics as omet
     g = np.load(os.path.join(golden_dir, 'metrics_golden.npz'))
     e = omet.pointset_errors(g['pred'], g['target'])
-    for k in ('plain', 'sc', 'pa'):
-        assert np.array_equal(e[k], g[k]), k
+    for k in ('plain', 'sc', 'pa'):          # the oracle works in float64, the reference's numpy in float32
+        assert np.allclose(e[k], g[k], rtol=2e-6, atol=1e-7), (k, np.abs(e[k] - g[k]).max())
 
 
 def test_proxy_representation(golden_dir):
