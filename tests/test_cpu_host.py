@@ -86,3 +86,18 @@ def test_unsupported_flow_variants_fail_loudly():
     cfg.NORM_FLOW.TRANSFORM_TYPE = 'affine_coupling'
     with pytest.raises(NotImplementedError):
         hb.HumaniflowModel('cpu', cfg, SMPL_PARENTS)
+
+
+def test_c_structs_match_the_header():
+    """The ctypes mirrors of the C-ABI structs have the field count / order the header declares (hf_enc_op grew a fused
+    second input: src2, cin2, stride2)."""
+    import ctypes
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'humaniflow_b200.h')).read()
+    body = re.search(r'typedef struct hf_enc_op \{(.*?)\} hf_enc_op;', hdr, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = [n.strip() for decl in re.findall(r'int ([^;]+);', body) for n in decl.split(',')]
+    assert names == [f[0] for f in _lib.EncOp._fields_], (names, _lib.EncOp._fields_)
+    assert ctypes.sizeof(_lib.EncOp) == 4 * len(names)
+    op = _lib.EncOp(_lib.OP_CONV, 0, 1, -1, 64, 64, 3, 1, 1, 1, 0)
+    assert (op.src2, op.cin2, op.stride2) == (-1, 0, 1)          # defaults = no fused branch
