@@ -139,3 +139,69 @@ def test_proxy_representation(golden_dir):
         assert torch.equal(r[key], torch.tensor(g['edge_%g_%d' % (thr, int(nms))])), (thr, nms)
     assert torch.equal(r['grad_magnitude'], torch.tensor(g['mag'])) and torch.equal(r['grad_orientation'], torch.tensor(g['ori']))
     assert torch.equal(opr.heatmaps(torch.tensor(g['j2d']), img.shape[-1]), torch.tensor(g['heat']))
+
+
+def _model_problem(layers):
+    """Weights / inputs / noise of tests/golden/make_golden_model.py, regenerated from the same seeds."""
+    import humaniflow_b200 as hb
+    from humaniflow_b200.synthetic import SMPL_PARENTS
+    cfg = hb.get_model_cfg_defaults()
+    cfg.NUM_RESNET_LAYERS = layers
+    ours = hb.HumaniflowModel('cpu', cfg, SMPL_PARENTS)
+    shapes = {k: tuple(v.shape) for k, v in ours.state_dict().items() if not k.startswith('image_encoder.')}
+    sd = fill_state_dict(shapes, seed=700 + layers)
+    sd['init_glob'] = ours.state_dict()['init_glob'].clone()
+    sd['init_cam'] = ours.state_dict()['init_cam'].clone()
+    B, N, F = 5, 4, (512 if layers == 18 else 2048)
+    feats = det_input((B, F), 710 + layers).abs()
+    shape_eps = det_input((N, B, 10), 711 + layers).transpose(0, 1)               # rsample([N]).transpose(0, 1)
+    base_noise = torch.stack([det_input((B, N, 3), 720 + layers + j) for j in range(23)], 2) * 0.6
+    v_t = det_input((B, 23, 3), 760 + layers) * 0.7
+    v_t[0, 3] = 0.0
+    v_t[1, 5] = v_t[1, 5] / v_t[1, 5].norm() * 2.6
+    tgt = {'R': so3.so3_exp(v_t.double()).float(), 'shape': det_input((B, 10), 761 + layers),
+           'glob': so3.so3_exp(det_input((B, 3), 762 + layers).double() * 0.5).float(),
+           'v_alg': det_input((B, 23, 3), 763 + layers) * 0.8}
+    return cfg, SMPL_PARENTS, ours, shapes, sd, feats, shape_eps, base_noise, tgt
+
+
+def test_model_glue_against_the_real_reference_class(golden_dir):
+    """oracle/model.py::forward vs the REAL models/humaniflow_model.py::HumaniflowModel (heads, image-level features,
+    ancestor-ordered contexts, 2j+t module index, point estimate, injected-noise samples, teacher-forced log-likelihood),
+    at both encoder widths (ResNet-18: 512-d, ResNet-50: 2048-d features / 1024-d fc1)."""
+    from oracle import model as om
+    g = np.load(os.path.join(golden_dir, 'model_golden.npz'))
+    for layers in (18, 50):
+        t = lambda k: torch.tensor(g['r%d_%s' % (layers, k)])
+        cfg, parents, ours, shapes, sd, feats, shape_eps, base_noise, tgt = _model_problem(layers)
+        # state-dict key names (and with them the key -> joint mapping) are the reference's
+        assert sorted(shapes.keys()) == [str(k) for k in g['r%d_keys' % layers]]
+        anc = om.ancestors_of(parents)
+        assert [len(a) for a in anc] == t('anc_len').tolist() and [x for a in anc for x in a] == t('anc_flat').tolist()
+        with torch.no_grad():
+            ref = om.forward(sd, cfg, parents, input_feats=feats, num_samples=4, shape_eps=shape_eps, base_noise=base_noise)
+        for k in ('cam_wp', 'glob_rotmat', 'shape_mode', 'shape_log_std', 'shape_samples'):
+            assert torch.allclose(ref[k], t(k), atol=1e-6, rtol=1e-6), (layers, k)
+        assert torch.allclose(torch.exp(ref['shape_log_std']), t('scale_of_shape_dist'), atol=1e-6, rtol=1e-6)
+        for k in ('pose_axisangle_point_est', 'pose_rotmats_point_est', 'pose_rotmats_samples'):
+            assert (ref[k] - t(k)).abs().max().item() <= 2e-6, (layers, k, (ref[k] - t(k)).abs().max().item())
+        # contexts the reference computed on the way (recorded around compute_flow_context)
+        with torch.no_grad():
+            fe_pe = om.image_level_feats(sd, feats, ref['shape_mode'], ref['glob_rotmat'], ref['cam_wp'])
+            fe_s = om.image_level_feats(sd, feats, ref['shape_samples'], ref['glob_rotmat'], ref['cam_wp'])
+            for j in range(23):
+                c = om.flow_context(sd, j, anc[j], fe_pe, ref['pose_rotmats_point_est'])
+                assert torch.allclose(c, t('ctx_pe')[:, j], atol=5e-6, rtol=1e-5), (layers, j)
+                c = om.flow_context(sd, j, anc[j], fe_s, ref['pose_rotmats_samples'])
+                assert torch.allclose(c, t('ctx_s')[:, :, j], atol=5e-6, rtol=1e-5), (layers, j)
+            ll = om.forward(sd, cfg, parents, input_feats=feats, compute_point_est=False, shape_for_loglik=tgt['shape'],
+                            pose_R_for_loglik=tgt['R'], glob_R_for_loglik=tgt['glob'])
+        assert torch.allclose(torch.stack(ll['loglik_contexts'], 1), t('ctx_ll'), atol=5e-6, rtol=1e-5)
+        lp_ref = t('lp_SO3')
+        assert torch.equal(torch.isfinite(ll['pose_loglik']), torch.isfinite(lp_ref))
+        fin = torch.isfinite(lp_ref)
+        assert ((ll['pose_loglik'] - lp_ref).abs()[fin] / lp_ref.abs()[fin].clamp_min(1.0)).max().item() <= 1e-5
+        with torch.no_grad():
+            lp_alg = torch.stack([oflow.algebra_log_prob(om.joint_couplings(sd, j, 2), tgt['v_alg'][:, j], ll['loglik_contexts'][j],
+                                                         RADIUS, 0.6) for j in range(23)], 1)
+        assert ((lp_alg - t('lp_so3')).abs() / t('lp_so3').abs().clamp_min(1.0)).max().item() <= 1e-5
