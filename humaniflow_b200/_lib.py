@@ -68,6 +68,7 @@ SIGNATURES = {
     'hf_encoder_debug_op_output': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     'hf_debug_conv_stamps': (c_int, [c_void_p]),
     'hf_conv2d_nhwc': (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p]),
+    'hf_conv2d_nhwc_branch': (c_int, [c_void_p] * 5 + [c_int] * 9 + [c_void_p] + [c_int] * 5 + [c_void_p]),
 }
 
 _lib = None

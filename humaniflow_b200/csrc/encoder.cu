@@ -661,10 +661,12 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
 
 template <int BN, int STAGES, int SR, bool PAIR>
 int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
+    static int attr_dev_mask = 0;      // the attribute is per device: set it once per device this process launches on
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((attr_dev_mask >> (dev & 31)) & 1)) {
         HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr = true;
+        attr_dev_mask |= 1 << (dev & 31);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = p.grid; cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
@@ -820,11 +822,11 @@ extern "C" int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int n
         const hf_enc_op& op = ops[i];
         if (op.kind != HF_OP_CONV) continue;
         const int wi = op.weight_index;
-        if (wi < 0 || wi >= num_weights) { delete h; return hf::fail(HF_ERR_INVALID, "hf_encoder_create: weight index %d", wi); }
+        if (wi < 0 || wi >= num_weights) { hf_encoder_destroy(h); return hf::fail(HF_ERR_INVALID, "hf_encoder_create: weight index %d", wi); }
         const size_t n = (size_t)op.cout * ((size_t)op.ksize * op.ksize * op.cin + (op.src2 >= 0 ? op.cin2 : 0));
         int rc;
-        if ((rc = hf::upload((uint16_t**)&h->w_plain[wi], weights[wi], n))) return rc;
-        if ((rc = hf::upload(&h->bias[wi], bias[wi], (size_t)op.cout))) return rc;
+        if ((rc = hf::upload((uint16_t**)&h->w_plain[wi], weights[wi], n))) { hf_encoder_destroy(h); return rc; }
+        if ((rc = hf::upload(&h->bias[wi], bias[wi], (size_t)op.cout))) { hf_encoder_destroy(h); return rc; }
         h->w_cin[wi] = op.cin;
         if (i == 0) {
             // stem: (cout,7,7,32) -> (cout,7,8,32) with a zero 8th tap so that two taps x 32 ch form one 128-byte k-block
@@ -833,7 +835,7 @@ extern "C" int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int n
                 for (int kh = 0; kh < 7; ++kh)
                     for (int kw = 0; kw < 7; ++kw)
                         memcpy(&pk[(((size_t)co * 7 + kh) * 8 + kw) * STEM_CP], &weights[wi][(((size_t)co * 7 + kh) * 7 + kw) * STEM_CP], STEM_CP * 2);
-            if ((rc = hf::upload((uint16_t**)&h->w[wi], pk.data(), pk.size()))) return rc;
+            if ((rc = hf::upload((uint16_t**)&h->w[wi], pk.data(), pk.size()))) { hf_encoder_destroy(h); return rc; }
             if (in_channels <= 24) {   // compact variants: drop the (all-zero) channels 24..31
                 std::vector<uint16_t> p24((size_t)op.cout * 7 * 8 * 24, 0), q24((size_t)op.cout * 7 * 7 * 24, 0);
                 for (int co = 0; co < op.cout; ++co)
@@ -843,8 +845,8 @@ extern "C" int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int n
                             memcpy(&p24[(((size_t)co * 7 + kh) * 8 + kw) * 24], src, 24 * 2);
                             memcpy(&q24[(((size_t)co * 7 + kh) * 7 + kw) * 24], src, 24 * 2);
                         }
-                if ((rc = hf::upload((uint16_t**)&h->w_stem24, p24.data(), p24.size()))) return rc;
-                if ((rc = hf::upload((uint16_t**)&h->w_plain24, q24.data(), q24.size()))) return rc;
+                if ((rc = hf::upload((uint16_t**)&h->w_stem24, p24.data(), p24.size()))) { hf_encoder_destroy(h); return rc; }
+                if ((rc = hf::upload((uint16_t**)&h->w_plain24, q24.data(), q24.size()))) { hf_encoder_destroy(h); return rc; }
             }
         } else {
             h->w[wi] = h->w_plain[wi];
@@ -1006,6 +1008,20 @@ extern "C" int hf_conv2d_nhwc(const uint16_t* x, const uint16_t* w, const float*
                            (__nv_bfloat16*)y, B, H, W, cin, cout, ksize, stride, pad, relu, (cudaStream_t)stream);
     ConvPlan p;
     int rc = plan_conv(&p, 0, x, w, B, H, W, cin, cout, ksize, stride, pad, relu, 0, 0, y, res);
+    if (rc) return rc;
+    return launch_conv(p, bias, (cudaStream_t)stream);
+}
+
+extern "C" int hf_conv2d_nhwc_branch(const uint16_t* x, const uint16_t* w, const float* bias, const uint16_t* res, uint16_t* y,
+                                     int B, int H, int W, int cin, int cout, int ksize, int stride, int pad, int relu,
+                                     const uint16_t* x2, int H2, int W2, int cin2, int stride2, int impl, void* stream) {
+    if (!x || !w || !bias || !y || !x2) return hf::fail(HF_ERR_INVALID, "hf_conv2d_nhwc_branch: null argument");
+    if (impl == 1)
+        return launch_simt((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (const __nv_bfloat16*)res,
+                           (__nv_bfloat16*)y, B, H, W, cin, cout, ksize, stride, pad, relu, (cudaStream_t)stream, 0, 0,
+                           (const __nv_bfloat16*)x2, H2, W2, cin2, stride2);
+    ConvPlan p;
+    int rc = plan_conv(&p, 0, x, w, B, H, W, cin, cout, ksize, stride, pad, relu, 0, 0, y, res, x2, H2, W2, cin2, stride2);
     if (rc) return rc;
     return launch_conv(p, bias, (cudaStream_t)stream);
 }

@@ -171,12 +171,9 @@ extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const
     if (K < 0 || ldx < K || ldw < K || ldy < O) return hf::fail(HF_ERR_INVALID, "hf_linear: bad strides");
     const bool vec4 = (K % 4 == 0) && (K >= 64) && (ldw % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)W & 15) == 0) && (((uintptr_t)x & 15) == 0);
     if (vec4) {
-        static bool attr = false;
         const int smem = 2 * 32 * KC * (int)sizeof(float);
-        if (!attr) {
-            HF_CUDA(cudaFuncSetAttribute(linear_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr = true;
-        }
+        // per device / context attribute: set on every call (cheap), not cached in a process-wide static
+        HF_CUDA(cudaFuncSetAttribute(linear_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         dim3 grid(hf::div_up(O, LW), hf::div_up(M, 32));
         HF_CUDA(hf::launch_pdl(linear_vec_kernel, grid, dim3(LW * 32), (size_t)smem, (cudaStream_t)stream, x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate));
     } else {

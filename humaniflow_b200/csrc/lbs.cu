@@ -1025,12 +1025,8 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
             if (rc) return rc;
             hm->mapB_ptr = Fb; hm->mapB_M = M;
         }
-        static bool tc_attr = false;
         const size_t tc_smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_NS * h->J * 12 * sizeof(float) + 1024;
-        if (!tc_attr) {
-            HF_CUDA(cudaFuncSetAttribute(lbs_skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
-            tc_attr = true;
-        }
+        HF_CUDA(cudaFuncSetAttribute(lbs_skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // per device: every call
         if (tc_smem > 226 * 1024) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_forward: tile needs %zu B of shared memory", tc_smem);
         dim3 tgrid(h->Vp / 128, hf::div_up(M, TC_NS));
         HF_CUDA(hf::launch_pdl(lbs_skin_tc_kernel, tgrid, dim3(TC_THREADS), tc_smem, stream, hm->mapA, hm->mapB, h->vtemp, h->sj, h->sw,
@@ -1039,11 +1035,7 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     } else {
     constexpr int TS = kSPT * kSG;
     size_t smem = ((size_t)h->KP * TS + (size_t)TS * h->J * 12) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        HF_CUDA(cudaFuncSetAttribute(lbs_skin_kernel<kSPT, kSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    HF_CUDA(cudaFuncSetAttribute(lbs_skin_kernel<kSPT, kSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device: every call
     if (smem > 200 * 1024) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_forward: tile needs %zu B of shared memory", smem);
     dim3 grid(h->Vp / 128, hf::div_up(M, TS));
     lbs_skin_kernel<kSPT, kSG><<<grid, 128 * kSG, smem, stream>>>(h->blend, h->vtemp, h->sj, h->sw, F, A, transl, M,

@@ -119,11 +119,7 @@ extern "C" int hf_vertex_variance(const float* vertices, int B, int N, int V, fl
     if (N <= 0) return hf::fail(HF_ERR_INVALID, "hf_vertex_variance: N must be positive");
     const size_t smem = ((size_t)N * VC * 3 + VC * 3) * sizeof(float);
     if (smem > 200 * 1024) return hf::fail(HF_ERR_UNSUPPORTED, "hf_vertex_variance: %d samples per image exceed the shared-memory tile (max 532)", N);
-    static size_t attr = 0;
-    if (smem > attr) {
-        HF_CUDA(cudaFuncSetAttribute(vertex_variance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    HF_CUDA(cudaFuncSetAttribute(vertex_variance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device: every call
     HF_CUDA(hf::launch_pdl(vertex_variance_kernel, dim3(hf::div_up(V, VC), B), dim3(VV_THREADS), smem, (cudaStream_t)stream, vertices, B, N, V,
                            avg_dist, dir_std));
     HF_LAUNCH_CHECK();

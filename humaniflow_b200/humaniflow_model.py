@@ -63,9 +63,13 @@ class ConditionedSO3FlowDist:
 
     def __init__(self, model, joint, ctx_all, on_group):
         self.model, self.joint, self.ctx_all, self.on_group = model, joint, ctx_all, on_group
+        self._token = model._packed_version          # the packed weights these contexts were computed with
 
     def log_prob(self, value):
         m, lib = self.model, _lib.load()
+        if m._flow is None or m._packed_version is not self._token:
+            raise RuntimeError('humaniflow_b200: the model was re-packed (weights changed or moved) after this conditioned '
+                               'distribution was created; call forward(compute_for_loglik=True) again')
         R = self.ctx_all.shape[0]
         out = torch.empty(R, device=self.ctx_all.device, dtype=torch.float32)
         with torch.cuda.device(out.device):
@@ -101,6 +105,10 @@ class HumaniflowModel(nn.Module):
         self.register_buffer('init_glob', torch.eye(3)[None, :, :2].contiguous().view(-1, 6).float())   # rotmat_to_rot6d(I)
         self.num_cam_params = 3
         self.register_buffer('init_cam', torch.tensor([0.9, 0.0, 0.0]).float())
+        nf0 = model_cfg.NORM_FLOW
+        if len(nf0.TRANSFORM_NN_HIDDEN_DIMS) != 3 or nf0.NUM_TRANSFORMS != 2:
+            raise NotImplementedError('the flow kernels are specialised to the reference default: 2 transforms per joint, '
+                                      '3 hidden layers (configs/humaniflow_config.py:16-19)')
         if model_cfg.NUM_RESNET_LAYERS == 18:
             self.image_encoder = resnet18(in_channels=model_cfg.NUM_IN_CHANNELS, pretrained=False)
             input_feats_dim, fc1_dim = 512, 512
@@ -165,7 +173,7 @@ class HumaniflowModel(nn.Module):
         return [p for m in mods for p in m.parameters()]
 
     def _ensure_packed(self, device):
-        ver = tuple((p.data_ptr(), p._version) for p in self._head_params())
+        ver = tuple((p.data_ptr(), p._version) for p in self._head_params() + [self.init_glob, self.init_cam])
         if self._flow is not None and ver == self._packed_version:
             return
         self._drop()
@@ -191,8 +199,6 @@ class HumaniflowModel(nn.Module):
         cfg = _lib.FlowConfig(self.num_bodyparts, self.cfg.INPUT_SHAPE_GLOB_CAM_FEATS_DIM, nf.CONTEXT_DIM, nf.NUM_TRANSFORMS,
                               (ctypes.c_int * 3)(*nf.TRANSFORM_NN_HIDDEN_DIMS), nf.NUM_SPLINE_SEGMENTS, nb,
                               float(nf.COMPACT_SUPPORT_RADIUS), float(nf.BASE_DIST_STD))
-        if len(nf.TRANSFORM_NN_HIDDEN_DIMS) != 3:
-            raise NotImplementedError('flow kernels are specialised to 3 hidden layers')
         h = ctypes.c_void_p()
         with torch.cuda.device(device):
             _lib.check(lib.hf_flow_create(ctypes.byref(h), ctypes.byref(cfg), _lib.ptr(anc_t), _lib.ptr(offs_t), _lib.ptr(beta_w),

@@ -249,6 +249,13 @@ int hf_conv2d_nhwc(const uint16_t* x, const uint16_t* w, const float* bias, cons
                    uint16_t* y, int B, int H, int W, int cin, int cout, int ksize, int stride, int pad,
                    int relu, int impl, void* stream);
 
+/* Same, plus the fused 1x1 branch of hf_enc_op.src2 (a bottleneck block's downsample path, models/resnet.py:108-118):
+ * x2 (B,H2,W2,cin2) bf16 sampled with stride2 at the output pixels; w rows are [k*k*cin | cin2]; bias is the sum of both
+ * folded shifts.  Both convolutions accumulate in fp32 in one accumulator; the branch output is never rounded to bf16. */
+int hf_conv2d_nhwc_branch(const uint16_t* x, const uint16_t* w, const float* bias, const uint16_t* res,
+                          uint16_t* y, int B, int H, int W, int cin, int cout, int ksize, int stride, int pad,
+                          int relu, const uint16_t* x2, int H2, int W2, int cin2, int stride2, int impl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,3 +112,41 @@ def test_model_with_image_input():
     with pytest.raises(RuntimeError):
         m.train()
         m(x.cuda())
+
+
+BRANCH_CASES = [
+    # B, H, W, Cin, Cout, k, stride (main, always 1), Cin2, stride2 (branch), H2 = H * stride2
+    (2, 16, 16, 64, 256, 1, 64, 1),        # layer1 block 0: conv3 (64 -> 256) + 1x1 downsample of the block input (64 -> 256)
+    (2, 16, 16, 128, 512, 1, 256, 2),      # layer2 block 0: conv3 + stride-2 downsample of the 32x32 block input
+    (3, 8, 8, 256, 1024, 1, 512, 2),       # layer3 block 0, odd batch: partial tile, BN = 256
+    (2, 8, 8, 128, 128, 3, 64, 2),         # BasicBlock (ResNet-18): 3x3 conv2 + stride-2 1x1 downsample
+]
+
+
+@pytest.mark.parametrize('case', BRANCH_CASES)
+def test_fused_branch_conv(case):
+    """hf_enc_op.src2: the block's 1x1 downsample branch accumulated into the last conv's fp32 accumulator
+    (models/resnet.py:108-118: out = bn3(conv3(out)) + downsample(x); relu).  Reference = both convolutions in fp32 on the
+    bf16-rounded operands, summed BEFORE the single rounding to bf16."""
+    import torch.nn.functional as F
+    B, H, W, Ci, Co, k, Ci2, s2 = case
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(sum(case))
+    x = bf16r(torch.randn(B, H, W, Ci, generator=g))
+    x2 = bf16r(torch.randn(B, H * s2, W * s2, Ci2, generator=g))
+    w1 = bf16r(torch.randn(Co, k, k, Ci, generator=g) / (k * k * Ci) ** 0.5)
+    w2 = bf16r(torch.randn(Co, 1, 1, Ci2, generator=g) / Ci2 ** 0.5)
+    bias = torch.randn(Co, generator=g) * 0.1
+    y1 = F.conv2d(x.permute(0, 3, 1, 2), w1.permute(0, 3, 1, 2), padding=k // 2)
+    y2 = F.conv2d(x2.permute(0, 3, 1, 2), w2.permute(0, 3, 1, 2), stride=s2)
+    ref = bf16r(F.relu((y1 + y2).permute(0, 2, 3, 1) + bias))
+    wcat = torch.cat([w1.reshape(Co, -1), w2.reshape(Co, -1)], 1).contiguous()
+    for impl in (0, 1):
+        xd, x2d, wd, bd = _bits(x).cuda(), _bits(x2).cuda(), _bits(wcat).cuda(), bias.cuda()
+        y = torch.empty(B, H, W, Co, dtype=torch.int16, device='cuda')
+        _lib.check(lib.hf_conv2d_nhwc_branch(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), None, _lib.ptr(y), B, H, W, Ci, Co, k, 1, k // 2, 1,
+                                             _lib.ptr(x2d), H * s2, W * s2, Ci2, s2, impl, _lib.stream()))
+        torch.cuda.synchronize()
+        got = y.view(torch.bfloat16).float().cpu()
+        err = (got - ref).abs()
+        assert (err <= 2 ** -7 * ref.abs() + 1e-3).all(), (impl, err.max().item(), case)

@@ -31,12 +31,13 @@ def _run(m, feats, z, se, **kw):
              shape_eps=None if se is None else se.cuda(), **kw)
 
 
-@pytest.mark.parametrize('B,N,scale', [(3, 7, 1.0), (4, 25, 1.5), (32, 100, 1.0)])
-def test_sampling_and_point_estimate_parity(B, N, scale):
-    """(32,100) is BASELINE configs[1]: B=32, N=100, 23 joints, random-init flow + synthetic encoder features."""
-    m, sd, cfg = make_model(18, seed=0, flow_scale=scale)
+@pytest.mark.parametrize('B,N,scale,layers', [(3, 7, 1.0, 18), (4, 25, 1.5, 18), (32, 100, 1.0, 18), (5, 9, 1.5, 50), (32, 100, 1.0, 50)])
+def test_sampling_and_point_estimate_parity(B, N, scale, layers):
+    """(32,100) is BASELINE configs[1]: B=32, N=100, 23 joints, random-init flow + synthetic encoder features; layers=50 is
+    the benchmarked width (feats (32,2048), 2048->1024 fc1, 1024-wide heads, 2070-wide image-level Linear)."""
+    m, sd, cfg = make_model(layers, seed=0, flow_scale=scale)
     m = m.cuda()
-    feats, z, se = _noise(B, N)
+    feats, z, se = _noise(B, N, feat_dim=m.input_feats_dim)
     ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, num_samples=N, shape_eps=se, base_noise=z)
     out = _run(m, feats, z, se)
     assert out['pose_rotmats_samples'].shape == (B, N, 23, 3, 3) and out['pose_rotmats_samples'].dtype == torch.float32
@@ -82,15 +83,15 @@ def test_modes_of_forward():
     assert 'input_feats' in m(None, input_feats=feats.cuda(), return_input_feats=True)
 
 
-@pytest.mark.parametrize('scale', [1.0, 1.5])
-def test_log_prob_parity(scale):
+@pytest.mark.parametrize('scale,layers', [(1.0, 18), (1.5, 18), (1.0, 50)])
+def test_log_prob_parity(scale, layers):
     """Teacher-forced log-likelihood (humaniflow_model.py:314-320; losses/humaniflow_loss.py:25-35):
     targets include theta<1e-6, theta~pi/2 and |pi-theta|<1e-2, plus the model's own samples."""
-    m, sd, cfg = make_model(18, seed=4, flow_scale=scale)
+    m, sd, cfg = make_model(layers, seed=4, flow_scale=scale)
     m = m.cuda()
     Rt = special_rotations()                       # (40,3,3) f64
     B = Rt.shape[0]
-    feats, z, se = _noise(B, 1, seed=6)
+    feats, z, se = _noise(B, 1, seed=6, feat_dim=m.input_feats_dim)
     g = torch.Generator().manual_seed(7)
     perm = torch.stack([torch.randperm(B, generator=g) for _ in range(23)], 1)       # (B,23)
     pose_R = Rt[perm].float()                                                          # (B,23,3,3), every joint sees every case

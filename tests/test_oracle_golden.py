@@ -181,27 +181,29 @@ def test_model_glue_against_the_real_reference_class(golden_dir):
         with torch.no_grad():
             ref = om.forward(sd, cfg, parents, input_feats=feats, num_samples=4, shape_eps=shape_eps, base_noise=base_noise)
         for k in ('cam_wp', 'glob_rotmat', 'shape_mode', 'shape_log_std', 'shape_samples'):
-            assert torch.allclose(ref[k], t(k), atol=1e-6, rtol=1e-6), (layers, k)
+            assert torch.allclose(ref[k], t(k), atol=1e-5, rtol=1e-5), (layers, k)
         assert torch.allclose(torch.exp(ref['shape_log_std']), t('scale_of_shape_dist'), atol=1e-6, rtol=1e-6)
+        # fp32 on both sides, but the 23-joint chain amplifies the last-bit differences of differently blocked / threaded
+        # matmuls (observed up to 4e-5 with these N(0, 2/fan_in) weights); a glue error (order, index, concat) is O(1)
         for k in ('pose_axisangle_point_est', 'pose_rotmats_point_est', 'pose_rotmats_samples'):
-            assert (ref[k] - t(k)).abs().max().item() <= 2e-6, (layers, k, (ref[k] - t(k)).abs().max().item())
+            assert (ref[k] - t(k)).abs().max().item() <= 2e-4, (layers, k, (ref[k] - t(k)).abs().max().item())
         # contexts the reference computed on the way (recorded around compute_flow_context)
         with torch.no_grad():
             fe_pe = om.image_level_feats(sd, feats, ref['shape_mode'], ref['glob_rotmat'], ref['cam_wp'])
             fe_s = om.image_level_feats(sd, feats, ref['shape_samples'], ref['glob_rotmat'], ref['cam_wp'])
             for j in range(23):
                 c = om.flow_context(sd, j, anc[j], fe_pe, ref['pose_rotmats_point_est'])
-                assert torch.allclose(c, t('ctx_pe')[:, j], atol=5e-6, rtol=1e-5), (layers, j)
+                assert torch.allclose(c, t('ctx_pe')[:, j], atol=1e-4, rtol=1e-4), (layers, j)
                 c = om.flow_context(sd, j, anc[j], fe_s, ref['pose_rotmats_samples'])
-                assert torch.allclose(c, t('ctx_s')[:, :, j], atol=5e-6, rtol=1e-5), (layers, j)
+                assert torch.allclose(c, t('ctx_s')[:, :, j], atol=1e-4, rtol=1e-4), (layers, j)
             ll = om.forward(sd, cfg, parents, input_feats=feats, compute_point_est=False, shape_for_loglik=tgt['shape'],
                             pose_R_for_loglik=tgt['R'], glob_R_for_loglik=tgt['glob'])
-        assert torch.allclose(torch.stack(ll['loglik_contexts'], 1), t('ctx_ll'), atol=5e-6, rtol=1e-5)
+        assert torch.allclose(torch.stack(ll['loglik_contexts'], 1), t('ctx_ll'), atol=2e-5, rtol=1e-5)
         lp_ref = t('lp_SO3')
         assert torch.equal(torch.isfinite(ll['pose_loglik']), torch.isfinite(lp_ref))
         fin = torch.isfinite(lp_ref)
-        assert ((ll['pose_loglik'] - lp_ref).abs()[fin] / lp_ref.abs()[fin].clamp_min(1.0)).max().item() <= 1e-5
+        assert ((ll['pose_loglik'] - lp_ref).abs()[fin] / lp_ref.abs()[fin].clamp_min(1.0)).max().item() <= 1e-4
         with torch.no_grad():
             lp_alg = torch.stack([oflow.algebra_log_prob(om.joint_couplings(sd, j, 2), tgt['v_alg'][:, j], ll['loglik_contexts'][j],
                                                          RADIUS, 0.6) for j in range(23)], 1)
-        assert ((lp_alg - t('lp_so3')).abs() / t('lp_so3').abs().clamp_min(1.0)).max().item() <= 1e-5
+        assert ((lp_alg - t('lp_so3')).abs() / t('lp_so3').abs().clamp_min(1.0)).max().item() <= 1e-4
