@@ -235,6 +235,9 @@ def main():
         model = HumaniflowModel('cpu', cfg, list(SMPL_PARENTS)).eval()
         shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith('image_encoder.')}
         sd = fill_state_dict(shapes, seed=700 + layers)
+        for k in sd:            # N(0, 2/fan_in) is ~2.4x torch's default Linear init; halve it so the 23-joint chain is as
+            if sd[k].dim() >= 2:   # well-conditioned as a freshly initialised model (fp32 summation-order noise stays ~1e-6)
+                sd[k] = sd[k] * 0.5
         sd['init_glob'] = model.state_dict()['init_glob'].clone()
         sd['init_cam'] = model.state_dict()['init_cam'].clone()
         missing = model.load_state_dict(sd, strict=False)

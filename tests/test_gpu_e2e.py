@@ -28,9 +28,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize('layers', [18, 50])
 def test_cuda_model_against_real_reference_golden(layers):
-    """Same weights / features / noise as make_golden_model.py; tolerances: heads 2e-5, log_prob rel 1e-3, rotations 2e-4 (the
-    golden's N(0, 2/fan_in) weights make the 23-joint chain amplify fp32 summation-order differences to ~4e-5 already
-    between two CPU thread counts; with torch-default init the CUDA path holds 2e-5, tests/test_gpu_flow.py)."""
+    """Same weights / features / noise as make_golden_model.py; tolerances: heads 2e-5, rotations 5e-5, log_prob rel 1e-3."""
     g = np.load(os.path.join(GOLDEN, 'model_golden.npz'))
     t = lambda k: torch.tensor(g['r%d_%s' % (layers, k)])
     cfg = hb.get_model_cfg_defaults()
@@ -38,6 +36,7 @@ def test_cuda_model_against_real_reference_golden(layers):
     m = hb.HumaniflowModel('cpu', cfg, SMPL_PARENTS).eval()
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith('image_encoder.')}
     sd = fill_state_dict(shapes, seed=700 + layers)
+    sd = {k: (v * 0.5 if v.dim() >= 2 else v) for k, v in sd.items()}          # as in make_golden_model.py
     sd['init_glob'], sd['init_cam'] = m.state_dict()['init_glob'].clone(), m.state_dict()['init_cam'].clone()
     missing = m.load_state_dict(sd, strict=False)
     assert all(k.startswith('image_encoder.') for k in missing.missing_keys) and not missing.unexpected_keys
@@ -52,7 +51,7 @@ def test_cuda_model_against_real_reference_golden(layers):
     assert torch.allclose(out['shape_dist_for_loglik'].scale.cpu(), t('scale_of_shape_dist'), atol=2e-5, rtol=1e-5)
     for k in ('pose_axisangle_point_est', 'pose_rotmats_point_est', 'pose_rotmats_samples'):
         err = (out[k].cpu() - t(k)).abs().max().item()
-        assert err <= 2e-4, (k, err)
+        assert err <= 5e-5, (k, err)
     v_t = det_input((B, 23, 3), 760 + layers) * 0.7
     v_t[0, 3] = 0.0
     v_t[1, 5] = v_t[1, 5] / v_t[1, 5].norm() * 2.6
@@ -82,19 +81,20 @@ def _path(m, smpl, x, z, se):
     return out, so
 
 
-# Tolerances of the image -> vertex path with the bf16 encoder (measured on B200): feature rel-L2 <= 3e-2
-# (measured ~4e-3); the per-sample vertex error is dominated by the rotation error the feature error induces along the chain.
-E2E_FEAT_REL = 3e-2
-E2E_ROT_MAX = 0.25          # max |dR| entry over all samples / joints
-E2E_ROT_MEAN = 1e-2
-E2E_VERT_MAX = 0.25         # metres, max over all vertices of all samples
-E2E_VERT_MEAN = 1e-2        # metres, mean vertex L2
+# Tolerances of the image -> vertex path with the bf16 encoder, ~4x what was measured on B200 at B=32, N=100:
+# features rel-L2 3.0e-3, heads 1.2e-3, rotation entries max 2.8e-4 / mean 2.2e-5, vertex L2 max 1.05e-3 m / mean 1.4e-4 m.
+# I.e. from the IMAGE the 1e-4 m bar is met on average only; it is met strictly for identical (beta, theta) (test_gpu_lbs.py).
+E2E_FEAT_REL = 1.2e-2
+E2E_ROT_MAX = 1.2e-3        # max |dR| entry over all samples / joints
+E2E_ROT_MEAN = 1e-4
+E2E_VERT_MAX = 4e-3         # metres, max over all vertices of all samples
+E2E_VERT_MEAN = 6e-4        # metres, mean vertex L2
 
 
 @pytest.mark.parametrize('B,N', [(2, 10), (32, 100)])
 def test_config3_image_to_vertices(B, N):
     """BASELINE configs[2]: (B,18,256,256) -> ResNet-50 -> flow -> N SMPL meshes per image vs the fp32 oracle on the same image."""
-    m, sd, cfg = make_model(50, seed=40)
+    m, sd, cfg = make_model(50, seed=40, res_gain=0.3)
     m = m.cuda()
     data = smpl_data()
     smpl = hb.SMPL.from_arrays(data, create_transl=False).cuda()
@@ -132,7 +132,7 @@ def test_config3_image_to_vertices(B, N):
 def test_image_shards_reproduce_the_unsharded_rows_exactly(layers, size, B, world):
     """every rank runs the whole path on its image range with its slice of the global noise; the concatenated
     shards must equal the single-process result BIT FOR BIT (encoder features, heads, rotations, vertices, joints)."""
-    m, sd, cfg = make_model(layers, seed=50)
+    m, sd, cfg = make_model(layers, seed=50, res_gain=0.3)
     m = m.cuda()
     smpl = hb.SMPL.from_arrays(smpl_data(), create_transl=False).cuda()
     N = 6
@@ -153,4 +153,5 @@ def test_image_shards_reproduce_the_unsharded_rows_exactly(layers, size, B, worl
     for k in ('input_feats', 'cam_wp', 'glob_rotmat', 'shape_mode', 'shape_log_std', 'shape_samples', 'pose_rotmats_samples',
               'pose_rotmats_point_est', 'pose_axisangle_point_est'):
         assert torch.equal(torch.cat([p[k] for p in parts], 0), full[k]), k
+    assert torch.isfinite(v_full).all() and torch.isfinite(j_full).all()
     assert torch.equal(torch.cat(vparts, 0), v_full) and torch.equal(torch.cat(jparts, 0), j_full)

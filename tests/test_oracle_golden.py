@@ -150,6 +150,7 @@ def _model_problem(layers):
     ours = hb.HumaniflowModel('cpu', cfg, SMPL_PARENTS)
     shapes = {k: tuple(v.shape) for k, v in ours.state_dict().items() if not k.startswith('image_encoder.')}
     sd = fill_state_dict(shapes, seed=700 + layers)
+    sd = {k: (v * 0.5 if v.dim() >= 2 else v) for k, v in sd.items()}          # as in make_golden_model.py
     sd['init_glob'] = ours.state_dict()['init_glob'].clone()
     sd['init_cam'] = ours.state_dict()['init_cam'].clone()
     B, N, F = 5, 4, (512 if layers == 18 else 2048)
@@ -186,7 +187,7 @@ def test_model_glue_against_the_real_reference_class(golden_dir):
         # fp32 on both sides, but the 23-joint chain amplifies the last-bit differences of differently blocked / threaded
         # matmuls (observed up to 4e-5 with these N(0, 2/fan_in) weights); a glue error (order, index, concat) is O(1)
         for k in ('pose_axisangle_point_est', 'pose_rotmats_point_est', 'pose_rotmats_samples'):
-            assert (ref[k] - t(k)).abs().max().item() <= 2e-4, (layers, k, (ref[k] - t(k)).abs().max().item())
+            assert (ref[k] - t(k)).abs().max().item() <= 2e-5, (layers, k, (ref[k] - t(k)).abs().max().item())
         # contexts the reference computed on the way (recorded around compute_flow_context)
         with torch.no_grad():
             fe_pe = om.image_level_feats(sd, feats, ref['shape_mode'], ref['glob_rotmat'], ref['cam_wp'])

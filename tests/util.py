@@ -33,9 +33,11 @@ def smpl_data(real_regs=True):
     return _SMPL_CACHE[real_regs]
 
 
-def make_model(layers=18, seed=0, flow_scale=1.0, bn_stats=True, in_channels=18):
+def make_model(layers=18, seed=0, flow_scale=1.0, bn_stats=True, in_channels=18, res_gain=None):
     """HumaniflowModel with torch-default init (seeded); optional scaling of the flow weights to make the
-    splines less trivial, and non-trivial BatchNorm statistics so eval-mode BN is not a no-op."""
+    splines less trivial, and non-trivial BatchNorm statistics so eval-mode BN is not a no-op.  ``res_gain`` scales the last
+    BatchNorm of every residual block (the usual small-gamma initialisation of trained ResNets): without it the random-init
+    ResNet-50 features grow to O(100) through 16 un-normalised residual additions and the heads saturate."""
     torch.manual_seed(seed)
     cfg = hb.get_model_cfg_defaults()
     cfg.NUM_RESNET_LAYERS = layers
@@ -54,6 +56,8 @@ def make_model(layers=18, seed=0, flow_scale=1.0, bn_stats=True, in_channels=18)
                 v.copy_(torch.rand(v.shape, generator=g) * 0.5 + 0.75)
             if bn_stats and ('.bn' in k or 'downsample.1' in k or k.startswith('image_encoder.bn1')) and k.endswith('.bias'):
                 v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+            if res_gain is not None and (('.bn3.' in k) or (layers == 18 and '.bn2.' in k)) and (k.endswith('.weight') or k.endswith('.bias')):
+                v.mul_(res_gain)
     m.eval()
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     return m, sd, cfg
