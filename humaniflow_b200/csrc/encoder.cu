@@ -74,6 +74,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
     // bit 2 skip the weight loads
     constexpr int BROWS = PAIR ? BN / 2 : BN;     // weight rows staged by this CTA
     constexpr int A_BYTES = 128 * 128, B_BYTES = BROWS * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+    if (dbg & 256) num_tiles = 0;                  // timing experiment: prologue + teardown only
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;           // persistent worker id (a CTA or a CTA pair)
@@ -241,7 +242,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                 const uint32_t sb = lt % SR, k = lt / SR;
                 mbar_wait(sfree0 + 8 * sb, (k & 1u) ^ 1u);
                 const uint32_t rb = rfull0 + 8 * sb;
-                if (has_res) {
+                if (has_res && !(dbg & 128)) {
                     mbar_expect_tx(rb, SBUF_BYTES);
 #pragma unroll
                     for (int x = 0; x < BN / 64; ++x)
@@ -276,9 +277,10 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
             // converted (tcgen05.wait::ld waits for every outstanding load, so the next one is issued right after it)
             constexpr int NCH = HALF / 32;
             uint32_t v[2][32];
-            if (!dual) tmem_ld32(trow, v[0]);
+            if (!dual && !(dbg & 32)) tmem_ld32(trow, v[0]);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
+                if (dbg & 32) continue;
                 const int col = colhalf * HALF + ch * 32;                  // first column (within the BN tile) of this chunk
                 float4 bb[8];
                 const float4* bp = reinterpret_cast<const float4*>(bias + n0 + col);
@@ -342,9 +344,11 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x == 64) {
                 if (lt == 0) conv_stamp(dbg, 6);                    // first tile converted into the staging buffer
+                if (!(dbg & 64)) {
 #pragma unroll
                 for (int x = 0; x < BN / 64; ++x)
                     tma_store_4d(&maps.o, sbuf_base + sb * SBUF_BYTES + x * 16384, n0 + x * 64, tw * g.TW, th * g.TH, tb * g.TB);
+                }
                 bulk_commit();
                 if (SR == 1) {                            // single staging tile: recycle it as soon as this store has read it
                     bulk_wait_read<0>();
@@ -933,6 +937,11 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
         nchw_to_nhwc_pad_kernel<<<blocks, 256, 0, stream>>>(input, stem_in, B, h->in_channels, H, W, h->stem_cp, Hp, Wp, 3, 3);   // follows a memset: plain launch
         HF_LAUNCH_CHECK();
     }
+    // profiling aid (HF_ENC_TIMING=1): CUDA events around every op of this call, per-op times printed to stderr
+    static const bool op_timing = getenv("HF_ENC_TIMING") != nullptr;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() { if (op_timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); evs.push_back(e); } };
+    mark();
     for (size_t i = 0; i < h->ops.size(); ++i) {
         const hf_enc_op& op = h->ops[i];
         if (op.kind == HF_OP_CONV) {
@@ -963,7 +972,26 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
             avgpool_kernel<<<grid, 128, 0, stream>>>(buf(op.src), feats, B, in.H * in.W, in.C);
             HF_LAUNCH_CHECK();
         }
+        mark();
         if (h->debug_stop == (int)i) break;
+    }
+    if (op_timing) {
+        cudaStreamSynchronize(stream);
+        float tot = 0.f;
+        for (size_t i = 0; i + 1 < evs.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+            tot += ms;
+            const hf_enc_op& op = h->ops[i];
+            if (op.kind == HF_OP_CONV) {
+                const ConvPlan& p = h->plans[i];
+                const double gf = 2.0 * B * p.g.Ho * p.g.Wo * (double)op.cout * ((double)op.ksize * op.ksize * op.cin + (op.src2 >= 0 ? op.cin2 : 0)) * 1e-9;
+                fprintf(stderr, "op %2zu conv k%d s%d %4d->%4d @%3dx%-3d bn %3d st %d sr %d res %d tiles %5d nkb %2d grid %3d : %7.2f us  %6.1f TF/s\n", i, op.ksize, op.stride,
+                        op.cin + (op.src2 >= 0 ? op.cin2 : 0), op.cout, p.g.Ho, p.g.Wo, p.bn, p.stages, p.sr, p.has_res, p.num_tiles, p.g.nkb, p.grid.x, ms * 1e3, gf / ms);
+            } else fprintf(stderr, "op %2zu kind %d : %7.2f us\n", i, op.kind, ms * 1e3);
+        }
+        fprintf(stderr, "encoder ops total %.1f us\n", tot * 1e3);
+        for (auto e : evs) cudaEventDestroy(e);
     }
     return HF_OK;
 }

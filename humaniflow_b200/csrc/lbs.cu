@@ -16,6 +16,7 @@
 #include <vector>
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 
 #define HF_MAXJ 24
 #define HF_MAXB 16
@@ -37,7 +38,8 @@ struct hf_smpl {
     __nv_bfloat16* Pbf;
     CUtensorMap mapA;
     int impl;                 // 0 = persistent fp16 tcgen05 blend (product path), 1 = FP32 CUDA-core blend (debug
-                              // cross-check), 2 = split-bf16 three-pass tcgen05 blend (high-precision cross-check)
+                              // cross-check), 2 = split-bf16 three-pass tcgen05 blend (high-precision cross-check),
+                              // 3 = lanes-as-samples fp16 tcgen05 blend (round-2 experiment, slower: DESIGN.md 4.1)
     // product path: fp16 basis [3][Vp][LBS_K2] scaled by 2^k = pose block | shape hi | shape hi | shape lo
     __half* Pf16;
     float inv_scale;
@@ -46,6 +48,13 @@ struct hf_smpl {
     int* vflag;
     CUtensorMap mapA2;
     const void* mapB2_ptr; int mapB2_M; CUtensorMap mapB2;
+    // round-2 experiment (impl 3, lbs_skin_tc3_kernel): lanes = samples.  Basis rows re-ordered so that inside every
+    // 32-vertex tile the vertices are sorted by their skinning-joint signature (runs of equal joints -> the 3x4 transforms
+    // stay in registers); per sorted position one 64-byte record {v_template, original index, weights, joints, flagged slot}
+    __half* Pf16s; float4* vconst; CUtensorMap mapP3;
+    const void* mapF3_ptr; int mapF3_M; CUtensorMap mapF3;
+    int NF;                   // vertices read by the joint picks / extra regressors ("flagged"), each with a slot in xvt
+    int *pick_f, *csr_f;      // flagged slot of every pick / CSR entry
     // cached tensor map of the per-call coefficient matrix
     const void* mapB_ptr; int mapB_M; CUtensorMap mapB;
 };
@@ -71,7 +80,7 @@ lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotma
                                 const float* __restrict__ transl, const float* __restrict__ J0,
                                 const float* __restrict__ Jd, Parents par, int M, int J, int nb, int KP,
                                 int J_out, float* __restrict__ F, __half* __restrict__ Fh, float* __restrict__ A,
-                                float* __restrict__ joints) {
+                                float* __restrict__ At, float* __restrict__ joints) {
     __shared__ __align__(16) float Gs[HF_MAXJ][PS][12];
     __shared__ float Js[HF_MAXJ][PS][3];
     __shared__ float Rs[PS][PR];
@@ -172,7 +181,11 @@ lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotma
             g.w = gp.x * tx + gp.y * ty + gp.z * tz + gp.w;
         }
         *reinterpret_cast<float4*>(&Gs[i][sl][r * 4]) = g;
-        *reinterpret_cast<float4*>(Am + i * 12) = make_float4(g.x, g.y, g.z, g.w - (g.x * jx + g.y * jy + g.z * jz));
+        const float aw = g.w - (g.x * jx + g.y * jy + g.z * jz);
+        if (At)     // layout of the round-2 skinning kernel: At[sample tile][joint][128 samples][3 x 4]
+            *reinterpret_cast<float4*>(At + (((size_t)(m >> 7) * J + i) * 128 + (m & 127)) * 12 + r * 4) = make_float4(g.x, g.y, g.z, aw);
+        else
+        *reinterpret_cast<float4*>(Am + i * 12) = make_float4(g.x, g.y, g.z, aw);
         jm[i * 3] = g.w + tr;
     }
 }
@@ -511,7 +524,7 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const bool new_tile = st != cur_st;
                 for (int it = 0; it < T2_NIT; ++it, ++kbc) {
                     const uint32_t sg = kbc % T2_STAGES, ph = (kbc / T2_STAGES) & 1u;
-                    mbar_wait(empty0 + 8 * sg, ph ^ 1u);
+                    mbar_wait_long(empty0 + 8 * sg, ph ^ 1u);
                     const uint32_t fb = full0 + 8 * sg;
                     mbar_expect_tx(fb, 16384);
                     const int c = it / T2_KBLK, kb = it - c * T2_KBLK;
@@ -519,7 +532,7 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     // switch the resident sample tile once the ring is primed with the new unit's first blocks: the old
                     // tile's coefficients / transforms are free when every epilogue warp has finished its last unit
                     if (new_tile && it == (T2_STAGES < T2_NIT ? T2_STAGES : T2_NIT) - 1) {
-                        if (cur_st >= 0) mbar_wait(sdone, (sc - 1) & 1u);
+                        if (cur_st >= 0) mbar_wait_long(sdone, (sc - 1) & 1u);
                         const int m0 = st * T2_NS;
                         const int rows = min(T2_NS, M - m0);
                         const uint32_t abytes = (uint32_t)(rows * J12 * 4);
@@ -539,13 +552,13 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             int cur_st = -1;
             for (int u = u0; u < u1; ++u, ++lt) {
                 const int st = u / nvt;
-                if (st != cur_st) { mbar_wait(bfull, sc & 1u); ++sc; cur_st = st; }
+                if (st != cur_st) { mbar_wait_long(bfull, sc & 1u); ++sc; cur_st = st; }
                 const uint32_t buf = lt & 1u;
-                mbar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1u) ^ 1u);
+                mbar_wait_long(tempty0 + 8 * buf, ((lt >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 for (int it = 0; it < T2_NIT; ++it, ++kbc) {
                     const uint32_t sg = kbc % T2_STAGES, ph = (kbc / T2_STAGES) & 1u;
-                    mbar_wait(full0 + 8 * sg, ph);
+                    mbar_wait_long(full0 + 8 * sg, ph);
                     tcgen05_fence_after();
                     const int c = it / T2_KBLK, kb = it - c * T2_KBLK;
                     const uint64_t da = umma_desc_sw128(tile_base + sg * 16384), db = umma_desc_sw128(bres + kb * (T2_NS * 128));
@@ -673,6 +686,317 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Round-2 experiment (impl 3; measured slower than the product kernel above, kept as a cross-check):
+// fp16 tensor-core blend + CUDA-core skinning with LANES = SAMPLES.
+//   unit = 128 samples x 32 vertices.  D[s][(c, v)] = sum_k f[s][k] P_c[v][k]: the per-sample coefficient tile is the
+//   RESIDENT A operand (4 k-blocks x [128 rows][128 B] = 64 KB per sample tile), the basis rows of the unit's 32 vertices
+//   (3 coordinates -> N = 96) stream through a TMA ring as the B operand; accumulators double-buffered in TMEM (2 x 96
+//   columns).  Epilogue warp (q, g): TMEM lane quarter q = 32 samples, 8 of the unit's 32 vertices.  Every vertex is
+//   warp-uniform, so its weights / joints come from one 64-byte record (uniform loads) and the 3x4 transforms of its <= 4
+//   joints live in REGISTERS, re-loaded (coalesced over the samples, At[tile][joint][12][128]) only when the joint of a
+//   slot changes; vertices are pre-sorted inside each 32-tile by joint signature, so changes are rare.  Results are
+//   transposed through a shared-memory tile (pitch 97, conflict-free) and leave as 128-byte row segments of
+//   vertices[m][v][3]; vertices that feed a joint pick / extra regressor are also written to xvt[tile][slot][c][sample].
+#ifndef T3_BRANCHY
+#define T3_BRANCHY 1
+#endif
+constexpr int T3_MS = 128, T3_NV = 32, T3_N = 3 * T3_NV, T3_STAGES = 6, T3_STAGE_BYTES = T3_N * 128;
+constexpr int T3_EPI_WARPS = 16, T3_THREADS = (2 + T3_EPI_WARPS) * 32;
+constexpr int T3_KBLK = LBS_K2 / 64, T3_ARES_BYTES = T3_KBLK * T3_MS * 128;
+constexpr int T3_PITCH = T3_N + 1, T3_STG_BYTES = 4 * 32 * T3_PITCH * 4 + T3_EPI_WARPS * 512 + 16;
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+}
+
+template <bool TRANSL>
+__global__ void __launch_bounds__(T3_THREADS, 1)
+lbs_skin_tc3_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapF,
+                    const float4* __restrict__ vconst, const float* __restrict__ At, const float* __restrict__ transl,
+                    int M, int V, int Vp, int J, float inv_scale, int nvt, int num_units, int NF,
+                    float* __restrict__ vertices, float* __restrict__ xvt, int dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * T3_STAGES + 6];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ares = tile_base + T3_STAGES * T3_STAGE_BYTES;            // resident A operand: 4 k-blocks [128 rows][128 B]
+    float* stg = reinterpret_cast<float*>(smem_raw + (ares + T3_ARES_BYTES - smem_u32(smem_raw)));   // [4 quarters][32][T3_PITCH]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[T3_STAGES]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * T3_STAGES]), tempty0 = smem_u32(&bars[2 * T3_STAGES + 2]);
+    const uint32_t afull = smem_u32(&bars[2 * T3_STAGES + 4]), sdone = smem_u32(&bars[2 * T3_STAGES + 5]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T3_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, T3_EPI_WARPS); }
+        mbar_init(afull, 1);
+        mbar_init(sdone, T3_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const int u0 = (int)((long long)blockIdx.x * num_units / gridDim.x);
+    const int u1 = (int)((long long)(blockIdx.x + 1) * num_units / gridDim.x);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t kbc = 0, sc = 0;
+            int cur_st = -1;
+            for (int u = u0; u < u1; ++u) {
+                const int st = u / nvt, vt = u - st * nvt;
+                const bool new_tile = st != cur_st;
+                for (int kb = 0; kb < T3_KBLK; ++kb, ++kbc) {
+                    const uint32_t sg = kbc % T3_STAGES, ph = (kbc / T3_STAGES) & 1u;
+                    mbar_wait_long(empty0 + 8 * sg, ph ^ 1u);
+                    const uint32_t fb = full0 + 8 * sg, dst = tile_base + sg * T3_STAGE_BYTES;
+                    mbar_expect_tx(fb, T3_STAGE_BYTES);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) tma_load_2d(dst + c * (T3_NV * 128), &mapP, fb, kb * 64, c * Vp + vt * T3_NV);
+                    // switch the resident sample tile once this unit's basis blocks are on their way: the old tile's
+                    // coefficients are free when every epilogue warp has finished its last unit (its MMAs completed before)
+                    if (new_tile && kb == T3_KBLK - 1) {
+                        if (cur_st >= 0) mbar_wait_long(sdone, (sc - 1) & 1u);
+                        mbar_expect_tx(afull, (uint32_t)T3_ARES_BYTES);
+#pragma unroll
+                        for (int k = 0; k < T3_KBLK; ++k) tma_load_2d(ares + k * (T3_MS * 128), &mapF, afull, k * 64, st * T3_MS);
+                        cur_st = st; ++sc;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(T3_MS, T3_N);
+            uint32_t kbc = 0, lt = 0, sc = 0;
+            int cur_st = -1;
+            for (int u = u0; u < u1; ++u, ++lt) {
+                const int st = u / nvt;
+                if (st != cur_st) { mbar_wait_long(afull, sc & 1u); ++sc; cur_st = st; }
+                const uint32_t buf = lt & 1u;
+                mbar_wait_long(tempty0 + 8 * buf, ((lt >> 1) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d = tmem_base + buf * T3_N;
+                for (int kb = 0; kb < T3_KBLK; ++kb, ++kbc) {
+                    const uint32_t sg = kbc % T3_STAGES, ph = (kbc / T3_STAGES) & 1u;
+                    mbar_wait_long(full0 + 8 * sg, ph);
+                    tcgen05_fence_after();
+                    const uint64_t da = umma_desc_sw128(ares + kb * (T3_MS * 128)), db = umma_desc_sw128(tile_base + sg * T3_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(empty0 + 8 * sg);
+                }
+                umma_commit(tfull0 + 8 * buf);
+            }
+        }
+    } else {
+        const int q = warp & 3, g = (warp - 2) >> 2;        // TMEM lane quarter (32 samples), group of 8 vertices
+        const int sl = q * 32 + lane;                        // sample within the tile
+        float* sq = stg + q * (32 * T3_PITCH);               // this quarter's staging rows [32][T3_PITCH]
+        float4* rec = reinterpret_cast<float4*>(stg + 4 * 32 * T3_PITCH) + (warp - 2) * 32;   // this warp's 8 vertex records (512 B)
+        const uint32_t bar_id = 1 + q;
+        float T[4][12];
+        float trx = 0.f, try_ = 0.f, trz = 0.f;
+        uint32_t lt = 0, curpack = 0xffffffffu;               // joints (one byte per slot) of the transforms held in T
+        int cur_st = -1;
+        const float* Ab = At;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int e = 0; e < 12; ++e) T[k][e] = 0.f;
+        // records of the warp's 8 vertices of a unit = 512 contiguous bytes = one 16-byte load per lane, fetched one unit ahead
+        float4 rnext = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u0 < u1) rnext = __ldg(vconst + ((size_t)(u0 % nvt) * T3_NV + g * 8) * 4 + lane);
+        for (int u = u0; u < u1; ++u, ++lt) {
+            const int st = u / nvt, vt = u - st * nvt;
+            const uint32_t buf = lt & 1u;
+            const int m = st * T3_MS + sl;
+            if (st != cur_st) {
+                cur_st = st;
+                Ab = At + ((size_t)st * J * 128 + sl) * 12;
+                curpack = 0xffffffffu;                               // register-resident transforms belong to the old tile
+                if (TRANSL && m < M) { trx = __ldg(transl + (size_t)m * 3); try_ = __ldg(transl + (size_t)m * 3 + 1); trz = __ldg(transl + (size_t)m * 3 + 2); }
+            }
+            rec[lane] = rnext;
+            if (u + 1 < u1) rnext = __ldg(vconst + ((size_t)((u + 1) % nvt) * T3_NV + g * 8) * 4 + lane);
+            __syncwarp();
+            mbar_wait_long(tfull0 + 8 * buf, (lt >> 1) & 1u);
+            tcgen05_fence_after();
+            if (dbg & 1) {     // timing experiment (HF_LBS_DBG=1): skip the epilogue work, keep the protocol
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(tempty0 + 8 * buf); if (u + 1 < u1 && (u + 1) / nvt != st) mbar_arrive(sdone); }
+                continue;
+            }
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * T3_N + (uint32_t)(g * 8);
+            // one vertex per iteration (rolled loop: the body is large and its control flow data dependent); the accumulator
+            // columns of vertex i+1 are requested before vertex i is processed
+            uint32_t nx, ny, nz;
+            tmem_ld1(ta, nx); tmem_ld1(ta + T3_NV, ny); tmem_ld1(ta + 2 * T3_NV, nz);
+            // software pipeline: record (shared memory, broadcast) + control words (shuffles) of vertex i+1 are fetched while
+            // vertex i is processed, so the per-vertex dependency chain is only the FMA part
+            float4 n0 = rec[0], n1 = rec[1], n3 = rec[3];
+            uint32_t nctrl = __shfl_sync(0xffffffffu, __float_as_uint(n3.x), 0);
+            uint32_t njpack = __shfl_sync(0xffffffffu, __float_as_uint(n3.z), 0);
+            uint32_t nlmask = __shfl_sync(0xffffffffu, __float_as_uint(n3.w), 0);
+#pragma unroll 1
+            for (int i = 0; i < ((dbg & 8) ? 0 : 8); ++i) {
+                tmem_ld_wait();
+                const uint32_t px = nx, py = ny, pz = nz;
+                const float4 c0 = n0, c1 = n1, c3 = n3;
+                const uint32_t ctrl = nctrl, jpack = njpack, lmask = nlmask;
+                const float4* rp = rec + i * 4;
+                if (i < 7) {
+                    tmem_ld1(ta + i + 1, nx); tmem_ld1(ta + T3_NV + i + 1, ny); tmem_ld1(ta + 2 * T3_NV + i + 1, nz);
+                    n0 = rp[4]; n1 = rp[5]; n3 = rp[7];
+                }
+                if (dbg & 16) { if (px == 0x12345678u && py == pz) sq[lane] = 1.f; continue; }   // timing experiment: TMEM loads only
+                const float x = fmaf(__uint_as_float(px), inv_scale, c0.x);
+                const float y = fmaf(__uint_as_float(py), inv_scale, c0.y);
+                const float z = fmaf(__uint_as_float(pz), inv_scale, c0.z);
+                if ((jpack ^ curpack) & lmask) {                             // rare with sorted tiles: a live slot's joint run ended
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t jb = (jpack >> (8 * k)) & 0xffu;
+                        if (jb != 0xffu && jb != ((curpack >> (8 * k)) & 0xffu)) {
+                            const float4* ap = reinterpret_cast<const float4*>(Ab + (size_t)jb * (128 * 12));
+                            const float4 r0 = __ldg(ap), r1 = __ldg(ap + 1), r2 = __ldg(ap + 2);
+                            T[k][0] = r0.x; T[k][1] = r0.y; T[k][2] = r0.z; T[k][3] = r0.w;
+                            T[k][4] = r1.x; T[k][5] = r1.y; T[k][6] = r1.z; T[k][7] = r1.w;
+                            T[k][8] = r2.x; T[k][9] = r2.y; T[k][10] = r2.z; T[k][11] = r2.w;
+                            curpack = (curpack & ~(0xffu << (8 * k))) | (jb << (8 * k));
+                        }
+                    }
+                }
+#if T3_BRANCHY
+                // skip dead slots (slots are compacted live-first, slot 0 is always live): ns = live slots - 1, warp-uniform
+                const uint32_t ns = ctrl & 3u;
+                float ox, oy, oz;
+                ox = c1.x * fmaf(T[0][0], x, fmaf(T[0][1], y, fmaf(T[0][2], z, T[0][3])));
+                oy = c1.x * fmaf(T[0][4], x, fmaf(T[0][5], y, fmaf(T[0][6], z, T[0][7])));
+                oz = c1.x * fmaf(T[0][8], x, fmaf(T[0][9], y, fmaf(T[0][10], z, T[0][11])));
+                if (ns >= 1u) {
+                    ox = fmaf(c1.y, fmaf(T[1][0], x, fmaf(T[1][1], y, fmaf(T[1][2], z, T[1][3]))), ox);
+                    oy = fmaf(c1.y, fmaf(T[1][4], x, fmaf(T[1][5], y, fmaf(T[1][6], z, T[1][7]))), oy);
+                    oz = fmaf(c1.y, fmaf(T[1][8], x, fmaf(T[1][9], y, fmaf(T[1][10], z, T[1][11]))), oz);
+                    if (ns >= 2u) {
+                        ox = fmaf(c1.z, fmaf(T[2][0], x, fmaf(T[2][1], y, fmaf(T[2][2], z, T[2][3]))), ox);
+                        oy = fmaf(c1.z, fmaf(T[2][4], x, fmaf(T[2][5], y, fmaf(T[2][6], z, T[2][7]))), oy);
+                        oz = fmaf(c1.z, fmaf(T[2][8], x, fmaf(T[2][9], y, fmaf(T[2][10], z, T[2][11]))), oz);
+                        if (ns >= 3u) {
+                            ox = fmaf(c1.w, fmaf(T[3][0], x, fmaf(T[3][1], y, fmaf(T[3][2], z, T[3][3]))), ox);
+                            oy = fmaf(c1.w, fmaf(T[3][4], x, fmaf(T[3][5], y, fmaf(T[3][6], z, T[3][7]))), oy);
+                            oz = fmaf(c1.w, fmaf(T[3][8], x, fmaf(T[3][9], y, fmaf(T[3][10], z, T[3][11]))), oz);
+                        }
+                    }
+                }
+#else
+                // all four slots, branch-free: dead slots carry weight 0 and whatever (finite) transform the slot held last, so
+                // the 12 inner products are independent FMA chains the scheduler can interleave (the branchy form, which skips
+                // dead slots, measured latency-bound at 4 warps per scheduler)
+                const float wk[4] = {c1.x, c1.y, c1.z, c1.w};
+                float ox = 0.f, oy = 0.f, oz = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ox = fmaf(wk[k], fmaf(T[k][0], x, fmaf(T[k][1], y, fmaf(T[k][2], z, T[k][3]))), ox);
+                    oy = fmaf(wk[k], fmaf(T[k][4], x, fmaf(T[k][5], y, fmaf(T[k][6], z, T[k][7]))), oy);
+                    oz = fmaf(wk[k], fmaf(T[k][8], x, fmaf(T[k][9], y, fmaf(T[k][10], z, T[k][11]))), oz);
+                }
+#endif
+                if (TRANSL) { ox += trx; oy += try_; oz += trz; }
+                float* so = sq + lane * T3_PITCH + __float_as_int(c0.w);     // c0.w = 3 * (original index inside the 32-tile)
+                so[0] = ox; so[1] = oy; so[2] = oz;
+                if ((ctrl & 0x100u) && m < M) {                    // vertex feeds a joint pick / regressor: sample-contiguous copy
+                    float* xo = xvt + (((size_t)st * NF + __float_as_int(c3.y)) * 3) * 128 + sl;
+                    xo[0] = ox; xo[128] = oy; xo[256] = oz;
+                }
+                nctrl = __shfl_sync(0xffffffffu, __float_as_uint(n3.x), 0);
+                njpack = __shfl_sync(0xffffffffu, __float_as_uint(n3.z), 0);
+                nlmask = __shfl_sync(0xffffffffu, __float_as_uint(n3.w), 0);
+            }
+            // accumulator fully read (the last vertex's columns were waited for inside the loop): hand the TMEM buffer back
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            // the quarter's 32 x 96 tile is complete when its four warps have written their 8 vertices each
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            {
+                const int ebase = vt * T3_N;                         // first float of this unit inside a sample's vertex row
+                const int emax = V * 3;
+                const bool full = ebase + T3_N <= emax;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = g * 8 + i;                         // sample row of this quarter written by this warp
+                    const int mr = st * T3_MS + q * 32 + r;
+                    if (mr < M && !(dbg & 4)) {
+                        float* out = vertices + (size_t)mr * emax + ebase + lane;
+                        const float* sr = sq + r * T3_PITCH + lane;
+                        if (dbg & 2) { if (sr[0] + sr[32] + sr[64] == 123.456f) out[0] = 0.f; }
+                        else if (full) { __stcs(out, sr[0]); __stcs(out + 32, sr[32]); __stcs(out + 64, sr[64]); }
+                        else {
+#pragma unroll
+                            for (int c3i = 0; c3i < 3; ++c3i)
+                                if (ebase + c3i * 32 + lane < emax) __stcs(out + c3i * 32, sr[c3i * 32]);
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");    // staging rows may be overwritten by the next unit
+            if (lane == 0 && u + 1 < u1 && (u + 1) / nvt != st) mbar_arrive(sdone);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// joints[J ..) from the sample-contiguous copies of the flagged vertices written by lbs_skin_tc3_kernel:
+// xvt[tile][slot][c][128 samples].  Block = (sample tile, chunk of XT_ROWS output rows), thread = sample; every row is summed in
+// CSR order (fixed order -> deterministic).
+constexpr int XT_ROWS = 6;
+__global__ void __launch_bounds__(128)
+lbs_extra_joints_t_kernel(const float* __restrict__ xvt, const int* __restrict__ pick_f, const int* __restrict__ csr_ptr,
+                          const int* __restrict__ csr_f, const float* __restrict__ csr_val, int M, int J, int nvj, int nextra,
+                          int J_out, int NF, float* __restrict__ joints) {
+    HF_PDL_SYNC();
+    const int st = blockIdx.x, s = threadIdx.x, m = st * 128 + s;
+    if (m >= M) return;
+    const float* xb = xvt + (size_t)st * NF * 3 * 128 + s;
+    const int r0 = blockIdx.y * XT_ROWS, r1 = min(r0 + XT_ROWS, nvj + nextra);
+    for (int r = r0; r < r1; ++r) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (r < nvj) {
+            const float* p = xb + (size_t)pick_f[r] * 3 * 128;
+            x = p[0]; y = p[128]; z = p[256];
+        } else {
+            const int row = r - nvj;
+            for (int e = csr_ptr[row]; e < csr_ptr[row + 1]; ++e) {
+                const float w = csr_val[e];
+                const float* p = xb + (size_t)csr_f[e] * 3 * 128;
+                x = fmaf(w, p[0], x); y = fmaf(w, p[128], y); z = fmaf(w, p[256], z);
+            }
+        }
+        float* o = joints + ((size_t)m * J_out + J + r) * 3;
+        o[0] = x; o[1] = y; o[2] = z;
     }
 }
 
@@ -863,6 +1187,7 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
         if ((rc = encode_map(&h->mapA, h->Pbf, 2, dims, st, box))) return rc;
         h->impl = 0; h->mapB_ptr = nullptr; h->mapB_M = 0;
     }
+    std::vector<__half> pf;
     {   // fp16 basis for the product path: row (c, v) = [posedirs (208) | shape hi (16) | shape hi (16) | shape lo (16)] * 2^k
         if (9 * (J - 1) > LBS_K2_POSE || nb > 16) { delete h; return hf::fail(HF_ERR_UNSUPPORTED, "hf_smpl_create: J=%d nb=%d exceed the fp16 blend layout", J, nb); }
         float mx = 0.f;
@@ -871,7 +1196,7 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
         if (mx > 0.f) { std::frexp(mx, &ex); }            // mx = m * 2^ex, 0.5 <= m < 1
         const float scale = std::ldexp(1.f, 10 - ex);       // max |entry| * scale in [512, 1024): far from fp16 overflow and subnormals
         h->inv_scale = 1.f / scale;
-        std::vector<__half> pf((size_t)3 * Vp * LBS_K2, __float2half(0.f));
+        pf.assign((size_t)3 * Vp * LBS_K2, __float2half(0.f));
         for (int c = 0; c < 3; ++c)
             for (int v = 0; v < V; ++v) {
                 __half* row = &pf[((size_t)c * Vp + v) * LBS_K2];
@@ -906,6 +1231,70 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
         for (int e = 0; e < h->nnz; ++e) vflag[col[e]] = 1;
         if ((rc = hf::upload(&h->vflag, vflag.data(), vflag.size()))) return rc;
     }
+    {   // round-2 experiment (impl 3): per-tile sorted vertex order, basis rows in that order, 64-byte per-vertex records, flagged slots
+        const int nvt3 = Vp / T3_NV;
+        auto key = [&](int v, int k) -> int { return (v < V && k < nslots && sw[(size_t)k * Vp + v] != 0.f) ? sj[(size_t)k * Vp + v] : 999; };
+        std::vector<int> order((size_t)Vp);
+        for (int t = 0; t < nvt3; ++t) {
+            int idx[T3_NV];
+            for (int i = 0; i < T3_NV; ++i) idx[i] = t * T3_NV + i;
+            std::stable_sort(idx, idx + T3_NV, [&](int a, int b) {
+                if ((a < V) != (b < V)) return a < V;                 // padding vertices last
+                for (int k = 0; k < 4; ++k) { const int ka = key(a, k), kb = key(b, k); if (ka != kb) return ka < kb; }
+                return false;
+            });
+            for (int i = 0; i < T3_NV; ++i) order[(size_t)t * T3_NV + i] = idx[i];
+        }
+        std::vector<int> fmap((size_t)Vp, -1), vflag_h((size_t)Vp, 0);
+        for (int r = 0; r < nvj; ++r) vflag_h[vj[r]] = 1;
+        for (int e = 0; e < h->nnz; ++e) vflag_h[col[e]] = 1;
+        int NF = 0;
+        for (int v = 0; v < V; ++v) if (vflag_h[v]) fmap[v] = NF++;
+        h->NF = std::max(NF, 1);
+        std::vector<int> pick_f(std::max(nvj, 1), 0), csr_f(col.size(), 0);
+        for (int r = 0; r < nvj; ++r) pick_f[r] = fmap[vj[r]];
+        for (int e = 0; e < h->nnz; ++e) csr_f[e] = fmap[col[e]];
+        if ((rc = hf::upload(&h->pick_f, pick_f.data(), pick_f.size()))) return rc;
+        if ((rc = hf::upload(&h->csr_f, csr_f.data(), csr_f.size()))) return rc;
+        std::vector<float> vc((size_t)Vp * 16, 0.f);
+        std::vector<__half> ps((size_t)3 * Vp * LBS_K2, __float2half(0.f));
+        for (int p2 = 0; p2 < Vp; ++p2) {
+            const int v = order[p2];
+            float* rec = &vc[(size_t)p2 * 16];
+            int li = v % T3_NV, jj[4] = {0, 0, 0, 0}, f = -1;
+            float ww[4] = {0.f, 0.f, 0.f, 0.f};
+            if (v < V) {
+                for (int c = 0; c < 3; ++c) rec[c] = vt[(size_t)c * Vp + v];
+                for (int k = 0; k < std::min(nslots, 4); ++k) { ww[k] = sw[(size_t)k * Vp + v]; jj[k] = sj[(size_t)k * Vp + v]; }
+                f = fmap[v];
+                for (int c = 0; c < 3; ++c)
+                    memcpy(&ps[((size_t)c * Vp + p2) * LBS_K2], &pf[((size_t)c * Vp + v) * LBS_K2], LBS_K2 * sizeof(__half));
+            }
+            const int li3 = li * 3;
+            memcpy(&rec[3], &li3, 4);
+            for (int k = 0; k < 4; ++k) { rec[4 + k] = ww[k]; memcpy(&rec[8 + k], &jj[k], 4); }
+            // control word: live slots - 1 | flagged << 8; jpack: joint of every live slot, one byte each (0xff = dead slot)
+            int live = 0;
+            for (int k = 0; k < 4; ++k) live += ww[k] != 0.f;
+            unsigned ctrl = (unsigned)std::max(live - 1, 0), jpack = 0;
+            for (int k = 0; k < 4; ++k) jpack |= (unsigned)((v < V && k < live) ? jj[k] : 0xff) << (8 * k);
+            if (f >= 0) ctrl |= 0x100u;
+            memcpy(&rec[12], &ctrl, 4);
+            const int fi = std::max(f, 0);
+            memcpy(&rec[13], &fi, 4);
+            memcpy(&rec[14], &jpack, 4);
+            unsigned lmask = 0;
+            for (int k = 0; k < 4; ++k) if (v < V && k < live) lmask |= 0xffu << (8 * k);
+            memcpy(&rec[15], &lmask, 4);
+        }
+        if ((rc = hf::upload((float**)&h->vconst, vc.data(), vc.size()))) return rc;
+        if ((rc = hf::upload(&h->Pf16s, ps.data(), ps.size()))) return rc;
+        const uint64_t dims[2] = {(uint64_t)LBS_K2, (uint64_t)3 * Vp};
+        const uint64_t st[1] = {(uint64_t)LBS_K2 * 2};
+        const uint32_t box[2] = {64, (uint32_t)T3_NV};
+        if ((rc = encode_map(&h->mapP3, h->Pf16s, 2, dims, st, box))) return rc;
+        h->mapF3_ptr = nullptr; h->mapF3_M = 0;
+    }
     if ((rc = hf::upload(&h->csr_ptr, ptr.data(), ptr.size()))) return rc;
     if ((rc = hf::upload(&h->csr_col, col.data(), col.size()))) return rc;
     if ((rc = hf::upload(&h->csr_val, val.data(), val.size()))) return rc;
@@ -916,18 +1305,25 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
 extern "C" void hf_smpl_destroy(hf_smpl_t* h) {
     if (!h) return;
     cudaFree(h->blend); cudaFree(h->vtemp); cudaFree(h->J0); cudaFree(h->Jd); cudaFree(h->sj);
-    cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->Pf16); cudaFree(h->vflag); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
+    cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->Pf16); cudaFree(h->Pf16s); cudaFree(h->vconst); cudaFree(h->pick_f); cudaFree(h->csr_f); cudaFree(h->vflag); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
     delete h;
 }
 
 extern "C" int hf_smpl_num_joints_out(const hf_smpl_t* h) { return h->J + h->nvj + h->nextra; }
 
+// workspace layout: F [M][KP] f32 | A [M][J][12] f32 | coefficient rows (fp16 [M][256] or split bf16 [M][512]), 256-aligned |
+// At [tiles][J][12][128] f32 | xvt [tiles][NF][3][128] f32   (tiles = ceil(M / 128); the last two feed lbs_skin_tc3_kernel)
+static size_t lbs_ws_off_at(const hf_smpl* h, int M) {
+    return (((size_t)M * (h->KP + h->J * 12) * sizeof(float) + 255) & ~(size_t)255) + (((size_t)M * 2 * LBS_KH * 2 + 255) & ~(size_t)255);
+}
 extern "C" size_t hf_lbs_workspace_bytes(const hf_smpl_t* h, int M) {
-    return (size_t)M * (h->KP + h->J * 12) * sizeof(float) + (size_t)M * 2 * LBS_KH * 2 + 256;
+    const size_t tiles = (size_t)hf::div_up(M, T3_MS);
+    return lbs_ws_off_at(h, M) + tiles * h->J * 12 * 128 * sizeof(float) + tiles * h->NF * 3 * 128 * sizeof(float) + 512;
 }
 
 extern "C" int hf_lbs_set_impl(hf_smpl_t* h, int impl) {
-    if (!h || impl < 0 || impl > 2) return hf::fail(HF_ERR_INVALID, "hf_lbs_set_impl: bad argument");
+    if (!h || impl < 0 || impl > 3) return hf::fail(HF_ERR_INVALID, "hf_lbs_set_impl: bad argument");
+    if (impl == 3 && h->nslots > 4) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_set_impl: the lanes-as-samples kernel holds 4 skinning slots in registers, model has %d", h->nslots);
     h->impl = impl;
     return HF_OK;
 }
@@ -966,18 +1362,55 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
         return hf::fail(HF_ERR_INVALID, "hf_lbs_forward: workspace too small (%zu < %zu)", workspace_bytes,
                         hf_lbs_workspace_bytes(h, M));
     cudaStream_t stream = (cudaStream_t)stream_;
-    float* F = (float*)workspace;
+    uint8_t* wsb = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float* F = (float*)wsb;
     float* A = F + (size_t)M * h->KP;
-    __nv_bfloat16* Fb = (__nv_bfloat16*)(((uintptr_t)(A + (size_t)M * h->J * 12) + 255) & ~(uintptr_t)255);
+    __nv_bfloat16* Fb = (__nv_bfloat16*)(wsb + (((size_t)M * (h->KP + h->J * 12) * sizeof(float) + 255) & ~(size_t)255));
+    const int tiles3 = hf::div_up(M, T3_MS);
+    float* At = (float*)(wsb + lbs_ws_off_at(h, M));
+    float* xvt = At + (size_t)tiles3 * h->J * 12 * 128;
     const int J_out = hf_smpl_num_joints_out(h);
     Parents par;
     for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
     static const int stage_mask = getenv("HF_LBS_STAGES") ? atoi(getenv("HF_LBS_STAGES")) : 7;   // profiling aid: bit 0 pose, 1 skin, 2 extra joints
     if (stage_mask & 1)
     HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, PS)), dim3(PTHREADS), 0, stream, betas, rotmats, transl, h->J0, h->Jd, par, M,
-                           h->J, h->nb, h->KP, J_out, h->impl != 1 ? (float*)nullptr : F, h->impl == 0 ? (__half*)Fb : (__half*)nullptr, A, joints));
+                           h->J, h->nb, h->KP, J_out, h->impl != 1 ? (float*)nullptr : F, (h->impl == 0 || h->impl == 3) ? (__half*)Fb : (__half*)nullptr, A,
+                           h->impl == 3 ? At : (float*)nullptr, joints));
     HF_LAUNCH_CHECK();
     if (!(stage_mask & 2)) {
+    } else if (h->impl == 3) {
+        __half* Fh = (__half*)Fb;
+        hf_smpl* hm = const_cast<hf_smpl*>(h);
+        if (hm->mapF3_ptr != (const void*)Fh || hm->mapF3_M != M) {
+            const uint64_t dims[2] = {(uint64_t)LBS_K2, (uint64_t)M};
+            const uint64_t st[1] = {(uint64_t)LBS_K2 * 2};
+            const uint32_t box[2] = {64, (uint32_t)T3_MS};
+            int rc = encode_map(&hm->mapF3, Fh, 2, dims, st, box);
+            if (rc) return rc;
+            hm->mapF3_ptr = Fh; hm->mapF3_M = M;
+        }
+        const size_t t3_smem = (size_t)T3_STAGES * T3_STAGE_BYTES + T3_ARES_BYTES + T3_STG_BYTES + 1024;
+        const int nvt = h->Vp / T3_NV, num_units = nvt * tiles3;
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        auto launch = [&](auto kern) -> int {
+            HF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3_smem));
+            HF_CUDA(hf::launch_pdl(kern, dim3(std::min(num_units, sms)), dim3(T3_THREADS), t3_smem, stream, hm->mapP3, hm->mapF3, (const float4*)h->vconst,
+                                   (const float*)At, transl, M, h->V, h->Vp, h->J, h->inv_scale, nvt, num_units, h->NF, vertices, xvt, getenv("HF_LBS_DBG") ? atoi(getenv("HF_LBS_DBG")) : 0));
+            return HF_OK;
+        };
+        int rc = transl ? launch(lbs_skin_tc3_kernel<true>) : launch(lbs_skin_tc3_kernel<false>);
+        if (rc) return rc;
+        HF_LAUNCH_CHECK();
+        if ((stage_mask & 4) && h->nvj + h->nextra > 0) {
+            HF_CUDA(hf::launch_pdl(lbs_extra_joints_t_kernel, dim3(tiles3, hf::div_up(h->nvj + h->nextra, XT_ROWS)), dim3(128), 0, stream, (const float*)xvt,
+                                   (const int*)h->pick_f, (const int*)h->csr_ptr, (const int*)h->csr_f, (const float*)h->csr_val, M, h->J, h->nvj, h->nextra,
+                                   J_out, h->NF, joints));
+            HF_LAUNCH_CHECK();
+        }
+        return HF_OK;
     } else if (h->impl == 0) {
         __half* Fh = (__half*)Fb;
         hf_smpl* hm = const_cast<hf_smpl*>(h);

@@ -149,7 +149,7 @@ class SMPL(nn.Module):
 
     def set_impl(self, impl):
         """0 = persistent fp16 tcgen05 blend (product path), 1 = FP32 CUDA-core blend, 2 = split-bf16 three-pass tcgen05
-        blend (both cross-checks)."""
+        blend (both cross-checks), 3 = lanes-as-samples fp16 blend (round-2 experiment)."""
         self._impl = impl
         for h in self._handles.values():
             _lib.check(_lib.load().hf_lbs_set_impl(h, impl))

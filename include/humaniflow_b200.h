@@ -59,7 +59,8 @@ int hf_smpl_num_joints_out(const hf_smpl_t* h);
 size_t hf_lbs_workspace_bytes(const hf_smpl_t* h, int M);
 
 /* impl: 0 = persistent fp16 tcgen05 blend (product path: pose terms one fp16 product each, shape terms a three-product
- * split; vertex error <= 5e-5 m), 1 = FP32 CUDA-core blend, 2 = split-bf16 three-pass tcgen05 blend (cross-checks). */
+ * split; vertex error <= 5e-5 m), 1 = FP32 CUDA-core blend, 2 = split-bf16 three-pass tcgen05 blend (cross-checks),
+ * 3 = the same fp16 blend with TMEM lanes = samples and register-resident joint transforms (experiment, <= 4 influences). */
 int hf_lbs_set_impl(hf_smpl_t* h, int impl);
 
 /* betas (M,num_betas); rotmats (M,J,3,3) = [global_orient | body_pose] (the `pose2rot=False` form);

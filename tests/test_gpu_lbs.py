@@ -159,3 +159,28 @@ def test_sample_tile_switches(M):
     cc = smpl(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False)
     smpl.set_impl(0)
     assert (out.vertices - cc.vertices).norm(dim=-1).max().item() <= TOL_M      # every row, against the FP32 CUDA-core path
+
+
+@pytest.mark.parametrize('M,with_transl', [(37, False), (200, True), (1000, False)])
+def test_lanes_as_samples_kernel_cross_check(M, with_transl):
+    """impl 3 (round-2 experiment: TMEM lanes = samples, joint transforms in registers along per-tile sorted vertices, flagged
+    vertices through a sample-contiguous side buffer) against the oracle and, row by row, against the FP32 CUDA-core path;
+    covers ragged sample tiles, sample-tile switches and the translation."""
+    smpl = _smpl(create_transl=False)
+    data = smpl_data()
+    betas, theta = _inputs(M, seed=300 + M, pose_std=0.6)
+    R = so3.batch_rodrigues(theta.reshape(-1, 3)).view(M, 24, 3, 3)
+    transl = torch.randn(M, 3, generator=torch.Generator().manual_seed(M)) * 0.3 if with_transl else None
+    args = dict(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False,
+                transl=None if transl is None else transl.cuda())
+    smpl.set_impl(3)
+    t3 = smpl(**args)
+    smpl.set_impl(1)
+    cc = smpl(**args)
+    smpl.set_impl(0)
+    rows = sorted(set([0, 1, M // 2, M - 2, M - 1]))
+    v_ref, j_ref = osmpl.smpl_forward(data, betas[rows], R[rows][:, 1:], R[rows][:, :1], pose2rot=False,
+                                      transl=None if transl is None else transl[rows])
+    assert _l2(t3.vertices[rows], v_ref) <= TOL_M and _l2(t3.joints[rows], j_ref) <= TOL_M
+    assert (t3.vertices - cc.vertices).norm(dim=-1).max().item() <= TOL_M
+    assert (t3.joints - cc.joints).norm(dim=-1).max().item() <= TOL_M

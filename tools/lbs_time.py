@@ -19,7 +19,7 @@ styles = [os.environ['HF_SKIN']] if 'HF_SKIN' in os.environ else ['random', 'bod
 iters = int(os.environ.get('HF_ITERS', 20))
 for style in styles:
     smpl = hb.SMPL.from_arrays(synthetic_smpl_data(seed=0, skinning=style), create_transl=False).cuda()
-    for impl in ([0] if 'HF_SKIN' in os.environ else [0, 2]):
+    for impl in ([int(os.environ.get('HF_IMPL', 0))] if 'HF_SKIN' in os.environ else [0, 3, 2]):
         smpl.set_impl(impl)
         for _ in range(3):
             smpl.lbs(betas, R)
