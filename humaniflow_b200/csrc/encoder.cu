@@ -52,6 +52,7 @@ __device__ __forceinline__ void conv_stamp(int dbg, int slot) {
     }
 }
 
+constexpr int CONV_MAX_KB = 96;     // k-blocks per tile (3x3 x 512 channels = 72; checked on the host)
 constexpr int CONV_THREADS = 416;   // warp 0 operand TMA, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue, warp 10 residual TMA,
                                     // warps 11 / 12: second operand-TMA / MMA issuer (odd k-blocks)
 
@@ -96,6 +97,25 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 4 + 2 * SR];
     __shared__ uint32_t tmem_base_s;
+    // per-k-block load coordinates {tensor-map index (-1 = fused branch input), channel offset, dw, dh}: they do not depend on
+    // the tile, and computing them in the single-thread producer loop (two integer divisions per k-block) measured ~110 cycles
+    // of the ~350 a producer iteration takes (tools/ubench/tma_ring.cu)
+    __shared__ int4 ktab[CONV_MAX_KB];
+    for (int kb = threadIdx.x; kb < g.nkb; kb += CONV_THREADS) {
+        int mi, c0, d1, d2;
+        if (kb >= g.nkb1) { mi = -1; c0 = (kb - g.nkb1) * 64; d1 = 0; d2 = 0; }
+        else if (g.kind == 0) {
+            const int cpb = g.cin >> 6;
+            const int tap = kb / cpb, cb = kb - tap * cpb;
+            const int kh = tap / g.ksize, kw = tap - kh * g.ksize;
+            const int dw = kw - g.pad, dh = kh - g.pad;
+            c0 = cb * 64;
+            if (g.stride == 1) { mi = 0; d1 = dw; d2 = dh; }
+            else { const int pw = dw & 1, phh = dh & 1; mi = phh * 2 + pw; d1 = (dw - pw) >> 1; d2 = (dh - phh) >> 1; }
+        } else if (g.kind == 1) { const int kh1 = kb >> 2, q4 = kb & 3; mi = kh1 & 1; c0 = 0; d1 = q4; d2 = kh1 >> 1; }
+        else { const int kh = kb / 3, cb = kb - kh * 3; mi = kh & 1; c0 = cb * 64; d1 = 0; d2 = kh >> 1; }
+        ktab[kb] = make_int4(mi, c0, d1, d2);
+    }
     const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sbuf_base = tile_base + STAGES * STAGE_BYTES;
     uint8_t* sbuf_ptr = smem_raw + (sbuf_base - smem_u32(smem_raw));
@@ -138,11 +158,10 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
             // ONE thread walks the loop: an mbarrier parity wait is only safe for a waiter that goes on to the next use of
             // the barrier itself (31 more lanes polling would race with the phases lane 0 starts), and a lane-0 poll with the
             // other lanes parked at a warp barrier inside the loop measured 2x slower than leaving them out altogether
-            const int cpb = g.cin >> 6;   // 64-channel blocks per tap (generic)
             const uint32_t full_lead = PAIR ? mapa_rank(full0, 0) : full0;   // pair: both CTAs' loads complete on the leader's barrier
             const uint32_t my_bytes = ((dbg & 2) ? 0u : (uint32_t)A_BYTES) + ((dbg & 4) ? 0u : (uint32_t)B_BYTES);
             const uint32_t tx_bytes = PAIR ? 2 * my_bytes : my_bytes;
-            const int kind = g.kind, ksize = g.ksize, pad = g.pad, stride = g.stride, nkb = g.nkb, kstep = dual ? 2 : 1;
+            const int nkb = g.nkb, kstep = dual ? 2 : 1;
             uint32_t base = 0;                                        // k-blocks of all previous tiles (ring position)
             int nt = cta % ntn, mt = cta / ntn;                      // tile = mt * ntn + nt, advanced by nworkers per step
             const int step_nt = nworkers % ntn, step_mt = nworkers / ntn;
@@ -154,34 +173,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                 const int wo0 = tw * g.TW, ho0 = th * g.TH, b0 = tb * g.TB, n0 = nt * BN + (int)rank * BROWS;
                 for (int kb = dual ? (int)((base ^ (uint32_t)t) & 1u) : 0; kb < nkb; kb += kstep) {
                     const uint32_t kbc = base + (uint32_t)kb, st = kbc % STAGES, ph = (kbc / STAGES) & 1u;
-                    mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                    mbar_wait_long(empty0 + 8 * st, ph ^ 1u);
                     const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
                     const uint32_t fb = full_lead + 8 * st;
                     if (leader) mbar_expect_tx(full0 + 8 * st, tx_bytes);
-                    int mi, c0, c1, c2;
+                    const int4 kt = ktab[kb];
+                    const int mi = kt.x, c0 = kt.y, c1 = wo0 + kt.z, c2 = ho0 + kt.w;
                     const CUtensorMap* amap;
-                    if (kb >= g.nkb1) {         // fused 1x1 branch: channel block of the second input at the output pixel
-                        mi = -1; c0 = (kb - g.nkb1) * 64; c1 = wo0; c2 = ho0;
-                    } else
-                    if (kind == 0) {            // (kh, kw) = filter tap, cb = 64-channel block within the tap
-                        const int tap = kb / cpb, cb = kb - tap * cpb;
-                        const int kh = tap / ksize, kw = tap - kh * ksize;
-                        const int dw = kw - pad, dh = kh - pad;
-                        c0 = cb * 64;
-                        if (stride == 1) { mi = 0; c1 = wo0 + dw; c2 = ho0 + dh; }
-                        else {
-                            const int pw = dw & 1, phh = dh & 1;
-                            mi = phh * 2 + pw;
-                            c1 = wo0 + ((dw - pw) >> 1);
-                            c2 = ho0 + ((dh - phh) >> 1);
-                        }
-                    } else if (kind == 1) {
-                        const int kh1 = kb >> 2, q = kb & 3;
-                        mi = kh1 & 1; c0 = 0; c1 = wo0 + q; c2 = ho0 + (kh1 >> 1);
-                    } else {   // compact stem: 8 taps x 24 ch = 192 contiguous elements per (pixel, kh), 3 k-blocks
-                        const int kh = kb / 3, cb = kb - kh * 3;
-                        mi = kh & 1; c0 = cb * 64; c1 = wo0; c2 = ho0 + (kh >> 1);
-                    }
                     amap = mi < 0 ? &maps.a2 : &maps.a[mi];
                     if (PAIR) {
                         if (!(dbg & 2)) tma_load_4d_2cta(sa, amap, fb, c0, c1, c2, b0);
@@ -204,13 +202,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
             uint32_t lt = 0, base = 0;                               // base = k-blocks of all previous tiles (ring position)
             for (int tile = cta; tile < num_tiles; tile += nworkers, ++lt) {
                 const uint32_t buf = lt & 1u;
-                mbar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1u) ^ 1u);
+                mbar_wait_long(tempty0 + 8 * buf, ((lt >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t d = tmem_base + (buf * NACC + (uint32_t)t) * BN;
                 const int kb0 = dual ? (int)((base ^ (uint32_t)t) & 1u) : 0;     // this issuer's first k-block of the tile
                 for (int kb = kb0; kb < nkb; kb += kstep) {
                     const uint32_t kbc = base + (uint32_t)kb, st = kbc % STAGES, ph = (kbc / STAGES) & 1u;
-                    mbar_wait(full0 + 8 * st, ph);
+                    mbar_wait_long(full0 + 8 * st, ph);
                     tcgen05_fence_after();
                     if (lt == 0 && kb == 0) conv_stamp(dbg, 3);                  // first operand stage landed
                     const uint32_t sa = tile_base + st * STAGE_BYTES, sb = sa + A_BYTES;
@@ -240,7 +238,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvMaps maps, const ConvGeom g, con
                 const int th = t % g.tiles_h;
                 const int tb = t / g.tiles_h;
                 const uint32_t sb = lt % SR, k = lt / SR;
-                mbar_wait(sfree0 + 8 * sb, (k & 1u) ^ 1u);
+                mbar_wait_long(sfree0 + 8 * sb, (k & 1u) ^ 1u);
                 const uint32_t rb = rfull0 + 8 * sb;
                 if (has_res && !(dbg & 128)) {
                     mbar_expect_tx(rb, SBUF_BYTES);
@@ -589,6 +587,7 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
         }
     }
     g.nkb1 = g.nkb;
+    if (g.nkb + (x2 ? cin2 / 64 : 0) > CONV_MAX_KB) return hf::fail(HF_ERR_UNSUPPORTED, "conv: %d k-blocks per tile exceed %d", g.nkb + (x2 ? cin2 / 64 : 0), CONV_MAX_KB);
     if (x2) {   // fused 1x1 branch: second input (B,H2,W2,cin2) sampled with stride2 at the output pixels, K appended
         if (kind != 0 || cin2 % 64 || stride2 < 1 || (H2 - 1) / stride2 + 1 != g.Ho || (W2 - 1) / stride2 + 1 != g.Wo)
             return hf::fail(HF_ERR_UNSUPPORTED, "conv: fused 1x1 branch does not match the output geometry");
@@ -603,8 +602,12 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
     }
     const int tiles_m = g.tiles_w * g.tiles_h * g.tiles_b;
     p->bn = (cout % 128 == 0) ? 128 : 64;
-    // 256-wide tiles for wide layers without residual: a third fewer operand bytes per FLOP through the L2->SM fabric
-    if (res == nullptr && cout % 256 == 0 && tiles_m * (cout / 256) >= num_sms()) p->bn = 256;
+    // 256-wide tiles for wide layers with enough tiles: 512 tensor-pipe cycles per k-block behind every 16 KB activation tile
+    // and every barrier round trip (a single issuer then keeps the pipe > 90 % busy, tools/ubench/tma_ring.cu), half the tiles.
+    // The rule looks at the layer only (>= 8 such tiles per image), never at the batch size: the accumulation order of a
+    // layer must not depend on how many images share the launch, or shards would not reproduce the unsharded result.
+    static const int bn256_env = getenv("HF_CONV_BN256") ? atoi(getenv("HF_CONV_BN256")) : 1;     // bit 0: layers without residual, bit 1: with
+    if (cout % 256 == 0 && (g.Ho * g.Wo / 128) * (cout / 256) >= 8 && ((res == nullptr) ? (bn256_env & 1) : (bn256_env & 2))) p->bn = 256;
     {
         const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)B};
         const uint64_t st[3] = {(uint64_t)cout * 2, (uint64_t)g.Wo * cout * 2, (uint64_t)g.Ho * g.Wo * cout * 2};
@@ -640,7 +643,7 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
         // HF_CONV_CFG bits (A/B switches, default all on): 1 = four-slot ring for residual layers, 2 = eight stages for the
         // 64-wide layers, 4 = six stages + one staging tile also for layers with two tiles per CTA
         static const int cfg_env = getenv("HF_CONV_CFG") ? atoi(getenv("HF_CONV_CFG")) : 7;
-        if (p->bn == 256)      { p->stages = 3; p->sr = 1; }
+        if (p->bn == 256)      { p->stages = p->has_res ? 2 : 3; p->sr = p->has_res ? 2 : 1; }
         else if (p->bn == 128) { p->stages = p->has_res ? ((cfg_env & 1) ? 4 : 3) : 4; p->sr = p->has_res ? 3 : 2; }
         else                   { p->stages = p->has_res ? 5 : ((cfg_env & 2) ? 8 : 6); p->sr = p->has_res ? 4 : 2; }
     }
@@ -665,12 +668,12 @@ int plan_conv(ConvPlan* p, int kind, const void* x, const void* w, int B, int H,
 
 template <int BN, int STAGES, int SR, bool PAIR>
 int launch_conv_t(const ConvPlan& p, const float* bias, cudaStream_t s) {
-    static int attr_dev_mask = 0;      // the attribute is per device: set it once per device this process launches on
+    static size_t attr_bytes[32] = {};   // the attribute is per device: raise it (to what this plan needs) once per device
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!((attr_dev_mask >> (dev & 31)) & 1)) {
-        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_dev_mask |= 1 << (dev & 31);
+    if (attr_bytes[dev & 31] < p.smem) {
+        HF_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, STAGES, SR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        attr_bytes[dev & 31] = p.smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = p.grid; cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
@@ -703,7 +706,7 @@ int launch_conv(const ConvPlan& p, const float* bias, cudaStream_t s) {
         if (p.bn == 128) return p.has_res ? launch_conv_t<128, 4, 3, true>(p, bias, s) : launch_conv_t<128, 5, 2, true>(p, bias, s);
         return p.has_res ? launch_conv_t<64, 6, 4, true>(p, bias, s) : launch_conv_t<64, 7, 2, true>(p, bias, s);
     }
-    if (p.bn == 256) return launch_conv_t<256, 3, 1, false>(p, bias, s);
+    if (p.bn == 256) return p.has_res ? launch_conv_t<256, 2, 2, false>(p, bias, s) : launch_conv_t<256, 3, 1, false>(p, bias, s);
     if (p.bn == 128 && !p.has_res && p.stages == 6) return launch_conv_t<128, 6, 1, false>(p, bias, s);
     if (p.bn == 128 && !p.has_res && p.stages == 2) return launch_conv_t<128, 2, 2, false>(p, bias, s);
     if (p.bn == 128 && !p.has_res && p.stages == 3) return launch_conv_t<128, 3, 2, false>(p, bias, s);
