@@ -48,6 +48,7 @@ SIGNATURES = {
     'hf_vertex_variance': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'hf_pointset_errors': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'hf_proxy_rep': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_float, c_int, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'hf_proxy_rep_staged': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_float, c_int, ctypes.c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'hf_project_joints2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float, c_void_p, c_void_p]),
     'hf_flow_create': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(FlowConfig)] + [c_void_p] * 7),
     'hf_flow_destroy': (None, [c_void_p]),
@@ -63,6 +64,10 @@ SIGNATURES = {
     'hf_encoder_destroy': (None, [c_void_p]),
     'hf_encoder_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
     'hf_encoder_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'hf_encoder_forward_bf16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'hf_encoder_forward_staged': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'hf_encoder_stem_input': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int)]),
+    'hf_encoder_invalidate': (c_int, [c_void_p]),
     'hf_encoder_stem_channels': (c_int, [c_void_p]),
     'hf_encoder_set_impl': (c_int, [c_void_p, c_int]),
     'hf_encoder_debug_op_output': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),

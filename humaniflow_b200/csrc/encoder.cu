@@ -413,7 +413,10 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv
 
 // ------------------------------------------------------------------ layout / pooling kernels
 // fp32 NCHW -> bf16 NHWC with channel padding and spatial zero border (stem input).
-__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
+__device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename TIn>
+__global__ void nchw_to_nhwc_pad_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
                                         int H, int W, int Cp, int Hp, int Wp, int top, int left) {
     // one thread per (b, h, w): reads C strided planes (coalesced over w), writes Cp contiguous bf16
     HF_PDL_SYNC();
@@ -424,14 +427,14 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __nv_bfloat
         const int h = (int)(p % H);
         const int b = (int)(p / H);
         __nv_bfloat16* o = y + (((size_t)b * Hp + h + top) * Wp + w + left) * Cp;
-        const float* xi = x + ((size_t)b * C * H + h) * W + w;
+        const TIn* xi = x + ((size_t)b * C * H + h) * W + w;
         for (int c0 = 0; c0 < Cp; c0 += 8) {
             uint32_t pk[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int ca = c0 + 2 * i, cb = ca + 1;
-                const float fa = ca < C ? __ldg(xi + (size_t)ca * H * W) : 0.f;
-                const float fb = cb < C ? __ldg(xi + (size_t)cb * H * W) : 0.f;
+                const float fa = ca < C ? ld_as_float(xi + (size_t)ca * H * W) : 0.f;
+                const float fb = cb < C ? ld_as_float(xi + (size_t)cb * H * W) : 0.f;
                 __nv_bfloat162 hh = __floats2bfloat162_rn(fa, fb);
                 pk[i] = *reinterpret_cast<uint32_t*>(&hh);
             }
@@ -889,23 +892,29 @@ extern "C" size_t hf_encoder_workspace_bytes(const hf_encoder_t* h, int B, int H
     return stem_in_bytes(B, H, W) + (size_t)num_buffers(h) * max_act + 1024;
 }
 
-extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, int H, int W, float* feats, void* workspace,
-                                  size_t workspace_bytes, void* stream_) {
-    if (!h || !input || !feats || !workspace) return hf::fail(HF_ERR_INVALID, "hf_encoder_forward: null argument");
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace {
+// Geometry of one call: shapes of every op, workspace carve-up, launch plans (re-built when the geometry or the workspace
+// changes).  The padded stem input lives at the start of the workspace; its border and channel padding are zeroed when the
+// plans are built and must stay zero afterwards: the workspace contents belong to the encoder between calls with the same
+// geometry (hf_encoder_invalidate forces a rebuild + re-zeroing, e.g. after the caller recycled the memory).
+struct EncCall {
     OpShapes shp;
-    size_t max_act = 0;
-    int rc = infer_shapes(h, B, H, W, shp, &max_act);
+    size_t max_act, sib;
+    uint8_t* ws;
+    __nv_bfloat16* stem_in;
+    int Hp, Wp;
+};
+
+int enc_prepare(hf_encoder* h, int B, int H, int W, void* workspace, size_t workspace_bytes, cudaStream_t stream, EncCall& c) {
+    int rc = infer_shapes(h, B, H, W, c.shp, &c.max_act);
     if (rc) return rc;
     const size_t need = hf_encoder_workspace_bytes(h, B, H, W);
-    if (workspace_bytes < need) return hf::fail(HF_ERR_INVALID, "hf_encoder_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
-    uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
-    __nv_bfloat16* stem_in = (__nv_bfloat16*)ws;
-    const size_t sib = stem_in_bytes(B, H, W);
-    auto buf = [&](int id) { return (__nv_bfloat16*)(ws + sib + (size_t)id * max_act); };
-    const int Hp = H + 6, Wp = W + 8;
-
-    // (re)build the launch plans when the geometry or workspace changes
+    if (workspace_bytes < need) return hf::fail(HF_ERR_INVALID, "hf_encoder: workspace too small (%zu < %zu)", workspace_bytes, need);
+    c.ws = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    c.stem_in = (__nv_bfloat16*)c.ws;
+    c.sib = stem_in_bytes(B, H, W);
+    c.Hp = H + 6; c.Wp = W + 8;
+    auto buf = [&](int id) { return (__nv_bfloat16*)(c.ws + c.sib + (size_t)id * c.max_act); };
     if (h->pB != B || h->pH != H || h->pW != W || h->pws != workspace) {
         h->plans.assign(h->ops.size(), ConvPlan());
         for (size_t i = 0; i < h->ops.size(); ++i) {
@@ -914,32 +923,90 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
             if (i == 0) {
                 rc = HF_ERR_UNSUPPORTED;
                 if (h->w_stem24) {   // compact stem first; its sliding-window tensor map may be refused by the driver
-                    rc = plan_conv(&h->plans[i], 2, stem_in, h->w_stem24, B, H, W, 24, op.cout, 7, 2, 3, op.relu, Hp, Wp, buf(op.dst), nullptr);
+                    rc = plan_conv(&h->plans[i], 2, c.stem_in, h->w_stem24, B, H, W, 24, op.cout, 7, 2, 3, op.relu, c.Hp, c.Wp, buf(op.dst), nullptr);
                     if (rc == HF_OK) h->stem_cp = 24;
                 }
                 if (rc != HF_OK) {
-                    rc = plan_conv(&h->plans[i], 1, stem_in, h->w[op.weight_index], B, H, W, STEM_CP, op.cout, 7, 2, 3, op.relu, Hp, Wp, buf(op.dst), nullptr);
+                    rc = plan_conv(&h->plans[i], 1, c.stem_in, h->w[op.weight_index], B, H, W, STEM_CP, op.cout, 7, 2, 3, op.relu, c.Hp, c.Wp, buf(op.dst), nullptr);
                     h->stem_cp = STEM_CP;
                 }
             } else {
-                const BufShape in = shp.in[i];
+                const BufShape in = c.shp.in[i];
                 if (op.cin % 64 != 0) return hf::fail(HF_ERR_UNSUPPORTED, "encoder: conv %zu has cin %d (must be a multiple of 64)", i, op.cin);
-                const BufShape in2 = shp.in2[i];
+                const BufShape in2 = c.shp.in2[i];
                 rc = plan_conv(&h->plans[i], 0, buf(op.src), h->w[op.weight_index], B, in.H, in.W, op.cin, op.cout, op.ksize, op.stride, op.pad, op.relu, 0, 0,
                                buf(op.dst), op.res >= 0 ? buf(op.res) : nullptr, op.src2 >= 0 ? buf(op.src2) : nullptr, in2.H, in2.W, op.cin2, op.stride2);
             }
             if (rc) return rc;
         }
         // zero the padded stem input once: borders and channel padding stay zero, the interior is rewritten per call
-        HF_CUDA(cudaMemsetAsync(stem_in, 0, sib, stream));
+        HF_CUDA(cudaMemsetAsync(c.stem_in, 0, c.sib, stream));
         h->pB = B; h->pH = H; h->pW = W; h->pws = workspace;
     }
-    {
+    return HF_OK;
+}
+
+int enc_run_ops(hf_encoder* h, const EncCall& c, int B, int H, int W, float* feats, cudaStream_t stream);
+}  // namespace
+
+extern "C" int hf_encoder_invalidate(hf_encoder_t* h) {
+    if (!h) return hf::fail(HF_ERR_INVALID, "hf_encoder_invalidate: null handle");
+    h->pB = h->pH = h->pW = 0; h->pws = nullptr;
+    return HF_OK;
+}
+
+// input_kind: 0 = fp32 NCHW, 1 = bf16 NCHW, 2 = already staged (the caller filled hf_encoder_stem_input's buffer)
+static int enc_forward_any(hf_encoder_t* h, const void* input, int input_kind, int B, int H, int W, float* feats, void* workspace,
+                           size_t workspace_bytes, void* stream_) {
+    if (!h || (!input && input_kind != 2) || !feats || !workspace) return hf::fail(HF_ERR_INVALID, "hf_encoder_forward: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EncCall c;
+    int rc = enc_prepare(h, B, H, W, workspace, workspace_bytes, stream, c);
+    if (rc) return rc;
+    if (input_kind != 2) {
         const size_t total = (size_t)B * H * W;
         int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
-        nchw_to_nhwc_pad_kernel<<<blocks, 256, 0, stream>>>(input, stem_in, B, h->in_channels, H, W, h->stem_cp, Hp, Wp, 3, 3);   // follows a memset: plain launch
+        // follows a memset on the first call: plain launch
+        if (input_kind == 0) nchw_to_nhwc_pad_kernel<float><<<blocks, 256, 0, stream>>>((const float*)input, c.stem_in, B, h->in_channels, H, W, h->stem_cp, c.Hp, c.Wp, 3, 3);
+        else nchw_to_nhwc_pad_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)input, c.stem_in, B, h->in_channels, H, W, h->stem_cp, c.Hp, c.Wp, 3, 3);
         HF_LAUNCH_CHECK();
     }
+    return enc_run_ops(h, c, B, H, W, feats, stream);
+}
+
+extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, int H, int W, float* feats, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    return enc_forward_any(h, input, 0, B, H, W, feats, workspace, workspace_bytes, stream);
+}
+extern "C" int hf_encoder_forward_bf16(hf_encoder_t* h, const uint16_t* input, int B, int H, int W, float* feats, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+    return enc_forward_any(h, input, 1, B, H, W, feats, workspace, workspace_bytes, stream);
+}
+extern "C" int hf_encoder_forward_staged(hf_encoder_t* h, int B, int H, int W, float* feats, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+    return enc_forward_any(h, nullptr, 2, B, H, W, feats, workspace, workspace_bytes, stream);
+}
+extern "C" int hf_encoder_stem_input(hf_encoder_t* h, int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream,
+                                     void** staged, int* dims) {
+    if (!h || !workspace || !staged || !dims) return hf::fail(HF_ERR_INVALID, "hf_encoder_stem_input: null argument");
+    EncCall c;
+    int rc = enc_prepare(h, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream, c);
+    if (rc) return rc;
+    *staged = c.stem_in;
+    dims[0] = c.Hp; dims[1] = c.Wp; dims[2] = h->stem_cp; dims[3] = 3; dims[4] = 3;      // {Hp, Wp, Cp, top, left}
+    return HF_OK;
+}
+
+namespace {
+int enc_run_ops(hf_encoder* h, const EncCall& c, int B, int H, int W, float* feats, cudaStream_t stream) {
+    const OpShapes& shp = c.shp;
+    const size_t max_act = c.max_act, sib = c.sib;
+    uint8_t* ws = c.ws;
+    __nv_bfloat16* stem_in = c.stem_in;
+    const int Hp = c.Hp, Wp = c.Wp;
+    int rc = HF_OK;
+    auto buf = [&](int id) { return (__nv_bfloat16*)(ws + sib + (size_t)id * max_act); };
+    (void)H; (void)W;
     // profiling aid (HF_ENC_TIMING=1): CUDA events around every op of this call, per-op times printed to stderr
     static const bool op_timing = getenv("HF_ENC_TIMING") != nullptr;
     std::vector<cudaEvent_t> evs;
@@ -998,6 +1065,7 @@ extern "C" int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, in
     }
     return HF_OK;
 }
+}  // namespace
 
 // Bring-up aid: run the program up to and including op `op_index`, then copy that op's output activation
 // (bf16 NHWC) to `out` and report its dims {H, W, C}.

@@ -8,6 +8,7 @@
 // produces a 32 x 16 pixel tile of all 1+J channels from an RGB halo tile held in shared memory.  Every stage is defined on
 // the image domain and zero outside it, exactly like the zero padding of the reference's chained nn.Conv2d modules.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -26,7 +27,8 @@ struct ProxyParams {
 
 __global__ void __launch_bounds__(PR_THREADS)
 proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints2D, const float* __restrict__ vis, int C, int H,
-                 int W, int J, ProxyParams prm, float* __restrict__ out, float* __restrict__ dbg_mag, float* __restrict__ dbg_ori) {
+                 int W, int J, ProxyParams prm, float* __restrict__ out, float* __restrict__ dbg_mag, float* __restrict__ dbg_ori,
+                 __nv_bfloat16* __restrict__ staged, int Hp, int Wp, int Cp, int top, int left) {
     HF_PDL_SYNC();
     __shared__ float s_rgb[RH][RW];
     __shared__ float s_hb[HH][HW_];
@@ -104,6 +106,32 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
         }
         if (e < prm.threshold) e = 0.f;
         const size_t pix = (size_t)y * W + x;
+        if (staged) {
+            // the encoder's stem input layout directly: bf16 NHWC, Cp channels per pixel (1 + J used, rest zero), inside the
+            // zero border of the (Hp, Wp) padded image -> no fp32 NCHW intermediate and no layout kernel
+            float ch[32];
+            ch[0] = e;
+#pragma unroll 1
+            for (int j = 0; j < J; ++j) {
+                const float u = __ldg(joints2D + ((size_t)b * J + j) * 2), v = __ldg(joints2D + ((size_t)b * J + j) * 2 + 1);
+                const float a = ((float)y - v) / prm.heat_std, c2 = ((float)x - u) / prm.heat_std;
+                float hh = expf(-(a * a) / 2.f - (c2 * c2) / 2.f);
+                if (vis) hh *= __ldg(vis + (size_t)b * J + j);
+                ch[1 + j] = hh;
+            }
+            for (int j = 1 + J; j < 32; ++j) ch[j] = 0.f;
+            __nv_bfloat16* o = staged + (((size_t)b * Hp + y + top) * Wp + x + left) * Cp;
+            for (int c0 = 0; c0 < Cp; c0 += 8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(ch[c0 + 2 * i], ch[c0 + 2 * i + 1]);
+                    pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(o + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            continue;
+        }
         out[(size_t)b * (1 + J) * HWp + pix] = e;
         if (dbg_mag) dbg_mag[(size_t)b * HWp + pix] = m;
         if (dbg_ori) dbg_ori[(size_t)b * HWp + pix] = ori;
@@ -131,7 +159,25 @@ extern "C" int hf_proxy_rep(const float* rgb, const float* joints2D, const float
     prm.threshold = threshold; prm.nms = nms; prm.heat_std = heat_std;
     dim3 grid(hf::div_up(W, PT_W), hf::div_up(H, PT_H), B);
     HF_CUDA(hf::launch_pdl(proxy_rep_kernel, grid, dim3(PR_THREADS), 0, (cudaStream_t)stream, rgb, joints2D, joints_vis, C, H, W, J, prm,
-                           out, dbg_mag, dbg_ori));
+                           out, dbg_mag, dbg_ori, (__nv_bfloat16*)nullptr, 0, 0, 0, 0, 0));
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
+
+extern "C" int hf_proxy_rep_staged(const float* rgb, const float* joints2D, const float* joints_vis, int B, int C, int H, int W, int J,
+                                   const float* gauss5, float threshold, int nms, float heat_std, uint16_t* staged, int Hp, int Wp,
+                                   int Cp, int top, int left, void* stream) {
+    if (!rgb || !staged || !gauss5 || (J > 0 && !joints2D)) return hf::fail(HF_ERR_INVALID, "hf_proxy_rep_staged: null argument");
+    if (B <= 0 || H <= 0 || W <= 0) return HF_OK;
+    if (C < 1 || heat_std <= 0.f) return hf::fail(HF_ERR_INVALID, "hf_proxy_rep_staged: bad channel count / heatmap std");
+    if (1 + J > Cp || Cp > 32 || Cp % 8 || H + top > Hp || W + left > Wp)
+        return hf::fail(HF_ERR_INVALID, "hf_proxy_rep_staged: %d channels / %dx%d image do not fit the staged layout (%d, %d, %d)", 1 + J, H, W, Hp, Wp, Cp);
+    ProxyParams prm;
+    for (int i = 0; i < 5; ++i) prm.g[i] = gauss5[i];
+    prm.threshold = threshold; prm.nms = nms; prm.heat_std = heat_std;
+    dim3 grid(hf::div_up(W, PT_W), hf::div_up(H, PT_H), B);
+    HF_CUDA(hf::launch_pdl(proxy_rep_kernel, grid, dim3(PR_THREADS), 0, (cudaStream_t)stream, rgb, joints2D, joints_vis, C, H, W, J, prm,
+                           (float*)nullptr, (float*)nullptr, (float*)nullptr, (__nv_bfloat16*)staged, Hp, Wp, Cp, top, left));
     HF_LAUNCH_CHECK();
     return HF_OK;
 }

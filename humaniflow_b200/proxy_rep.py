@@ -64,8 +64,32 @@ class CannyEdgeDetector(nn.Module):
 
 
 def build_proxy_representation(rgb, joints2D, joints_vis=None, edge_nms=True, edge_threshold=0.0, edge_gaussian_std=1.0,
-                               heatmap_std=4.0):
+                               heatmap_std=4.0, encoder=None):
     """rgb (B,3,H,W) in [0,1], joints2D (B,17,2) pixel (column,row), joints_vis (B,17) bool/float or None ->
-    (B,18,H,W) fp32 = cat[edge map, heatmaps * vis]; defaults = configs/humaniflow_config.py:29-34."""
-    out, _, _ = _run(rgb, joints2D, joints_vis, _gaussian_taps(5, edge_gaussian_std), edge_threshold, edge_nms, heatmap_std)
-    return out
+    (B,18,H,W) fp32 = cat[edge map, heatmaps * vis]; defaults = configs/humaniflow_config.py:29-34.
+
+    ``encoder=model.image_encoder``: the kernel writes straight into that encoder's staged stem input (bf16 NHWC inside the
+    encoder's workspace) and a ``StagedInput`` handle is returned instead of a tensor; ``model(handle, ...)`` then skips the
+    fp32 NCHW intermediate and the layout pass ("fused into the encoder's first-layer staging")."""
+    taps = _gaussian_taps(5, edge_gaussian_std)
+    if encoder is None:
+        out, _, _ = _run(rgb, joints2D, joints_vis, taps, edge_threshold, edge_nms, heatmap_std)
+        return out
+    from .resnet import StagedInput
+    _lib.require_cuda('proxy representation')
+    if not rgb.is_cuda:
+        raise RuntimeError('humaniflow_b200.proxy_rep: inputs must be CUDA tensors (no CPU fallback)')
+    x = _lib.f32c(rgb)
+    B, C, H, W = x.shape
+    j = _lib.f32c(joints2D).to(x.device)
+    J = j.shape[1]
+    if 1 + J != encoder.in_channels:
+        raise ValueError('encoder expects %d channels, proxy representation has %d' % (encoder.in_channels, 1 + J))
+    v = None if joints_vis is None else _lib.f32c(joints_vis.to(torch.float32)).to(x.device)
+    p, (Hp, Wp, Cp, top, left) = encoder.stem_input(B, H, W, x.device)
+    g = (ctypes.c_float * 5)(*[float(t) for t in taps])
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().hf_proxy_rep_staged(_lib.ptr(x), _lib.ptr(j), _lib.ptr(v), B, C, H, W, J, ctypes.cast(g, ctypes.c_void_p),
+                                                   float(edge_threshold), int(bool(edge_nms)), float(heatmap_std), p, Hp, Wp, Cp,
+                                                   top, left, _lib.stream()))
+    return StagedInput(encoder, B, H, W, x.device)

@@ -18,6 +18,15 @@ from . import _lib
 STEM_CIN = 32
 
 
+class StagedInput:
+    """Handle of an encoder input that already sits in the encoder's staged stem layout (written there by a producer
+    kernel, see ``ResNet.stem_input``).  Accepted by ``ResNet.forward`` / ``HumaniflowModel.forward`` in place of the image."""
+
+    def __init__(self, encoder, B, H, W, device):
+        self.encoder, self.B, self.H, self.W, self.device = encoder, B, H, W, torch.device(device)
+        self.shape = (B, encoder.in_channels, H, W)
+
+
 class _Block(nn.Module):
     def __init__(self, kind, inplanes, planes, stride, downsample):
         super().__init__()
@@ -174,15 +183,12 @@ class ResNet(nn.Module):
         if self._enc is not None:
             _lib.check(_lib.load().hf_encoder_set_impl(self._enc, impl))
 
-    def forward(self, x):
-        """(B,C,H,W) fp32 CUDA -> (B, feat_dim) fp32.  models/resnet.py:202-217 in eval mode."""
+    def _ready(self, dev, B, H, W):
+        """Packed weights on `dev` + a workspace large enough for (B,H,W)."""
         _lib.require_cuda('ResNet.forward')
-        if not x.is_cuda:
-            raise RuntimeError('humaniflow_b200 encoder: input must be a CUDA tensor (no CPU fallback)')
         if self.training:
             raise RuntimeError('humaniflow_b200 encoder implements eval-mode BatchNorm only; call .eval()')
         lib = _lib.load()
-        dev = x.device
         ver = self._version()
         if self._enc is None or ver != self._packed_version:
             self._drop()
@@ -190,19 +196,52 @@ class ResNet(nn.Module):
             self._packed_version = ver
             if getattr(self, '_impl', 0):
                 _lib.check(lib.hf_encoder_set_impl(self._enc, self._impl))
-        x = _lib.f32c(x)
-        B, C, H, W = x.shape
-        if C != self.in_channels:
-            raise ValueError('expected %d input channels, got %d' % (self.in_channels, C))
         with torch.cuda.device(dev):
             nbytes = lib.hf_encoder_workspace_bytes(self._enc, B, H, W)
             if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
                 self._ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
                 if os.environ.get('HF_POISON_WS'):      # debugging aid: make any read of uninitialised scratch visible
                     self._ws.fill_(0x7f)
+        return lib
+
+    def stem_input(self, B, H, W, device):
+        """(pointer, (Hp, Wp, Cp, top, left)) of the staged stem input inside the encoder's workspace: bf16 NHWC with a zero
+        border.  A producer kernel fills the interior (``proxy_rep.build_proxy_representation(..., encoder=...)``), then
+        ``forward(StagedInput)`` runs the trunk without the NCHW -> NHWC conversion pass."""
+        dev = torch.device(device)
+        lib = self._ready(dev, B, H, W)
+        p = ctypes.c_void_p()
+        dims = (ctypes.c_int * 5)()
+        with torch.cuda.device(dev):
+            _lib.check(lib.hf_encoder_stem_input(self._enc, B, H, W, _lib.ptr(self._ws), self._ws.numel(), _lib.stream(),
+                                                 ctypes.byref(p), dims))
+        return p, tuple(dims)
+
+    def forward(self, x):
+        """(B,C,H,W) fp32 (or bf16 / fp16: half the host->device bytes) CUDA tensor, or a ``StagedInput`` -> (B, feat_dim) fp32.
+        models/resnet.py:202-217 in eval mode."""
+        if isinstance(x, StagedInput):
+            if x.encoder is not self:
+                raise ValueError('StagedInput belongs to another encoder')
+            lib = self._ready(x.device, x.B, x.H, x.W)
+            feats = torch.empty(x.B, self.feat_dim, device=x.device, dtype=torch.float32)
+            with torch.cuda.device(x.device):
+                _lib.check(lib.hf_encoder_forward_staged(self._enc, x.B, x.H, x.W, _lib.ptr(feats), _lib.ptr(self._ws),
+                                                         self._ws.numel(), _lib.stream()))
+            return feats
+        if not x.is_cuda:
+            raise RuntimeError('humaniflow_b200 encoder: input must be a CUDA tensor (no CPU fallback)')
+        dev = x.device
+        B, C, H, W = x.shape
+        if C != self.in_channels:
+            raise ValueError('expected %d input channels, got %d' % (self.in_channels, C))
+        lib = self._ready(dev, B, H, W)
+        half = x.dtype in (torch.bfloat16, torch.float16)
+        x = x.detach().to(torch.bfloat16).contiguous() if half else _lib.f32c(x)
+        with torch.cuda.device(dev):
             feats = torch.empty(B, self.feat_dim, device=dev, dtype=torch.float32)
-            _lib.check(lib.hf_encoder_forward(self._enc, _lib.ptr(x), B, H, W, _lib.ptr(feats), _lib.ptr(self._ws),
-                                              self._ws.numel(), _lib.stream()))
+            fn = lib.hf_encoder_forward_bf16 if half else lib.hf_encoder_forward
+            _lib.check(fn(self._enc, _lib.ptr(x), B, H, W, _lib.ptr(feats), _lib.ptr(self._ws), self._ws.numel(), _lib.stream()))
         return feats
 
     def __del__(self):

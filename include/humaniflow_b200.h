@@ -63,7 +63,9 @@ size_t hf_lbs_workspace_bytes(const hf_smpl_t* h, int M);
  * 3 = the same fp16 blend with TMEM lanes = samples and register-resident joint transforms (experiment, <= 4 influences). */
 int hf_lbs_set_impl(hf_smpl_t* h, int impl);
 
-/* betas (M,num_betas); rotmats (M,J,3,3) = [global_orient | body_pose] (the `pose2rot=False` form);
+/* Threading contract of every handle in this header: calls on ONE handle must not overlap (one stream / one host thread at a
+ * time); the per-call tensor maps of the workspace are cached inside the handle.  Use one handle per stream.
+ * betas (M,num_betas); rotmats (M,J,3,3) = [global_orient | body_pose] (the `pose2rot=False` form);
  * transl (M,3) or NULL.  vertices (M,V,3); joints (M,J_out,3).  models/smpl.py:27-41. */
 int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats, const float* transl,
                    float* vertices, float* joints, void* workspace, size_t workspace_bytes,
@@ -110,6 +112,13 @@ int hf_pointset_errors(const float* pred, const float* target, int B, int N, int
 int hf_proxy_rep(const float* rgb, const float* joints2D, const float* joints_vis, int B, int C, int H, int W, int J,
                  const float* gauss5, float threshold, int nms, float heat_std, float* out, float* dbg_mag, float* dbg_ori,
                  void* stream);
+
+/* Same computation, written straight into the encoder's stem input (SURVEY.md 8f N4 as worded: "fused into the encoder's
+ * first-layer staging"): staged = the buffer hf_encoder_stem_input returns, bf16 NHWC (B, Hp, Wp, Cp) with the image at
+ * (top, left) inside a zero border and channels 1+J..Cp-1 zero.  Follow with hf_encoder_forward_staged. */
+int hf_proxy_rep_staged(const float* rgb, const float* joints2D, const float* joints_vis, int B, int C, int H, int W, int J,
+                        const float* gauss5, float threshold, int nms, float heat_std, uint16_t* staged, int Hp, int Wp, int Cp,
+                        int top, int left, void* stream);
 
 /* fp32 axis-angle -> rotation matrices, n rows.  Replaces smplx `lbs.batch_rodrigues`
  * (used by SMPL.forward when pose2rot=True and at models/humaniflow_model.py:299). */
@@ -224,9 +233,24 @@ int hf_encoder_create(hf_encoder_t** out, const hf_enc_op* ops, int num_ops,
                       int in_channels, int stem_cin, int feat_dim);
 void hf_encoder_destroy(hf_encoder_t* h);
 size_t hf_encoder_workspace_bytes(const hf_encoder_t* h, int B, int H, int W);
-/* input (B,in_channels,H,W) fp32 NCHW -> feats (B,feat_dim) fp32. */
+/* input (B,in_channels,H,W) fp32 NCHW -> feats (B,feat_dim) fp32.
+ * Workspace contract: one stream at a time per handle; between calls with the same (B,H,W,workspace) the workspace
+ * contents belong to the encoder (the zero border / channel padding of the staged stem input is written once, when the
+ * launch plans are built).  A caller that recycled or overwrote the memory calls hf_encoder_invalidate first. */
 int hf_encoder_forward(hf_encoder_t* h, const float* input, int B, int H, int W, float* feats,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* Same with a bf16 NCHW input (half the host->device bytes of the fp32 form; the encoder rounds to bf16 anyway). */
+int hf_encoder_forward_bf16(hf_encoder_t* h, const uint16_t* input, int B, int H, int W, float* feats,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* The staged stem input inside the workspace: bf16 NHWC (B, Hp, Wp, Cp), image at (top, left) inside a zero border.
+ * dims receives {Hp, Wp, Cp, top, left}.  A producer kernel (hf_proxy_rep_staged) fills the interior, then
+ * hf_encoder_forward_staged runs the trunk without the NCHW->NHWC conversion pass. */
+int hf_encoder_stem_input(hf_encoder_t* h, int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream,
+                          void** staged, int* dims);
+int hf_encoder_forward_staged(hf_encoder_t* h, int B, int H, int W, float* feats, void* workspace,
+                              size_t workspace_bytes, void* stream);
+/* Forget the cached launch plans: the next call re-builds them and re-zeroes the staged input's padding. */
+int hf_encoder_invalidate(hf_encoder_t* h);
 /* Channels per pixel of the staged stem input chosen at the first forward: 24 (compact stem, sliding-window
  * tensor map) or 32 (pixel-pair layout, used when the driver refuses the overlapping map or in_channels > 24). */
 int hf_encoder_stem_channels(const hf_encoder_t* h);

@@ -150,3 +150,30 @@ def test_fused_branch_conv(case):
         got = y.view(torch.bfloat16).float().cpu()
         err = (got - ref).abs()
         assert (err <= 2 ** -7 * ref.abs() + 1e-3).all(), (impl, err.max().item(), case)
+
+
+@pytest.mark.parametrize('layers,size,B', [(18, 64, 3), (50, 256, 2)])
+def test_staged_and_bf16_inputs_match_the_fp32_input_bit_for_bit(layers, size, B):
+    """hf_proxy_rep_staged writes the proxy representation straight into the encoder's bf16 NHWC stem input
+    (no fp32 NCHW intermediate, no layout pass); the bf16 NCHW entry point halves the host->device bytes.  Both round the
+    same fp32 values to bf16 with the same rounding, so the features must be IDENTICAL to the fp32 NCHW path."""
+    from humaniflow_b200.proxy_rep import build_proxy_representation
+    from humaniflow_b200.resnet import StagedInput
+    m, sd, cfg = make_model(layers, seed=60 + layers, res_gain=0.3)
+    enc = m.image_encoder.cuda()
+    g = torch.Generator().manual_seed(7)
+    rgb = torch.rand(B, 3, size, size, generator=g).cuda()
+    j2d = (torch.rand(B, 17, 2, generator=g) * size).cuda()
+    vis = (torch.rand(B, 17, generator=g) > 0.2).cuda()
+    proxy = build_proxy_representation(rgb, j2d, vis)                       # (B,18,H,W) fp32
+    ref = enc(proxy).clone()
+    staged = build_proxy_representation(rgb, j2d, vis, encoder=enc)
+    assert isinstance(staged, StagedInput) and staged.shape == (B, 18, size, size)
+    got = enc(staged).clone()
+    assert torch.equal(got, ref)
+    again = enc(build_proxy_representation(rgb, j2d, vis, encoder=enc))   # the zero border survives repeated use
+    assert torch.equal(again, ref)
+    assert torch.equal(enc(proxy.to(torch.bfloat16)), ref)
+    assert torch.equal(enc(proxy), ref)                                     # and the fp32 path after the staged one
+    out = m.cuda()(staged, num_samples=2)
+    assert out['pose_rotmats_samples'].shape == (B, 2, 23, 3, 3)
