@@ -42,11 +42,13 @@ SIGNATURES = {
     'hf_lbs_workspace_bytes': (c_size_t, [c_void_p, c_int]),
     'hf_lbs_set_impl': (c_int, [c_void_p, c_int]),
     'hf_lbs_forward': (c_int, [c_void_p] * 7 + [c_size_t, c_int, c_void_p]),
+    'hf_lbs_forward_split': (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 4 + [c_size_t, c_int, c_void_p]),
     'hf_rodrigues': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'hf_lbs_tpose': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'hf_smpl_dims': (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 5),
     'hf_vertex_variance': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'hf_pointset_errors': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'hf_sample_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'hf_proxy_rep': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_float, c_int, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'hf_proxy_rep_staged': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_float, c_int, ctypes.c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'hf_project_joints2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float, c_void_p, c_void_p]),

@@ -76,7 +76,7 @@ struct Parents { int p[HF_MAXJ]; };
 // warps 1..3 write the blend coefficients.
 constexpr int PS = 8, PTHREADS = 128, PR = HF_MAXJ * 9 + 1;
 __global__ void __launch_bounds__(PTHREADS)
-lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats,
+lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats, const float* __restrict__ glob, int rep,
                                 const float* __restrict__ transl, const float* __restrict__ J0,
                                 const float* __restrict__ Jd, Parents par, int M, int J, int nb, int KP,
                                 int J_out, float* __restrict__ F, __half* __restrict__ Fh, float* __restrict__ A,
@@ -94,10 +94,23 @@ lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotma
     for (int k = tid; k < J3; k += PTHREADS) J0s[k] = J0[k];
     HF_PDL_SYNC();
     {
+        if (glob) {   // split form: rotmats = body rotations (M, J-1, 3, 3), glob (M / rep, 3, 3) shared by `rep` consecutive samples
+            const int B9 = J9 - 9;
+            const float* Rm = rotmats + (size_t)mb * B9;
+            for (int e = tid; e < ns * B9; e += PTHREADS) {
+                const int s2 = e / B9;
+                Rs[s2][9 + e - s2 * B9] = __ldg(Rm + e);
+            }
+            for (int e = tid; e < ns * 9; e += PTHREADS) {
+                const int s2 = e / 9;
+                Rs[s2][e - s2 * 9] = __ldg(glob + (size_t)((mb + s2) / rep) * 9 + (e - s2 * 9));
+            }
+        } else {
         const float* Rm = rotmats + (size_t)mb * J9;
         for (int e = tid; e < ns * J9; e += PTHREADS) {
             const int s2 = e / J9;
             Rs[s2][e - s2 * J9] = __ldg(Rm + e);
+        }
         }
         for (int e = tid; e < ns * nb; e += PTHREADS) {
             const int s2 = e / nb;
@@ -192,7 +205,7 @@ lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotma
 
 // Split-bf16 blend coefficients for the tensor-core path: Fb[m] = [hi(KH) | lo(KH)] of (beta | vec(R_i - I)),
 // zero padded; one thread per element, coalesced bf16 writes.
-__global__ void lbs_coef_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats, int M, int J, int nb,
+__global__ void lbs_coef_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats, int split, int M, int J, int nb,
                                 __nv_bfloat16* __restrict__ Fb) {
     HF_PDL_SYNC();
     const size_t total = (size_t)M * LBS_KH;
@@ -202,7 +215,7 @@ __global__ void lbs_coef_kernel(const float* __restrict__ betas, const float* __
         if (k < nb) f = __ldg(betas + (size_t)m * nb + k);
         else if (k < nb + 9 * (J - 1)) {
             const int q = k - nb, i = q / 9 + 1, el = q - (i - 1) * 9;
-            f = __ldg(rotmats + ((size_t)m * J + i) * 9 + el) - ((el % 4 == 0) ? 1.f : 0.f);
+            f = __ldg(rotmats + (split ? ((size_t)m * (J - 1) + i - 1) : ((size_t)m * J + i)) * 9 + el) - ((el % 4 == 0) ? 1.f : 0.f);
         }
         const __nv_bfloat16 hi = __float2bfloat16_rn(f);
         Fb[(size_t)m * 2 * LBS_KH + k] = hi;
@@ -1353,10 +1366,11 @@ int hf_smpl_tpose_tables(const hf_smpl* h, const float** blend, const float** vt
     return HF_OK;
 }
 
-extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats,
-                              const float* transl, float* vertices, float* joints, void* workspace,
-                              size_t workspace_bytes, int M, void* stream_) {
+static int lbs_forward_any(const hf_smpl_t* h, const float* betas, const float* rotmats, const float* glob, int rep,
+                           const float* transl, float* vertices, float* joints, void* workspace,
+                           size_t workspace_bytes, int M, void* stream_) {
     if (!h || !betas || !rotmats || !vertices || !joints) return hf::fail(HF_ERR_INVALID, "hf_lbs_forward: null argument");
+    if (glob && (rep < 1 || M % rep)) return hf::fail(HF_ERR_INVALID, "hf_lbs_forward_split: M = %d is not a multiple of rep = %d", M, rep);
     if (M <= 0) return HF_OK;
     if (!workspace || workspace_bytes < hf_lbs_workspace_bytes(h, M))
         return hf::fail(HF_ERR_INVALID, "hf_lbs_forward: workspace too small (%zu < %zu)", workspace_bytes,
@@ -1374,7 +1388,7 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
     for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
     static const int stage_mask = getenv("HF_LBS_STAGES") ? atoi(getenv("HF_LBS_STAGES")) : 7;   // profiling aid: bit 0 pose, 1 skin, 2 extra joints
     if (stage_mask & 1)
-    HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, PS)), dim3(PTHREADS), 0, stream, betas, rotmats, transl, h->J0, h->Jd, par, M,
+    HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, PS)), dim3(PTHREADS), 0, stream, betas, rotmats, glob, rep, transl, h->J0, h->Jd, par, M,
                            h->J, h->nb, h->KP, J_out, h->impl != 1 ? (float*)nullptr : F, (h->impl == 0 || h->impl == 3) ? (__half*)Fb : (__half*)nullptr, A,
                            h->impl == 3 ? At : (float*)nullptr, joints));
     HF_LAUNCH_CHECK();
@@ -1447,7 +1461,7 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
         HF_LAUNCH_CHECK();
     } else if (h->impl == 2) {
         HF_CUDA(hf::launch_pdl(lbs_coef_kernel, dim3(std::min(hf::div_up(M * LBS_KH, 256), 148 * 16)), dim3(256), 0, stream, betas, rotmats,
-                               M, h->J, h->nb, Fb));
+                               glob ? 1 : 0, M, h->J, h->nb, Fb));
         HF_LAUNCH_CHECK();
         hf_smpl* hm = const_cast<hf_smpl*>(h);
         if (hm->mapB_ptr != (const void*)Fb || hm->mapB_M != M) {
@@ -1480,6 +1494,19 @@ extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const floa
         if (rc) return rc;
     }
     return HF_OK;
+}
+
+extern "C" int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats,
+                              const float* transl, float* vertices, float* joints, void* workspace,
+                              size_t workspace_bytes, int M, void* stream) {
+    return lbs_forward_any(h, betas, rotmats, nullptr, 1, transl, vertices, joints, workspace, workspace_bytes, M, stream);
+}
+
+extern "C" int hf_lbs_forward_split(const hf_smpl_t* h, const float* betas, const float* body_rotmats, const float* glob_rotmats,
+                                    int rep, const float* transl, float* vertices, float* joints, void* workspace,
+                                    size_t workspace_bytes, int M, void* stream) {
+    if (!glob_rotmats) return hf::fail(HF_ERR_INVALID, "hf_lbs_forward_split: null argument");
+    return lbs_forward_any(h, betas, body_rotmats, glob_rotmats, rep, transl, vertices, joints, workspace, workspace_bytes, M, stream);
 }
 
 extern "C" int hf_rodrigues(const float* aa, float* R, int n, void* stream) {

@@ -194,7 +194,64 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
     }
 }
 
+// Per-image sample statistics of point sets (B, N, P, D), D in {2, 3} (metrics/eval_metrics_tracker.py:330-433):
+//   out[b][0] = mean over (samples, points) of w_p ||x_{n,p} - mean_n x_{.,p}||            sample diversity (:397-433)
+//   out[b][1] = sum over (samples, points) of w_p ||x_{n,p} - t_p|| / (N * sum_p w_p)       samples-L2E (:339-374); 0 without target
+// w = per-image point weights (visibility flags) or 1.  One block per image, a thread per point (strided), fp64 block sums
+// in a fixed order.
+template <int D>
+__global__ void __launch_bounds__(ME_THREADS)
+sample_stats_kernel(const float* __restrict__ pts, const float* __restrict__ target, const float* __restrict__ weights, int N, int P,
+                    float* __restrict__ out) {
+    HF_PDL_SYNC();
+    __shared__ double scratch[(ME_THREADS / 32) * 3 + 3];
+    const int b = blockIdx.x;
+    const float* xb = pts + (size_t)b * N * P * D;
+    double v[3] = {0.0, 0.0, 0.0};       // diversity sum, L2E sum, weight sum
+    for (int p = threadIdx.x; p < P; p += ME_THREADS) {
+        const float w = weights ? __ldg(weights + (size_t)b * P + p) : 1.f;
+        float mu[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) mu[d] = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float* x = xb + ((size_t)n * P + p) * D;
+#pragma unroll
+            for (int d = 0; d < D; ++d) mu[d] += __ldg(x + d);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) mu[d] /= (float)N;
+        float t[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) t[d] = target ? __ldg(target + ((size_t)b * P + p) * D + d) : 0.f;
+        float div = 0.f, l2e = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float* x = xb + ((size_t)n * P + p) * D;
+            float a = 0.f, c = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) { const float xv = __ldg(x + d); a += (xv - mu[d]) * (xv - mu[d]); c += (xv - t[d]) * (xv - t[d]); }
+            div += sqrtf(a); l2e += sqrtf(c);
+        }
+        v[0] += (double)(w * div); v[1] += (double)(w * l2e); v[2] += (double)w;
+    }
+    block_sum<3>(v, scratch);
+    if (threadIdx.x == 0) {
+        out[(size_t)b * 2] = (float)(v[0] / ((double)N * (double)P));
+        out[(size_t)b * 2 + 1] = target ? (float)(v[1] / ((double)N * v[2])) : 0.f;
+    }
+}
+
 }  // namespace
+
+extern "C" int hf_sample_stats(const float* points, const float* target, const float* weights, int B, int N, int P, int D, float* out,
+                               void* stream) {
+    if (!points || !out) return hf::fail(HF_ERR_INVALID, "hf_sample_stats: null argument");
+    if (B <= 0 || N <= 0 || P <= 0) return HF_OK;
+    if (D == 3) HF_CUDA(hf::launch_pdl(sample_stats_kernel<3>, dim3(B), dim3(ME_THREADS), 0, (cudaStream_t)stream, points, target, weights, N, P, out));
+    else if (D == 2) HF_CUDA(hf::launch_pdl(sample_stats_kernel<2>, dim3(B), dim3(ME_THREADS), 0, (cudaStream_t)stream, points, target, weights, N, P, out));
+    else return hf::fail(HF_ERR_INVALID, "hf_sample_stats: D must be 2 or 3");
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
 
 extern "C" int hf_pointset_errors(const float* pred, const float* target, int B, int N, int P, float* out, void* stream) {
     if (!pred || !target || !out) return hf::fail(HF_ERR_INVALID, "hf_pointset_errors: null argument");

@@ -36,3 +36,27 @@ def samples_min(per_sample_errors):
     """(B,N) per-sample mean errors -> (B,) error of the best sample of every image
     (eval_metrics_tracker.py:201-280: argmin over the samples of the mean error)."""
     return per_sample_errors.min(dim=1).values
+
+
+def sample_stats(points, target=None, weights=None):
+    """points (B,N,P,D) CUDA fp32 with D = 3 (sampled vertices / 3-D joints) or 2 (projected joints); target (B,P,D) or None;
+    weights (B,P) visibility flags or None -> dict of (B,) per-frame values:
+      'diversity'  mean over (samples, points) of w ||x - mean over the samples||   (eval_metrics_tracker.py:397-433:
+                   verts3D_sample_diversity, joints3D_sample_diversity and its (in)visible-joint forms)
+      'l2e'        sum w ||x - target|| / (N sum w)                                  (:339-374: (input_)joints2Dsamples-L2E)"""
+    _lib.require_cuda('sample_stats')
+    if not points.is_cuda:
+        raise RuntimeError('humaniflow_b200.metrics: inputs must be CUDA tensors (no CPU fallback)')
+    x = _lib.f32c(points)
+    B, N, P, D = x.shape
+    t = None if target is None else _lib.f32c(target).to(x.device)
+    w = None if weights is None else _lib.f32c(weights.to(torch.float32)).to(x.device)
+    if t is not None and t.shape != (B, P, D):
+        raise ValueError('target shape %s does not match points %s' % (tuple(t.shape), tuple(x.shape)))
+    out = torch.empty(B, 2, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().hf_sample_stats(_lib.ptr(x), _lib.ptr(t), _lib.ptr(w), B, N, P, D, _lib.ptr(out), _lib.stream()))
+    res = {'diversity': out[:, 0]}
+    if t is not None:
+        res['l2e'] = out[:, 1]
+    return res

@@ -184,6 +184,33 @@ class SMPL(nn.Module):
                                           _lib.ptr(joints), _lib.ptr(ws), ws.numel(), M, _lib.stream()))
         return verts, joints
 
+    def forward_samples(self, betas, body_rotmats, glob_rotmats, samples_per_image, transl=None, out_vertices=None, out_joints=None):
+        """The sampled bodies of a batch in one call, with the rotations as HumaniflowModel returns them: betas (B*N,nb),
+        body_rotmats (B*N,23,3,3), glob_rotmats (B,3,3) shared by the N samples of each image (predict_humaniflow.py:138-141
+        expands and concatenates them first).  Returns an SMPLOutput with vertices (B*N,V,3) and joints (B*N,90,3)."""
+        _lib.require_cuda('SMPL.forward_samples')
+        if not betas.is_cuda:
+            raise RuntimeError('humaniflow_b200.SMPL: inputs must be CUDA tensors (no CPU fallback)')
+        lib = _lib.load()
+        dev = betas.device
+        betas, body, glob = _lib.f32c(betas), _lib.f32c(body_rotmats), _lib.f32c(glob_rotmats)
+        M, N = body.shape[0], int(samples_per_image)
+        assert betas.shape[0] == M and glob.shape[0] * N == M and body.shape[1] == self.NUM_BODY_JOINTS
+        transl = None if transl is None else _lib.f32c(transl).expand(M, 3).contiguous()
+        h = self._handle(dev)
+        V = self.v_template.shape[0]
+        verts = torch.empty(M, V, 3, device=dev, dtype=torch.float32) if out_vertices is None else out_vertices
+        joints = torch.empty(M, self.num_joints_out, 3, device=dev, dtype=torch.float32) if out_joints is None else out_joints
+        with torch.cuda.device(dev):
+            nbytes = lib.hf_lbs_workspace_bytes(h, M)
+            ws = self._ws.get(dev)
+            if ws is None or ws.numel() < nbytes:
+                ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
+                self._ws[dev] = ws
+            _lib.check(lib.hf_lbs_forward_split(h, _lib.ptr(betas), _lib.ptr(body), _lib.ptr(glob), N, _lib.ptr(transl), _lib.ptr(verts),
+                                                _lib.ptr(joints), _lib.ptr(ws), ws.numel(), M, _lib.stream()))
+        return SMPLOutput(vertices=verts, joints=joints, full_pose=None, betas=betas, global_orient=glob, body_pose=body)
+
     def tpose(self, betas=None, transl=None):
         """T-pose meshes: what ``forward(betas=...)`` returns with the default zero pose (predict_humaniflow.py:147,
         evaluate_humaniflow.py:131-133), computed without pose blend and skinning.  betas (M,nb) CUDA fp32."""

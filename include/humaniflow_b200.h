@@ -71,6 +71,13 @@ int hf_lbs_forward(const hf_smpl_t* h, const float* betas, const float* rotmats,
                    float* vertices, float* joints, void* workspace, size_t workspace_bytes,
                    int M, void* stream);
 
+/* Same with the rotations as the model produces them (models/humaniflow_model.py:272,311 + predict_humaniflow.py:138-141):
+ * body_rotmats (M,J-1,3,3) and ONE global rotation per image, glob_rotmats (M/rep,3,3), shared by the `rep` consecutive
+ * samples of that image: no concatenated (M,J,3,3) copy has to be built first. */
+int hf_lbs_forward_split(const hf_smpl_t* h, const float* betas, const float* body_rotmats, const float* glob_rotmats,
+                         int rep, const float* transl, float* vertices, float* joints, void* workspace,
+                         size_t workspace_bytes, int M, void* stream);
+
 /* T-pose forward (zero pose): vertices = v_template + shapedirs.betas (+ transl), joints as hf_lbs_forward would give for
  * identity rotations.  Replaces models/smpl.py:27-41 called with the default pose (predict_humaniflow.py:147,
  * evaluate_humaniflow.py:131-133); skips pose blend and skinning. */
@@ -101,6 +108,14 @@ int hf_project_joints2d(const float* joints, const float* cam_wp, const int* joi
  * (PVE, PVE-SC, PVE-PA, PVE-T(-SC), MPJPE(-SC/-PA) and their samples_min forms are sums / minima of these values).
  * ---------------------------------------------------------------------------------------------- */
 int hf_pointset_errors(const float* pred, const float* target, int B, int N, int P, float* out, void* stream);
+
+/* Per-image sample statistics of sampled point sets: points (B,N,P,D), D = 3 (vertices / 3-D joints) or 2 (projected joints);
+ * target (B,P,D) or NULL; weights (B,P) (visibility flags) or NULL = 1.  out (B,2):
+ *   [0] sample diversity = mean over (samples, points) of w ||x - mean over the samples||
+ *       (metrics/eval_metrics_tracker.py:397-433: verts3D / joints3D / joints3D_(in)vis _sample_diversity, per frame)
+ *   [1] samples-L2E = sum w ||x - target|| / (N sum w)   (:339-374: joints2Dsamples-L2E, input_joints2Dsamples-L2E). */
+int hf_sample_stats(const float* points, const float* target, const float* weights, int B, int N, int P, int D, float* out,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Input proxy representation: rgb (B,C,H,W) fp32 + joints2D (B,J,2) = (column, row) pixel

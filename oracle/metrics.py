@@ -45,3 +45,16 @@ def pointset_errors(pred, target):
     dist = lambda a: np.linalg.norm(a - t, axis=-1).mean(-1)
     pa = align_procrustes(p.reshape(B * N, P, 3), t.reshape(B * N, P, 3)).reshape(p.shape)
     return {'plain': dist(p), 'sc': dist(align_scale_translation(p, t)), 'pa': dist(pa)}
+
+
+def sample_stats(points, target=None, weights=None):
+    """points (B,N,P,D), target (B,P,D) or None, weights (B,P) or None -> per-frame sample diversity and samples-L2E
+    (metrics/eval_metrics_tracker.py:397-433 and :339-374, the per-frame values those blocks append)."""
+    x = points.astype(np.float64)
+    w = np.ones(x.shape[0:1] + x.shape[2:3]) if weights is None else weights.astype(np.float64)
+    dist_from_mean = np.linalg.norm(x - x.mean(axis=1)[:, None], axis=-1) * w[:, None, :]
+    out = {'diversity': dist_from_mean.mean(axis=(1, 2))}
+    if target is not None:
+        l2e = np.linalg.norm(x - target.astype(np.float64)[:, None], axis=-1) * w[:, None, :]
+        out['l2e'] = l2e.sum(axis=(1, 2)) / (w.sum(axis=-1) * x.shape[1])
+    return out

@@ -184,3 +184,22 @@ def test_lanes_as_samples_kernel_cross_check(M, with_transl):
     assert _l2(t3.vertices[rows], v_ref) <= TOL_M and _l2(t3.joints[rows], j_ref) <= TOL_M
     assert (t3.vertices - cc.vertices).norm(dim=-1).max().item() <= TOL_M
     assert (t3.joints - cc.joints).norm(dim=-1).max().item() <= TOL_M
+
+
+@pytest.mark.parametrize('impl', [0, 1, 2, 3])
+def test_forward_samples_split_rotations(impl):
+    """hf_lbs_forward_split (body rotations + one global rotation per image shared by its N samples) gives bit-identical
+    results to hf_lbs_forward on the expanded / concatenated (M,24,3,3) tensor, for every blend implementation."""
+    smpl = _smpl(create_transl=False)
+    B, N = 5, 7
+    M = B * N
+    betas, theta = _inputs(M, seed=400, pose_std=0.5)
+    R = so3.batch_rodrigues(theta.reshape(-1, 3)).view(M, 24, 3, 3)
+    glob = R[::N, 0].contiguous()                                         # (B,3,3)
+    body = R[:, 1:].contiguous()
+    full = torch.cat([glob[:, None].expand(-1, N, -1, -1).reshape(M, 1, 3, 3), body], 1).contiguous()
+    smpl.set_impl(impl)
+    a = smpl.lbs(betas.cuda(), full.cuda())
+    b = smpl.forward_samples(betas.cuda(), body.cuda(), glob.cuda(), N)
+    smpl.set_impl(0)
+    assert torch.equal(a[0], b.vertices) and torch.equal(a[1], b.joints)

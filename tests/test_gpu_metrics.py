@@ -59,3 +59,22 @@ def test_no_cpu_fallback():
     from humaniflow_b200.metrics import pointset_errors
     with pytest.raises(RuntimeError):
         pointset_errors(torch.zeros(1, 2, 5, 3), torch.zeros(1, 5, 3))
+
+
+def test_sample_stats_golden_and_oracle():
+    """hf_sample_stats (sample diversity, samples-L2E; eval_metrics_tracker.py:339-433) vs golden vectors of the REAL tracker class
+    and vs the oracle at the benchmark size (32 images x 100 sampled meshes)."""
+    from humaniflow_b200.metrics import sample_stats
+    g = np.load(os.path.join(GOLDEN, 'tracker_golden.npz'))
+    cu = lambda k: torch.tensor(g[k].astype(np.float32)).cuda()
+    vis = cu('in_vis')
+    assert _close(sample_stats(cu('verts'))['diversity'].cpu().numpy(), g['verts3D_sample_diversity'])
+    assert _close(sample_stats(cu('j3d'))['diversity'].cpu().numpy(), g['joints3D_sample_diversity'])
+    assert _close(sample_stats(cu('j3d'), weights=1.0 - vis)['diversity'].cpu().numpy(), g['joints3D_invis_sample_diversity'])
+    assert _close(sample_stats(cu('j3d'), weights=vis)['diversity'].cpu().numpy(), g['joints3D_vis_sample_diversity'])
+    assert _close(sample_stats(cu('j2d_samples'), cu('tgt_j2d'), cu('tgt_vis'))['l2e'].cpu().numpy(), g['joints2Dsamples_L2E'])
+    assert _close(sample_stats(cu('j2d_samples'), cu('in_j2d'), vis)['l2e'].cpu().numpy(), g['input_joints2Dsamples_L2E'])
+    rs = np.random.RandomState(5)
+    x = (rs.standard_normal((32, 100, 6890, 3)) * 0.05 + rs.standard_normal((32, 1, 6890, 3)) * 0.3).astype(np.float32)
+    got = sample_stats(torch.tensor(x).cuda())['diversity'].cpu().numpy()
+    assert got.shape == (32,) and _close(got, omet.sample_stats(x)['diversity'])

@@ -208,3 +208,18 @@ def test_model_glue_against_the_real_reference_class(golden_dir):
             lp_alg = torch.stack([oflow.algebra_log_prob(om.joint_couplings(sd, j, 2), tgt['v_alg'][:, j], ll['loglik_contexts'][j],
                                                          RADIUS, 0.6) for j in range(23)], 1)
         assert ((lp_alg - t('lp_so3')).abs() / t('lp_so3').abs().clamp_min(1.0)).max().item() <= 1e-4
+
+
+def test_sample_stats_against_the_real_tracker(golden_dir):
+    """oracle/metrics.py::sample_stats vs the per-frame values of the REAL metrics/eval_metrics_tracker.py::EvalMetricsTracker
+    (sample diversity of vertices / joints incl. the (in)visible-joint forms, samples-L2E against labels and against the input joints)."""
+    from oracle import metrics as omet
+    g = np.load(os.path.join(golden_dir, 'tracker_golden.npz'))
+    close = lambda a, b: np.allclose(a, b, rtol=2e-6, atol=1e-7)
+    assert close(omet.sample_stats(g['verts'])['diversity'], g['verts3D_sample_diversity'])
+    assert close(omet.sample_stats(g['j3d'])['diversity'], g['joints3D_sample_diversity'])
+    vis = g['in_vis'].astype(np.float64)
+    assert close(omet.sample_stats(g['j3d'], weights=1.0 - vis)['diversity'], g['joints3D_invis_sample_diversity'])
+    assert close(omet.sample_stats(g['j3d'], weights=vis)['diversity'], g['joints3D_vis_sample_diversity'])
+    assert close(omet.sample_stats(g['j2d_samples'], g['tgt_j2d'], g['tgt_vis'])['l2e'], g['joints2Dsamples_L2E'])
+    assert close(omet.sample_stats(g['j2d_samples'], g['in_j2d'], vis)['l2e'], g['input_joints2Dsamples_L2E'])
