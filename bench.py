@@ -152,7 +152,7 @@ def workload_config(args, images_per_step=None):
     return {'workload': 'predict_B%d_N%d_resnet%d_18ch_256px_smpl6890' % (args.B, args.N, args.layers),
             'images_per_gpu_per_step': images_per_step if images_per_step is not None else args.B,
             'samples_per_image': args.N, 'encoder': 'resnet%d' % args.layers, 'joints': 23, 'vertices': 6890,
-            'l2_policy': 'inputs+outputs (151 MB in, 268 MB out per step) exceed the 126 MB L2; no explicit flush',
+            'l2_policy': 'inputs + outputs of a step (151 MB image batch in, 268 MB of meshes out) exceed the 126 MB L2; no explicit flush',
             'sharding': 'image axis across ranks, all_gather of per-image metric rows'}
 
 
@@ -181,7 +181,10 @@ def bind_to_gpu_numa_node(gpu_index):
 def run_ours(args):
     import humaniflow_b200 as hb
     from humaniflow_b200 import _lib
-    from humaniflow_b200.sharding import gather_rows, sample_diversity_rows
+    from humaniflow_b200.graphs import CudaGraphRunner, predict_step
+    from humaniflow_b200.metrics import pointset_errors, sample_stats, samples_min
+    from humaniflow_b200.proxy_rep import build_proxy_representation
+    from humaniflow_b200.sharding import gather_rows
     from humaniflow_b200.synthetic import SMPL_PARENTS, synthetic_proxy_input, synthetic_smpl_data
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -201,32 +204,44 @@ def run_ours(args):
     cfg.NUM_RESNET_LAYERS = args.layers
     model = hb.HumaniflowModel(dev, cfg, SMPL_PARENTS).eval().to(dev)
     smpl = hb.SMPL.from_arrays(synthetic_smpl_data(seed=0, skinning='body_parts'), create_transl=False).to(dev)
+    V, JO = smpl.v_template.shape[0], smpl.num_joints_out
     x_host = synthetic_proxy_input(B, 18, 256, seed=1 + rank).pin_memory()
     x_dev = x_host.to(dev)
     g = torch.Generator().manual_seed(2 + rank)
     z = (torch.randn(B, N, 23, 3, generator=g) * 0.6).to(dev)
     se = torch.randn(B, N, 10, generator=g).to(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    use_graph = not args.no_graph
 
+    def maxms(ms):
+        t = torch.tensor([ms], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---------------------------------------------------------------- the step (one pass of the hot path over one batch)
+    # image -> encoder -> heads -> 23-joint flow (N draws / image + point estimate) -> SMPL LBS of the B*N bodies -> per-image metric
+    # row (sample diversity of the 90 joints, eval_metrics_tracker.py:405-410) reduced on the device
+    def step_fn(x, z_, se_):
+        out, verts, joints = predict_step(model, smpl, x, z_, se_)
+        rows = sample_stats(joints.view(B, N, JO, 3))['diversity'].view(B, 1)
+        return verts, joints, rows
+
+    launches0 = _lib.launch_count()
+    step_fn(x_dev, z, se)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - launches0                    # kernels of this library per step (eager count; a graph replays the same)
+    runner = CudaGraphRunner(step_fn, x_dev, z, se) if use_graph else None
+    do_step = (lambda: runner(None, None, None)) if use_graph else (lambda: step_fn(x_dev, z, se))
     pending, last_metric = [None], [None]
 
-    def step(x, marks=None, outs=None):
-        out = model(x, num_samples=N, base_noise=z, shape_eps=se)
-        if marks is not None:
-            marks[0].record()
-        R = out['pose_rotmats_samples'].view(B * N, 23, 3, 3)
-        glob = out['glob_rotmat'][:, None].expand(-1, N, -1, -1).reshape(B * N, 1, 3, 3)
-        so = smpl(betas=out['shape_samples'].view(B * N, 10), body_pose=R, global_orient=glob, pose2rot=False,
-                  out_vertices=None if outs is None else outs[0], out_joints=None if outs is None else outs[1])
-        if marks is not None:
-            marks[1].record()
-        # per-image metric row (sample diversity: mean over joints of the std over samples), gathered across ranks;
-        # the collective is asynchronous: its result is read when the NEXT step issues its own gather, so the cross-rank
+    def step_and_gather():
+        verts, joints, rows = do_step()
+        # gathered across ranks asynchronously: the result is read when the NEXT step issues its own gather, so the cross-rank
         # rendezvous never stalls the following step's kernels
         if pending[0] is not None:
             last_metric[0] = pending[0].result()
-        pending[0] = gather_rows(sample_diversity_rows(so.joints, B, N), num_images=world * B, async_op=True)
-        return so, pending[0]
+        pending[0] = gather_rows(rows, num_images=world * B, async_op=True)
 
     def sync_all():
         if pending[0] is not None:
@@ -237,181 +252,181 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput (`value`)
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev)
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step_and_gather()
     sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
     e0, e1 = ev(), ev()
-    enc_marks = [(ev(), ev(), ev()) for _ in range(args.steps)]
     e0.record()
-    for i in range(args.steps):
-        enc_marks[i][2].record()
-        step(x_dev, marks=enc_marks[i])
+    for _ in range(args.steps):
+        step_and_gather()
     e1.record()
     sync_all()
-    launches = _lib.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
+    ms_step = maxms(e0.elapsed_time(e1)) / args.steps
     value = world * B * N / (ms_step * 1e-3)
-    ms_model = statistics.mean(m[2].elapsed_time(m[0]) for m in enc_marks)
-    ms_lbs = statistics.mean(m[0].elapsed_time(m[1]) for m in enc_marks)
+    # the same step issued eagerly (one driver call per kernel), for the record
+    for _ in range(3):
+        step_fn(x_dev, z, se)
+    torch.cuda.synchronize()
+    a, b_ = ev(), ev()
+    a.record()
+    for _ in range(10):
+        step_fn(x_dev, z, se)
+    b_.record()
+    torch.cuda.synchronize()
+    ms_eager = a.elapsed_time(b_) / 10
 
-    # ---------------- per-stage kernel times, measured live with CUDA events on the launching stream
-    def time_call(fn, iters=10):
-        fn(); torch.cuda.synchronize()
-        a, b = ev(), ev()
+    # ---------------------------------------------------------------- per-stage times (CUDA events on the launching stream; each stage
+    # replayed from its own CUDA graph so that the host's launch rate is not part of the number)
+    def time_stage(fn, *inputs, iters=20):
+        r = CudaGraphRunner(fn, *inputs) if use_graph else None
+        call = (lambda: r(*[None] * len(inputs))) if use_graph else (lambda: fn(*inputs))
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        a, b2 = ev(), ev()
         a.record()
         for _ in range(iters):
-            fn()
-        b.record()
+            call()
+        b2.record()
         torch.cuda.synchronize()
-        return a.elapsed_time(b) / iters
+        return a.elapsed_time(b2) / iters
 
     with torch.no_grad():
-        feats = model.image_encoder(x_dev)
-        ms_enc = time_call(lambda: model.image_encoder(x_dev))
-        ms_flow = time_call(lambda: model(None, input_feats=feats, num_samples=N, base_noise=z, shape_eps=se))
-        out = model(None, input_feats=feats, num_samples=N, base_noise=z, shape_eps=se)
-        R = out['pose_rotmats_samples'].view(B * N, 23, 3, 3)
-        full = torch.cat([out['glob_rotmat'][:, None].expand(-1, N, -1, -1).reshape(B * N, 1, 3, 3), R], 1).contiguous()
-        betas = out['shape_samples'].view(B * N, 10).contiguous()
-        ms_lbs_k = time_call(lambda: smpl.lbs(betas, full))
+        feats = model.image_encoder(x_dev).clone()
+        ms_enc = time_stage(lambda x: model.image_encoder(x), x_dev)
+        ms_flow = time_stage(lambda f, z_, se_: model(None, input_feats=f, num_samples=N, base_noise=z_, shape_eps=se_)['pose_rotmats_samples'], feats, z, se)
+        o = model(None, input_feats=feats, num_samples=N, base_noise=z, shape_eps=se)
+        R = o['pose_rotmats_samples'].view(B * N, 23, 3, 3).clone()
+        glob = o['glob_rotmat'].clone()
+        betas = o['shape_samples'].view(B * N, 10).clone()
+        ms_lbs = time_stage(lambda b3, r3, g3: smpl.forward_samples(b3, r3, g3, N).vertices, betas, R, glob)
     pk = peaks()
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # FMA lanes x 2 x max SM clock: datasheet-derived, not in MEASURED_PEAKS.json
     stages = {
         'encoder': {'ms': ms_enc, 'bound': 'tensor', 'achieved': ENC_FLOP_PER_IMAGE[args.layers] * B / (ms_enc * 1e-3) / 1e12,
-                    'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s'},
-        'flow': {'ms': ms_flow, 'bound': 'fp32-fma', 'achieved_tflops': FLOW_FLOP_PER_SAMPLE * B * N / (ms_flow * 1e-3) / 1e12,
+                    'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'peak_source': pk['source'] + ' (burst bf16: the stage is timed alone for < 1 s at max clocks)'},
+        'flow': {'ms': ms_flow, 'bound': 'fp32-fma', 'achieved': FLOW_FLOP_PER_SAMPLE * B * N / (ms_flow * 1e-3) / 1e12, 'peak': fp32_peak,
+                 'unit': 'TFLOP/s', 'peak_source': 'datasheet-derived: 148 SMs x 128 FMA lanes x 2 x 1.965 GHz',
                  'achieved_gbs': FLOW_BYTES_PER_SAMPLE * B * N / (ms_flow * 1e-3) / 1e9},
-        'lbs': {'ms': ms_lbs_k, 'bound': 'hbm', 'achieved': LBS_BYTES_PER_SAMPLE * B * N / (ms_lbs_k * 1e-3) / 1e9,
-                'peak': pk['hbm_gbs'], 'unit': 'GB/s'},
+        'lbs': {'ms': ms_lbs, 'bound': 'hbm', 'achieved': LBS_BYTES_PER_SAMPLE * B * N / (ms_lbs * 1e-3) / 1e9,
+                'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'peak_source': pk['source'] + ' (copy bandwidth)'},
     }
-    for s in ('encoder', 'lbs'):
-        stages[s]['frac'] = stages[s]['achieved'] / stages[s]['peak']
-    dom = 'encoder' if ms_enc >= ms_lbs_k else 'lbs'
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if dom == 'encoder' and args.layers == 50 and B == 32 and os.path.exists(tpath):
-        traffic = json.load(open(tpath))['dram_bytes_per_step']     # ncu dram bytes of the 49 conv launches of one forward
-    roofline = {'kernel': 'conv_tcgen05_kernel (ResNet-%d trunk, 49 launches per step)' % args.layers if dom == 'encoder' else 'lbs_skin_tc2_kernel (+ pose / extra-joint kernels)',
-                'bound': stages[dom]['bound'], 'achieved': stages[dom]['achieved'], 'peak': stages[dom]['peak'],
-                'unit': stages[dom]['unit'], 'frac': stages[dom]['frac'], 'traffic': traffic,
-                'peak_source': pk['source'] + (' (sustained bf16)' if dom == 'encoder' else ' (copy bandwidth)')}
+    for s_ in stages.values():
+        s_['frac'] = s_['achieved'] / s_['peak']
+    dom = max(('encoder', 'flow', 'lbs'), key=lambda k: stages[k]['ms'])
+    traffic, traffic_src = None, None
+    for tag in ('r02', 'r01'):
+        tpath = os.path.join(ROOT, 'profiles', '%s_traffic.json' % tag)
+        if dom == 'encoder' and args.layers == 50 and B == 32 and os.path.exists(tpath):
+            traffic = json.load(open(tpath))['dram_bytes_per_step']
+            traffic_src = 'profiles/%s_traffic.json (ncu dram__bytes of the conv launches of one forward; not measured in this run)' % tag
+            break
+    kname = {'encoder': 'conv_tcgen05_kernel (ResNet-%d trunk, 49 launches per step)' % args.layers,
+             'flow': 'flow_sample_kernel', 'lbs': 'lbs_skin_tc2_kernel (+ pose / extra-joint kernels)'}[dom]
+    roofline = {'kernel': kname, 'bound': stages[dom]['bound'] if dom != 'flow' else 'tensor', 'achieved': stages[dom]['achieved'],
+                'peak': stages[dom]['peak'], 'unit': stages[dom]['unit'], 'frac': stages[dom]['frac'], 'traffic': traffic,
+                'traffic_source': traffic_src, 'peak_source': stages[dom]['peak_source']}
 
-    # ---------------- end to end through the public API with HOST buffers (H2D of the images, D2H of the meshes)
-    # Every step copies its own input from pinned host memory and its own result back to pinned host memory, all
-    # inside the timed region.  Steps are software-pipelined over three streams (H2D | compute | D2H) with
-    # double-buffered staging, so the copy of step i+1 / i-1 overlaps the kernels of step i (PCIe is full duplex).
-    V = smpl.v_template.shape[0]
-    v_host = [torch.empty(B * N, V, 3).pin_memory() for _ in range(2)]
-    j_host = [torch.empty(B * N, smpl.num_joints_out, 3).pin_memory() for _ in range(2)]
-    x_stage = [torch.empty_like(x_dev) for _ in range(2)]
-    out_dev = [(torch.empty(B * N, V, 3, device=dev), torch.empty(B * N, smpl.num_joints_out, 3, device=dev)) for _ in range(2)]
-    ev_copied = [torch.cuda.Event() for _ in range(2)]  # outputs of buffer b have been copied to the host
+    # ---------------------------------------------------------------- end to end with HOST buffers
+    # Every step copies its own input from pinned host memory and its own result back to pinned host memory inside the timed
+    # region.  Steps are software-pipelined over three streams (H2D | kernels | D2H) with two sets of buffers, so the copy of step
+    # i+1 / i-1 overlaps the kernels of step i (PCIe is full duplex).  Three forms:
+    #   e2e             RGB crops + 2-D joints in (25 MB) -> proxy representation built on the device, straight into the encoder's
+    #                   staging layout -> the step -> per-sample PVE / PVE-SC / PVE-PA reduced on the device -> (B,4) rows out: what
+    #                   evaluate_humaniflow.py:227-258 becomes with SURVEY 8f N1 + N4 in place.  This is the headline.
+    #   e2e_evaluate    the 18-channel proxy representation comes from the host (bf16: 75 MB), metric rows out
+    #   e2e_all_meshes  fp32 proxy representation in (151 MB), EVERY sampled mesh out (268 MB): bounded by the host's PCIe / memory path
+    tgt = smpl.tpose(torch.zeros(B, 10, device=dev)).vertices.clone()                 # synthetic ground-truth meshes
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     s_main = torch.cuda.current_stream()
-    ev_in = [torch.cuda.Event() for _ in range(2)]      # input buffer b filled
-    ev_used = [torch.cuda.Event() for _ in range(2)]    # input buffer b consumed by the encoder
-    ev_done = [torch.cuda.Event() for _ in range(2)]    # outputs of the step using buffer b are ready
-    keep = [None, None]
 
-    def e2e_steps(n):
-        for b in range(2):
-            ev_used[b].record(s_main)
-            ev_copied[b].record(s_out)
-        for i in range(n):
-            b = i & 1
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(ev_used[b])
-                x_stage[b].copy_(x_host, non_blocking=True)
-                ev_in[b].record(s_in)
-            s_main.wait_event(ev_in[b])
-            s_main.wait_event(ev_copied[b])           # device output buffer b is free again
-            so, metric = step(x_stage[b], outs=out_dev[b])
-            ev_used[b].record(s_main)
-            ev_done[b].record(s_main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_done[b])
-                v_host[b].copy_(so.vertices, non_blocking=True)
-                j_host[b].copy_(so.joints, non_blocking=True)
+    def metric_rows(verts):
+        err = pointset_errors(verts.view(B, N, V, 3), tgt)
+        return torch.stack([samples_min(err['plain']), samples_min(err['sc']), samples_min(err['pa']), err['plain'].mean(1)], 1)
+
+    def rgb_fn(rgb, j2d, z_, se_):
+        staged = build_proxy_representation(rgb, j2d, encoder=model.image_encoder)
+        _, verts, _ = predict_step(model, smpl, staged, z_, se_)
+        return metric_rows(verts)
+
+    def eval_fn(xh, z_, se_):
+        _, verts, _ = predict_step(model, smpl, xh, z_, se_)
+        return metric_rows(verts)
+
+    def mesh_fn(xf, z_, se_):
+        _, verts, joints = predict_step(model, smpl, xf, z_, se_)
+        return verts, joints
+
+    def pipelined(fn, host_inputs, dev_examples, host_outputs, steps_list):
+        """Generic double-buffered H2D | compute | D2H pipeline around `fn` (graph-captured once per buffer set)."""
+        nin = len(host_inputs)
+        runners, stat_in = [], []
+        for _b in range(2):
+            if use_graph:
+                r = CudaGraphRunner(fn, *dev_examples, z, se)
+                runners.append(r)
+                stat_in.append(r.static_in[:nin])
+            else:
+                runners.append(None)
+                stat_in.append([d.clone() for d in dev_examples])
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_used = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_copied = [torch.cuda.Event() for _ in range(2)]
+        keep = [None, None]
+
+        def run(n):
+            for b in range(2):
+                ev_used[b].record(s_main)
                 ev_copied[b].record(s_out)
-            keep[b] = so
-        s_main.wait_stream(s_out)
-        s_main.wait_stream(s_in)
+            for i in range(n):
+                b = i & 1
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_used[b])
+                    for d, h in zip(stat_in[b], host_inputs):
+                        d.copy_(h, non_blocking=True)
+                    ev_in[b].record(s_in)
+                s_main.wait_event(ev_in[b])
+                s_main.wait_event(ev_copied[b])          # the outputs of this buffer set have left the device
+                outs = runners[b](*[None] * (nin + 2)) if use_graph else fn(*stat_in[b], z, se)
+                outs = outs if isinstance(outs, tuple) else (outs,)
+                ev_used[b].record(s_main)
+                ev_done[b].record(s_main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[b])
+                    for o_, h in zip(outs, host_outputs[b]):
+                        h.copy_(o_, non_blocking=True)
+                    ev_copied[b].record(s_out)
+                keep[b] = outs
+            s_main.wait_stream(s_out)
+            s_main.wait_stream(s_in)
 
-    # evaluate-style end to end (BASELINE configs[3]): the per-sample PVE / PVE-SC / PVE-PA errors against a
-    # target mesh per image are reduced on the device (hf_pointset_errors) and only the per-image rows go back to the host
-    from humaniflow_b200.metrics import pointset_errors, samples_min
-    tgt = smpl.tpose(torch.zeros(B, 10, device=dev)).vertices.clone()                 # synthetic ground-truth meshes
-    rows_host = [torch.empty(B, 4).pin_memory() for _ in range(2)]
-    ev_rows = [torch.cuda.Event() for _ in range(2)]
+        res = []
+        for n in steps_list:
+            run(3)
+            sync_all()
+            a, b2 = ev(), ev()
+            a.record()
+            run(n)
+            b2.record()
+            sync_all()
+            res.append(maxms(a.elapsed_time(b2)) / n)
+        return res[0]
 
-    def eval_steps(n):
-        for b in range(2):
-            ev_used[b].record(s_main)
-            ev_rows[b].record(s_out)
-        for i in range(n):
-            b = i & 1
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(ev_used[b])
-                x_stage[b].copy_(x_host, non_blocking=True)
-                ev_in[b].record(s_in)
-            s_main.wait_event(ev_in[b])
-            s_main.wait_event(ev_rows[b])
-            so, metric = step(x_stage[b], outs=out_dev[b])
-            err = pointset_errors(so.vertices.view(B, N, V, 3), tgt)
-            rows = torch.stack([samples_min(err['plain']), samples_min(err['sc']), samples_min(err['pa']), err['plain'].mean(1)], 1)
-            ev_used[b].record(s_main)
-            ev_done[b].record(s_main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_done[b])
-                rows_host[b].copy_(rows, non_blocking=True)
-                ev_rows[b].record(s_out)
-            keep[b] = (so, rows)
-        s_main.wait_stream(s_out)
-        s_main.wait_stream(s_in)
-
-    # image-to-metrics end to end (SURVEY 8f N4 + N1 around the hot path): the host sends the RGB crops and 2-D joints, the
-    # proxy representation is built on the device (hf_proxy_rep), and only the per-image metric rows come back
-    from humaniflow_b200.proxy_rep import build_proxy_representation
     rgb_host = torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
     j2d_host = (torch.rand(B, 17, 2, generator=torch.Generator().manual_seed(8 + rank)) * 256).pin_memory()
-    rgb_stage = [torch.empty(B, 3, 256, 256, device=dev) for _ in range(2)]
-    j2d_stage = [torch.empty(B, 17, 2, device=dev) for _ in range(2)]
+    rows_host = [[torch.empty(B, 4).pin_memory()] for _ in range(2)]
+    rgb_ms = pipelined(rgb_fn, [rgb_host, j2d_host], [rgb_host.to(dev), j2d_host.to(dev)], rows_host, [args.steps])
+    xh_host = x_host.to(torch.bfloat16).pin_memory()
+    eval_ms = pipelined(eval_fn, [xh_host], [xh_host.to(dev)], rows_host, [args.steps])
+    mesh_host = [[torch.empty(B * N, V, 3).pin_memory(), torch.empty(B * N, JO, 3).pin_memory()] for _ in range(2)]
+    mesh_ms = pipelined(mesh_fn, [x_host], [x_dev], mesh_host, [args.steps])
 
-    def rgb_steps(n):
-        for b in range(2):
-            ev_used[b].record(s_main)
-            ev_rows[b].record(s_out)
-        for i in range(n):
-            b = i & 1
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(ev_used[b])
-                rgb_stage[b].copy_(rgb_host, non_blocking=True)
-                j2d_stage[b].copy_(j2d_host, non_blocking=True)
-                ev_in[b].record(s_in)
-            s_main.wait_event(ev_in[b])
-            s_main.wait_event(ev_rows[b])
-            so, metric = step(build_proxy_representation(rgb_stage[b], j2d_stage[b]), outs=out_dev[b])
-            err = pointset_errors(so.vertices.view(B, N, V, 3), tgt)
-            rows = torch.stack([samples_min(err['plain']), samples_min(err['sc']), samples_min(err['pa']), err['plain'].mean(1)], 1)
-            ev_used[b].record(s_main)
-            ev_done[b].record(s_main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_done[b])
-                rows_host[b].copy_(rows, non_blocking=True)
-                ev_rows[b].record(s_out)
-            keep[b] = (so, rows)
-        s_main.wait_stream(s_out)
-        s_main.wait_stream(s_in)
-
-    # PCIe sanity numbers for the e2e line (plain pinned copies of the same buffers, not part of any timed region)
+    # PCIe sanity numbers (plain pinned copies of the same buffers, not part of any timed region)
     def copy_gbs(dst, src, iters=3):
         dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
         c0, c1 = ev(), ev()
@@ -421,62 +436,36 @@ def run_ours(args):
         c1.record(); torch.cuda.synchronize()
         return src.numel() * src.element_size() * iters / (c0.elapsed_time(c1) * 1e-3) / 1e9
     v_dev_tmp = torch.empty(B * N, V, 3, device=dev)
-    pcie = {'h2d_gbs': copy_gbs(x_stage[0], x_host), 'd2h_gbs': copy_gbs(v_host[0], v_dev_tmp)}
+    pcie = {'h2d_gbs': copy_gbs(torch.empty_like(x_dev), x_host), 'd2h_gbs': copy_gbs(mesh_host[0][0], v_dev_tmp)}
     del v_dev_tmp
-    e2e_steps(5)
-    sync_all()
-    a, b_ev = ev(), ev()
-    a.record()
-    e2e_steps(args.steps)
-    b_ev.record()
-    sync_all()
-    t = torch.tensor([a.elapsed_time(b_ev)], device=dev)
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = t.item() / args.steps
-    eval_steps(5)
-    sync_all()
-    a2, b2 = ev(), ev()
-    a2.record()
-    eval_steps(args.steps)
-    b2.record()
-    sync_all()
-    t = torch.tensor([a2.elapsed_time(b2)], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    eval_ms = t.item() / args.steps
-    rgb_steps(5)
-    sync_all()
-    a3, b3 = ev(), ev()
-    a3.record()
-    rgb_steps(args.steps)
-    b3.record()
-    sync_all()
-    t = torch.tensor([a3.elapsed_time(b3)], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    rgb_ms = t.item() / args.steps
+        pl = [None] * world
+        dist.all_gather_object(pl, pcie)
+        pcie = {'per_rank': pl}
     clocks = sampler.stop() if rank == 0 else None
 
-    line = None
     if rank == 0:
+        per = world * B * N
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': W,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16 (encoder) / f32 (flow, LBS; f64 exp/log maps)',
             'data': 'synthetic (random-init weights; SMPL-shaped synthetic body model, skinning weights grouped by body part like the real SMPL)', 'config': workload_config(args),
-            'e2e': {'value': world * B * N / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': (v_host[0].numel() + j_host[0].numel()) * 4,
+            'e2e': {'value': per / (rgb_ms * 1e-3), 'unit': UNIT, 'ms_per_step': rgb_ms,
+                    'h2d_bytes_per_step': (rgb_host.numel() + j2d_host.numel()) * 4, 'd2h_bytes_per_step': rows_host[0][0].numel() * 4,
+                    'what': 'RGB crops + 2-D joints from pinned host memory -> proxy representation on the device (hf_proxy_rep_staged, straight into the '
+                            'encoder staging layout) -> the step -> per-sample PVE / PVE-SC / PVE-PA reduced on the device (hf_pointset_errors) -> '
+                            '(B,4) metric rows to pinned host memory',
                     'pipelining': 'H2D | kernels | D2H on three streams, double-buffered', 'pcie_measured': pcie},
-            'e2e_evaluate': {'value': world * B * N / (eval_ms * 1e-3), 'unit': UNIT, 'ms_per_step': eval_ms,
-                             'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': rows_host[0].numel() * 4,
-                             'what': 'same step + per-sample PVE / PVE-SC / PVE-PA against one target mesh per image reduced on the '
-                                     'device (hf_pointset_errors); only the (B,4) per-image rows are copied back'},
-            'e2e_from_rgb': {'value': world * B * N / (rgb_ms * 1e-3), 'unit': UNIT, 'ms_per_step': rgb_ms,
-                             'h2d_bytes_per_step': (rgb_host.numel() + j2d_host.numel()) * 4, 'd2h_bytes_per_step': rows_host[0].numel() * 4,
-                             'what': 'RGB crops + 2-D joints from the host -> proxy representation on the device (hf_proxy_rep) -> the '
-                                     'step -> on-device PVE / PVE-SC / PVE-PA rows back to the host'},
-            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'stages': stages,
-            'step_breakdown_ms': {'model_forward': ms_model, 'lbs': ms_lbs},
+            'e2e_evaluate': {'value': per / (eval_ms * 1e-3), 'unit': UNIT, 'ms_per_step': eval_ms,
+                             'h2d_bytes_per_step': xh_host.numel() * 2, 'd2h_bytes_per_step': rows_host[0][0].numel() * 4,
+                             'what': '18-channel proxy representation from the host as bf16 (hf_encoder_forward_bf16) -> the step + on-device metric rows'},
+            'e2e_all_meshes': {'value': per / (mesh_ms * 1e-3), 'unit': UNIT, 'ms_per_step': mesh_ms,
+                               'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': (mesh_host[0][0].numel() + mesh_host[0][1].numel()) * 4,
+                               'what': 'fp32 proxy representation in, EVERY sampled mesh (vertices + joints) out; bounded by the host PCIe / memory path'},
+            'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
+            'execution': 'one CUDA graph replay per step (humaniflow_b200.graphs.CudaGraphRunner)' if use_graph else 'eager launches',
+            'clocks': clocks, 'roofline': roofline, 'stages': stages,
+            'step_breakdown_ms': {'graph_replay': ms_step, 'eager_launches': ms_eager, 'sum_of_stages': ms_enc + ms_flow + ms_lbs},
         }
         if world == 1 and not args.no_cpu_baseline:
             if _FULL_AFFINITY:
@@ -484,9 +473,9 @@ def run_ours(args):
             cores = len(os.sched_getaffinity(0))
             torch.set_num_threads(cores)
             Bc = min(B, args.ref_images)
-            val, sec = time_cpu(Bc, N, args.layers, steps=2, warmup=1)
+            val, sec = time_cpu(Bc, N, args.layers, steps=3, warmup=1)
             line['cpu_baseline'] = {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                                    'sample': '%d images x %d samples, 2 timed passes after 1 warm-up (%.1f s per pass); oracle/ = CPU '
+                                    'sample': '%d images x %d samples, 3 timed passes after 1 warm-up (%.1f s per pass); oracle/ = CPU '
                                               'restatement of the reference path' % (Bc, N, sec)}
         print(json.dumps(line))
     if dist is not None:
@@ -503,7 +492,8 @@ def main():
     ap.add_argument('--B', type=int, default=32, help='images per GPU per step')
     ap.add_argument('--N', type=int, default=100, help='pose samples per image')
     ap.add_argument('--layers', type=int, default=50)
-    ap.add_argument('--ref-images', type=int, default=8, help='images per step of the CPU arm (bounded sample)')
+    ap.add_argument('--ref-images', type=int, default=32, help='images per step of the CPU arm (default: the full batch)')
+    ap.add_argument('--no-graph', action='store_true', help='issue every kernel launch from Python instead of replaying CUDA graphs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
