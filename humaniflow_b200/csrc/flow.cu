@@ -24,9 +24,11 @@
 namespace {
 
 constexpr int FEATS = 256, CTX = 64, H1 = 64, H2 = 32, H3 = 32, NRAW = 62, NBINS = 8;
-// coupling block layout (floats, k-major matrices [K][O])
-constexpr int OFF_W0 = 0, OFF_B0 = 65 * 64, OFF_W1 = OFF_B0 + 64, OFF_B1 = OFF_W1 + 64 * 32,
-              OFF_W2 = OFF_B1 + 32, OFF_B2 = OFF_W2 + 32 * 32, OFF_W3 = OFF_B2 + 32, OFF_B3 = OFF_W3 + 32 * 64,
+// coupling block layout (floats, k-major matrices [K][O + WPAD]: rows padded by 4 floats so that the four k-slices of a
+// dense_layer tile fall into different shared-memory banks)
+constexpr int WPAD = 4, CTXP = CTX + WPAD;
+constexpr int OFF_W0 = 0, OFF_B0 = 65 * (64 + WPAD), OFF_W1 = OFF_B0 + 64, OFF_B1 = OFF_W1 + 64 * (32 + WPAD),
+              OFF_W2 = OFF_B1 + 32, OFF_B2 = OFF_W2 + 32 * (32 + WPAD), OFF_W3 = OFF_B2 + 32, OFF_B3 = OFF_W3 + 32 * (64 + WPAD),
               COUPLING_FLOATS = OFF_B3 + 64;
 
 struct FlowParams {
@@ -47,69 +49,118 @@ struct FlowParams {
 __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expm1f(x); }
 
 // ---- register-tiled partial GEMM of one warp: part[32][NR] = sum_{k in [k0,k1)} W[k][ob*32 + :] x X[k][:] ----
+// packed fp32 x 2 FMA (Blackwell FFMA2): d = a * b + c on both halves, each half rounded like a scalar fmaf, so results are
+// bit-identical to the scalar form at half the issue slots
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n"
+        ".reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %3};\n"
+        "mov.b64 rb, {%4, %5};\n"
+        "mov.b64 rc, {%6, %7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rd;\n"
+        "}\n" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
 template <int NR, bool SMEMW = false, int UNR = 4, bool PART_T = false, typename XRow>
 __device__ __forceinline__ void warp_gemm(const float* __restrict__ W, int ldw, int ob, int k0, int k1, XRow xrow,
                                           float* __restrict__ part, int lane) {
-    constexpr int SPL = NR / 4;
+    constexpr int SPL = NR / 4, SP2 = SPL / 2;
     const int oi = lane & 7, sq = lane >> 3;
-    float acc[4][SPL];
+    float2 acc[4][SP2];                    // [output][row pair]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int s = 0; s < SPL; ++s) acc[i][s] = 0.f;
+        for (int s = 0; s < SP2; ++s) acc[i][s] = make_float2(0.f, 0.f);
     const float* wp = W + ob * 32 + oi * 4;
 #pragma unroll UNR
     for (int k = k0; k < k1; ++k) {
         const float4 w = SMEMW ? *reinterpret_cast<const float4*>(wp + (size_t)k * ldw)
                                : __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * ldw));
         const float2* xp = reinterpret_cast<const float2*>(xrow(k) + sq * SPL);
+        const float2 w0 = make_float2(w.x, w.x), w1 = make_float2(w.y, w.y), w2 = make_float2(w.z, w.z), w3 = make_float2(w.w, w.w);
 #pragma unroll
-        for (int q = 0; q < SPL / 2; ++q) {
+        for (int q = 0; q < SP2; ++q) {
             const float2 x = xp[q];
-            acc[0][2 * q] = fmaf(w.x, x.x, acc[0][2 * q]); acc[0][2 * q + 1] = fmaf(w.x, x.y, acc[0][2 * q + 1]);
-            acc[1][2 * q] = fmaf(w.y, x.x, acc[1][2 * q]); acc[1][2 * q + 1] = fmaf(w.y, x.y, acc[1][2 * q + 1]);
-            acc[2][2 * q] = fmaf(w.z, x.x, acc[2][2 * q]); acc[2][2 * q + 1] = fmaf(w.z, x.y, acc[2][2 * q + 1]);
-            acc[3][2 * q] = fmaf(w.w, x.x, acc[3][2 * q]); acc[3][2 * q + 1] = fmaf(w.w, x.y, acc[3][2 * q + 1]);
+            acc[0][q] = fma2(w0, x, acc[0][q]);
+            acc[1][q] = fma2(w1, x, acc[1][q]);
+            acc[2][q] = fma2(w2, x, acc[2][q]);
+            acc[3][q] = fma2(w3, x, acc[3][q]);
         }
     }
     if (PART_T) {   // partial tile transposed [row][32 outputs]: one 128-bit store per row, bank-conflict free
 #pragma unroll
-        for (int r = 0; r < SPL; ++r)
-            *reinterpret_cast<float4*>(part + (sq * SPL + r) * 32 + oi * 4) = make_float4(acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
+        for (int q = 0; q < SP2; ++q) {
+            *reinterpret_cast<float4*>(part + (sq * SPL + 2 * q) * 32 + oi * 4) = make_float4(acc[0][q].x, acc[1][q].x, acc[2][q].x, acc[3][q].x);
+            *reinterpret_cast<float4*>(part + (sq * SPL + 2 * q + 1) * 32 + oi * 4) = make_float4(acc[0][q].y, acc[1][q].y, acc[2][q].y, acc[3][q].y);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float2* pp = reinterpret_cast<float2*>(part + (oi * 4 + i) * NR + sq * SPL);
 #pragma unroll
-            for (int q = 0; q < SPL / 2; ++q) pp[q] = make_float2(acc[i][2 * q], acc[i][2 * q + 1]);
+            for (int q = 0; q < SP2; ++q) pp[q] = acc[i][q];
         }
     }
 }
 
-// A dense layer over the CTA: OT output tiles of 32, K split over HF_NW/OT warps, partials in scratch,
-// then bias + activation into dst[O][NR].  ACT: 0 none, 1 ELU, 2 ReLU.  Ends with __syncthreads().
+// A dense layer over the CTA (the layers of the chain are tiny: 32-64 outputs x NR <= 24 rows x K <= 65): bias + activation
+// into dst[O][NR].  ACT: 0 none, 1 ELU, 2 ReLU.  Ends with ONE __syncthreads().
+// Mapping: a tile = 4 outputs x 4 rows (16 accumulators); the four lanes of a tile take every fourth k (packed fp32x2 FMAs,
+// one 128-bit load of 4 weights + one of 4 row values per k) and combine their partial sums with two xor-shuffles; lane i of
+// the tile then finishes output i of the tile.  No shared-memory round trip, no second barrier: the earlier form (K split
+// over the 16 warps, partial tiles through shared memory, two barriers) measured ~1.9 k cycles per layer against ~0.4 k of
+// FMA work.  W rows are padded by 4 floats (LDW = O + 4) so the four k-slices of a tile hit different banks.
 template <int NR, int OT, int ACT, bool SMEMW = false, typename XRow>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias, int K,
                                             XRow xrow, float* scratch, float* dst, const float* add = nullptr) {
-    constexpr int NS = HF_NW / OT;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ob = warp / NS, sp = warp - ob * NS;
-    const int chunk = (K + NS - 1) / NS;
-    const int k0 = min(sp * chunk, K), k1 = min(k0 + chunk, K);
-    warp_gemm<NR, SMEMW, 4, true>(W, OT * 32, ob, k0, k1, xrow, scratch + warp * 32 * NR, lane);
-    __syncthreads();
-    for (int e = threadIdx.x; e < OT * 32 * NR; e += HF_NT) {
-        // consecutive threads -> consecutive outputs of one row: conflict-free reads of the transposed partial tiles
-        const int ol = e & 31, s = (e >> 5) % NR, ob2 = e / (32 * NR);
-        const int o = ob2 * 32 + ol;
-        float a = SMEMW ? bias[o] : __ldg(bias + o);
-        if (add) a += add[o * NR + s];
-        const float* p = scratch + (ob2 * NS) * 32 * NR + s * 32 + ol;
+    constexpr int O = OT * 32, LDW = O + 4, RG = NR / 4, NTILE = (O / 4) * RG;
+    static_assert(NR % 4 == 0 && NTILE * 4 <= HF_NT, "dense_layer tile mapping");
+    (void)scratch;
+    const int tile = threadIdx.x >> 2, ks = threadIdx.x & 3;
+    if (tile < NTILE) {                     // whole warps (NTILE * 4 is a multiple of 32 for NR in {8, 16, 24})
+        const int og = tile / RG, rg = tile - og * RG;
+        float2 acc[4][2];
 #pragma unroll
-        for (int q = 0; q < NS; ++q) a += p[q * 32 * NR];
-        if (ACT == 1) a = elu(a);
-        if (ACT == 2) a = fmaxf(a, 0.f);
-        dst[o * NR + s] = a;
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+        const float* wp = W + og * 4;
+#pragma unroll 4
+        for (int k = ks; k < K; k += 4) {
+            const float4 w = SMEMW ? *reinterpret_cast<const float4*>(wp + (size_t)k * LDW)
+                                   : __ldg(reinterpret_cast<const float4*>(wp + (size_t)k * LDW));
+            const float4 x = *reinterpret_cast<const float4*>(xrow(k) + rg * 4);
+            const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+            const float2 w0 = make_float2(w.x, w.x), w1 = make_float2(w.y, w.y), w2 = make_float2(w.z, w.z), w3 = make_float2(w.w, w.w);
+            acc[0][0] = fma2(w0, xa, acc[0][0]); acc[0][1] = fma2(w0, xb, acc[0][1]);
+            acc[1][0] = fma2(w1, xa, acc[1][0]); acc[1][1] = fma2(w1, xb, acc[1][1]);
+            acc[2][0] = fma2(w2, xa, acc[2][0]); acc[2][1] = fma2(w2, xb, acc[2][1]);
+            acc[3][0] = fma2(w3, xa, acc[3][0]); acc[3][1] = fma2(w3, xb, acc[3][1]);
+        }
+        // sum the four k-slices (fixed order: (0+1) + (2+3) in every lane), then lane ks finishes output ks of the tile
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float vx = acc[i][h].x, vy = acc[i][h].y;
+                vx += __shfl_xor_sync(0xffffffffu, vx, 1); vy += __shfl_xor_sync(0xffffffffu, vy, 1);
+                vx += __shfl_xor_sync(0xffffffffu, vx, 2); vy += __shfl_xor_sync(0xffffffffu, vy, 2);
+                if (i == ks) { r[2 * h] = vx; r[2 * h + 1] = vy; }
+            }
+        }
+        const int o = og * 4 + ks;
+        const float b = SMEMW ? bias[o] : __ldg(bias + o);
+        float* dp = dst + o * NR + rg * 4;
+        float4 a4 = add ? *reinterpret_cast<const float4*>(add + o * NR + rg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float v[4] = {r[0] + b + a4.x, r[1] + b + a4.y, r[2] + b + a4.z, r[3] + b + a4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (ACT == 1) v[q] = elu(v[q]);
+            if (ACT == 2) v[q] = fmaxf(v[q], 0.f);
+        }
+        *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
     }
     __syncthreads();
 }
@@ -383,7 +434,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // shared-memory layout of the sampling kernel (floats)
 template <int NR>
 struct SampleSmem {
-    static constexpr int ANC_MAX = 7 * 9 * CTX + CTX;     // deepest SMPL joint has 7 ancestors; checked on the host
+    static constexpr int ANC_MAX = 7 * 9 * CTXP + CTX;     // deepest SMPL joint has 7 ancestors; checked on the host
     static constexpr int Wanc = 0;
     static constexpr int Wc0 = Wanc + ANC_MAX;
     static constexpr int Wc1 = Wc0 + COUPLING_FLOATS;
@@ -402,7 +453,9 @@ template <int NR>
 __global__ void __launch_bounds__(HF_NT, 1)
 flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict__ img_base, const float* __restrict__ betas,
                    const int* __restrict__ img_index, const float* __restrict__ base_noise, int R, int Rn,
-                   float* __restrict__ rotmats, float* __restrict__ axisangle_pe, float* __restrict__ Uscratch) {
+                   float* __restrict__ rotmats, float* __restrict__ axisangle_pe, float* __restrict__ Uscratch, int dbg) {
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    auto lap = [&](int c) { if (dbg) { const long long t = clock64(); tph[c] += t - tlast; tlast = t; } };
     using L = SmemLayout<NR>;
     using S = SampleSmem<NR>;
     extern __shared__ __align__(16) float smraw[];
@@ -414,7 +467,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = smem_u32(&wbar[0]);
     float* Ucta = Uscratch + (size_t)blockIdx.x * P.J * CTX * NR;
-    auto joint_bytes_anc = [&](int j) { return (uint32_t)((9 * P.anc_cnt[j] * CTX + CTX) * 4); };
+    auto joint_bytes_anc = [&](int j) { return (uint32_t)((9 * P.anc_cnt[j] * CTXP + CTX) * 4); };
     auto issue_anc = [&](int j) {
         mbar_expect_tx(bar0, joint_bytes_anc(j));
         bulk_load_1d(smem_u32(smraw + S::Wanc), P.jpack + P.off_jb[j], joint_bytes_anc(j), bar0);
@@ -422,7 +475,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
     auto issue_cpl = [&](int j, int t) {
         mbar_expect_tx(bar0 + 8 * (1 + t), COUPLING_FLOATS * 4);
         bulk_load_1d(smem_u32(smraw + (t ? S::Wc1 : S::Wc0)),
-                     P.jpack + P.off_jb[j] + 9 * P.anc_cnt[j] * CTX + CTX + t * COUPLING_FLOATS, COUPLING_FLOATS * 4,
+                     P.jpack + P.off_jb[j] + 9 * P.anc_cnt[j] * CTXP + CTX + t * COUPLING_FLOATS, COUPLING_FLOATS * 4,
                      bar0 + 8 * (1 + t));
     };
     auto fetch_U = [&](int j) {   // 64 x NR floats, contiguous in the scratch
@@ -445,6 +498,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
                                 Ucta + (size_t)(t >> 1) * CTX * NR + (t & 1) * 32 * NR, lane);
     __threadfence();
     __syncthreads();
+    lap(0);
     fetch_U(0);
 
     for (int j = 0; j < P.J; ++j) {
@@ -453,6 +507,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
         cp_async_wait_all();
         mbar_wait(bar0, par);
         __syncthreads();
+        lap(1);
         // base sample (zero for point-estimate rows); first permutation is the identity.  Written here (row CTX of
         // Cs and Zs are not touched by the context layer), ordered by the layer's own barriers.
         if (tid < NR) {
@@ -466,17 +521,21 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
             sm[L::Cs + CTX * NR + tid] = z0;
         }
         // context = ELU(U_j + b + Wanc . vec(ancestor rotations))
-        dense_layer<NR, 2, 1, true>(smraw + S::Wanc, smraw + S::Wanc + Ka * CTX, Ka, AncRow{sm + L::Ps, P.anc[j], NR},
+        dense_layer<NR, 2, 1, true>(smraw + S::Wanc, smraw + S::Wanc + Ka * CTXP, Ka, AncRow{sm + L::Ps, P.anc[j], NR},
                                     sm + L::Scratch, sm + L::Cs, Us + (j & 1) * CTX * NR);
+        lap(2);
         if (j + 1 < P.J) {
             if (tid == 0) issue_anc(j + 1);
             fetch_U(j + 1);
         }
         for (int t = 0; t < P.T; ++t) {
             mbar_wait(bar0 + 8 * (1 + t), par);
+            lap(1);
             coupling_nn_smem<NR>(smraw + (t ? S::Wc1 : S::Wc0), sm);
+            lap(3);
             if (tid == 0 && j + 1 < P.J) issue_cpl(j + 1, t);
             spline_knots<NR>(sm + L::Raw, P.radius, sm + L::Ha);
+            lap(4);
             // spline on the two trailing coordinates, then rotate the vector for the next Permute
             // (pyro_conditional_norm_flow.py:46-62: with <=2 transforms the only non-identity Permute is [1,2,0],
             //  applied to the running vector before the second coupling).
@@ -498,6 +557,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
                 }
             }
             __syncthreads();
+            lap(5);
         }
         // radial tanh -> exp map -> store (shared copy feeds the descendants' contexts)
         if (tid < NR) {
@@ -524,7 +584,11 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
             }
         }
         __syncthreads();
+        lap(6);
     }
+    if (dbg && blockIdx.x == 0 && tid == 0)
+        printf("flow phases (cycles, CTA 0): prologue %lld | weight waits %lld | context layers %lld | coupling MLPs %lld | knots %lld | spline %lld | exp map + store %lld\n",
+               tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6]);
 }
 
 // =====================================  contexts for teacher forcing  =====================================
@@ -737,9 +801,9 @@ extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const 
         }
         const int Kc = FEATS + 9 * a;
         P.off_ctxW[j] = (int)pack.size();
-        pack.resize(pack.size() + (size_t)Kc * CTX);
+        pack.resize(pack.size() + (size_t)Kc * CTXP, 0.f);
         for (int k = 0; k < Kc; ++k)
-            for (int o = 0; o < CTX; ++o) pack[P.off_ctxW[j] + k * CTX + o] = ctx_weight[j][(size_t)o * Kc + k];
+            for (int o = 0; o < CTX; ++o) pack[P.off_ctxW[j] + k * CTXP + o] = ctx_weight[j][(size_t)o * Kc + k];
         P.off_ctxB[j] = (int)pack.size();
         pack.insert(pack.end(), ctx_bias[j], ctx_bias[j] + CTX);
         for (int t = 0; t < P.T; ++t) {
@@ -752,7 +816,7 @@ extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const 
             for (int l = 0; l < 4; ++l) {
                 for (int k = 0; k < Ks[l]; ++k)
                     for (int o = 0; o < Os[l]; ++o)
-                        pack[base + offW[l] + k * Op[l] + o] = nn_weight[li + l][(size_t)o * Ks[l] + k];
+                        pack[base + offW[l] + k * (Op[l] + WPAD) + o] = nn_weight[li + l][(size_t)o * Ks[l] + k];
                 for (int o = 0; o < Os[l]; ++o) pack[base + offB[l] + o] = nn_bias[li + l][o];
             }
         }
@@ -766,7 +830,7 @@ extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const 
             for (int o = 0; o < CTX; ++o) wfeat[(size_t)k * P.J * CTX + j * CTX + o] = ctx_weight[j][(size_t)o * Kc + k];
         P.off_jb[j] = (int)jpack.size();
         for (int k = 0; k < 9 * a; ++k)
-            for (int o = 0; o < CTX; ++o) jpack.push_back(ctx_weight[j][(size_t)o * Kc + FEATS + k]);
+            for (int o = 0; o < CTXP; ++o) jpack.push_back(o < CTX ? ctx_weight[j][(size_t)o * Kc + FEATS + k] : 0.f);
         jpack.insert(jpack.end(), ctx_bias[j], ctx_bias[j] + CTX);
         for (int t = 0; t < 2; ++t) {
             if (t < P.T) jpack.insert(jpack.end(), pack.begin() + P.off_nn[j][t], pack.begin() + P.off_nn[j][t] + COUPLING_FLOATS);
@@ -819,7 +883,7 @@ extern "C" int hf_flow_sample(const hf_flow_t* h, const float* img_base, const f
         int rc = set_smem(flow_sample_kernel<NR>, smem);
         if (rc) return rc;
         HF_CUDA(hf::launch_pdl(flow_sample_kernel<NR>, dim3(hf::div_up(R, NR)), dim3(HF_NT), smem, (cudaStream_t)stream, h->P, img_base, betas,
-                               img_index, base_noise, R, Rn, rotmats, axisangle_pe, (float*)workspace));
+                               img_index, base_noise, R, Rn, rotmats, axisangle_pe, (float*)workspace, getenv("HF_FLOW_DBG") ? 1 : 0));
     });
     HF_LAUNCH_CHECK();
     return HF_OK;
