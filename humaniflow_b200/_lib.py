@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libhumaniflow_b200.so')
+LIB_PATH = os.environ.get('HF_LIB_PATH') or os.path.join(_HERE, 'lib', 'libhumaniflow_b200.so')   # HF_LIB_PATH: A/B builds of the same ABI (tools/)
 
 c_void_p, c_int, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
 

@@ -12,7 +12,8 @@
 
 namespace {
 
-constexpr int ME_THREADS = 256;
+constexpr int ME_THREADS = 128;     // block per point set; eight such blocks per SM overlap the single-thread 3x3 solve of one set with the passes of the others
+constexpr int SS_THREADS = 256;     // sample_stats
 
 // Jacobi eigen-decomposition of a symmetric 3x3 matrix (fp64): A = V diag(w) V^T, columns of V orthonormal.
 __device__ void eig_sym3(double A[3][3], double V[3][3], double w[3]) {
@@ -54,8 +55,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // block-wide sums of NV doubles per thread -> every thread gets the totals (through shared memory)
-template <int NV>
-__device__ void block_sum(double* v, double* scratch /* [ME_THREADS/32][NV] + [NV] */) {
+template <int NV, int NTHR = ME_THREADS>
+__device__ void block_sum(double* v, double* scratch /* [NTHR/32][NV] + [NV] */) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -65,17 +66,17 @@ __device__ void block_sum(double* v, double* scratch /* [ME_THREADS/32][NV] + [N
     __syncthreads();
     if (threadIdx.x < NV) {
         double s = 0.0;
-        for (int w = 0; w < ME_THREADS / 32; ++w) s += scratch[w * NV + threadIdx.x];
-        scratch[(ME_THREADS / 32) * NV + threadIdx.x] = s;
+        for (int w = 0; w < NTHR / 32; ++w) s += scratch[w * NV + threadIdx.x];
+        scratch[(NTHR / 32) * NV + threadIdx.x] = s;
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = scratch[(ME_THREADS / 32) * NV + i];
+    for (int i = 0; i < NV; ++i) v[i] = scratch[(NTHR / 32) * NV + i];
     __syncthreads();
 }
 
 // pred (B*N, P, 3), target (B, P, 3) -> out (B*N, 3) = [plain, SC, PA] mean point errors
-__global__ void __launch_bounds__(ME_THREADS)
+__global__ void __launch_bounds__(ME_THREADS, 8)
 pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__ target, int N, int P, float* __restrict__ out) {
     HF_PDL_SYNC();
     __shared__ double scratch[(ME_THREADS / 32 + 1) * 18];
@@ -92,6 +93,7 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
         float sp[3] = {0.f, 0.f, 0.f}, st[3] = {0.f, 0.f, 0.f}, spp = 0.f, stt = 0.f, k[9], e = 0.f;
 #pragma unroll
         for (int i = 0; i < 9; ++i) k[i] = 0.f;
+#pragma unroll 4
         for (int i = threadIdx.x; i < P; i += ME_THREADS) {
             // moments are taken about the first point of each set (shift invariance of the centred quantities): no
             // cancellation when the sets sit far from the origin (camera-space meshes)
@@ -174,6 +176,7 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
     double e2[2];
     {
         float esc = 0.f, epa = 0.f;
+#pragma unroll 4
         for (int i = threadIdx.x; i < P; i += ME_THREADS) {
             const float px = __ldg(p + i * 3), py = __ldg(p + i * 3 + 1), pz = __ldg(p + i * 3 + 2);
             const float tx = __ldg(t + i * 3), ty = __ldg(t + i * 3 + 1), tz = __ldg(t + i * 3 + 2);
@@ -200,15 +203,15 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
 // w = per-image point weights (visibility flags) or 1.  One block per image, a thread per point (strided), fp64 block sums
 // in a fixed order.
 template <int D>
-__global__ void __launch_bounds__(ME_THREADS)
+__global__ void __launch_bounds__(SS_THREADS)
 sample_stats_kernel(const float* __restrict__ pts, const float* __restrict__ target, const float* __restrict__ weights, int N, int P,
                     float* __restrict__ out) {
     HF_PDL_SYNC();
-    __shared__ double scratch[(ME_THREADS / 32) * 3 + 3];
+    __shared__ double scratch[(SS_THREADS / 32) * 3 + 3];
     const int b = blockIdx.x;
     const float* xb = pts + (size_t)b * N * P * D;
     double v[3] = {0.0, 0.0, 0.0};       // diversity sum, L2E sum, weight sum
-    for (int p = threadIdx.x; p < P; p += ME_THREADS) {
+    for (int p = threadIdx.x; p < P; p += SS_THREADS) {
         const float w = weights ? __ldg(weights + (size_t)b * P + p) : 1.f;
         float mu[D];
 #pragma unroll
@@ -233,7 +236,7 @@ sample_stats_kernel(const float* __restrict__ pts, const float* __restrict__ tar
         }
         v[0] += (double)(w * div); v[1] += (double)(w * l2e); v[2] += (double)w;
     }
-    block_sum<3>(v, scratch);
+    block_sum<3, SS_THREADS>(v, scratch);
     if (threadIdx.x == 0) {
         out[(size_t)b * 2] = (float)(v[0] / ((double)N * (double)P));
         out[(size_t)b * 2 + 1] = target ? (float)(v[1] / ((double)N * v[2])) : 0.f;
@@ -246,8 +249,8 @@ extern "C" int hf_sample_stats(const float* points, const float* target, const f
                                void* stream) {
     if (!points || !out) return hf::fail(HF_ERR_INVALID, "hf_sample_stats: null argument");
     if (B <= 0 || N <= 0 || P <= 0) return HF_OK;
-    if (D == 3) HF_CUDA(hf::launch_pdl(sample_stats_kernel<3>, dim3(B), dim3(ME_THREADS), 0, (cudaStream_t)stream, points, target, weights, N, P, out));
-    else if (D == 2) HF_CUDA(hf::launch_pdl(sample_stats_kernel<2>, dim3(B), dim3(ME_THREADS), 0, (cudaStream_t)stream, points, target, weights, N, P, out));
+    if (D == 3) HF_CUDA(hf::launch_pdl(sample_stats_kernel<3>, dim3(B), dim3(SS_THREADS), 0, (cudaStream_t)stream, points, target, weights, N, P, out));
+    else if (D == 2) HF_CUDA(hf::launch_pdl(sample_stats_kernel<2>, dim3(B), dim3(SS_THREADS), 0, (cudaStream_t)stream, points, target, weights, N, P, out));
     else return hf::fail(HF_ERR_INVALID, "hf_sample_stats: D must be 2 or 3");
     HF_LAUNCH_CHECK();
     return HF_OK;

@@ -35,8 +35,15 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
     __shared__ float s_bl[BH][BW];
     __shared__ float s_gx[MH][MW], s_gy[MH][MW];
     __shared__ float s_mag[MH][MW];
+    __shared__ float s_edge[PT_H][PT_W];
+    __shared__ float s_j[32][3];
     const int b = blockIdx.z, x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
     const int tid = threadIdx.x;
+    if (staged && tid < J) {
+        s_j[tid][0] = __ldg(joints2D + ((size_t)b * J + tid) * 2);
+        s_j[tid][1] = __ldg(joints2D + ((size_t)b * J + tid) * 2 + 1);
+        s_j[tid][2] = vis ? __ldg(vis + (size_t)b * J + tid) : 1.f;
+    }
     for (int i = tid; i < MH * MW; i += PR_THREADS) { s_gx[i / MW][i % MW] = 0.f; s_gy[i / MW][i % MW] = 0.f; }
     for (int c = 0; c < C; ++c) {
         const float* src = rgb + ((size_t)b * C + c) * H * W;
@@ -106,32 +113,7 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
         }
         if (e < prm.threshold) e = 0.f;
         const size_t pix = (size_t)y * W + x;
-        if (staged) {
-            // the encoder's stem input layout directly: bf16 NHWC, Cp channels per pixel (1 + J used, rest zero), inside the
-            // zero border of the (Hp, Wp) padded image -> no fp32 NCHW intermediate and no layout kernel
-            float ch[32];
-            ch[0] = e;
-#pragma unroll 1
-            for (int j = 0; j < J; ++j) {
-                const float u = __ldg(joints2D + ((size_t)b * J + j) * 2), v = __ldg(joints2D + ((size_t)b * J + j) * 2 + 1);
-                const float a = ((float)y - v) / prm.heat_std, c2 = ((float)x - u) / prm.heat_std;
-                float hh = expf(-(a * a) / 2.f - (c2 * c2) / 2.f);
-                if (vis) hh *= __ldg(vis + (size_t)b * J + j);
-                ch[1 + j] = hh;
-            }
-            for (int j = 1 + J; j < 32; ++j) ch[j] = 0.f;
-            __nv_bfloat16* o = staged + (((size_t)b * Hp + y + top) * Wp + x + left) * Cp;
-            for (int c0 = 0; c0 < Cp; c0 += 8) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(ch[c0 + 2 * i], ch[c0 + 2 * i + 1]);
-                    pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-                }
-                *reinterpret_cast<uint4*>(o + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-            continue;
-        }
+        if (staged) { s_edge[r][q] = e; continue; }
         out[(size_t)b * (1 + J) * HWp + pix] = e;
         if (dbg_mag) dbg_mag[(size_t)b * HWp + pix] = m;
         if (dbg_ori) dbg_ori[(size_t)b * HWp + pix] = ori;
@@ -142,6 +124,38 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
             float h = expf(-(a * a) / 2.f - (c2 * c2) / 2.f);
             if (vis) h *= __ldg(vis + (size_t)b * J + j);
             out[((size_t)b * (1 + J) + 1 + j) * HWp + pix] = h;
+        }
+    }
+    if (staged) {
+        // the encoder's stem input layout directly: bf16 NHWC, Cp channels per pixel (edge map, J heatmaps, zero padding) inside the
+        // zero border of the (Hp, Wp) padded image.  One 16-byte store per (pixel, group of 8 channels); consecutive threads write
+        // consecutive 16-byte pieces, so a warp writes 512 contiguous bytes.
+        __syncthreads();
+        const int G = Cp >> 3;
+        for (int i = tid; i < PT_H * PT_W * G; i += PR_THREADS) {
+            const int pixl = i / G, grp = i - pixl * G;
+            const int r = pixl / PT_W, q = pixl - r * PT_W, y = y0 + r, x = x0 + q;
+            if (y >= H || x >= W) continue;
+            float ch[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int cc = grp * 8 + c;
+                float val = 0.f;
+                if (cc == 0) val = s_edge[r][q];
+                else if (cc <= J) {
+                    const float a = ((float)y - s_j[cc - 1][1]) / prm.heat_std, c2 = ((float)x - s_j[cc - 1][0]) / prm.heat_std;
+                    val = expf(-(a * a) / 2.f - (c2 * c2) / 2.f);
+                    if (vis) val *= s_j[cc - 1][2];
+                }
+                ch[c] = val;
+            }
+            uint32_t pk[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(ch[2 * c], ch[2 * c + 1]);
+                pk[c] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(staged + (((size_t)b * Hp + y + top) * Wp + x + left) * Cp + grp * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
     }
 }

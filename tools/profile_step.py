@@ -20,10 +20,10 @@ x = synthetic_proxy_input(B, 18, 256, seed=1).cuda()
 g = torch.Generator().manual_seed(2)
 z = (torch.randn(B, N, 23, 3, generator=g) * 0.6).cuda()
 se = torch.randn(B, N, 10, generator=g).cuda()
-for _ in range(steps):
-    out = model(x, num_samples=N, base_noise=z, shape_eps=se)
-    R = out['pose_rotmats_samples'].view(B * N, 23, 3, 3)
-    glob = out['glob_rotmat'][:, None].expand(-1, N, -1, -1).reshape(B * N, 1, 3, 3)
-    so = smpl(betas=out['shape_samples'].view(B * N, 10), body_pose=R, global_orient=glob, pose2rot=False)
+from humaniflow_b200.graphs import predict_step  # noqa: E402
+from humaniflow_b200.metrics import sample_stats  # noqa: E402
+for _ in range(steps):          # the step bench.py times (issued eagerly here: ncu profiles kernel by kernel)
+    out, verts, joints = predict_step(model, smpl, x, z, se)
+    rows = sample_stats(joints.view(B, N, -1, 3))['diversity']
     torch.cuda.synchronize()
-print('done', so.vertices.shape)
+print('done', verts.shape)
