@@ -12,7 +12,7 @@
 
 namespace {
 
-constexpr int ME_THREADS = 128;     // block per point set; eight such blocks per SM overlap the single-thread 3x3 solve of one set with the passes of the others
+constexpr int ME_THREADS = 256;     // block per point set; eight such blocks per SM overlap the single-thread 3x3 solve of one set with the passes of the others
 constexpr int SS_THREADS = 256;     // sample_stats
 
 // Jacobi eigen-decomposition of a symmetric 3x3 matrix (fp64): A = V diag(w) V^T, columns of V orthonormal.
@@ -21,7 +21,7 @@ __device__ void eig_sym3(double A[3][3], double V[3][3], double w[3]) {
         for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 12; ++sweep) {
         const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
-        if (off < 1e-300) break;
+        if (off <= 1e-18 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2])) || off < 1e-300) break;     // converged (Jacobi: quadratic, ~5 sweeps)
         for (int p = 0; p < 2; ++p)
             for (int q = p + 1; q < 3; ++q) {
                 if (fabs(A[p][q]) < 1e-300) continue;
@@ -76,16 +76,31 @@ __device__ void block_sum(double* v, double* scratch /* [NTHR/32][NV] + [NV] */)
 }
 
 // pred (B*N, P, 3), target (B, P, 3) -> out (B*N, 3) = [plain, SC, PA] mean point errors
-__global__ void __launch_bounds__(ME_THREADS, 8)
+// STAGE: the predicted point set (P x 3 floats, 83 KB for a mesh) is copied into shared memory once (8-byte cp.async, all in
+// flight at once) and both passes read it from there: HBM is read once per set, the second pass never misses L2
+template <bool STAGE>
+__global__ void __launch_bounds__(ME_THREADS, STAGE ? 2 : 4)
 pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__ target, int N, int P, float* __restrict__ out) {
     HF_PDL_SYNC();
+    extern __shared__ __align__(16) float pstage[];
     __shared__ double scratch[(ME_THREADS / 32 + 1) * 18];
     __shared__ float xf[16];                                   // SC: s, mu1, mu2;  PA: scale*R (9), t (3)
     const int m = blockIdx.x, b = m / N;
     const float* p = pred + (size_t)m * P * 3;
     const float* t = target + (size_t)b * P * 3;
+    if (STAGE) {
+        const int n2 = (P * 3) >> 1;                           // 8-byte pieces (the set starts 8-byte aligned: checked on the host)
+        for (int i = threadIdx.x; i < n2; i += ME_THREADS)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(pstage + 2 * i)), "l"(p + 2 * i) : "memory");
+        if ((P * 3) & 1) { if (threadIdx.x == 0) pstage[P * 3 - 1] = __ldg(p + P * 3 - 1); }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        p = pstage;
+    }
+#define LDP(ptr) (STAGE ? *(ptr) : __ldg(ptr))
     // pass 1: raw moments + the plain error
-    const float p0x = __ldg(p), p0y = __ldg(p + 1), p0z = __ldg(p + 2), t0x = __ldg(t), t0y = __ldg(t + 1), t0z = __ldg(t + 2);
+    const float p0x = LDP(p), p0y = LDP(p + 1), p0z = LDP(p + 2), t0x = __ldg(t), t0y = __ldg(t + 1), t0z = __ldg(t + 2);
     double v[18];
 #pragma unroll
     for (int i = 0; i < 18; ++i) v[i] = 0.0;
@@ -93,14 +108,12 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
         float sp[3] = {0.f, 0.f, 0.f}, st[3] = {0.f, 0.f, 0.f}, spp = 0.f, stt = 0.f, k[9], e = 0.f;
 #pragma unroll
         for (int i = 0; i < 9; ++i) k[i] = 0.f;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < P; i += ME_THREADS) {
-            // moments are taken about the first point of each set (shift invariance of the centred quantities): no
-            // cancellation when the sets sit far from the origin (camera-space meshes)
-            const float dx = __ldg(p + i * 3) - __ldg(t + i * 3), dy = __ldg(p + i * 3 + 1) - __ldg(t + i * 3 + 1),
-                        dz = __ldg(p + i * 3 + 2) - __ldg(t + i * 3 + 2);
-            const float px = __ldg(p + i * 3) - p0x, py = __ldg(p + i * 3 + 1) - p0y, pz = __ldg(p + i * 3 + 2) - p0z;
-            const float tx = __ldg(t + i * 3) - t0x, ty = __ldg(t + i * 3 + 1) - t0y, tz = __ldg(t + i * 3 + 2) - t0z;
+        // moments are taken about the first point of each set (shift invariance of the centred quantities): no
+        // cancellation when the sets sit far from the origin (camera-space meshes)
+        auto acc1 = [&](float qx, float qy, float qz, float ux, float uy, float uz) {
+            const float dx = qx - ux, dy = qy - uy, dz = qz - uz;
+            const float px = qx - p0x, py = qy - p0y, pz = qz - p0z;
+            const float tx = ux - t0x, ty = uy - t0y, tz = uz - t0z;
             sp[0] += px; sp[1] += py; sp[2] += pz;
             st[0] += tx; st[1] += ty; st[2] += tz;
             spp += px * px + py * py + pz * pz;
@@ -109,7 +122,28 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
             k[3] += py * tx; k[4] += py * ty; k[5] += py * tz;
             k[6] += pz * tx; k[7] += pz * ty; k[8] += pz * tz;
             e += sqrtf(dx * dx + dy * dy + dz * dz);
+        };
+        int i0 = 0;
+        if (STAGE) {
+            // four points (48 contiguous bytes) per thread and iteration: three 16-byte shared-memory loads of the staged set,
+            // six 8-byte loads of the target; with the loop unrolled every target load of a thread is in flight at once
+            const int ng = P >> 2;
+#pragma unroll 2
+            for (int gq = threadIdx.x; gq < ng; gq += ME_THREADS) {
+                const float4* ps = reinterpret_cast<const float4*>(p + gq * 12);
+                const float2* tg = reinterpret_cast<const float2*>(t + gq * 12);
+                const float4 a = ps[0], b4 = ps[1], c = ps[2];
+                const float2 u0 = __ldg(tg), u1 = __ldg(tg + 1), u2 = __ldg(tg + 2), u3 = __ldg(tg + 3), u4 = __ldg(tg + 4), u5 = __ldg(tg + 5);
+                acc1(a.x, a.y, a.z, u0.x, u0.y, u1.x);
+                acc1(a.w, b4.x, b4.y, u1.y, u2.x, u2.y);
+                acc1(b4.z, b4.w, c.x, u3.x, u3.y, u4.x);
+                acc1(c.y, c.z, c.w, u4.y, u5.x, u5.y);
+            }
+            i0 = ng << 2;
         }
+#pragma unroll 4
+        for (int i = i0 + threadIdx.x; i < P; i += ME_THREADS)
+            acc1(LDP(p + i * 3), LDP(p + i * 3 + 1), LDP(p + i * 3 + 2), __ldg(t + i * 3), __ldg(t + i * 3 + 1), __ldg(t + i * 3 + 2));
         for (int i = 0; i < 3; ++i) { v[i] = sp[i]; v[3 + i] = st[i]; }
         v[6] = spp; v[7] = stt;
         for (int i = 0; i < 9; ++i) v[8 + i] = k[i];
@@ -132,7 +166,11 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
             for (int j = 0; j < 3; ++j) K[i][j] = v[8 + i * 3 + j] - n * mu1[i] * mu2[j];
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) KtK[i][j] = K[0][i] * K[0][j] + K[1][i] * K[1][j] + K[2][i] * K[2][j];
+#ifndef PSE_NOSOLVE
         eig_sym3(KtK, V, w);
+#else
+        for (int i = 0; i < 3; ++i) { w[i] = KtK[i][i]; for (int j = 0; j < 3; ++j) V[i][j] = i == j; }
+#endif
         int order[3] = {0, 1, 2};                                  // singular values in descending order, as numpy returns them
         for (int a = 0; a < 2; ++a)
             for (int c = a + 1; c < 3; ++c)
@@ -176,17 +214,33 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
     double e2[2];
     {
         float esc = 0.f, epa = 0.f;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < P; i += ME_THREADS) {
-            const float px = __ldg(p + i * 3), py = __ldg(p + i * 3 + 1), pz = __ldg(p + i * 3 + 2);
-            const float tx = __ldg(t + i * 3), ty = __ldg(t + i * 3 + 1), tz = __ldg(t + i * 3 + 2);
+        auto acc2 = [&](float px, float py, float pz, float tx, float ty, float tz) {
             float dx = (px - m1x) * s_sc + m2x - tx, dy = (py - m1y) * s_sc + m2y - ty, dz = (pz - m1z) * s_sc + m2z - tz;
             esc += sqrtf(dx * dx + dy * dy + dz * dz);
             dx = r0 * px + r1 * py + r2 * pz + t0 - tx;
             dy = r3 * px + r4 * py + r5 * pz + t1 - ty;
             dz = r6 * px + r7 * py + r8 * pz + t2 - tz;
             epa += sqrtf(dx * dx + dy * dy + dz * dz);
+        };
+        int i0 = 0;
+        if (STAGE) {
+            const int ng = P >> 2;
+#pragma unroll 2
+            for (int gq = threadIdx.x; gq < ng; gq += ME_THREADS) {
+                const float4* ps = reinterpret_cast<const float4*>(p + gq * 12);
+                const float2* tg = reinterpret_cast<const float2*>(t + gq * 12);
+                const float4 a = ps[0], b4 = ps[1], c = ps[2];
+                const float2 u0 = __ldg(tg), u1 = __ldg(tg + 1), u2 = __ldg(tg + 2), u3 = __ldg(tg + 3), u4 = __ldg(tg + 4), u5 = __ldg(tg + 5);
+                acc2(a.x, a.y, a.z, u0.x, u0.y, u1.x);
+                acc2(a.w, b4.x, b4.y, u1.y, u2.x, u2.y);
+                acc2(b4.z, b4.w, c.x, u3.x, u3.y, u4.x);
+                acc2(c.y, c.z, c.w, u4.y, u5.x, u5.y);
+            }
+            i0 = ng << 2;
         }
+#pragma unroll 4
+        for (int i = i0 + threadIdx.x; i < P; i += ME_THREADS)
+            acc2(LDP(p + i * 3), LDP(p + i * 3 + 1), LDP(p + i * 3 + 2), __ldg(t + i * 3), __ldg(t + i * 3 + 1), __ldg(t + i * 3 + 2));
         e2[0] = esc; e2[1] = epa;
     }
     block_sum<2>(e2, scratch);
@@ -195,6 +249,7 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
         out[(size_t)m * 3 + 1] = (float)(e2[0] / (double)P);
         out[(size_t)m * 3 + 2] = (float)(e2[1] / (double)P);
     }
+#undef LDP
 }
 
 // Per-image sample statistics of point sets (B, N, P, D), D in {2, 3} (metrics/eval_metrics_tracker.py:330-433):
@@ -260,7 +315,12 @@ extern "C" int hf_pointset_errors(const float* pred, const float* target, int B,
     if (!pred || !target || !out) return hf::fail(HF_ERR_INVALID, "hf_pointset_errors: null argument");
     if (B <= 0 || N <= 0) return HF_OK;
     if (P < 3) return hf::fail(HF_ERR_INVALID, "hf_pointset_errors: at least 3 points per set are needed (got %d)", P);
-    HF_CUDA(hf::launch_pdl(pointset_errors_kernel, dim3(B * N), dim3(ME_THREADS), 0, (cudaStream_t)stream, pred, target, N, P, out));
+    const size_t stage_bytes = (size_t)P * 3 * sizeof(float);
+    if (stage_bytes <= 100 * 1024 && ((uintptr_t)pred & 7) == 0 && ((uintptr_t)target & 7) == 0 && (P * 3 * sizeof(float)) % 8 == 0) {    // two sets per SM
+        HF_CUDA(cudaFuncSetAttribute(pointset_errors_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        HF_CUDA(hf::launch_pdl(pointset_errors_kernel<true>, dim3(B * N), dim3(ME_THREADS), stage_bytes, (cudaStream_t)stream, pred, target, N, P, out));
+    } else
+        HF_CUDA(hf::launch_pdl(pointset_errors_kernel<false>, dim3(B * N), dim3(ME_THREADS), 0, (cudaStream_t)stream, pred, target, N, P, out));
     HF_LAUNCH_CHECK();
     return HF_OK;
 }
