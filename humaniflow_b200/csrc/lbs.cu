@@ -86,7 +86,10 @@ lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotma
     __shared__ float Rs[PS][PR];
     __shared__ float Bs[PS][HF_MAXB];
     __shared__ float Jds[HF_MAXJ * 3 * HF_MAXB], J0s[HF_MAXJ * 3];
+    __shared__ int pars[HF_MAXJ];          // kinematic tree: a dynamically indexed by-value kernel parameter compiles into one
+                                           // predicated constant load per joint per step (ncu: a third of this kernel's stall samples)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < HF_MAXJ) pars[tid] = par.p[tid];
     const int mb = blockIdx.x * PS;                              // first sample of this block
     const int ns = min(PS, M - mb);
     const int J9 = J * 9, J3 = J * 3;
@@ -179,7 +182,7 @@ lbs_pose_kernel(const float* __restrict__ betas, const float* __restrict__ rotma
     float* Am = A + (size_t)m * J * 12 + r * 4;
     float* jm = joints + (size_t)m * J_out * 3 + r;
     for (int i = 0; i < J; ++i) {
-        const int p = par.p[i];
+        const int p = pars[i];
         const float* Ri = Rm + i * 9;
         const float jx = Js[i][sl][0], jy = Js[i][sl][1], jz = Js[i][sl][2];
         float4 g;
@@ -496,7 +499,7 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const float* __restrict__ vtemp, const int* __restrict__ sj, const float* __restrict__ sw,
                     const float* __restrict__ A, const float* __restrict__ transl, int M, int V, int Vp, int J,
                     int nslots, float inv_scale, int nvt, int num_units, float* __restrict__ vertices,
-                    const int* __restrict__ vflag) {
+                    const int* __restrict__ vflag, float* __restrict__ xv, int NF) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * T2_STAGES + 6];
     __shared__ uint32_t tmem_base_s;
@@ -598,7 +601,8 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const int m0 = st * T2_NS;
             // per-vertex constants first (global loads in flight while the accumulator is still being produced)
             const float t0 = __ldg(vtemp + v), t1 = __ldg(vtemp + Vp + v), t2 = __ldg(vtemp + 2 * Vp + v);
-            const uint64_t pol = __ldg(vflag + v) ? pol_last : pol_first;   // vertices that feed a joint pick / regressor stay in L2
+            const int fidx = __ldg(vflag + v);                       // >= 0: vertex feeds a joint pick / regressor (slot in xv)
+            const uint64_t pol = fidx >= 0 ? pol_last : pol_first;
             float wgt[NSLOT > 0 ? NSLOT : 1];
             int jo[NSLOT > 0 ? NSLOT : 1];
             uint32_t live = 0;                                       // slots with a non-zero weight somewhere in this warp
@@ -662,6 +666,16 @@ lbs_skin_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                             o[s][2] = fmaf(w, fmaf(r2.x, x[s], fmaf(r2.y, y[s], fmaf(r2.z, z[s], r2.w))), o[s][2]);
                         }
                     }
+                }
+                if (fidx >= 0) {      // ~4 % of the vertices: compact per-sample copy xv[m][slot][3] for the extra-joint kernel
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)
+                        if (s0 + s < rows) {
+                            float* xo = xv + ((size_t)(m0 + s0 + s) * NF + fidx) * 3;
+                            float tx = 0.f, ty = 0.f, tz = 0.f;
+                            if (TRANSL) { const int mm = m0 + s0 + s; tx = __ldg(transl + mm * 3); ty = __ldg(transl + mm * 3 + 1); tz = __ldg(transl + mm * 3 + 2); }
+                            xo[0] = o[s][0] + tx; xo[1] = o[s][1] + ty; xo[2] = o[s][2] + tz;
+                        }
                 }
                 if (store_v) {
                     float* out = vertices + ((size_t)(m0 + s0) * V + v) * 3;
@@ -1013,6 +1027,35 @@ lbs_extra_joints_t_kernel(const float* __restrict__ xvt, const int* __restrict__
     }
 }
 
+// joints[J ..) from the compact copies xv[m][slot][3] of the flagged vertices (written by the skinning epilogue): a warp per
+// sample, a lane per output row (picks, then the CSR regressor rows summed in CSR order); a sample's 3.3 KB are contiguous,
+// so there are no dependent gathers into the 265 MB vertex array.
+__global__ void __launch_bounds__(128)
+lbs_extra_joints_c_kernel(const float* __restrict__ xv, const int* __restrict__ pick_f, const int* __restrict__ csr_ptr,
+                          const int* __restrict__ csr_f, const float* __restrict__ csr_val, int M, int J, int nvj, int nextra,
+                          int J_out, int NF, float* __restrict__ joints) {
+    HF_PDL_SYNC();
+    const int m = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float* xb = xv + (size_t)m * NF * 3;
+    for (int r = lane; r < nvj + nextra; r += 32) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (r < nvj) {
+            const float* p = xb + (size_t)__ldg(pick_f + r) * 3;
+            x = p[0]; y = p[1]; z = p[2];
+        } else {
+            const int row = r - nvj;
+            for (int e = __ldg(csr_ptr + row); e < __ldg(csr_ptr + row + 1); ++e) {
+                const float w = __ldg(csr_val + e);
+                const float* p = xb + (size_t)__ldg(csr_f + e) * 3;
+                x = fmaf(w, p[0], x); y = fmaf(w, p[1], y); z = fmaf(w, p[2], z);
+            }
+        }
+        float* o = joints + ((size_t)m * J_out + J + r) * 3;
+        o[0] = x; o[1] = y; o[2] = z;
+    }
+}
+
 // joints[J .. J+nvj) = picked vertices; joints[J+nvj ..) = sparse regressors applied to the final vertices.
 // One block per sample: every (row, vertex) entry of the picks + CSR regressors is fetched by its own thread (all
 // gathers of a sample in flight at once), then one thread per output row sums its entries in CSR order.
@@ -1239,9 +1282,12 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
     if (vj.empty()) vj.push_back(0);
     if ((rc = hf::upload(&h->vj, vj.data(), vj.size()))) return rc;
     {
+        // vflag[v] = slot of vertex v in the compact "flagged vertices" copy (vertices read by a joint pick / regressor), else -1
         std::vector<int> vflag((size_t)Vp, 0);
         for (int r = 0; r < nvj; ++r) vflag[vj[r]] = 1;
         for (int e = 0; e < h->nnz; ++e) vflag[col[e]] = 1;
+        int nf = 0;
+        for (int v = 0; v < Vp; ++v) vflag[v] = (v < V && vflag[v]) ? nf++ : -1;
         if ((rc = hf::upload(&h->vflag, vflag.data(), vflag.size()))) return rc;
     }
     {   // round-2 experiment (impl 3): per-tile sorted vertex order, basis rows in that order, 64-byte per-vertex records, flagged slots
@@ -1445,7 +1491,8 @@ static int lbs_forward_any(const hf_smpl_t* h, const float* betas, const float* 
         auto launch = [&](auto kern) -> int {
             HF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
             HF_CUDA(hf::launch_pdl(kern, dim3(std::min(num_units, sms)), dim3(T2_THREADS), t2_smem, stream, hm->mapA2, hm->mapB2,
-                                   h->vtemp, h->sj, h->sw, A, transl, M, h->V, h->Vp, h->J, h->nslots, h->inv_scale, nvt, num_units, vertices, h->vflag));
+                                   h->vtemp, h->sj, h->sw, A, transl, M, h->V, h->Vp, h->J, h->nslots, h->inv_scale, nvt, num_units, vertices, h->vflag,
+                                   xvt, h->NF));
             return HF_OK;
         };
         int rc;
@@ -1459,6 +1506,12 @@ static int lbs_forward_any(const hf_smpl_t* h, const float* betas, const float* 
         }
         if (rc) return rc;
         HF_LAUNCH_CHECK();
+        if ((stage_mask & 4) && h->nvj + h->nextra > 0) {
+            HF_CUDA(hf::launch_pdl(lbs_extra_joints_c_kernel, dim3(hf::div_up(M, 4)), dim3(128), 0, stream, (const float*)xvt, (const int*)h->pick_f,
+                                   (const int*)h->csr_ptr, (const int*)h->csr_f, (const float*)h->csr_val, M, h->J, h->nvj, h->nextra, J_out, h->NF, joints));
+            HF_LAUNCH_CHECK();
+        }
+        return HF_OK;
     } else if (h->impl == 2) {
         HF_CUDA(hf::launch_pdl(lbs_coef_kernel, dim3(std::min(hf::div_up(M * LBS_KH, 256), 148 * 16)), dim3(256), 0, stream, betas, rotmats,
                                glob ? 1 : 0, M, h->J, h->nb, Fb));
