@@ -15,6 +15,7 @@
 #include "tma.cuh"
 #include <vector>
 #include <cmath>
+#include <cstring>
 
 #define HF_FJ 23          // max body parts
 #define HF_FANC 23        // max ancestors per joint
@@ -249,6 +250,76 @@ __device__ __forceinline__ float spline_forward(const float* raw, int rs, int d,
     return num / den;
 }
 
+// Sampling-kernel variant: one pass over 8 lanes per (row, d) computes BOTH softmax / cumulative-knot vectors plus every bin's
+// derivative (softplus) and lambda (sigmoid), so that the two threads per row that evaluate the spline afterwards only search the
+// bin and do the rational arithmetic.  KN[(row*2 + d)*36 + ...] = [widths 9 | heights 9 | derivatives 9 | lambdas 8 | pad].
+// Same per-element formulas as spline_knots / spline_select (bit-identical results).  Ends with __syncthreads().
+constexpr int KNF = 36;
+template <int NR>
+__device__ __forceinline__ void spline_knots_full(const float* __restrict__ raw, float bound, float* __restrict__ KN) {
+    const float lo = -bound, hi = bound;
+    for (int t = threadIdx.x; t < NR * 16; t += HF_NT) {      // NR*2 groups of 8 lanes
+        const int g = t >> 3, b = t & 7;
+        const int row = g >> 1, d = g & 1;
+        const float xw = raw[(d * NBINS + b) * NR + row], xh = raw[(2 * NBINS + d * NBINS + b) * NR + row];
+        const float xd = raw[(4 * NBINS + d * (NBINS - 1) + min(b, NBINS - 2)) * NR + row];
+        const float xl = raw[(4 * NBINS + 2 * (NBINS - 1) + d * NBINS + b) * NR + row];
+        float mw = xw, mh = xh;
+#pragma unroll
+        for (int sft = 1; sft < 8; sft <<= 1) {
+            mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, sft, 8));
+            mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, sft, 8));
+        }
+        const float ew = expf(xw - mw), eh = expf(xh - mh);
+        float sw = ew, sh = eh;
+#pragma unroll
+        for (int sft = 1; sft < 8; sft <<= 1) {
+            sw += __shfl_xor_sync(0xffffffffu, sw, sft, 8);
+            sh += __shfl_xor_sync(0xffffffffu, sh, sft, 8);
+        }
+        float cw = 1e-3f + 0.992f * (ew / sw), ch = 1e-3f + 0.992f * (eh / sh);
+#pragma unroll
+        for (int sft = 1; sft < 8; sft <<= 1) {              // inclusive scans over the 8 lanes
+            const float uw = __shfl_up_sync(0xffffffffu, cw, sft, 8), uh = __shfl_up_sync(0xffffffffu, ch, sft, 8);
+            if (b >= sft) { cw += uw; ch += uh; }
+        }
+        const float sp = (xd > 20.f) ? xd : log1pf(expf(xd));
+        const float lam = 0.95f * (1.f / (1.f + expf(-xl))) + 0.025f;
+        float* k = KN + g * KNF;
+        k[b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * cw + lo;
+        k[9 + b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * ch + lo;
+        k[18 + b + 1] = (b == NBINS - 1) ? 0.999f : 1e-3f + sp;
+        k[27 + b] = lam;
+        if (b == 0) { k[0] = lo; k[9] = lo; k[18] = 0.999f; }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float spline_forward_pre(float x, float bound, const float* kn) {
+    if (!(x >= -bound && x <= bound)) return x;
+    int idx = -1;
+#pragma unroll
+    for (int b = 0; b <= NBINS; ++b) idx += (x >= kn[b] + 1e-6f) ? 1 : 0;
+    idx = max(0, min(idx, NBINS - 1));
+    const float in_cw = kn[idx], in_w = kn[idx + 1] - in_cw, in_ch = kn[9 + idx], in_h = kn[9 + idx + 1] - in_ch;
+    const float d0 = kn[18 + idx], d1 = kn[18 + idx + 1], lam = kn[27 + idx];
+    const float delta = in_h / in_w;
+    const float wb = sqrtf(d0 / d1);
+    const float wc = (lam * d0 + (1.f - lam) * wb * d1) / delta;
+    const float ya = in_ch, yb = in_h + in_ch;
+    const float yc = ((1.f - lam) * ya + lam * wb * yb) / ((1.f - lam) + lam * wb);
+    const float theta = (x - in_cw) / in_w;
+    float num, den;
+    if (theta <= lam) {
+        num = ya * (lam - theta) + wc * yc * theta;
+        den = (lam - theta) + wc * theta;
+    } else {
+        num = wc * yc * (1.f - theta) + wb * yb * (theta - lam);
+        den = wc * (1.f - theta) + wb * (theta - lam);
+    }
+    return num / den;
+}
+
 // inverse spline; *fwd_logdet receives the FORWARD log|dy/dx| evaluated through the inverse formulas
 // (pyro Spline._inverse caches -logabsdet of the inverse direction).
 __device__ __forceinline__ float spline_inverse(const float* raw, int rs, int d, float y, float bound,
@@ -443,17 +514,141 @@ struct SampleSmem {
     static constexpr int Total = Act + (SmemLayout<NR>::Total - SmemLayout<NR>::Ps);
 };
 
+// =====================================  context prologue on the tensor cores  =====================================
+// U[r][j*64 + o] = sum_k Wfeat_j[o][k] F[r][k] for all rows and joints is one (R x 256) x (256 x J*64) GEMM with no dependency on
+// the chain: 1.2 GMAC at B=32, N=100, 22 % of the sampling kernel when every CTA did its own 24 rows on the CUDA cores (each CTA
+// re-read the whole 1.5 MB matrix from L2).  Here it runs as split-tf32 on tcgen05: x = hi + lo with hi = tf32(x) (round to
+// nearest) and lo = x - hi (exact in fp32; the MMA reads its upper 10 mantissa bits), D = Fhi Whi + Fhi Wlo + Flo Whi with fp32
+// accumulation in TMEM.  The dropped terms (lo x lo, the truncated tail of lo) are <= 2^-21 of a product, unbiased.
+//   flow_feats_split_kernel : F = ELU(img_base[img] + betaW . beta) -> [R][512] = [hi(256) | lo(256)]
+//   flow_ctx_gemm_kernel    : tile 128 rows x 128 outputs (two joints), K in 8 steps of 32 floats (128-byte swizzled rows),
+//                             3-stage TMA ring of 64 KB stages; 8 epilogue warps (TMEM lane quarter x joint) write U in the
+//                             layout the sampling kernel streams ([row group of NR][joint][o][NR]).
+constexpr int CG_STAGES = 3, CG_THREADS = 320, CG_BN = 128;
+constexpr int CG_STAGE_BYTES = 2 * 128 * 128 + 2 * CG_BN * 128;
+
+__global__ void flow_feats_split_kernel(const FlowParams P, const float* __restrict__ img_base, const float* __restrict__ betas,
+                                        const int* __restrict__ img_index, int R, float* __restrict__ F) {
+    HF_PDL_SYNC();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;          // one thread: 4 consecutive features of one row
+    if (e >= R * (FEATS / 4)) return;
+    const int r = e / (FEATS / 4), o = (e - r * (FEATS / 4)) * 4;
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(img_base + (size_t)__ldg(img_index + r) * FEATS + o));
+    float a[4] = {b4.x, b4.y, b4.z, b4.w};
+    for (int l = 0; l < P.nb; ++l) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(P.betaW + l * FEATS + o));
+        const float bt = __ldg(betas + (size_t)r * P.nb + l);
+        a[0] = fmaf(w.x, bt, a[0]); a[1] = fmaf(w.y, bt, a[1]); a[2] = fmaf(w.z, bt, a[2]); a[3] = fmaf(w.w, bt, a[3]);
+    }
+    float hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float x = elu(a[i]);
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+        hi[i] = __uint_as_float(hb);
+        lo[i] = x - hi[i];
+    }
+    *reinterpret_cast<float4*>(F + (size_t)r * 2 * FEATS + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(F + (size_t)r * 2 * FEATS + FEATS + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__global__ void __launch_bounds__(CG_THREADS, 1)
+flow_ctx_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapW, int R, int J, int NR,
+                     float* __restrict__ U) {
+    extern __shared__ uint8_t cg_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * CG_STAGES + 1];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t tile_base = (smem_u32(cg_smem) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * CG_BN;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[CG_STAGES]), tfull = smem_u32(&bars[2 * CG_STAGES]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CG_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)CG_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    HF_PDL_SYNC();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr int NIT = FEATS / 32;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < NIT; ++it) {
+                const int st = it % CG_STAGES;
+                const uint32_t ph = (uint32_t)(it / CG_STAGES) & 1u;
+                mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                const uint32_t sa = tile_base + st * CG_STAGE_BYTES, fb = full0 + 8 * st;
+                mbar_expect_tx(fb, CG_STAGE_BYTES);
+                tma_load_2d(sa, &mapF, fb, it * 32, m0);
+                tma_load_2d(sa + 16384, &mapF, fb, FEATS + it * 32, m0);
+                tma_load_2d(sa + 32768, &mapW, fb, it * 32, n0);                      // rows past J*64 are zero-filled
+                tma_load_2d(sa + 32768 + CG_BN * 128, &mapW, fb, FEATS + it * 32, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, CG_BN);
+            for (int it = 0; it < NIT; ++it) {
+                const int st = it % CG_STAGES;
+                const uint32_t ph = (uint32_t)(it / CG_STAGES) & 1u;
+                mbar_wait(full0 + 8 * st, ph);
+                tcgen05_fence_after();
+                const uint32_t sa = tile_base + st * CG_STAGE_BYTES;
+                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + 16384);
+                const uint64_t b_hi = umma_desc_sw128(sa + 32768), b_lo = umma_desc_sw128(sa + 32768 + CG_BN * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, (uint32_t)((it | k) != 0));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1u);
+                umma_commit(empty0 + 8 * st);
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;     // TMEM lane quarter (= warp % 4), joint of the pair
+        const int r = m0 + q * 32 + lane, j = blockIdx.y * 2 + half;
+        mbar_wait_warp(tfull, 0);
+        tcgen05_fence_after();
+        uint32_t v[64];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+        tmem_ld32(ta, v);
+        tmem_ld32(ta + 32, v + 32);
+        tmem_ld_wait();
+        if (r < R && j < J) {
+            float* dst = U + ((size_t)(r / NR) * J + j) * CTX * NR + (r % NR);
+#pragma unroll
+            for (int o = 0; o < CTX; ++o) dst[o * NR] = __uint_as_float(v[o]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)CG_BN) : "memory");
+    }
+}
+
 // =====================================  sampling  =====================================
 // One CTA owns NR rows for the whole tree.
-//  prologue : image features -> U[j] = Wfeat_j . feats for all joints (one long fp32 GEMM with no dependency chain,
-//             parked in an L2-resident scratch, laid out so that a joint's 64 x NR block is contiguous)
+//  prologue : image features -> U[j] = Wfeat_j . feats for all joints, computed BEFORE this kernel by flow_ctx_gemm_kernel
+//             (tensor cores, split tf32) and parked in an L2-resident scratch, laid out so that a joint's 64 x NR block is
+//             contiguous; with have_U = 0 the CTA computes its own rows on the CUDA cores (cross-check path)
 //  chain    : per joint, weights arrive in shared memory by 1-D bulk copies issued one joint ahead (mbarrier
 //             complete_tx), U(j) by cp.async; every dense layer then runs on low-latency LDS operands.
 template <int NR>
 __global__ void __launch_bounds__(HF_NT, 1)
 flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict__ img_base, const float* __restrict__ betas,
                    const int* __restrict__ img_index, const float* __restrict__ base_noise, int R, int Rn,
-                   float* __restrict__ rotmats, float* __restrict__ axisangle_pe, float* __restrict__ Uscratch, int dbg) {
+                   float* __restrict__ rotmats, float* __restrict__ axisangle_pe, float* __restrict__ Uscratch, int have_U, int dbg) {
     long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
     auto lap = [&](int c) { if (dbg) { const long long t = clock64(); tph[c] += t - tlast; tlast = t; } };
     using L = SmemLayout<NR>;
@@ -488,16 +683,18 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
         for (int i = 0; i < 3; ++i) mbar_init(bar0 + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid == 0) { issue_anc(0); issue_cpl(0, 0); if (P.T > 1) issue_cpl(0, 1); }     // weights: constant, no dependency on the predecessor
     HF_PDL_SYNC();
-    image_feats<NR>(P, img_base, betas, img_index, r0, R, Fs);
-    __syncthreads();
-    if (tid == 0) { issue_anc(0); issue_cpl(0, 0); if (P.T > 1) issue_cpl(0, 1); }
-    // prologue GEMM: 2*J output tiles of 32, full K = FEATS per warp (no split, no barrier)
-    for (int t = warp; t < 2 * P.J; t += HF_NW)
-        warp_gemm<NR, false, 8>(P.wfeat + t * 32, P.J * CTX, 0, 0, FEATS, PlainRow{Fs, NR},
-                                Ucta + (size_t)(t >> 1) * CTX * NR + (t & 1) * 32 * NR, lane);
-    __threadfence();
-    __syncthreads();
+    if (!have_U) {
+        // CUDA-core prologue (cross-check path, HF_FLOW_SIMT_PROLOGUE=1): 2*J output tiles of 32, full K = FEATS per warp
+        image_feats<NR>(P, img_base, betas, img_index, r0, R, Fs);
+        __syncthreads();
+        for (int t = warp; t < 2 * P.J; t += HF_NW)
+            warp_gemm<NR, false, 8>(P.wfeat + t * 32, P.J * CTX, 0, 0, FEATS, PlainRow{Fs, NR},
+                                    Ucta + (size_t)(t >> 1) * CTX * NR + (t & 1) * 32 * NR, lane);
+        __threadfence();
+        __syncthreads();
+    }
     lap(0);
     fetch_U(0);
 
@@ -534,7 +731,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
             coupling_nn_smem<NR>(smraw + (t ? S::Wc1 : S::Wc0), sm);
             lap(3);
             if (tid == 0 && j + 1 < P.J) issue_cpl(j + 1, t);
-            spline_knots<NR>(sm + L::Raw, P.radius, sm + L::Ha);
+            spline_knots_full<NR>(sm + L::Raw, P.radius, sm + L::Ha);      // 72 x NR floats: spans Ha and the start of Hb (both free here)
             lap(4);
             // spline on the two trailing coordinates, then rotate the vector for the next Permute
             // (pyro_conditional_norm_flow.py:46-62: with <=2 transforms the only non-identity Permute is [1,2,0],
@@ -543,7 +740,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
                 const int s = tid >> 1, d = tid & 1;
                 const float x = sm[L::Zs + (1 + d) * NR + s];
                 const float y0 = sm[L::Zs + s];
-                const float mine = spline_forward(sm + L::Raw + s, NR, d, x, P.radius, sm + L::Ha + (s * 2 + d) * 18);
+                const float mine = spline_forward_pre(x, P.radius, sm + L::Ha + (s * 2 + d) * KNF);
                 const unsigned act = __activemask();
                 const float other = __shfl_xor_sync(act, mine, 1);
                 if (d == 0) {
@@ -753,6 +950,9 @@ struct hf_flow {
     float* betaW;
     float* wfeat;
     float* jpack;
+    float* wsplit;                // [J*64][512] = [tf32 hi (256) | lo (256)] of the feature part of every context Linear
+    CUtensorMap mapW;
+    const void* mapF_ptr; int mapF_R; CUtensorMap mapF;     // cached activation map (workspace pointer and row count)
 };
 
 namespace {
@@ -761,6 +961,10 @@ template <typename K>
 int set_smem(K kernel, size_t bytes) {
     HF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return HF_OK;
+}
+
+size_t flow_ws_u_bytes(const hf_flow* h, int R, int nr) {
+    return (((size_t)hf::div_up(R, nr) * h->P.J * CTX * nr * sizeof(float)) + 255) & ~(size_t)255;
 }
 
 int pick_rows(int R) {
@@ -837,6 +1041,22 @@ extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const 
             else jpack.resize(jpack.size() + COUPLING_FLOATS, 0.f);
         }
     }
+    std::vector<float> wsplit((size_t)P.J * CTX * 2 * FEATS);
+    for (int j = 0; j < P.J; ++j) {
+        const int Kc = FEATS + 9 * P.anc_cnt[j];
+        for (int o = 0; o < CTX; ++o)
+            for (int k = 0; k < FEATS; ++k) {
+                const float w = ctx_weight[j][(size_t)o * Kc + k];
+                uint32_t u;
+                memcpy(&u, &w, 4);
+                u = (u + 0x1000u) & 0xffffe000u;            // tf32: round to nearest (ties away), as cvt.rna.tf32.f32
+                float hi;
+                memcpy(&hi, &u, 4);
+                if (!std::isfinite(hi)) hi = w;
+                wsplit[((size_t)j * CTX + o) * 2 * FEATS + k] = hi;
+                wsplit[((size_t)j * CTX + o) * 2 * FEATS + FEATS + k] = w - hi;
+            }
+    }
     std::vector<float> bw((size_t)P.nb * FEATS);
     for (int l = 0; l < P.nb; ++l)
         for (int o = 0; o < FEATS; ++o) bw[l * FEATS + o] = beta_weight[(size_t)o * P.nb + l];
@@ -845,6 +1065,13 @@ extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const 
     if ((rc = hf::upload(&h->betaW, bw.data(), bw.size()))) return rc;
     if ((rc = hf::upload(&h->wfeat, wfeat.data(), wfeat.size()))) return rc;
     if ((rc = hf::upload(&h->jpack, jpack.data(), jpack.size()))) return rc;
+    if ((rc = hf::upload(&h->wsplit, wsplit.data(), wsplit.size()))) return rc;
+    {
+        const uint64_t dims[2] = {(uint64_t)(2 * FEATS), (uint64_t)(P.J * CTX)}, strides[1] = {(uint64_t)(2 * FEATS * 4)};
+        const uint32_t box[2] = {32, (uint32_t)CG_BN};
+        if ((rc = encode_map(&h->mapW, h->wsplit, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
+    }
+    h->mapF_ptr = nullptr; h->mapF_R = 0;
     P.pack = h->pack; P.betaW = h->betaW; P.wfeat = h->wfeat; P.jpack = h->jpack;
     *out = h;
     return HF_OK;
@@ -852,7 +1079,7 @@ extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const 
 
 extern "C" void hf_flow_destroy(hf_flow_t* h) {
     if (!h) return;
-    cudaFree(h->pack); cudaFree(h->betaW); cudaFree(h->wfeat); cudaFree(h->jpack);
+    cudaFree(h->pack); cudaFree(h->betaW); cudaFree(h->wfeat); cudaFree(h->jpack); cudaFree(h->wsplit);
     delete h;
 }
 
@@ -866,7 +1093,7 @@ extern "C" void hf_flow_destroy(hf_flow_t* h) {
 extern "C" size_t hf_flow_workspace_bytes(const hf_flow_t* h, int R) {
     if (!h || R <= 0) return 0;
     const int nr = pick_rows(R);
-    return (size_t)hf::div_up(R, nr) * h->P.J * CTX * nr * sizeof(float);
+    return flow_ws_u_bytes(h, R, nr) + (size_t)R * 2 * FEATS * sizeof(float);     // U | F = [R][hi | lo]
 }
 
 extern "C" int hf_flow_sample(const hf_flow_t* h, const float* img_base, const float* betas, const int* img_index,
@@ -878,12 +1105,34 @@ extern "C" int hf_flow_sample(const hf_flow_t* h, const float* img_base, const f
     if (!workspace || workspace_bytes < hf_flow_workspace_bytes(h, R) || ((uintptr_t)workspace & 15))
         return hf::fail(HF_ERR_INVALID, "hf_flow_sample: workspace too small or unaligned (%zu < %zu)", workspace_bytes, hf_flow_workspace_bytes(h, R));
     const int nr = pick_rows(R);
+    const int have_U = getenv("HF_FLOW_SIMT_PROLOGUE") ? 0 : 1;
+    if (have_U) {
+        // context prologue on the tensor cores: features (split tf32) -> U for all joints
+        float* F = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + flow_ws_u_bytes(h, R, nr));
+        hf_flow* hm = const_cast<hf_flow*>(h);
+        if (hm->mapF_ptr != F || hm->mapF_R != R) {
+            const uint64_t dims[2] = {(uint64_t)(2 * FEATS), (uint64_t)R}, strides[1] = {(uint64_t)(2 * FEATS * 4)};
+            const uint32_t box[2] = {32, 128};
+            int rc = encode_map(&hm->mapF, F, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+            if (rc) return rc;
+            hm->mapF_ptr = F; hm->mapF_R = R;
+        }
+        HF_CUDA(hf::launch_pdl(flow_feats_split_kernel, dim3(hf::div_up(R * (FEATS / 4), 256)), dim3(256), 0, (cudaStream_t)stream, h->P, img_base, betas,
+                               img_index, R, F));
+        HF_LAUNCH_CHECK();
+        const size_t gsmem = CG_STAGES * CG_STAGE_BYTES + 1024;
+        int rc = set_smem(flow_ctx_gemm_kernel, gsmem);
+        if (rc) return rc;
+        HF_CUDA(hf::launch_pdl(flow_ctx_gemm_kernel, dim3(hf::div_up(R, 128), hf::div_up(h->P.J * CTX, CG_BN)), dim3(CG_THREADS), gsmem, (cudaStream_t)stream, h->mapF, h->mapW, R,
+                               h->P.J, nr, (float*)workspace));
+        HF_LAUNCH_CHECK();
+    }
     HF_DISPATCH_ROWS(nr, {
         const size_t smem = SampleSmem<NR>::Total * sizeof(float);
         int rc = set_smem(flow_sample_kernel<NR>, smem);
         if (rc) return rc;
         HF_CUDA(hf::launch_pdl(flow_sample_kernel<NR>, dim3(hf::div_up(R, NR)), dim3(HF_NT), smem, (cudaStream_t)stream, h->P, img_base, betas,
-                               img_index, base_noise, R, Rn, rotmats, axisangle_pe, (float*)workspace, getenv("HF_FLOW_DBG") ? 1 : 0));
+                               img_index, base_noise, R, Rn, rotmats, axisangle_pe, (float*)workspace, have_U, getenv("HF_FLOW_DBG") ? 1 : 0));
     });
     HF_LAUNCH_CHECK();
     return HF_OK;

@@ -22,20 +22,29 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // y[m][o] (+)= act(sum_k x[m][k] W[o][k] + b[o]) for a tile of 32 batch rows.  K % 4 == 0, 16-byte aligned rows.
-// A warp owns one output neuron; lanes split K (coalesced 128-bit weight loads, each weight read once per row
-// tile); the 32 x KC activation chunk is staged in shared memory with cp.async, double buffered, and shared by the
-// 8 warps of the CTA; per-row partial sums are reduced with shuffles at the end.
+// A warp owns LNB = 4 output neurons; lanes split K (coalesced 128-bit weight loads, each weight read once per row tile); the
+// 32 x KC activation chunk is staged in shared memory with cp.async, double buffered, and shared by the 8 warps of the CTA.  One
+// 128-bit shared load of x feeds 16 FMAs (4 neurons x 4 k), which keeps the shared-memory pipe (4 wavefronts per load) below the
+// FMA pipe; per-row partial sums are reduced across lanes with a 31-shuffle transpose-reduction per neuron.
+// blockIdx.z = K-slice: with kslice < K every CTA handles k in [z * kslice, +kslice) and writes raw partial sums to
+// partial[z][M][O]; linear_reduce_kernel adds the slices in a fixed order and applies bias / activation.
+constexpr int LNB = 4;
 __global__ void __launch_bounds__(LW * 32)
 linear_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, int ldw,
                   const float* __restrict__ b, float* __restrict__ y, int ldy, int M, int K, int O, int act,
-                  int accumulate) {
+                  int accumulate, int kslice, float* __restrict__ partial) {
     extern __shared__ __align__(16) float xs[];           // [2][32][KC]
     HF_PDL_SYNC();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o = blockIdx.x * LW + warp;
+    const int o0 = (blockIdx.x * LW + warp) * LNB;
     const int m0 = blockIdx.y * 32;
-    const int oc = min(o, O - 1);
-    const float4* wrow = reinterpret_cast<const float4*>(W + (size_t)oc * ldw);
+    const int kz = blockIdx.z * kslice;
+    x += kz; W += kz;
+    const int Kfull = K;
+    K = min(kslice, K - kz);
+    const float4* wrow[LNB];
+#pragma unroll
+    for (int n = 0; n < LNB; ++n) wrow[n] = reinterpret_cast<const float4*>(W + (size_t)min(o0 + n, O - 1) * ldw);
     auto stage = [&](int buf, int kc) {
         const int kn4 = min(KC, K - kc) >> 2;              // float4 per row in this chunk
         for (int idx = threadIdx.x; idx < 32 * kn4; idx += LW * 32) {
@@ -45,9 +54,11 @@ linear_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
         }
         cp_async_commit();
     };
-    float acc[32];
+    float acc[LNB][32];
 #pragma unroll
-    for (int m = 0; m < 32; ++m) acc[m] = 0.f;
+    for (int n = 0; n < LNB; ++n)
+#pragma unroll
+        for (int m = 0; m < 32; ++m) acc[n][m] = 0.f;
     const int nchunks = (K + KC - 1) / KC;
     stage(0, 0);
     for (int c = 0; c < nchunks; ++c) {
@@ -56,30 +67,59 @@ linear_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
         __syncthreads();
         const float* xb = xs + (size_t)(c & 1) * 32 * KC;
         for (int k4 = lane; k4 < kn4; k4 += 32) {
-            const float4 w = __ldg(wrow + (kc >> 2) + k4);
+            float4 w[LNB];
+#pragma unroll
+            for (int n = 0; n < LNB; ++n) w[n] = __ldg(wrow[n] + (kc >> 2) + k4);
 #pragma unroll
             for (int m = 0; m < 32; ++m) {
                 const float4 xv = *reinterpret_cast<const float4*>(xb + m * KC + k4 * 4);
-                acc[m] = fmaf(w.x, xv.x, fmaf(w.y, xv.y, fmaf(w.z, xv.z, fmaf(w.w, xv.w, acc[m]))));
+#pragma unroll
+                for (int n = 0; n < LNB; ++n)
+                    acc[n][m] = fmaf(w[n].x, xv.x, fmaf(w[n].y, xv.y, fmaf(w[n].z, xv.z, fmaf(w[n].w, xv.w, acc[n][m]))));
             }
         }
         __syncthreads();
     }
-    float mine = 0.f;
-#pragma unroll
-    for (int m = 0; m < 32; ++m) {
-        float v = acc[m];
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
-        if (lane == m) mine = v;
-    }
     const int r = m0 + lane;
-    if (o < O && r < M) {
-        float* dst = y + (size_t)r * ldy + o;
-        float a = mine + (b ? __ldg(b + o) : 0.f);
-        if (accumulate) a += *dst;
-        *dst = act_fn(a, act);
+#pragma unroll
+    for (int n = 0; n < LNB; ++n) {
+        // transpose-reduction: after the step with stride s a lane keeps the half of the rows selected by its bit s; lane l ends
+        // with the sum over all lanes of row l in acc[n][0]
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+#pragma unroll
+            for (int i = 0; i < sft; ++i) {
+                const bool up = (lane & sft) != 0;
+                const float keep = up ? acc[n][i + sft] : acc[n][i];
+                const float send = up ? acc[n][i] : acc[n][i + sft];
+                acc[n][i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+            }
+        }
+        const float mine = acc[n][0];
+        const int o = o0 + n;
+        if (o < O && r < M) {
+            if (kslice < Kfull) { partial[((size_t)blockIdx.z * M + r) * O + o] = mine; continue; }
+            float* dst = y + (size_t)r * ldy + o;
+            float a = mine + (b ? __ldg(b + o) : 0.f);
+            if (accumulate) a += *dst;
+            *dst = act_fn(a, act);
+        }
     }
+}
+
+// y[m][o] (+)= act(sum_z partial[z][m][o] + b[o]): slices added in index order (deterministic)
+__global__ void linear_reduce_kernel(const float* __restrict__ partial, int nz, const float* __restrict__ b, float* __restrict__ y, int ldy,
+                                     int M, int O, int act, int accumulate) {
+    HF_PDL_SYNC();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M * O) return;
+    const int r = e / O, o = e - r * O;
+    float a = 0.f;
+    for (int z = 0; z < nz; ++z) a += partial[(size_t)z * M * O + e];
+    a += b ? __ldg(b + o) : 0.f;
+    float* dst = y + (size_t)r * ldy + o;
+    if (accumulate) a += *dst;
+    *dst = act_fn(a, act);
 }
 
 // Generic small-K fallback (K not a multiple of 4 or unaligned rows): lane = batch row, broadcast weight loads.
@@ -174,8 +214,32 @@ extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const
         const int smem = 2 * 32 * KC * (int)sizeof(float);
         // per device / context attribute: set on every call (cheap), not cached in a process-wide static
         HF_CUDA(cudaFuncSetAttribute(linear_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        dim3 grid(hf::div_up(O, LW), hf::div_up(M, 32));
-        HF_CUDA(hf::launch_pdl(linear_vec_kernel, grid, dim3(LW * 32), (size_t)smem, (cudaStream_t)stream, x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate));
+        // K-slices: up to one CTA per SM, slices a multiple of 128 floats
+        const int ctas = hf::div_up(O, LW * LNB) * hf::div_up(M, 32);
+        int nz = 1;
+        while (nz < 8 && ctas * nz * 2 <= 148 && (K % (nz * 2 * 128)) == 0) nz *= 2;   // one CTA per SM (255 registers x 256 threads): stay within one wave
+        static float* scratch[16] = {};          // per device, grown on demand (single-stream contract; sized outside graph capture by the warm-up call)
+        static size_t scratch_floats[16] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        float* part = nullptr;
+        if (nz > 1) {
+            const size_t need = (size_t)nz * M * O;
+            if (scratch_floats[dev & 15] < need) {
+                if (scratch[dev & 15]) cudaFree(scratch[dev & 15]);
+                HF_CUDA(cudaMalloc(&scratch[dev & 15], need * sizeof(float)));
+                scratch_floats[dev & 15] = need;
+            }
+            part = scratch[dev & 15];
+        }
+        dim3 grid(hf::div_up(O, LW * LNB), hf::div_up(M, 32), nz);
+        HF_CUDA(hf::launch_pdl(linear_vec_kernel, grid, dim3(LW * 32), (size_t)smem, (cudaStream_t)stream, x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate,
+                               nz > 1 ? K / nz : K, part));
+        if (nz > 1) {
+            HF_LAUNCH_CHECK();
+            HF_CUDA(hf::launch_pdl(linear_reduce_kernel, dim3(hf::div_up(M * O, 256)), dim3(256), 0, (cudaStream_t)stream, (const float*)part, nz, b, y, ldy, M, O,
+                                   act, accumulate));
+        }
     } else {
         dim3 grid(hf::div_up(O, 4), hf::div_up(M, 32));
         HF_CUDA(hf::launch_pdl(linear_small_kernel, grid, dim3(128), 0, (cudaStream_t)stream, x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate));

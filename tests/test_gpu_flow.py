@@ -55,6 +55,24 @@ def test_sampling_and_point_estimate_parity(B, N, scale, layers):
     assert (torch.linalg.det(R) - 1).abs().max().item() <= 1e-6
 
 
+def test_tensor_core_prologue_against_the_cuda_core_prologue(monkeypatch):
+    """The image-feature part of every context Linear runs as split-tf32 on tcgen05 (flow_ctx_gemm_kernel); the fp32 CUDA-core
+    prologue inside the sampling kernel is kept as a cross-check (HF_FLOW_SIMT_PROLOGUE=1).  Both must agree far inside ROT_TOL,
+    and both must meet ROT_TOL against the oracle, at a row count that is not a multiple of the 128-row tile."""
+    m, sd, cfg = make_model(50, seed=4)
+    m = m.cuda()
+    B, N = 7, 37
+    feats, z, se = _noise(B, N, seed=9, feat_dim=m.input_feats_dim)
+    ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, num_samples=N, shape_eps=se, base_noise=z)['pose_rotmats_samples']
+    tc = _run(m, feats, z, se)['pose_rotmats_samples'].cpu().clone()
+    monkeypatch.setenv('HF_FLOW_SIMT_PROLOGUE', '1')
+    simt = _run(m, feats, z, se)['pose_rotmats_samples'].cpu().clone()
+    monkeypatch.delenv('HF_FLOW_SIMT_PROLOGUE')
+    e_tc, e_simt, d = (tc - ref).abs().max().item(), (simt - ref).abs().max().item(), (tc - simt).abs().max().item()
+    print('prologue: tensor-core vs oracle %.2e, CUDA-core vs oracle %.2e, between them %.2e' % (e_tc, e_simt, d))
+    assert e_tc <= ROT_TOL and e_simt <= ROT_TOL and d <= ROT_TOL
+
+
 def test_modes_of_forward():
     m, sd, cfg = make_model(18, seed=2)
     m = m.cuda()
