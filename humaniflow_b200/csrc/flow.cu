@@ -701,8 +701,11 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
     for (int j = 0; j < P.J; ++j) {
         const uint32_t par = (uint32_t)j & 1u;
         const int Ka = 9 * P.anc_cnt[j];
+        // one thread observes each weight barrier, the next CTA barrier publishes that to the rest: 512 threads polling the same
+        // mbarrier cost ~450 cycles per wait
         cp_async_wait_all();
-        mbar_wait(bar0, par);
+        if (tid == 0) mbar_wait(bar0, par);                // ancestor block
+        if (tid == 32) mbar_wait(bar0 + 8, par);           // first coupling (the second: below); a completed wait is still ~150 cycles, so in parallel
         __syncthreads();
         lap(1);
         // base sample (zero for point-estimate rows); first permutation is the identity.  Written here (row CTX of
@@ -726,8 +729,6 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
             fetch_U(j + 1);
         }
         for (int t = 0; t < P.T; ++t) {
-            mbar_wait(bar0 + 8 * (1 + t), par);
-            lap(1);
             coupling_nn_smem<NR>(smraw + (t ? S::Wc1 : S::Wc0), sm);
             lap(3);
             if (tid == 0 && j + 1 < P.J) issue_cpl(j + 1, t);
@@ -753,6 +754,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
                     }
                 }
             }
+            if (tid == 2 * NR + 32 && t + 1 < P.T) mbar_wait(bar0 + 8 * (2 + t), par);       // next coupling's weights (issued a whole joint ago)
             __syncthreads();
             lap(5);
         }
