@@ -36,14 +36,23 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
     __shared__ float s_gx[MH][MW], s_gy[MH][MW];
     __shared__ float s_mag[MH][MW];
     __shared__ float s_edge[PT_H][PT_W];
-    __shared__ float s_j[32][3];
+    // heatmaps are separable: exp(-(a*a)/2 - (c*c)/2) with a = (row - v)/std, c = (col - u)/std.  The two halves are computed once
+    // per (joint, tile row) and (joint, tile column) -- same operations in the same order as the per-pixel formula, so the
+    // values are bit-identical -- and a pixel costs one subtraction and one expf per joint instead of two divisions as well.
+    __shared__ float s_hrow[32][PT_H], s_hcol[32][PT_W], s_vis[32];
     const int b = blockIdx.z, x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
     const int tid = threadIdx.x;
-    if (staged && tid < J) {
-        s_j[tid][0] = __ldg(joints2D + ((size_t)b * J + tid) * 2);
-        s_j[tid][1] = __ldg(joints2D + ((size_t)b * J + tid) * 2 + 1);
-        s_j[tid][2] = vis ? __ldg(vis + (size_t)b * J + tid) : 1.f;
+    for (int i = tid; i < J * (PT_H + PT_W); i += PR_THREADS) {
+        const int j = i / (PT_H + PT_W), k = i - j * (PT_H + PT_W);
+        if (k < PT_H) {
+            const float a = ((float)(y0 + k) - __ldg(joints2D + ((size_t)b * J + j) * 2 + 1)) / prm.heat_std;
+            s_hrow[j][k] = -(a * a) / 2.f;
+        } else {
+            const float c2 = ((float)(x0 + k - PT_H) - __ldg(joints2D + ((size_t)b * J + j) * 2)) / prm.heat_std;
+            s_hcol[j][k - PT_H] = (c2 * c2) / 2.f;
+        }
     }
+    if (tid < J) s_vis[tid] = vis ? __ldg(vis + (size_t)b * J + tid) : 1.f;
     for (int i = tid; i < MH * MW; i += PR_THREADS) { s_gx[i / MW][i % MW] = 0.f; s_gy[i / MW][i % MW] = 0.f; }
     for (int c = 0; c < C; ++c) {
         const float* src = rgb + ((size_t)b * C + c) * H * W;
@@ -119,10 +128,8 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
         if (dbg_ori) dbg_ori[(size_t)b * HWp + pix] = ori;
         // heatmaps: exp(-((row - v) / std)^2 / 2 - ((col - u) / std)^2 / 2), joints2D = (u, v) = (column, row)
         for (int j = 0; j < J; ++j) {
-            const float u = __ldg(joints2D + ((size_t)b * J + j) * 2), v = __ldg(joints2D + ((size_t)b * J + j) * 2 + 1);
-            const float a = ((float)y - v) / prm.heat_std, c2 = ((float)x - u) / prm.heat_std;
-            float h = expf(-(a * a) / 2.f - (c2 * c2) / 2.f);
-            if (vis) h *= __ldg(vis + (size_t)b * J + j);
+            float h = expf(s_hrow[j][r] - s_hcol[j][q]);
+            if (vis) h *= s_vis[j];
             out[((size_t)b * (1 + J) + 1 + j) * HWp + pix] = h;
         }
     }
@@ -139,15 +146,13 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
             float ch[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
+                // branch-free: channel 0 = edge map, 1..J = heatmaps, the rest zero padding (grp differs between neighbouring threads)
                 const int cc = grp * 8 + c;
-                float val = 0.f;
-                if (cc == 0) val = s_edge[r][q];
-                else if (cc <= J) {
-                    const float a = ((float)y - s_j[cc - 1][1]) / prm.heat_std, c2 = ((float)x - s_j[cc - 1][0]) / prm.heat_std;
-                    val = expf(-(a * a) / 2.f - (c2 * c2) / 2.f);
-                    if (vis) val *= s_j[cc - 1][2];
-                }
-                ch[c] = val;
+                const bool heat = cc >= 1 && cc <= J;
+                const int j = heat ? cc - 1 : 0;
+                float val = expf(s_hrow[j][r] - s_hcol[j][q]);
+                if (vis) val *= s_vis[j];
+                ch[c] = heat ? val : (cc == 0 ? s_edge[r][q] : 0.f);
             }
             uint32_t pk[4];
 #pragma unroll
@@ -168,6 +173,7 @@ extern "C" int hf_proxy_rep(const float* rgb, const float* joints2D, const float
     if (!rgb || !out || !gauss5 || (J > 0 && !joints2D)) return hf::fail(HF_ERR_INVALID, "hf_proxy_rep: null argument");
     if (B <= 0 || H <= 0 || W <= 0) return HF_OK;
     if (C < 1 || heat_std <= 0.f) return hf::fail(HF_ERR_INVALID, "hf_proxy_rep: bad channel count / heatmap std");
+    if (J > 32) return hf::fail(HF_ERR_UNSUPPORTED, "hf_proxy_rep: at most 32 joints (got %d)", J);
     ProxyParams prm;
     for (int i = 0; i < 5; ++i) prm.g[i] = gauss5[i];
     prm.threshold = threshold; prm.nms = nms; prm.heat_std = heat_std;
