@@ -182,7 +182,7 @@ def run_ours(args):
     import humaniflow_b200 as hb
     from humaniflow_b200 import _lib
     from humaniflow_b200.graphs import CudaGraphRunner, predict_step
-    from humaniflow_b200.metrics import pointset_errors, sample_stats, samples_min
+    from humaniflow_b200.metrics import pointset_error_rows, sample_stats
     from humaniflow_b200.proxy_rep import build_proxy_representation
     from humaniflow_b200.sharding import gather_rows
     from humaniflow_b200.synthetic import SMPL_PARENTS, synthetic_proxy_input, synthetic_smpl_data
@@ -336,7 +336,7 @@ def run_ours(args):
     # region.  Steps are software-pipelined over three streams (H2D | kernels | D2H) with two sets of buffers, so the copy of step
     # i+1 / i-1 overlaps the kernels of step i (PCIe is full duplex).  Three forms:
     #   e2e             RGB crops + 2-D joints in (25 MB) -> proxy representation built on the device, straight into the encoder's
-    #                   staging layout -> the step -> per-sample PVE / PVE-SC / PVE-PA reduced on the device -> (B,4) rows out: what
+    #                   staging layout -> the step -> per-sample PVE / PVE-SC / PVE-PA reduced on the device -> (B,6) rows out: what
     #                   evaluate_humaniflow.py:227-258 becomes with SURVEY 8f N1 + N4 in place.  This is the headline.
     #   e2e_evaluate    the 18-channel proxy representation comes from the host (bf16: 75 MB), metric rows out
     #   e2e_all_meshes  fp32 proxy representation in (151 MB), EVERY sampled mesh out (268 MB): bounded by the host's PCIe / memory path
@@ -345,8 +345,8 @@ def run_ours(args):
     s_main = torch.cuda.current_stream()
 
     def metric_rows(verts):
-        err = pointset_errors(verts.view(B, N, V, 3), tgt)
-        return torch.stack([samples_min(err['plain']), samples_min(err['sc']), samples_min(err['pa']), err['plain'].mean(1)], 1)
+        # (B,6): [min over the samples of PVE / PVE-SC / PVE-PA | their means over the samples]; two launches
+        return pointset_error_rows(verts.view(B, N, V, 3), tgt)
 
     def rgb_fn(rgb, j2d, z_, se_):
         staged = build_proxy_representation(rgb, j2d, encoder=model.image_encoder)
@@ -419,7 +419,7 @@ def run_ours(args):
 
     rgb_host = torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
     j2d_host = (torch.rand(B, 17, 2, generator=torch.Generator().manual_seed(8 + rank)) * 256).pin_memory()
-    rows_host = [[torch.empty(B, 4).pin_memory()] for _ in range(2)]
+    rows_host = [[torch.empty(B, 6).pin_memory()] for _ in range(2)]
     rgb_ms = pipelined(rgb_fn, [rgb_host, j2d_host], [rgb_host.to(dev), j2d_host.to(dev)], rows_host, [args.steps])
     xh_host = x_host.to(torch.bfloat16).pin_memory()
     eval_ms = pipelined(eval_fn, [xh_host], [xh_host.to(dev)], rows_host, [args.steps])
@@ -454,7 +454,7 @@ def run_ours(args):
                     'h2d_bytes_per_step': (rgb_host.numel() + j2d_host.numel()) * 4, 'd2h_bytes_per_step': rows_host[0][0].numel() * 4,
                     'what': 'RGB crops + 2-D joints from pinned host memory -> proxy representation on the device (hf_proxy_rep_staged, straight into the '
                             'encoder staging layout) -> the step -> per-sample PVE / PVE-SC / PVE-PA reduced on the device (hf_pointset_errors) -> '
-                            '(B,4) metric rows to pinned host memory',
+                            '(B,6) metric rows (best-sample and sample-mean PVE / PVE-SC / PVE-PA) to pinned host memory',
                     'pipelining': 'H2D | kernels | D2H on three streams, double-buffered', 'pcie_measured': pcie},
             'e2e_evaluate': {'value': per / (eval_ms * 1e-3), 'unit': UNIT, 'ms_per_step': eval_ms,
                              'h2d_bytes_per_step': xh_host.numel() * 2, 'd2h_bytes_per_step': rows_host[0][0].numel() * 4,

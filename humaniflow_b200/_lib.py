@@ -49,6 +49,7 @@ SIGNATURES = {
     'hf_vertex_variance': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'hf_pointset_errors': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'hf_sample_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'hf_samples_reduce': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'hf_proxy_rep': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_float, c_int, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'hf_proxy_rep_staged': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_float, c_int, ctypes.c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'hf_project_joints2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float, c_void_p, c_void_p]),

@@ -298,7 +298,53 @@ sample_stats_kernel(const float* __restrict__ pts, const float* __restrict__ tar
     }
 }
 
+// out[b][k] = min over the samples, out[b][K + k] = mean over the samples of err[b][n][k]; one CTA (128 threads) per image,
+// fixed reduction order (thread-strided partials, then a shuffle / shared-memory tree).
+__global__ void __launch_bounds__(128)
+samples_reduce_kernel(const float* __restrict__ err, int N, int K, float* __restrict__ out) {
+    HF_PDL_SYNC();
+    __shared__ float s_min[4][8], s_sum[4][8];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        float mn[8], sm[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { mn[k] = INFINITY; sm[k] = 0.f; }
+        for (int n = tid; n < N; n += 128) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k0 + k < K) {
+                    const float v = err[((size_t)b * N + n) * K + k0 + k];
+                    mn[k] = fminf(mn[k], v);
+                    sm[k] += v;
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], sft));
+                sm[k] += __shfl_xor_sync(0xffffffffu, sm[k], sft);
+            }
+            if (lane == 0) { s_min[warp][k] = mn[k]; s_sum[warp][k] = sm[k]; }
+        }
+        __syncthreads();
+        if (tid < 8 && k0 + tid < K) {
+            out[(size_t)b * 2 * K + k0 + tid] = fminf(fminf(s_min[0][tid], s_min[1][tid]), fminf(s_min[2][tid], s_min[3][tid]));
+            out[(size_t)b * 2 * K + K + k0 + tid] = ((s_sum[0][tid] + s_sum[1][tid]) + (s_sum[2][tid] + s_sum[3][tid])) / (float)N;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
+
+extern "C" int hf_samples_reduce(const float* err, int B, int N, int K, float* out, void* stream) {
+    if (!err || !out) return hf::fail(HF_ERR_INVALID, "hf_samples_reduce: null argument");
+    if (B <= 0 || N <= 0 || K <= 0) return HF_OK;
+    HF_CUDA(hf::launch_pdl(samples_reduce_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, err, N, K, out));
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
 
 extern "C" int hf_sample_stats(const float* points, const float* target, const float* weights, int B, int N, int P, int D, float* out,
                                void* stream) {

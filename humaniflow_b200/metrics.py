@@ -32,6 +32,27 @@ def pointset_errors(pred, target):
     return {k: v[:, 0] for k, v in res.items()} if squeeze else res
 
 
+def pointset_error_rows(pred, target):
+    """pred (B,N,P,3), target (B,P,3) -> (B,6) per-image rows [min over the samples of plain / sc / pa | mean over the samples of
+    plain / sc / pa]: hf_pointset_errors followed by ONE reduction launch (hf_samples_reduce) -- the evaluation loop's
+    "samples_min" and sample-mean metrics of a batch, ready for a single small device->host copy."""
+    _lib.require_cuda('pointset_error_rows')
+    if not pred.is_cuda or pred.dim() != 4:
+        raise RuntimeError('humaniflow_b200.metrics: pred must be a (B,N,P,3) CUDA tensor (no CPU fallback)')
+    p = _lib.f32c(pred)
+    t = _lib.f32c(target).to(p.device)
+    B, N, P, _ = p.shape
+    if t.shape != (B, P, 3):
+        raise ValueError('target shape %s does not match predictions %s' % (tuple(t.shape), tuple(p.shape)))
+    err = torch.empty(B, N, 3, device=p.device, dtype=torch.float32)
+    rows = torch.empty(B, 6, device=p.device, dtype=torch.float32)
+    lib = _lib.load()
+    with torch.cuda.device(p.device):
+        _lib.check(lib.hf_pointset_errors(_lib.ptr(p), _lib.ptr(t), B, N, P, _lib.ptr(err), _lib.stream()))
+        _lib.check(lib.hf_samples_reduce(_lib.ptr(err), B, N, 3, _lib.ptr(rows), _lib.stream()))
+    return rows
+
+
 def samples_min(per_sample_errors):
     """(B,N) per-sample mean errors -> (B,) error of the best sample of every image
     (eval_metrics_tracker.py:201-280: argmin over the samples of the mean error)."""

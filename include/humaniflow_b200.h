@@ -109,6 +109,11 @@ int hf_project_joints2d(const float* joints, const float* cam_wp, const int* joi
  * ---------------------------------------------------------------------------------------------- */
 int hf_pointset_errors(const float* pred, const float* target, int B, int N, int P, float* out, void* stream);
 
+/* Per-image reduction over the samples of per-sample error values: err (B,N,K) -> out (B,2K) = [min over n (K) | mean over n (K)].
+ * The "samples_min" metrics of metrics/eval_metrics_tracker.py:201-280 are the minimum over the samples of the per-sample mean
+ * error (argmin + gather there), the sample-mean forms are the mean; one launch instead of one reduction per metric. */
+int hf_samples_reduce(const float* err, int B, int N, int K, float* out, void* stream);
+
 /* Per-image sample statistics of sampled point sets: points (B,N,P,D), D = 3 (vertices / 3-D joints) or 2 (projected joints);
  * target (B,P,D) or NULL; weights (B,P) (visibility flags) or NULL = 1.  out (B,2):
  *   [0] sample diversity = mean over (samples, points) of w ||x - mean over the samples||

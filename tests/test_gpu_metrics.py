@@ -78,3 +78,19 @@ def test_sample_stats_golden_and_oracle():
     x = (rs.standard_normal((32, 100, 6890, 3)) * 0.05 + rs.standard_normal((32, 1, 6890, 3)) * 0.3).astype(np.float32)
     got = sample_stats(torch.tensor(x).cuda())['diversity'].cpu().numpy()
     assert got.shape == (32,) and _close(got, omet.sample_stats(x)['diversity'])
+
+
+def test_pointset_error_rows_is_min_and_mean_of_the_per_sample_errors():
+    """hf_samples_reduce: (B,N,3) per-sample errors -> (B,6) = [min over samples | mean over samples], against torch on the
+    output of hf_pointset_errors itself (exact for the minimum, fp32 summation-order tolerance for the mean)."""
+    from humaniflow_b200.metrics import pointset_error_rows, pointset_errors
+    g = torch.Generator().manual_seed(11)
+    for B, N, P in [(3, 7, 50), (2, 300, 17), (1, 1, 9)]:
+        pred = torch.randn(B, N, P, 3, generator=g).cuda()
+        tgt = torch.randn(B, P, 3, generator=g).cuda()
+        err = pointset_errors(pred, tgt)
+        rows = pointset_error_rows(pred, tgt)
+        assert rows.shape == (B, 6)
+        for k, name in enumerate(('plain', 'sc', 'pa')):
+            assert torch.equal(rows[:, k], err[name].min(dim=1).values)
+            assert torch.allclose(rows[:, 3 + k], err[name].double().mean(dim=1).float(), rtol=1e-6, atol=1e-7)

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import humaniflow_b200 as hb  # noqa: E402
 from humaniflow_b200.graphs import predict_step  # noqa: E402
-from humaniflow_b200.metrics import pointset_errors, samples_min  # noqa: E402
+from humaniflow_b200.metrics import pointset_error_rows  # noqa: E402
 from humaniflow_b200.proxy_rep import build_proxy_representation  # noqa: E402
 from humaniflow_b200.synthetic import SMPL_PARENTS, synthetic_smpl_data  # noqa: E402
 
@@ -27,7 +27,6 @@ tgt = smpl.tpose(torch.zeros(B, 10, device='cuda')).vertices.clone()
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     staged = build_proxy_representation(rgb, j2d, encoder=model.image_encoder)
     _, verts, _ = predict_step(model, smpl, staged, z, se)
-    err = pointset_errors(verts.view(B, N, -1, 3), tgt)
-    rows = torch.stack([samples_min(err['plain']), samples_min(err['sc']), samples_min(err['pa']), err['plain'].mean(1)], 1)
+    rows = pointset_error_rows(verts.view(B, N, -1, 3), tgt)
     torch.cuda.synchronize()
 print('done')
