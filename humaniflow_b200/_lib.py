@@ -42,6 +42,8 @@ SIGNATURES = {
     'hf_lbs_workspace_bytes': (c_size_t, [c_void_p, c_int]),
     'hf_lbs_set_impl': (c_int, [c_void_p, c_int]),
     'hf_lbs_forward': (c_int, [c_void_p] * 7 + [c_size_t, c_int, c_void_p]),
+    'hf_lbs_backward_workspace_bytes': (c_size_t, [c_void_p, c_int]),
+    'hf_lbs_backward': (c_int, [c_void_p] * 7 + [c_void_p, c_size_t, c_int, c_void_p]),
     'hf_lbs_forward_split': (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 4 + [c_size_t, c_int, c_void_p]),
     'hf_rodrigues': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'hf_lbs_tpose': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

@@ -57,6 +57,11 @@ struct hf_smpl {
     int *pick_f, *csr_f;      // flagged slot of every pick / CSR entry
     // cached tensor map of the per-call coefficient matrix
     const void* mapB_ptr; int mapB_M; CUtensorMap mapB;
+    // backward: transpose of (joint picks + extra regressors) per vertex, rows numbered from the first
+    // non-chain output joint; blend basis as split tf32 [256][2 * 3Vp] = [hi | lo] (built on the first hf_lbs_backward call)
+    int *csc_ptr, *csc_row; float* csc_val;
+    float* blend_split; CUtensorMap mapBs;
+    const void* mapG_ptr; int mapG_M; CUtensorMap mapG;
 };
 
 int hf_lbs_extra_joints(const hf_smpl* h, const float* vertices, float* joints, int M, cudaStream_t stream);
@@ -1354,6 +1359,23 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
         if ((rc = encode_map(&h->mapP3, h->Pf16s, 2, dims, st, box))) return rc;
         h->mapF3_ptr = nullptr; h->mapF3_M = 0;
     }
+    {   // per-vertex transpose of the output-joint rows that read vertices: picks (weight 1) then the regressor rows
+        std::vector<std::vector<std::pair<int, float>>> byv((size_t)V);
+        for (int r = 0; r < nvj; ++r) byv[vertex_joint_ids[r]].push_back({r, 1.f});
+        for (int r = 0; r < nextra; ++r)
+            for (int e = ptr[r]; e < ptr[r + 1]; ++e) byv[col[e]].push_back({nvj + r, val[e]});
+        std::vector<int> cptr((size_t)Vp + 1, 0), crow;
+        std::vector<float> cval;
+        for (int v = 0; v < Vp; ++v) {
+            if (v < V) for (auto& pr : byv[v]) { crow.push_back(pr.first); cval.push_back(pr.second); }
+            cptr[v + 1] = (int)crow.size();
+        }
+        if (crow.empty()) { crow.push_back(0); cval.push_back(0.f); }
+        if ((rc = hf::upload(&h->csc_ptr, cptr.data(), cptr.size()))) return rc;
+        if ((rc = hf::upload(&h->csc_row, crow.data(), crow.size()))) return rc;
+        if ((rc = hf::upload(&h->csc_val, cval.data(), cval.size()))) return rc;
+        h->blend_split = nullptr; h->mapG_ptr = nullptr; h->mapG_M = 0;
+    }
     if ((rc = hf::upload(&h->csr_ptr, ptr.data(), ptr.size()))) return rc;
     if ((rc = hf::upload(&h->csr_col, col.data(), col.size()))) return rc;
     if ((rc = hf::upload(&h->csr_val, val.data(), val.size()))) return rc;
@@ -1365,6 +1387,7 @@ extern "C" void hf_smpl_destroy(hf_smpl_t* h) {
     if (!h) return;
     cudaFree(h->blend); cudaFree(h->vtemp); cudaFree(h->J0); cudaFree(h->Jd); cudaFree(h->sj);
     cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->Pf16); cudaFree(h->Pf16s); cudaFree(h->vconst); cudaFree(h->pick_f); cudaFree(h->csr_f); cudaFree(h->vflag); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
+    cudaFree(h->csc_ptr); cudaFree(h->csc_row); cudaFree(h->csc_val); cudaFree(h->blend_split);
     delete h;
 }
 
@@ -1566,5 +1589,440 @@ extern "C" int hf_rodrigues(const float* aa, float* R, int n, void* stream) {
     if (n <= 0) return HF_OK;
     rodrigues_kernel<<<hf::div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(aa, R, n);
     HF_LAUNCH_CHECK();
+    return HF_OK;
+}
+
+
+// =====================================================================================================================
+// Backward of the LBS forward (the gradient a fitting / training loop needs through models/smpl.py:27-41
+// and [upstream] smplx lbs): d loss / d (betas, rotation matrices) from d loss / d (vertices, 90 joints).  fp32 throughout.
+//
+//   forward      p = v_template + [S | P] f            f = (beta | vec(R_i - I))         (blend)
+//                v = sum_k w_vk (A_k.R p + A_k.t)      A_k from the kinematic chain        (skinning)
+//                joints = (chain translations | picked vertices | regressor rows . v)
+//   backward  1. lbs_bwd_vertex_kernel  per (vertex, sample): g = dL/dv (+ the rows of dL/djoints that read v), recompute p,
+//                                       dL/dp = T.R^T g -> G2 (split tf32 [M][hi 3Vp | lo 3Vp]);  dL/dA_k += w_vk g (x) [p;1]
+//                                       (shared-memory atomics per CTA, per-vertex-tile partials to global)
+//             2. gemm_tf32x3_kernel     dL/df = G2 . [S | P]^T as split-tf32 tcgen05 GEMM, K = 3Vp split across CTAs
+//             3. lbs_bwd_chain_kernel   sums the partials, walks the chain backwards (thread per sample), adds the pose-feature and
+//                                       joint-regressor terms: dL/dR (M,J,3,3), dL/dbeta (M,nb)
+// The shared-memory atomics make the summation order of dL/dA run-dependent (differences at the fp32 rounding level).
+namespace {
+
+constexpr int BW_SPT = 4, BW_SG = 4, BW_TS = BW_SPT * BW_SG;
+
+__global__ void __launch_bounds__(128 * BW_SG, 1)
+lbs_bwd_vertex_kernel(const float* __restrict__ blend, const float* __restrict__ vtemp, const int* __restrict__ sj,
+                      const float* __restrict__ sw, const float* __restrict__ F, const float* __restrict__ A,
+                      const int* __restrict__ csc_ptr, const int* __restrict__ csc_row, const float* __restrict__ csc_val,
+                      const float* __restrict__ gV, const float* __restrict__ gJ, int M, int V, int Vp, int KB, int KP, int J, int J_out,
+                      int nslots, float* __restrict__ G2, float* __restrict__ part) {
+    extern __shared__ __align__(16) float smem[];
+    const int J12 = J * 12, NX = (J_out - J) * 3;
+    float* Fs = smem;                       // [KP][TS]
+    float* As = Fs + KP * BW_TS;            // [TS][J12]
+    float* gAs = As + BW_TS * J12;          // [TS][J12]
+    float* gXs = gAs + BW_TS * J12;         // [TS][NX]   dL/d(non-chain output joints)
+    const int m0 = blockIdx.y * BW_TS, tid = threadIdx.x;
+    for (int idx = tid; idx < BW_TS * KP; idx += 128 * BW_SG) {
+        const int s = idx / KP, k = idx - s * KP, m = m0 + s;
+        Fs[k * BW_TS + s] = (m < M) ? F[(size_t)m * KP + k] : 0.f;
+    }
+    for (int idx = tid; idx < BW_TS * J12; idx += 128 * BW_SG) {
+        const int s = idx / J12, m = m0 + s;
+        As[idx] = (m < M) ? A[(size_t)m * J12 + (idx - s * J12)] : 0.f;
+        gAs[idx] = 0.f;
+    }
+    for (int idx = tid; idx < BW_TS * NX; idx += 128 * BW_SG) {
+        const int s = idx / NX, m = m0 + s;
+        gXs[idx] = (gJ && m < M) ? gJ[((size_t)m * J_out + J) * 3 + (idx - s * NX)] : 0.f;
+    }
+    __syncthreads();
+    const int vl = tid & 127, sg = tid >> 7;
+    const int v = blockIdx.x * 128 + vl;          // < Vp (tables are padded)
+    float acc[BW_SPT][3];
+#pragma unroll
+    for (int s = 0; s < BW_SPT; ++s) acc[s][0] = acc[s][1] = acc[s][2] = 0.f;
+    const float* bp = blend + v;
+    const float* fs = Fs + sg * BW_SPT;
+#pragma unroll 4
+    for (int k = 0; k < KB; ++k) {
+        const float p0 = __ldg(bp + (size_t)(k * 3 + 0) * Vp), p1 = __ldg(bp + (size_t)(k * 3 + 1) * Vp), p2 = __ldg(bp + (size_t)(k * 3 + 2) * Vp);
+        const float4 f = *reinterpret_cast<const float4*>(fs + k * BW_TS);
+        acc[0][0] = fmaf(p0, f.x, acc[0][0]); acc[0][1] = fmaf(p1, f.x, acc[0][1]); acc[0][2] = fmaf(p2, f.x, acc[0][2]);
+        acc[1][0] = fmaf(p0, f.y, acc[1][0]); acc[1][1] = fmaf(p1, f.y, acc[1][1]); acc[1][2] = fmaf(p2, f.y, acc[1][2]);
+        acc[2][0] = fmaf(p0, f.z, acc[2][0]); acc[2][1] = fmaf(p1, f.z, acc[2][1]); acc[2][2] = fmaf(p2, f.z, acc[2][2]);
+        acc[3][0] = fmaf(p0, f.w, acc[3][0]); acc[3][1] = fmaf(p1, f.w, acc[3][1]); acc[3][2] = fmaf(p2, f.w, acc[3][2]);
+    }
+    const float t0 = vtemp[v], t1 = vtemp[Vp + v], t2 = vtemp[2 * Vp + v];
+    const int e0 = csc_ptr[v], e1 = csc_ptr[v + 1];
+#pragma unroll
+    for (int s = 0; s < BW_SPT; ++s) {
+        const int sl = sg * BW_SPT + s, m = m0 + sl;
+        const float p[3] = {acc[s][0] + t0, acc[s][1] + t1, acc[s][2] + t2};
+        float g[3] = {0.f, 0.f, 0.f};
+        if (m < M && v < V) {
+            if (gV) { const float* q = gV + ((size_t)m * V + v) * 3; g[0] = q[0]; g[1] = q[1]; g[2] = q[2]; }
+            for (int e = e0; e < e1; ++e) {
+                const float w = csc_val[e];
+                const float* q = gXs + sl * NX + csc_row[e] * 3;
+                g[0] = fmaf(w, q[0], g[0]); g[1] = fmaf(w, q[1], g[1]); g[2] = fmaf(w, q[2], g[2]);
+            }
+        }
+        float gp[3] = {0.f, 0.f, 0.f};
+        if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) {
+            for (int slot = 0; slot < nslots; ++slot) {
+                const float w = sw[slot * Vp + v];
+                if (w == 0.f) continue;
+                const int j = sj[slot * Vp + v];
+                const float* a = As + sl * J12 + j * 12;
+                float* ga = gAs + sl * J12 + j * 12;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float wg = w * g[r];
+                    gp[0] = fmaf(a[r * 4 + 0], wg, gp[0]); gp[1] = fmaf(a[r * 4 + 1], wg, gp[1]); gp[2] = fmaf(a[r * 4 + 2], wg, gp[2]);
+                    atomicAdd(ga + r * 4 + 0, wg * p[0]); atomicAdd(ga + r * 4 + 1, wg * p[1]); atomicAdd(ga + r * 4 + 2, wg * p[2]);
+                    atomicAdd(ga + r * 4 + 3, wg);
+                }
+            }
+        }
+        if (m < M) {
+            float* row = G2 + (size_t)m * 6 * Vp;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t hb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(gp[c]));
+                const float hi = __uint_as_float(hb);
+                row[c * Vp + v] = hi;
+                row[3 * Vp + c * Vp + v] = gp[c] - hi;
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < BW_TS * J12; idx += 128 * BW_SG) {
+        const int s = idx / J12, m = m0 + s;
+        if (m < M) part[((size_t)blockIdx.x * M + m) * J12 + (idx - s * J12)] = gAs[idx];
+    }
+}
+
+// blend [KB][3][Vp] fp32 -> [256][hi 3Vp | lo 3Vp] (rows >= KB zero)
+__global__ void lbs_blend_split_kernel(const float* __restrict__ blend, int KB, int Vp3, float* __restrict__ out) {
+    const size_t total = (size_t)256 * Vp3;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e / Vp3), c = (int)(e - (size_t)k * Vp3);
+        const float x = k < KB ? blend[(size_t)k * Vp3 + c] : 0.f;
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+        const float hi = __uint_as_float(hb);
+        out[(size_t)k * 2 * Vp3 + c] = hi;
+        out[(size_t)k * 2 * Vp3 + Vp3 + c] = x - hi;
+    }
+}
+
+// D[z][m][n] = sum over this CTA's K range of (Ahi + Alo)[m][k] (Bhi + Blo)[n][k] (dropping lo x lo): split-tf32 on tcgen05,
+// both operands K-major [rows][hi K | lo K].  Tile 128 x 128, 32-float k-steps, 3-stage TMA ring (the structure of
+// flow_ctx_gemm_kernel in flow.cu); grid (m tiles, n tiles, K splits).
+constexpr int GB_STAGES = 3, GB_THREADS = 320, GB_BN = 128, GB_STAGE_BYTES = 2 * 128 * 128 + 2 * GB_BN * 128;
+__global__ void __launch_bounds__(GB_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int lo_off, int ksteps_total,
+                   int ksteps_per_split, int M, int N, float* __restrict__ D) {
+    extern __shared__ uint8_t gb_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * GB_STAGES + 1];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t tile_base = (smem_u32(gb_smem) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * GB_BN;
+    const int k_begin = blockIdx.z * ksteps_per_split, nit = min(ksteps_per_split, ksteps_total - k_begin);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[GB_STAGES]), tfull = smem_u32(&bars[2 * GB_STAGES]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GB_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)GB_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    HF_PDL_SYNC();
+    const uint32_t tmem_base = tmem_base_s;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nit; ++it) {
+                const int st = it % GB_STAGES;
+                const uint32_t ph = (uint32_t)(it / GB_STAGES) & 1u;
+                mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                const uint32_t sa = tile_base + st * GB_STAGE_BYTES, fb = full0 + 8 * st;
+                const int kc = (k_begin + it) * 32;
+                mbar_expect_tx(fb, GB_STAGE_BYTES);
+                tma_load_2d(sa, &mapA, fb, kc, m0);
+                tma_load_2d(sa + 16384, &mapA, fb, lo_off + kc, m0);
+                tma_load_2d(sa + 32768, &mapB, fb, kc, n0);
+                tma_load_2d(sa + 32768 + GB_BN * 128, &mapB, fb, lo_off + kc, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, GB_BN);
+            for (int it = 0; it < nit; ++it) {
+                const int st = it % GB_STAGES;
+                const uint32_t ph = (uint32_t)(it / GB_STAGES) & 1u;
+                mbar_wait(full0 + 8 * st, ph);
+                tcgen05_fence_after();
+                const uint32_t sa = tile_base + st * GB_STAGE_BYTES;
+                const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + 16384);
+                const uint64_t b_hi = umma_desc_sw128(sa + 32768), b_lo = umma_desc_sw128(sa + 32768 + GB_BN * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, (uint32_t)((it | k) != 0));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1u);
+                umma_commit(empty0 + 8 * st);
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;     // TMEM lane quarter (= warp % 4), 64-column half
+        const int r = m0 + q * 32 + lane;
+        if (nit > 0) {
+            mbar_wait_warp(tfull, 0);
+            tcgen05_fence_after();
+        }
+        uint32_t v[64];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+        if (nit > 0) {
+            tmem_ld32(ta, v);
+            tmem_ld32(ta + 32, v + 32);
+            tmem_ld_wait();
+        } else {
+#pragma unroll
+            for (int o = 0; o < 64; ++o) v[o] = 0u;
+        }
+        if (r < M) {
+            float* dst = D + ((size_t)blockIdx.z * M + r) * N + n0 + half * 64;
+#pragma unroll
+            for (int o = 0; o < 64; o += 4)
+                if (n0 + half * 64 + o < N) *reinterpret_cast<float4*>(dst + o) = make_float4(__uint_as_float(v[o]), __uint_as_float(v[o + 1]), __uint_as_float(v[o + 2]), __uint_as_float(v[o + 3]));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)GB_BN) : "memory");
+    }
+}
+
+// Chain backward, BC samples per block.  All per-sample arrays live in shared memory as [element][sample] (conflict-free for the
+// one-thread-per-sample chain walk).  dL/dG of joint i is kept in the 12 floats of gA[i] (rotation part r*4+c, translation r*4+3).
+constexpr int BC = 16, BC_THREADS = 128;
+__global__ void __launch_bounds__(BC_THREADS)
+lbs_bwd_chain_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats, const float* __restrict__ J0, const float* __restrict__ Jd,
+                     Parents par, const float* __restrict__ part, int nvt, const float* __restrict__ cpart, int nz, int ldc,
+                     const float* __restrict__ gJ, int M, int J, int nb, int KB, int J_out, float* __restrict__ g_betas,
+                     float* __restrict__ g_rot) {
+    extern __shared__ __align__(16) float sm[];
+    const int J12 = J * 12, J9 = J * 9, J3 = J * 3;
+    float* gA = sm;                    // [J12][BC]
+    float* Gs = gA + J12 * BC;         // [J12][BC]  global transforms (rotation r*4+c, translation r*4+3)
+    float* Rs = Gs + J12 * BC;         // [J9][BC]   rotations in, dL/dR out
+    float* Js = Rs + J9 * BC;          // [J3][BC]   rest joints
+    float* gJs = Js + J3 * BC;         // [J3][BC]   dL/d(rest joints)
+    float* dc = gJs + J3 * BC;         // [KB][BC]   dL/d(blend coefficients)
+    float* Bs = dc + KB * BC;          // [nb][BC]
+    __shared__ int pars[HF_MAXJ];
+    const int tid = threadIdx.x, mb = blockIdx.x * BC, ns = min(BC, M - mb);
+    if (tid < HF_MAXJ) pars[tid] = par.p[tid];
+    HF_PDL_SYNC();
+    for (int idx = tid; idx < ns * J12; idx += BC_THREADS) {          // sum of the per-vertex-tile partials, fixed order
+        const int s = idx / J12, e = idx - s * J12;
+        float a = 0.f;
+        for (int t = 0; t < nvt; ++t) a += part[((size_t)t * M + mb + s) * J12 + e];
+        gA[e * BC + s] = a;
+    }
+    for (int idx = tid; idx < ns * KB; idx += BC_THREADS) {
+        const int s = idx / KB, k = idx - s * KB;
+        float a = 0.f;
+        for (int z = 0; z < nz; ++z) a += cpart[((size_t)z * M + mb + s) * ldc + k];
+        dc[k * BC + s] = a;
+    }
+    for (int idx = tid; idx < ns * J9; idx += BC_THREADS) {
+        const int s = idx / J9, e = idx - s * J9;
+        Rs[e * BC + s] = rotmats[(size_t)(mb + s) * J9 + e];
+    }
+    for (int idx = tid; idx < ns * nb; idx += BC_THREADS) {
+        const int s = idx / nb, l = idx - s * nb;
+        Bs[l * BC + s] = betas[(size_t)(mb + s) * nb + l];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < ns * J3; idx += BC_THREADS) {
+        const int s = idx / J3, jr = idx - s * J3;
+        float a = J0[jr];
+        for (int l = 0; l < nb; ++l) a = fmaf(Jd[jr * nb + l], Bs[l * BC + s], a);
+        Js[jr * BC + s] = a;
+        gJs[jr * BC + s] = 0.f;
+    }
+    __syncthreads();
+    if (tid < ns) {
+        const int s = tid, m = mb + s;
+#define GA(i, e) gA[((i) * 12 + (e)) * BC + s]
+#define GG(i, e) Gs[((i) * 12 + (e)) * BC + s]
+#define RR(i, e) Rs[((i) * 9 + (e)) * BC + s]
+#define JJ(i, c) Js[((i) * 3 + (c)) * BC + s]
+#define GJ(i, c) gJs[((i) * 3 + (c)) * BC + s]
+        // forward chain
+        for (int i = 0; i < J; ++i) {
+            if (i == 0) {
+                for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) GG(0, r * 4 + c) = RR(0, r * 3 + c); GG(0, r * 4 + 3) = JJ(0, r); }
+            } else {
+                const int p = pars[i];
+                const float d0 = JJ(i, 0) - JJ(p, 0), d1 = JJ(i, 1) - JJ(p, 1), d2 = JJ(i, 2) - JJ(p, 2);
+                for (int r = 0; r < 3; ++r) {
+                    const float g0 = GG(p, r * 4), g1 = GG(p, r * 4 + 1), g2 = GG(p, r * 4 + 2);
+                    for (int c = 0; c < 3; ++c) GG(i, r * 4 + c) = g0 * RR(i, c) + g1 * RR(i, 3 + c) + g2 * RR(i, 6 + c);
+                    GG(i, r * 4 + 3) = g0 * d0 + g1 * d1 + g2 * d2 + GG(p, r * 4 + 3);
+                }
+            }
+        }
+        // dL/dA -> dL/dG (in place): A.R = G.R, A.t = G.t - G.R J;  posed joint i = G_i.t
+        for (int i = 0; i < J; ++i) {
+            float gt[3];
+            for (int r = 0; r < 3; ++r) gt[r] = GA(i, r * 4 + 3);
+            for (int c = 0; c < 3; ++c) GJ(i, c) -= GG(i, c) * gt[0] + GG(i, 4 + c) * gt[1] + GG(i, 8 + c) * gt[2];
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 3; ++c) GA(i, r * 4 + c) -= gt[r] * JJ(i, c);
+                if (gJ) GA(i, r * 4 + 3) += gJ[((size_t)m * J_out + i) * 3 + r];
+            }
+        }
+        // children before parents
+        for (int i = J - 1; i >= 1; --i) {
+            const int p = pars[i];
+            const float d[3] = {JJ(i, 0) - JJ(p, 0), JJ(i, 1) - JJ(p, 1), JJ(i, 2) - JJ(p, 2)};
+            float gr[9], gt[3], R[9], gd[3] = {0.f, 0.f, 0.f}, gR[9];
+            for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) gr[r * 3 + c] = GA(i, r * 4 + c); gt[r] = GA(i, r * 4 + 3); }
+            for (int e = 0; e < 9; ++e) { R[e] = RR(i, e); gR[e] = 0.f; }
+            for (int r = 0; r < 3; ++r) {
+                const float gp0 = GG(p, r * 4), gp1 = GG(p, r * 4 + 1), gp2 = GG(p, r * 4 + 2);
+                // dL/dR_i = G_p.R^T dL/dG_i.R ; dL/d(J_i - J_p) = G_p.R^T dL/dG_i.t
+                for (int c = 0; c < 3; ++c) { gR[c] += gp0 * gr[r * 3 + c]; gR[3 + c] += gp1 * gr[r * 3 + c]; gR[6 + c] += gp2 * gr[r * 3 + c]; }
+                gd[0] += gp0 * gt[r]; gd[1] += gp1 * gt[r]; gd[2] += gp2 * gt[r];
+                // dL/dG_p.R += dL/dG_i.R R_i^T + dL/dG_i.t (x) d ; dL/dG_p.t += dL/dG_i.t
+                for (int c = 0; c < 3; ++c)
+                    GA(p, r * 4 + c) += gr[r * 3] * R[c * 3] + gr[r * 3 + 1] * R[c * 3 + 1] + gr[r * 3 + 2] * R[c * 3 + 2] + gt[r] * d[c];
+                GA(p, r * 4 + 3) += gt[r];
+            }
+            for (int c = 0; c < 3; ++c) { GJ(i, c) += gd[c]; GJ(p, c) -= gd[c]; }
+            for (int e = 0; e < 9; ++e) RR(i, e) = gR[e];
+        }
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) RR(0, r * 3 + c) = GA(0, r * 4 + c); GJ(0, r) += GA(0, r * 4 + 3); }
+#undef GA
+#undef GG
+#undef RR
+#undef JJ
+#undef GJ
+    }
+    __syncthreads();
+    for (int idx = tid; idx < ns * J9; idx += BC_THREADS) {          // + pose-feature term (f = R_i - I for i >= 1)
+        const int s = idx / J9, e = idx - s * J9;
+        float a = Rs[e * BC + s];
+        if (e >= 9) a += dc[(nb + e - 9) * BC + s];
+        g_rot[(size_t)(mb + s) * J9 + e] = a;
+    }
+    for (int idx = tid; idx < ns * nb; idx += BC_THREADS) {          // + joint-regressor term
+        const int s = idx / nb, l = idx - s * nb;
+        float a = dc[l * BC + s];
+        for (int jr = 0; jr < J3; ++jr) a = fmaf(Jd[jr * nb + l], gJs[jr * BC + s], a);
+        g_betas[(size_t)(mb + s) * nb + l] = a;
+    }
+}
+
+struct BwdLayout { size_t F, A, joints, G2, part, cpart, total; int nvt, nz, ksteps_per; };
+BwdLayout bwd_layout(const hf_smpl* h, int M) {
+    BwdLayout L;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const int J_out = h->J + h->nvj + h->nextra;
+    L.nvt = h->Vp / 128;
+    const int ksteps = 3 * h->Vp / 32, mt = hf::div_up(M, 128);
+    int nz = std::max(1, std::min(8, 148 / (mt * 2)));
+    L.ksteps_per = hf::div_up(ksteps, nz);
+    L.nz = hf::div_up(ksteps, L.ksteps_per);
+    size_t o = 0;
+    L.F = o; o = al(o + (size_t)M * h->KP * 4);
+    L.A = o; o = al(o + (size_t)M * h->J * 12 * 4);
+    L.joints = o; o = al(o + (size_t)M * J_out * 3 * 4);
+    L.G2 = o; o = al(o + (size_t)M * 6 * h->Vp * 4);
+    L.part = o; o = al(o + (size_t)L.nvt * M * h->J * 12 * 4);
+    L.cpart = o; o = al(o + (size_t)L.nz * M * 256 * 4);
+    L.total = o + 256;
+    return L;
+}
+
+}  // namespace
+
+extern "C" size_t hf_lbs_backward_workspace_bytes(const hf_smpl_t* h, int M) {
+    if (!h || M <= 0) return 0;
+    return bwd_layout(h, M).total;
+}
+
+extern "C" int hf_lbs_backward(hf_smpl_t* h, const float* betas, const float* rotmats, const float* grad_vertices, const float* grad_joints,
+                               float* grad_betas, float* grad_rotmats, void* workspace, size_t workspace_bytes, int M, void* stream_) {
+    if (!h || !betas || !rotmats || !grad_betas || !grad_rotmats) return hf::fail(HF_ERR_INVALID, "hf_lbs_backward: null argument");
+    if (M <= 0) return HF_OK;
+    const BwdLayout L = bwd_layout(h, M);
+    if (!workspace || workspace_bytes < L.total)
+        return hf::fail(HF_ERR_INVALID, "hf_lbs_backward: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+    if (3 * h->Vp % 32) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_backward: padded vertex count %d", h->Vp);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    uint8_t* wsb = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float *F = (float*)(wsb + L.F), *A = (float*)(wsb + L.A), *jtmp = (float*)(wsb + L.joints), *G2 = (float*)(wsb + L.G2);
+    float *part = (float*)(wsb + L.part), *cpart = (float*)(wsb + L.cpart);
+    const int J_out = hf_smpl_num_joints_out(h), Vp3 = 3 * h->Vp;
+    int rc;
+    if (!h->blend_split) {
+        HF_CUDA(cudaMalloc(&h->blend_split, (size_t)256 * 2 * Vp3 * sizeof(float)));
+        lbs_blend_split_kernel<<<1024, 256, 0, stream>>>(h->blend, h->KB, Vp3, h->blend_split);
+        HF_LAUNCH_CHECK();
+        const uint64_t dims[2] = {(uint64_t)(2 * Vp3), 256}, st[1] = {(uint64_t)(2 * Vp3) * 4};
+        const uint32_t box[2] = {32, (uint32_t)GB_BN};
+        if ((rc = encode_map(&h->mapBs, h->blend_split, 2, dims, st, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
+    }
+    if (h->mapG_ptr != (const void*)G2 || h->mapG_M != M) {
+        const uint64_t dims[2] = {(uint64_t)(2 * Vp3), (uint64_t)M}, st[1] = {(uint64_t)(2 * Vp3) * 4};
+        const uint32_t box[2] = {32, 128};
+        if ((rc = encode_map(&h->mapG, G2, 2, dims, st, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
+        h->mapG_ptr = G2; h->mapG_M = M;
+    }
+    Parents par;
+    for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
+    // forward quantities the backward needs: fp32 blend coefficients F and relative transforms A
+    HF_CUDA(hf::launch_pdl(lbs_pose_kernel, dim3(hf::div_up(M, PS)), dim3(PTHREADS), 0, stream, betas, rotmats, (const float*)nullptr, 1, (const float*)nullptr,
+                           h->J0, h->Jd, par, M, h->J, h->nb, h->KP, J_out, F, (__half*)nullptr, A, (float*)nullptr, jtmp));
+    HF_LAUNCH_CHECK();
+    {
+        const size_t smem = ((size_t)h->KP * BW_TS + 2 * (size_t)BW_TS * h->J * 12 + (size_t)BW_TS * (J_out - h->J) * 3) * sizeof(float);
+        HF_CUDA(cudaFuncSetAttribute(lbs_bwd_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HF_CUDA(hf::launch_pdl(lbs_bwd_vertex_kernel, dim3(L.nvt, hf::div_up(M, BW_TS)), dim3(128 * BW_SG), smem, stream, h->blend, h->vtemp, h->sj, h->sw,
+                               (const float*)F, (const float*)A, h->csc_ptr, h->csc_row, h->csc_val, grad_vertices, grad_joints, M, h->V, h->Vp, h->KB, h->KP,
+                               h->J, J_out, h->nslots, G2, part));
+        HF_LAUNCH_CHECK();
+    }
+    {
+        const size_t smem = (size_t)GB_STAGES * GB_STAGE_BYTES + 1024;
+        HF_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HF_CUDA(hf::launch_pdl(gemm_tf32x3_kernel, dim3(hf::div_up(M, 128), 256 / GB_BN, L.nz), dim3(GB_THREADS), smem, stream, h->mapG, h->mapBs, Vp3, Vp3 / 32,
+                               L.ksteps_per, M, 256, cpart));
+        HF_LAUNCH_CHECK();
+    }
+    {
+        const size_t smem = ((size_t)(2 * h->J * 12 + h->J * 9 + 2 * h->J * 3 + h->KB + h->nb) * BC) * sizeof(float);
+        HF_CUDA(cudaFuncSetAttribute(lbs_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HF_CUDA(hf::launch_pdl(lbs_bwd_chain_kernel, dim3(hf::div_up(M, BC)), dim3(BC_THREADS), smem, stream, betas, rotmats, (const float*)h->J0,
+                               (const float*)h->Jd, par, (const float*)part, L.nvt, (const float*)cpart, L.nz, 256, grad_joints, M, h->J, h->nb, h->KB, J_out,
+                               grad_betas, grad_rotmats));
+        HF_LAUNCH_CHECK();
+    }
     return HF_OK;
 }

@@ -63,6 +63,64 @@ def load_smpl_pkl(model_path, gender):
     }
 
 
+class _LBSFunction(torch.autograd.Function):
+    """Differentiable LBS: forward = hf_lbs_forward, backward = hf_lbs_backward.  The reference gets the
+    gradient from torch.autograd through smplx's lbs (models/smpl.py:27-41); here it is three launches of lbs.cu."""
+
+    @staticmethod
+    def forward(ctx, smpl, betas, rotmats, transl):
+        verts, joints = smpl._lbs_raw(betas, rotmats, transl)
+        ctx.set_materialize_grads(False)          # an unused output arrives as None, not as 80 KB of zeros per body
+        ctx.smpl = smpl
+        ctx.save_for_backward(betas, rotmats)
+        ctx.has_transl = transl is not None
+        return verts, joints
+
+    @staticmethod
+    def backward(ctx, g_verts, g_joints):
+        betas, rotmats = ctx.saved_tensors
+        smpl = ctx.smpl
+        if g_verts is None and g_joints is None:
+            return None, None, None, None
+        lib = _lib.load()
+        dev = betas.device
+        M = rotmats.shape[0]
+        gv = None if g_verts is None else _lib.f32c(g_verts)
+        gj = None if g_joints is None else _lib.f32c(g_joints)
+        g_betas = torch.empty_like(betas)
+        g_rot = torch.empty_like(rotmats)
+        h = smpl._handle(dev)
+        with torch.cuda.device(dev):
+            nbytes = lib.hf_lbs_backward_workspace_bytes(h, M)
+            ws = smpl._ws_bwd.get(dev)
+            if ws is None or ws.numel() < nbytes:
+                ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
+                smpl._ws_bwd[dev] = ws
+            _lib.check(lib.hf_lbs_backward(h, _lib.ptr(betas), _lib.ptr(rotmats), _lib.ptr(gv), _lib.ptr(gj), _lib.ptr(g_betas),
+                                           _lib.ptr(g_rot), _lib.ptr(ws), ws.numel(), M, _lib.stream()))
+        g_transl = None
+        if ctx.has_transl and ctx.needs_input_grad[3]:
+            g_transl = torch.zeros(M, 3, device=dev)
+            if gv is not None:
+                g_transl = g_transl + gv.sum(1)
+            if gj is not None:
+                g_transl = g_transl + gj.sum(1)
+        return None, g_betas, g_rot, g_transl
+
+
+def _rodrigues_torch(aa):
+    """(n,3) axis-angle -> (n,3,3), differentiable (torch ops; [upstream] smplx lbs.batch_rodrigues, same 1e-8 guard).  Only used
+    when a gradient is required through pose2rot=True; the inference path uses hf_rodrigues."""
+    angle = torch.norm(aa + 1e-8, dim=1, keepdim=True)
+    d = aa / angle
+    c, s_ = torch.cos(angle)[:, None], torch.sin(angle)[:, None]
+    rx, ry, rz = d[:, 0:1], d[:, 1:2], d[:, 2:3]
+    z = torch.zeros_like(rx)
+    K = torch.cat([z, -rz, ry, rz, z, -rx, -ry, rx, z], dim=1).view(-1, 3, 3)
+    eye = torch.eye(3, dtype=aa.dtype, device=aa.device)[None]
+    return eye + s_ * K + (1 - c) * torch.bmm(K, K)
+
+
 class SMPL(nn.Module):
     NUM_JOINTS = 23
     NUM_BODY_JOINTS = 23
@@ -109,6 +167,7 @@ class SMPL(nn.Module):
             self.transl = nn.Parameter(torch.zeros(batch_size, 3))
         self._handles = {}
         self._ws = {}
+        self._ws_bwd = {}
 
     @classmethod
     def from_arrays(cls, data, batch_size=1, num_betas=10, create_transl=True, **kwargs):
@@ -156,7 +215,24 @@ class SMPL(nn.Module):
 
     def lbs(self, betas, rotmats, transl=None, out_vertices=None, out_joints=None):
         """betas (M,nb), rotmats (M,24,3,3) fp32 CUDA -> vertices (M,V,3), joints (M,90,3).
-        ``out_vertices`` / ``out_joints``: optional preallocated fp32 CUDA outputs (serving loops that double-buffer)."""
+        ``out_vertices`` / ``out_joints``: optional preallocated fp32 CUDA outputs (serving loops that double-buffer).
+        When autograd is recording and an input requires a gradient, the call goes through _LBSFunction (CUDA backward)."""
+        if out_vertices is None and out_joints is None and torch.is_grad_enabled() and \
+                any(torch.is_tensor(t) and t.requires_grad for t in (betas, rotmats, transl)):
+            _lib.require_cuda('SMPL.forward')
+            if not rotmats.is_cuda:
+                raise RuntimeError('humaniflow_b200.SMPL: inputs must be CUDA tensors (no CPU fallback)')
+            M = rotmats.shape[0]
+            keep = lambda t: t.to(torch.float32).contiguous()          # stays on the autograd tape (f32c detaches)
+            betas = keep(betas)
+            if betas.shape[0] != M:
+                betas = betas.expand(int(M / betas.shape[0]), -1).contiguous()
+            rotmats = keep(rotmats)
+            transl = None if transl is None else keep(transl).expand(M, 3).contiguous()
+            return _LBSFunction.apply(self, betas, rotmats, transl)
+        return self._lbs_raw(betas, rotmats, transl, out_vertices, out_joints)
+
+    def _lbs_raw(self, betas, rotmats, transl=None, out_vertices=None, out_joints=None):
         _lib.require_cuda('SMPL.forward')
         if not betas.is_cuda:
             raise RuntimeError('humaniflow_b200.SMPL: inputs must be CUDA tensors (no CPU fallback)')
@@ -244,12 +320,16 @@ class SMPL(nn.Module):
             _lib.require_cuda('SMPL.forward')
             full_pose = torch.cat([global_orient.reshape(global_orient.shape[0], -1),
                                    body_pose.reshape(body_pose.shape[0], -1)], dim=1)
-            aa = _lib.f32c(full_pose).reshape(-1, 3)
-            if not aa.is_cuda:
+            if not full_pose.is_cuda:
                 raise RuntimeError('humaniflow_b200.SMPL: inputs must be CUDA tensors (no CPU fallback)')
-            rot = torch.empty(aa.shape[0], 3, 3, device=aa.device, dtype=torch.float32)
-            with torch.cuda.device(aa.device):
-                _lib.check(lib.hf_rodrigues(_lib.ptr(aa), _lib.ptr(rot), aa.shape[0], _lib.stream()))
+            want_grad = torch.is_grad_enabled() and full_pose.requires_grad and out_vertices is None and out_joints is None
+            aa = (full_pose.to(torch.float32) if want_grad else _lib.f32c(full_pose)).reshape(-1, 3)
+            if want_grad:
+                rot = _rodrigues_torch(aa)             # a gradient w.r.t. the axis-angle pose is wanted (fitting loops)
+            else:
+                rot = torch.empty(aa.shape[0], 3, 3, device=aa.device, dtype=torch.float32)
+                with torch.cuda.device(aa.device):
+                    _lib.check(lib.hf_rodrigues(_lib.ptr(aa), _lib.ptr(rot), aa.shape[0], _lib.stream()))
             rotmats = rot.view(full_pose.shape[0], -1, 3, 3)
         else:
             full_pose = torch.cat([global_orient.reshape(-1, 1, 3, 3), body_pose.reshape(body_pose.shape[0], -1, 3, 3)], dim=1)

@@ -78,6 +78,15 @@ int hf_lbs_forward_split(const hf_smpl_t* h, const float* betas, const float* bo
                          int rep, const float* transl, float* vertices, float* joints, void* workspace,
                          size_t workspace_bytes, int M, void* stream);
 
+/* Backward of hf_lbs_forward (the reference gets it from torch.autograd through models/smpl.py:27-41 and
+ * [upstream] smplx lbs.lbs, e.g. in a fitting loop that optimises pose / shape against 2-D joints):
+ *   grad_vertices (M,V,3) or NULL, grad_joints (M,J_out,3) or NULL  ->  grad_betas (M,num_betas), grad_rotmats (M,J,3,3).
+ * A translation only shifts the outputs: d loss / d transl = sum over vertices and joints of the incoming gradients (caller).
+ * fp32; the per-joint sums over the vertices use shared-memory atomics (run-to-run differences at the rounding level). */
+size_t hf_lbs_backward_workspace_bytes(const hf_smpl_t* h, int M);
+int hf_lbs_backward(hf_smpl_t* h, const float* betas, const float* rotmats, const float* grad_vertices, const float* grad_joints,
+                    float* grad_betas, float* grad_rotmats, void* workspace, size_t workspace_bytes, int M, void* stream);
+
 /* T-pose forward (zero pose): vertices = v_template + shapedirs.betas (+ transl), joints as hf_lbs_forward would give for
  * identity rotations.  Replaces models/smpl.py:27-41 called with the default pose (predict_humaniflow.py:147,
  * evaluate_humaniflow.py:131-133); skips pose blend and skinning. */

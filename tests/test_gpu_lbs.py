@@ -203,3 +203,70 @@ def test_forward_samples_split_rotations(impl):
     b = smpl.forward_samples(betas.cuda(), body.cuda(), glob.cuda(), N)
     smpl.set_impl(0)
     assert torch.equal(a[0], b.vertices) and torch.equal(a[1], b.joints)
+
+
+def _loss_weights(M, V, JO, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(M, V, 3, generator=g, dtype=torch.float64), torch.randn(M, JO, 3, generator=g, dtype=torch.float64)
+
+
+@pytest.mark.parametrize('M,use_verts,use_joints', [(5, True, True), (3, False, True), (20, True, False), (130, True, True)])
+def test_backward_against_autograd_through_the_oracle(M, use_verts, use_joints):
+    """hf_lbs_backward (three launches) against torch.autograd through the float64 oracle LBS, for a random
+    linear functional of the vertices and / or the 90 joints.  Tolerance: 2e-4 of the largest gradient entry per tensor (fp32
+    forward recompute + split-tf32 GEMM + atomics vs float64)."""
+    smpl = _smpl()
+    data = {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in smpl_data().items()}
+    betas, theta = _inputs(M, seed=40 + M, pose_std=0.6)
+    R = so3.batch_rodrigues(theta.reshape(-1, 3)).view(M, 24, 3, 3)
+    transl = torch.randn(M, 3, generator=torch.Generator().manual_seed(5))
+    wv, wj = _loss_weights(M, 6890, 90, seed=M)
+
+    b64, R64, t64 = betas.double().requires_grad_(), R.double().requires_grad_(), transl.double().requires_grad_()
+    v_ref, j_ref = osmpl.smpl_forward(data, b64, R64[:, 1:], R64[:, :1], pose2rot=False, transl=t64)
+    loss_ref = (v_ref * wv).sum() * float(use_verts) + (j_ref * wj).sum() * float(use_joints)
+    loss_ref.backward()
+
+    bc, Rc, tc = betas.cuda().requires_grad_(), R.cuda().requires_grad_(), transl.cuda().requires_grad_()
+    out = smpl(betas=bc, body_pose=Rc[:, 1:], global_orient=Rc[:, :1], transl=tc, pose2rot=False)
+    loss = 0.
+    if use_verts:
+        loss = loss + (out.vertices * wv.float().cuda()).sum()
+    if use_joints:
+        loss = loss + (out.joints * wj.float().cuda()).sum()
+    loss.backward()
+    for name, got, ref in (('betas', bc.grad, b64.grad), ('rotmats', Rc.grad, R64.grad), ('transl', tc.grad, t64.grad)):
+        err = (got.double().cpu() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        assert err <= 2e-4 * scale, (name, err, scale)
+
+
+def test_fitting_step_through_axis_angle_pose():
+    """The fitting-loop pattern: axis-angle pose and betas as leaf tensors, a joints loss, gradient descent through the CUDA
+    forward / backward; the gradients match autograd through the oracle and the loss goes down."""
+    smpl = _smpl(create_transl=False)
+    data = {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in smpl_data().items()}
+    M = 6
+    betas, theta = _inputs(M, seed=77, pose_std=0.4)
+    tb, tt = _inputs(M, seed=78, pose_std=0.4)
+    with torch.no_grad():
+        target = smpl(betas=tb.cuda(), body_pose=tt[:, 1:].reshape(M, 69).cuda(), global_orient=tt[:, 0].cuda()).joints
+    b64, th64 = betas.double().requires_grad_(), theta.double().requires_grad_()
+    _, j_ref = osmpl.smpl_forward(data, b64, th64[:, 1:].reshape(M, 69), th64[:, 0], pose2rot=True)
+    ((j_ref - target.double().cpu()) ** 2).sum().backward()
+
+    bc, thc = betas.cuda().requires_grad_(), theta.cuda().requires_grad_()
+    losses = []
+    for it in range(5):
+        out = smpl(betas=bc, body_pose=thc[:, 1:].reshape(M, 69), global_orient=thc[:, 0], pose2rot=True)
+        loss = ((out.joints - target) ** 2).sum()
+        bc.grad = thc.grad = None
+        loss.backward()
+        if it == 0:
+            for got, ref in ((bc.grad, b64.grad), (thc.grad, th64.grad)):
+                assert (got.double().cpu() - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+        losses.append(loss.item())
+        with torch.no_grad():
+            bc -= 0.02 * bc.grad
+            thc -= 0.02 * thc.grad
+    assert losses[-1] < 0.7 * losses[0], losses
