@@ -62,6 +62,10 @@ struct hf_smpl {
     int *csc_ptr, *csc_row; float* csc_val;
     float* blend_split; CUtensorMap mapBs;
     const void* mapG_ptr; int mapG_M; CUtensorMap mapG;
+    // joints-only backward: everything restricted to the NF vertices that a pick / regressor row reads (~4 %), padded to NFp
+    int NFp; int* fvert;                         // compact slot -> vertex
+    float* blend_split_c; CUtensorMap mapBsc;    // [256][hi 3*NFp | lo 3*NFp]
+    const void* mapGc_ptr; int mapGc_M; CUtensorMap mapGc;
 };
 
 int hf_lbs_extra_joints(const hf_smpl* h, const float* vertices, float* joints, int M, cudaStream_t stream);
@@ -1375,6 +1379,12 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
         if ((rc = hf::upload(&h->csc_row, crow.data(), crow.size()))) return rc;
         if ((rc = hf::upload(&h->csc_val, cval.data(), cval.size()))) return rc;
         h->blend_split = nullptr; h->mapG_ptr = nullptr; h->mapG_M = 0;
+        std::vector<int> fvert;
+        for (int v = 0; v < V; ++v) if (!byv[v].empty()) fvert.push_back(v);
+        h->NFp = std::max(128, hf::div_up((int)fvert.size(), 128) * 128);
+        fvert.resize((size_t)h->NFp, -1);
+        if ((rc = hf::upload(&h->fvert, fvert.data(), fvert.size()))) return rc;
+        h->blend_split_c = nullptr; h->mapGc_ptr = nullptr; h->mapGc_M = 0;
     }
     if ((rc = hf::upload(&h->csr_ptr, ptr.data(), ptr.size()))) return rc;
     if ((rc = hf::upload(&h->csr_col, col.data(), col.size()))) return rc;
@@ -1387,7 +1397,7 @@ extern "C" void hf_smpl_destroy(hf_smpl_t* h) {
     if (!h) return;
     cudaFree(h->blend); cudaFree(h->vtemp); cudaFree(h->J0); cudaFree(h->Jd); cudaFree(h->sj);
     cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->Pf16); cudaFree(h->Pf16s); cudaFree(h->vconst); cudaFree(h->pick_f); cudaFree(h->csr_f); cudaFree(h->vflag); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
-    cudaFree(h->csc_ptr); cudaFree(h->csc_row); cudaFree(h->csc_val); cudaFree(h->blend_split);
+    cudaFree(h->csc_ptr); cudaFree(h->csc_row); cudaFree(h->csc_val); cudaFree(h->blend_split); cudaFree(h->fvert); cudaFree(h->blend_split_c);
     delete h;
 }
 
@@ -1616,7 +1626,9 @@ lbs_bwd_vertex_kernel(const float* __restrict__ blend, const float* __restrict__
                       const float* __restrict__ sw, const float* __restrict__ F, const float* __restrict__ A,
                       const int* __restrict__ csc_ptr, const int* __restrict__ csc_row, const float* __restrict__ csc_val,
                       const float* __restrict__ gV, const float* __restrict__ gJ, int M, int V, int Vp, int KB, int KP, int J, int J_out,
-                      int nslots, float* __restrict__ G2, float* __restrict__ part) {
+                      int nslots, const int* __restrict__ vmap, int ncols, float* __restrict__ G2, float* __restrict__ part) {
+    // vmap != NULL: column c of this launch is vertex vmap[c] (or -1 = padding), ncols = padded number of columns (joints-only
+    // backward over the vertices a pick / regressor reads); vmap == NULL: column = vertex, ncols = Vp.
     extern __shared__ __align__(16) float smem[];
     const int J12 = J * 12, NX = (J_out - J) * 3;
     float* Fs = smem;                       // [KP][TS]
@@ -1638,8 +1650,11 @@ lbs_bwd_vertex_kernel(const float* __restrict__ blend, const float* __restrict__
         gXs[idx] = (gJ && m < M) ? gJ[((size_t)m * J_out + J) * 3 + (idx - s * NX)] : 0.f;
     }
     __syncthreads();
-    const int vl = tid & 127, sg = tid >> 7;
-    const int v = blockIdx.x * 128 + vl;          // < Vp (tables are padded)
+    const int vl = tid & 127, sg = tid >> 7, lane = tid & 31;
+    const int col = blockIdx.x * 128 + vl;        // < ncols
+    const int vraw = vmap ? vmap[col] : col;      // vertex (< Vp: tables are padded), -1 for a padding column
+    const bool live = vraw >= 0 && vraw < V;
+    const int v = vraw >= 0 ? vraw : 0;
     float acc[BW_SPT][3];
 #pragma unroll
     for (int s = 0; s < BW_SPT; ++s) acc[s][0] = acc[s][1] = acc[s][2] = 0.f;
@@ -1661,7 +1676,7 @@ lbs_bwd_vertex_kernel(const float* __restrict__ blend, const float* __restrict__
         const int sl = sg * BW_SPT + s, m = m0 + sl;
         const float p[3] = {acc[s][0] + t0, acc[s][1] + t1, acc[s][2] + t2};
         float g[3] = {0.f, 0.f, 0.f};
-        if (m < M && v < V) {
+        if (m < M && live) {
             if (gV) { const float* q = gV + ((size_t)m * V + v) * 3; g[0] = q[0]; g[1] = q[1]; g[2] = q[2]; }
             for (int e = e0; e < e1; ++e) {
                 const float w = csc_val[e];
@@ -1670,31 +1685,51 @@ lbs_bwd_vertex_kernel(const float* __restrict__ blend, const float* __restrict__
             }
         }
         float gp[3] = {0.f, 0.f, 0.f};
-        if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) {
-            for (int slot = 0; slot < nslots; ++slot) {
-                const float w = sw[slot * Vp + v];
-                if (w == 0.f) continue;
-                const int j = sj[slot * Vp + v];
+        const bool any_g = g[0] != 0.f || g[1] != 0.f || g[2] != 0.f;
+        // dL/dA_j += w_vj g (x) [p;1]: the lanes of a warp mostly share their joints, so the warp first sums the contributions of
+        // all lanes with the same joint (butterfly over the 12 entries) and then issues ONE 12-lane shared-memory atomic per
+        // distinct joint, instead of 12 per lane on a handful of addresses
+        for (int slot = 0; slot < nslots; ++slot) {
+            const float w = any_g ? sw[slot * Vp + v] : 0.f;
+            const int j = (w != 0.f) ? sj[slot * Vp + v] : -1;
+            if (j >= 0) {
                 const float* a = As + sl * J12 + j * 12;
-                float* ga = gAs + sl * J12 + j * 12;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float wg = w * g[r];
                     gp[0] = fmaf(a[r * 4 + 0], wg, gp[0]); gp[1] = fmaf(a[r * 4 + 1], wg, gp[1]); gp[2] = fmaf(a[r * 4 + 2], wg, gp[2]);
-                    atomicAdd(ga + r * 4 + 0, wg * p[0]); atomicAdd(ga + r * 4 + 1, wg * p[1]); atomicAdd(ga + r * 4 + 2, wg * p[2]);
-                    atomicAdd(ga + r * 4 + 3, wg);
                 }
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, j >= 0);
+            while (todo) {
+                const int jj = __shfl_sync(0xffffffffu, j, __ffs(todo) - 1);
+                const bool mine = j == jj;
+                float c[12];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float wg = mine ? w * g[r] : 0.f;
+                    c[r * 4 + 0] = wg * p[0]; c[r * 4 + 1] = wg * p[1]; c[r * 4 + 2] = wg * p[2]; c[r * 4 + 3] = wg;
+                }
+#pragma unroll
+                for (int e = 0; e < 12; ++e)
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) c[e] += __shfl_xor_sync(0xffffffffu, c[e], sft);
+                float mineval = 0.f;
+#pragma unroll
+                for (int e = 0; e < 12; ++e) mineval = (lane == e) ? c[e] : mineval;
+                if (lane < 12) atomicAdd(gAs + sl * J12 + jj * 12 + lane, mineval);
+                todo &= ~__ballot_sync(0xffffffffu, mine);
             }
         }
         if (m < M) {
-            float* row = G2 + (size_t)m * 6 * Vp;
+            float* row = G2 + (size_t)m * 6 * ncols;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 uint32_t hb;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(gp[c]));
                 const float hi = __uint_as_float(hb);
-                row[c * Vp + v] = hi;
-                row[3 * Vp + c * Vp + v] = gp[c] - hi;
+                row[c * ncols + col] = hi;
+                row[3 * ncols + c * ncols + col] = gp[c] - hi;
             }
         }
     }
@@ -1706,11 +1741,16 @@ lbs_bwd_vertex_kernel(const float* __restrict__ blend, const float* __restrict__
 }
 
 // blend [KB][3][Vp] fp32 -> [256][hi 3Vp | lo 3Vp] (rows >= KB zero)
-__global__ void lbs_blend_split_kernel(const float* __restrict__ blend, int KB, int Vp3, float* __restrict__ out) {
+// (vmap != NULL: compact columns, out is [256][hi 3*ncols | lo 3*ncols] with column (c, slot) = blend[k][c][vmap[slot]])
+__global__ void lbs_blend_split_kernel(const float* __restrict__ blend, int KB, int Vp, const int* __restrict__ vmap, int ncols,
+                                       float* __restrict__ out) {
+    const int Vp3 = 3 * ncols;
     const size_t total = (size_t)256 * Vp3;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int k = (int)(e / Vp3), c = (int)(e - (size_t)k * Vp3);
-        const float x = k < KB ? blend[(size_t)k * Vp3 + c] : 0.f;
+        const int cc = c / ncols, slot = c - cc * ncols;
+        const int v = vmap ? vmap[slot] : slot;
+        const float x = (k < KB && v >= 0) ? blend[((size_t)k * 3 + cc) * Vp + v] : 0.f;
         uint32_t hb;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
         const float hi = __uint_as_float(hb);
@@ -1818,7 +1858,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
 // Chain backward, BC samples per block.  All per-sample arrays live in shared memory as [element][sample] (conflict-free for the
 // one-thread-per-sample chain walk).  dL/dG of joint i is kept in the 12 floats of gA[i] (rotation part r*4+c, translation r*4+3).
-constexpr int BC = 16, BC_THREADS = 128;
+constexpr int BC = 16, BC_THREADS = 512;
 __global__ void __launch_bounds__(BC_THREADS)
 lbs_bwd_chain_kernel(const float* __restrict__ betas, const float* __restrict__ rotmats, const float* __restrict__ J0, const float* __restrict__ Jd,
                      Parents par, const float* __restrict__ part, int nvt, const float* __restrict__ cpart, int nz, int ldc,
@@ -1837,17 +1877,41 @@ lbs_bwd_chain_kernel(const float* __restrict__ betas, const float* __restrict__ 
     const int tid = threadIdx.x, mb = blockIdx.x * BC, ns = min(BC, M - mb);
     if (tid < HF_MAXJ) pars[tid] = par.p[tid];
     HF_PDL_SYNC();
-    for (int idx = tid; idx < ns * J12; idx += BC_THREADS) {          // sum of the per-vertex-tile partials, fixed order
-        const int s = idx / J12, e = idx - s * J12;
-        float a = 0.f;
-        for (int t = 0; t < nvt; ++t) a += part[((size_t)t * M + mb + s) * J12 + e];
-        gA[e * BC + s] = a;
+    // sums of the per-vertex-tile / per-K-split partials in a fixed order; four independent elements per thread so that the
+    // global loads of one step overlap (a single running sum serialises on the ~600-cycle load latency)
+    for (int idx0 = tid; idx0 < ns * J12; idx0 += 4 * BC_THREADS) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        size_t off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = min(idx0 + u * BC_THREADS, ns * J12 - 1), s = idx / J12;
+            off[u] = (size_t)(mb + s) * J12 + (idx - s * J12);
+        }
+        for (int t = 0; t < nvt; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] += part[(size_t)t * M * J12 + off[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * BC_THREADS;
+            if (idx < ns * J12) { const int s = idx / J12; gA[(idx - s * J12) * BC + s] = a[u]; }
+        }
     }
-    for (int idx = tid; idx < ns * KB; idx += BC_THREADS) {
-        const int s = idx / KB, k = idx - s * KB;
-        float a = 0.f;
-        for (int z = 0; z < nz; ++z) a += cpart[((size_t)z * M + mb + s) * ldc + k];
-        dc[k * BC + s] = a;
+    for (int idx0 = tid; idx0 < ns * KB; idx0 += 4 * BC_THREADS) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        size_t off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = min(idx0 + u * BC_THREADS, ns * KB - 1), s = idx / KB;
+            off[u] = (size_t)(mb + s) * ldc + (idx - s * KB);
+        }
+        for (int z = 0; z < nz; ++z)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] += cpart[(size_t)z * M * ldc + off[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * BC_THREADS;
+            if (idx < ns * KB) { const int s = idx / KB; dc[(idx - s * KB) * BC + s] = a[u]; }
+        }
     }
     for (int idx = tid; idx < ns * J9; idx += BC_THREADS) {
         const int s = idx / J9, e = idx - s * J9;
@@ -1868,61 +1932,98 @@ lbs_bwd_chain_kernel(const float* __restrict__ betas, const float* __restrict__ 
     __syncthreads();
     if (tid < ns) {
         const int s = tid, m = mb + s;
-#define GA(i, e) gA[((i) * 12 + (e)) * BC + s]
-#define GG(i, e) Gs[((i) * 12 + (e)) * BC + s]
-#define RR(i, e) Rs[((i) * 9 + (e)) * BC + s]
-#define JJ(i, c) Js[((i) * 3 + (c)) * BC + s]
-#define GJ(i, c) gJs[((i) * 3 + (c)) * BC + s]
+        // per-joint base pointers: the element offsets below are compile-time immediates of the shared-memory loads / stores
+        auto GAp = [&](int i) { return gA + i * 12 * BC + s; };
+        auto GGp = [&](int i) { return Gs + i * 12 * BC + s; };
+        auto RRp = [&](int i) { return Rs + i * 9 * BC + s; };
+        auto JJp = [&](int i) { return Js + i * 3 * BC + s; };
+        auto GJp = [&](int i) { return gJs + i * 3 * BC + s; };
         // forward chain
-        for (int i = 0; i < J; ++i) {
-            if (i == 0) {
-                for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) GG(0, r * 4 + c) = RR(0, r * 3 + c); GG(0, r * 4 + 3) = JJ(0, r); }
-            } else {
-                const int p = pars[i];
-                const float d0 = JJ(i, 0) - JJ(p, 0), d1 = JJ(i, 1) - JJ(p, 1), d2 = JJ(i, 2) - JJ(p, 2);
-                for (int r = 0; r < 3; ++r) {
-                    const float g0 = GG(p, r * 4), g1 = GG(p, r * 4 + 1), g2 = GG(p, r * 4 + 2);
-                    for (int c = 0; c < 3; ++c) GG(i, r * 4 + c) = g0 * RR(i, c) + g1 * RR(i, 3 + c) + g2 * RR(i, 6 + c);
-                    GG(i, r * 4 + 3) = g0 * d0 + g1 * d1 + g2 * d2 + GG(p, r * 4 + 3);
-                }
+        {
+            float* g0 = GGp(0); const float* r0 = RRp(0); const float* j0 = JJp(0);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g0[(r * 4 + c) * BC] = r0[(r * 3 + c) * BC];
+                g0[(r * 4 + 3) * BC] = j0[r * BC];
+            }
+        }
+        for (int i = 1; i < J; ++i) {
+            const int p = pars[i];
+            float* gi = GGp(i); const float* gpp = GGp(p); const float* ri = RRp(i); const float* ji = JJp(i); const float* jp = JJp(p);
+            float R[9], Gp[12];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) R[e] = ri[e * BC];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) Gp[e] = gpp[e * BC];
+            const float d0 = ji[0] - jp[0], d1 = ji[BC] - jp[BC], d2 = ji[2 * BC] - jp[2 * BC];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gi[(r * 4 + c) * BC] = Gp[r * 4] * R[c] + Gp[r * 4 + 1] * R[3 + c] + Gp[r * 4 + 2] * R[6 + c];
+                gi[(r * 4 + 3) * BC] = Gp[r * 4] * d0 + Gp[r * 4 + 1] * d1 + Gp[r * 4 + 2] * d2 + Gp[r * 4 + 3];
             }
         }
         // dL/dA -> dL/dG (in place): A.R = G.R, A.t = G.t - G.R J;  posed joint i = G_i.t
         for (int i = 0; i < J; ++i) {
-            float gt[3];
-            for (int r = 0; r < 3; ++r) gt[r] = GA(i, r * 4 + 3);
-            for (int c = 0; c < 3; ++c) GJ(i, c) -= GG(i, c) * gt[0] + GG(i, 4 + c) * gt[1] + GG(i, 8 + c) * gt[2];
+            float* ga = GAp(i); const float* gg = GGp(i); const float* ji = JJp(i); float* gj = GJp(i);
+            float gt[3], Jv[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { gt[r] = ga[(r * 4 + 3) * BC]; Jv[r] = ji[r * BC]; }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gj[c * BC] -= gg[c * BC] * gt[0] + gg[(4 + c) * BC] * gt[1] + gg[(8 + c) * BC] * gt[2];
+#pragma unroll
             for (int r = 0; r < 3; ++r) {
-                for (int c = 0; c < 3; ++c) GA(i, r * 4 + c) -= gt[r] * JJ(i, c);
-                if (gJ) GA(i, r * 4 + 3) += gJ[((size_t)m * J_out + i) * 3 + r];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) ga[(r * 4 + c) * BC] -= gt[r] * Jv[c];
+                if (gJ) ga[(r * 4 + 3) * BC] += gJ[((size_t)m * J_out + i) * 3 + r];
             }
         }
         // children before parents
         for (int i = J - 1; i >= 1; --i) {
             const int p = pars[i];
-            const float d[3] = {JJ(i, 0) - JJ(p, 0), JJ(i, 1) - JJ(p, 1), JJ(i, 2) - JJ(p, 2)};
-            float gr[9], gt[3], R[9], gd[3] = {0.f, 0.f, 0.f}, gR[9];
-            for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) gr[r * 3 + c] = GA(i, r * 4 + c); gt[r] = GA(i, r * 4 + 3); }
-            for (int e = 0; e < 9; ++e) { R[e] = RR(i, e); gR[e] = 0.f; }
+            float* ga = GAp(i); float* gap = GAp(p); const float* gpp = GGp(p); float* ri = RRp(i);
+            const float* ji = JJp(i); const float* jp = JJp(p); float* gji = GJp(i); float* gjp = GJp(p);
+            float gr[9], gt[3], R[9], Gp[9], gd[3] = {0.f, 0.f, 0.f}, gR[9], acc[12];
+#pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const float gp0 = GG(p, r * 4), gp1 = GG(p, r * 4 + 1), gp2 = GG(p, r * 4 + 2);
-                // dL/dR_i = G_p.R^T dL/dG_i.R ; dL/d(J_i - J_p) = G_p.R^T dL/dG_i.t
-                for (int c = 0; c < 3; ++c) { gR[c] += gp0 * gr[r * 3 + c]; gR[3 + c] += gp1 * gr[r * 3 + c]; gR[6 + c] += gp2 * gr[r * 3 + c]; }
-                gd[0] += gp0 * gt[r]; gd[1] += gp1 * gt[r]; gd[2] += gp2 * gt[r];
-                // dL/dG_p.R += dL/dG_i.R R_i^T + dL/dG_i.t (x) d ; dL/dG_p.t += dL/dG_i.t
-                for (int c = 0; c < 3; ++c)
-                    GA(p, r * 4 + c) += gr[r * 3] * R[c * 3] + gr[r * 3 + 1] * R[c * 3 + 1] + gr[r * 3 + 2] * R[c * 3 + 2] + gt[r] * d[c];
-                GA(p, r * 4 + 3) += gt[r];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { gr[r * 3 + c] = ga[(r * 4 + c) * BC]; Gp[r * 3 + c] = gpp[(r * 4 + c) * BC]; }
+                gt[r] = ga[(r * 4 + 3) * BC];
             }
-            for (int c = 0; c < 3; ++c) { GJ(i, c) += gd[c]; GJ(p, c) -= gd[c]; }
-            for (int e = 0; e < 9; ++e) RR(i, e) = gR[e];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) { R[e] = ri[e * BC]; gR[e] = 0.f; }
+#pragma unroll
+            for (int e = 0; e < 12; ++e) acc[e] = gap[e * BC];
+            const float d[3] = {ji[0] - jp[0], ji[BC] - jp[BC], ji[2 * BC] - jp[2 * BC]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                // dL/dR_i = G_p.R^T dL/dG_i.R ; dL/d(J_i - J_p) = G_p.R^T dL/dG_i.t
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { gR[c] += Gp[r * 3] * gr[r * 3 + c]; gR[3 + c] += Gp[r * 3 + 1] * gr[r * 3 + c]; gR[6 + c] += Gp[r * 3 + 2] * gr[r * 3 + c]; }
+                gd[0] += Gp[r * 3] * gt[r]; gd[1] += Gp[r * 3 + 1] * gt[r]; gd[2] += Gp[r * 3 + 2] * gt[r];
+                // dL/dG_p.R += dL/dG_i.R R_i^T + dL/dG_i.t (x) d ; dL/dG_p.t += dL/dG_i.t
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    acc[r * 4 + c] += gr[r * 3] * R[c * 3] + gr[r * 3 + 1] * R[c * 3 + 1] + gr[r * 3 + 2] * R[c * 3 + 2] + gt[r] * d[c];
+                acc[r * 4 + 3] += gt[r];
+            }
+#pragma unroll
+            for (int e = 0; e < 12; ++e) gap[e * BC] = acc[e];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { gji[c * BC] += gd[c]; gjp[c * BC] -= gd[c]; }
+#pragma unroll
+            for (int e = 0; e < 9; ++e) ri[e * BC] = gR[e];
         }
-        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) RR(0, r * 3 + c) = GA(0, r * 4 + c); GJ(0, r) += GA(0, r * 4 + 3); }
-#undef GA
-#undef GG
-#undef RR
-#undef JJ
-#undef GJ
+        {
+            const float* ga = GAp(0); float* r0 = RRp(0); float* gj = GJp(0);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) r0[(r * 3 + c) * BC] = ga[(r * 4 + c) * BC];
+                gj[r * BC] += ga[(r * 4 + 3) * BC];
+            }
+        }
     }
     __syncthreads();
     for (int idx = tid; idx < ns * J9; idx += BC_THREADS) {          // + pose-feature term (f = R_i - I for i >= 1)
@@ -1939,13 +2040,15 @@ lbs_bwd_chain_kernel(const float* __restrict__ betas, const float* __restrict__ 
     }
 }
 
-struct BwdLayout { size_t F, A, joints, G2, part, cpart, total; int nvt, nz, ksteps_per; };
-BwdLayout bwd_layout(const hf_smpl* h, int M) {
+struct BwdLayout { size_t F, A, joints, G2, part, cpart, total; int nvt, nz, ksteps_per, ncols; };
+// dense = a gradient w.r.t. all vertices comes in; otherwise only the NFp compact columns are processed
+BwdLayout bwd_layout(const hf_smpl* h, int M, bool dense) {
     BwdLayout L;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const int J_out = h->J + h->nvj + h->nextra;
-    L.nvt = h->Vp / 128;
-    const int ksteps = 3 * h->Vp / 32, mt = hf::div_up(M, 128);
+    L.ncols = dense ? h->Vp : h->NFp;
+    L.nvt = L.ncols / 128;
+    const int ksteps = 3 * L.ncols / 32, mt = hf::div_up(M, 128);
     int nz = std::max(1, std::min(8, 148 / (mt * 2)));
     L.ksteps_per = hf::div_up(ksteps, nz);
     L.nz = hf::div_up(ksteps, L.ksteps_per);
@@ -1953,7 +2056,7 @@ BwdLayout bwd_layout(const hf_smpl* h, int M) {
     L.F = o; o = al(o + (size_t)M * h->KP * 4);
     L.A = o; o = al(o + (size_t)M * h->J * 12 * 4);
     L.joints = o; o = al(o + (size_t)M * J_out * 3 * 4);
-    L.G2 = o; o = al(o + (size_t)M * 6 * h->Vp * 4);
+    L.G2 = o; o = al(o + (size_t)M * 6 * L.ncols * 4);
     L.part = o; o = al(o + (size_t)L.nvt * M * h->J * 12 * 4);
     L.cpart = o; o = al(o + (size_t)L.nz * M * 256 * 4);
     L.total = o + 256;
@@ -1964,36 +2067,43 @@ BwdLayout bwd_layout(const hf_smpl* h, int M) {
 
 extern "C" size_t hf_lbs_backward_workspace_bytes(const hf_smpl_t* h, int M) {
     if (!h || M <= 0) return 0;
-    return bwd_layout(h, M).total;
+    return bwd_layout(h, M, true).total;        // the dense layout is the larger one
 }
 
 extern "C" int hf_lbs_backward(hf_smpl_t* h, const float* betas, const float* rotmats, const float* grad_vertices, const float* grad_joints,
                                float* grad_betas, float* grad_rotmats, void* workspace, size_t workspace_bytes, int M, void* stream_) {
     if (!h || !betas || !rotmats || !grad_betas || !grad_rotmats) return hf::fail(HF_ERR_INVALID, "hf_lbs_backward: null argument");
     if (M <= 0) return HF_OK;
-    const BwdLayout L = bwd_layout(h, M);
+    const bool dense = grad_vertices != nullptr;
+    if (!dense && !grad_joints) return hf::fail(HF_ERR_INVALID, "hf_lbs_backward: both incoming gradients are NULL");
+    const BwdLayout L = bwd_layout(h, M, dense);
     if (!workspace || workspace_bytes < L.total)
         return hf::fail(HF_ERR_INVALID, "hf_lbs_backward: workspace too small (%zu < %zu)", workspace_bytes, L.total);
-    if (3 * h->Vp % 32) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_backward: padded vertex count %d", h->Vp);
+    if (3 * L.ncols % 32) return hf::fail(HF_ERR_UNSUPPORTED, "hf_lbs_backward: padded column count %d", L.ncols);
     cudaStream_t stream = (cudaStream_t)stream_;
     uint8_t* wsb = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float *F = (float*)(wsb + L.F), *A = (float*)(wsb + L.A), *jtmp = (float*)(wsb + L.joints), *G2 = (float*)(wsb + L.G2);
     float *part = (float*)(wsb + L.part), *cpart = (float*)(wsb + L.cpart);
-    const int J_out = hf_smpl_num_joints_out(h), Vp3 = 3 * h->Vp;
+    const int J_out = hf_smpl_num_joints_out(h), C3 = 3 * L.ncols;
     int rc;
-    if (!h->blend_split) {
-        HF_CUDA(cudaMalloc(&h->blend_split, (size_t)256 * 2 * Vp3 * sizeof(float)));
-        lbs_blend_split_kernel<<<1024, 256, 0, stream>>>(h->blend, h->KB, Vp3, h->blend_split);
+    float*& bsplit = dense ? h->blend_split : h->blend_split_c;
+    CUtensorMap& mapBs = dense ? h->mapBs : h->mapBsc;
+    if (!bsplit) {
+        HF_CUDA(cudaMalloc(&bsplit, (size_t)256 * 2 * C3 * sizeof(float)));
+        lbs_blend_split_kernel<<<1024, 256, 0, stream>>>(h->blend, h->KB, h->Vp, dense ? (const int*)nullptr : (const int*)h->fvert, L.ncols, bsplit);
         HF_LAUNCH_CHECK();
-        const uint64_t dims[2] = {(uint64_t)(2 * Vp3), 256}, st[1] = {(uint64_t)(2 * Vp3) * 4};
+        const uint64_t dims[2] = {(uint64_t)(2 * C3), 256}, st[1] = {(uint64_t)(2 * C3) * 4};
         const uint32_t box[2] = {32, (uint32_t)GB_BN};
-        if ((rc = encode_map(&h->mapBs, h->blend_split, 2, dims, st, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
+        if ((rc = encode_map(&mapBs, bsplit, 2, dims, st, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
     }
-    if (h->mapG_ptr != (const void*)G2 || h->mapG_M != M) {
-        const uint64_t dims[2] = {(uint64_t)(2 * Vp3), (uint64_t)M}, st[1] = {(uint64_t)(2 * Vp3) * 4};
+    const void*& mapG_ptr = dense ? h->mapG_ptr : h->mapGc_ptr;
+    int& mapG_M = dense ? h->mapG_M : h->mapGc_M;
+    CUtensorMap& mapG = dense ? h->mapG : h->mapGc;
+    if (mapG_ptr != (const void*)G2 || mapG_M != M) {
+        const uint64_t dims[2] = {(uint64_t)(2 * C3), (uint64_t)M}, st[1] = {(uint64_t)(2 * C3) * 4};
         const uint32_t box[2] = {32, 128};
-        if ((rc = encode_map(&h->mapG, G2, 2, dims, st, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
-        h->mapG_ptr = G2; h->mapG_M = M;
+        if ((rc = encode_map(&mapG, G2, 2, dims, st, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
+        mapG_ptr = G2; mapG_M = M;
     }
     Parents par;
     for (int i = 0; i < HF_MAXJ; ++i) par.p[i] = i < h->J ? h->parents[i] : 0;
@@ -2006,13 +2116,13 @@ extern "C" int hf_lbs_backward(hf_smpl_t* h, const float* betas, const float* ro
         HF_CUDA(cudaFuncSetAttribute(lbs_bwd_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HF_CUDA(hf::launch_pdl(lbs_bwd_vertex_kernel, dim3(L.nvt, hf::div_up(M, BW_TS)), dim3(128 * BW_SG), smem, stream, h->blend, h->vtemp, h->sj, h->sw,
                                (const float*)F, (const float*)A, h->csc_ptr, h->csc_row, h->csc_val, grad_vertices, grad_joints, M, h->V, h->Vp, h->KB, h->KP,
-                               h->J, J_out, h->nslots, G2, part));
+                               h->J, J_out, h->nslots, dense ? (const int*)nullptr : (const int*)h->fvert, L.ncols, G2, part));
         HF_LAUNCH_CHECK();
     }
     {
         const size_t smem = (size_t)GB_STAGES * GB_STAGE_BYTES + 1024;
         HF_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HF_CUDA(hf::launch_pdl(gemm_tf32x3_kernel, dim3(hf::div_up(M, 128), 256 / GB_BN, L.nz), dim3(GB_THREADS), smem, stream, h->mapG, h->mapBs, Vp3, Vp3 / 32,
+        HF_CUDA(hf::launch_pdl(gemm_tf32x3_kernel, dim3(hf::div_up(M, 128), 256 / GB_BN, L.nz), dim3(GB_THREADS), smem, stream, mapG, mapBs, C3, C3 / 32,
                                L.ksteps_per, M, 256, cpart));
         HF_LAUNCH_CHECK();
     }
