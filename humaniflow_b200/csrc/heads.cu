@@ -2,6 +2,7 @@
 // utils/rigid_transform_utils.py:86-100).  M is the image batch (tens of rows): these are latency-bound
 // GEMVs, written for coalesced weight streaming rather than tensor cores.
 #include "common.cuh"
+#include <mutex>
 
 namespace {
 
@@ -204,6 +205,37 @@ extern "C" int hf_heads_finish(const float* heads, const float* init_glob, const
     return HF_OK;
 }
 
+namespace {
+// Partial-sum buffer of the K-sliced layers: one per (device, stream), grown on demand, so that calls on different streams never
+// share it; calls on ONE stream are ordered by the stream.  Growing frees the old buffer (cudaFree synchronises the device) and is
+// not possible during stream capture -- the warm-up replay before a capture sizes it (CudaGraphRunner does three).
+int slice_scratch(cudaStream_t stream, size_t floats, float** out) {
+    struct Slot { int dev; cudaStream_t stream; float* p; size_t n; };
+    static Slot slots[64];
+    static int nslots = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    Slot* sl = nullptr;
+    for (int i = 0; i < nslots; ++i)
+        if (slots[i].dev == dev && slots[i].stream == stream) sl = &slots[i];
+    if (!sl) {
+        if (nslots == 64) return hf::fail(HF_ERR_UNSUPPORTED, "hf_linear: more than 64 (device, stream) pairs in use");
+        sl = &slots[nslots++];
+        *sl = Slot{dev, stream, nullptr, 0};
+    }
+    if (sl->n < floats) {
+        if (sl->p) cudaFree(sl->p);
+        sl->p = nullptr; sl->n = 0;
+        HF_CUDA(cudaMalloc(&sl->p, floats * sizeof(float)));
+        sl->n = floats;
+    }
+    *out = sl->p;
+    return HF_OK;
+}
+}  // namespace
+
 extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const float* b, float* y, int ldy,
                          int M, int K, int O, int act, int accumulate, void* stream) {
     if (!x || !W || !y) return hf::fail(HF_ERR_INVALID, "hf_linear: null argument");
@@ -218,19 +250,10 @@ extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const
         const int ctas = hf::div_up(O, LW * LNB) * hf::div_up(M, 32);
         int nz = 1;
         while (nz < 8 && ctas * nz * 2 <= 148 && (K % (nz * 2 * 128)) == 0) nz *= 2;   // one CTA per SM (255 registers x 256 threads): stay within one wave
-        static float* scratch[16] = {};          // per device, grown on demand (single-stream contract; sized outside graph capture by the warm-up call)
-        static size_t scratch_floats[16] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
         float* part = nullptr;
         if (nz > 1) {
-            const size_t need = (size_t)nz * M * O;
-            if (scratch_floats[dev & 15] < need) {
-                if (scratch[dev & 15]) cudaFree(scratch[dev & 15]);
-                HF_CUDA(cudaMalloc(&scratch[dev & 15], need * sizeof(float)));
-                scratch_floats[dev & 15] = need;
-            }
-            part = scratch[dev & 15];
+            int rc = slice_scratch((cudaStream_t)stream, (size_t)nz * M * O, &part);
+            if (rc) return rc;
         }
         dim3 grid(hf::div_up(O, LW * LNB), hf::div_up(M, 32), nz);
         HF_CUDA(hf::launch_pdl(linear_vec_kernel, grid, dim3(LW * 32), (size_t)smem, (cudaStream_t)stream, x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate,
