@@ -65,6 +65,7 @@ struct hf_smpl {
     // joints-only backward: everything restricted to the NF vertices that a pick / regressor row reads (~4 %), padded to NFp
     int NFp; int* fvert;                         // compact slot -> vertex
     float* blend_split_c; CUtensorMap mapBsc;    // [256][hi 3*NFp | lo 3*NFp]
+    float* blend_c;                              // [KB][3][NFp] fp32: the compact columns of `blend` (coalesced reads in the vertex pass)
     const void* mapGc_ptr; int mapGc_M; CUtensorMap mapGc;
 };
 
@@ -1381,10 +1382,18 @@ extern "C" int hf_smpl_create(hf_smpl_t** out, int V, int nb, int J, const float
         h->blend_split = nullptr; h->mapG_ptr = nullptr; h->mapG_M = 0;
         std::vector<int> fvert;
         for (int v = 0; v < V; ++v) if (!byv[v].empty()) fvert.push_back(v);
+        // ordered by skinning joints so that the lanes of a warp of the backward vertex pass share their joints
+        std::stable_sort(fvert.begin(), fvert.end(), [&](int a, int b) {
+            for (int k = 0; k < nslots; ++k) {
+                const int ja = sw[(size_t)k * Vp + a] != 0.f ? sj[(size_t)k * Vp + a] : 999, jb = sw[(size_t)k * Vp + b] != 0.f ? sj[(size_t)k * Vp + b] : 999;
+                if (ja != jb) return ja < jb;
+            }
+            return false;
+        });
         h->NFp = std::max(128, hf::div_up((int)fvert.size(), 128) * 128);
         fvert.resize((size_t)h->NFp, -1);
         if ((rc = hf::upload(&h->fvert, fvert.data(), fvert.size()))) return rc;
-        h->blend_split_c = nullptr; h->mapGc_ptr = nullptr; h->mapGc_M = 0;
+        h->blend_split_c = nullptr; h->blend_c = nullptr; h->mapGc_ptr = nullptr; h->mapGc_M = 0;
     }
     if ((rc = hf::upload(&h->csr_ptr, ptr.data(), ptr.size()))) return rc;
     if ((rc = hf::upload(&h->csr_col, col.data(), col.size()))) return rc;
@@ -1397,7 +1406,7 @@ extern "C" void hf_smpl_destroy(hf_smpl_t* h) {
     if (!h) return;
     cudaFree(h->blend); cudaFree(h->vtemp); cudaFree(h->J0); cudaFree(h->Jd); cudaFree(h->sj);
     cudaFree(h->sw); cudaFree(h->Pbf); cudaFree(h->Pf16); cudaFree(h->Pf16s); cudaFree(h->vconst); cudaFree(h->pick_f); cudaFree(h->csr_f); cudaFree(h->vflag); cudaFree(h->vj); cudaFree(h->csr_ptr); cudaFree(h->csr_col); cudaFree(h->csr_val);
-    cudaFree(h->csc_ptr); cudaFree(h->csc_row); cudaFree(h->csc_val); cudaFree(h->blend_split); cudaFree(h->fvert); cudaFree(h->blend_split_c);
+    cudaFree(h->csc_ptr); cudaFree(h->csc_row); cudaFree(h->csc_val); cudaFree(h->blend_split); cudaFree(h->fvert); cudaFree(h->blend_split_c); cudaFree(h->blend_c);
     delete h;
 }
 
@@ -1621,7 +1630,7 @@ namespace {
 
 constexpr int BW_SPT = 4, BW_SG = 4, BW_TS = BW_SPT * BW_SG;
 
-__global__ void __launch_bounds__(128 * BW_SG, 1)
+__global__ void __launch_bounds__(128 * BW_SG, 2)
 lbs_bwd_vertex_kernel(const float* __restrict__ blend, const float* __restrict__ vtemp, const int* __restrict__ sj,
                       const float* __restrict__ sw, const float* __restrict__ F, const float* __restrict__ A,
                       const int* __restrict__ csc_ptr, const int* __restrict__ csc_row, const float* __restrict__ csc_val,
@@ -1658,11 +1667,13 @@ lbs_bwd_vertex_kernel(const float* __restrict__ blend, const float* __restrict__
     float acc[BW_SPT][3];
 #pragma unroll
     for (int s = 0; s < BW_SPT; ++s) acc[s][0] = acc[s][1] = acc[s][2] = 0.f;
-    const float* bp = blend + v;
+    // `blend` is [KB][3][bstride]: the full table (column = vertex) or its compact copy (column = compact slot)
+    const float* bp = blend + (vmap ? col : v);
+    const int bstride = vmap ? ncols : Vp;
     const float* fs = Fs + sg * BW_SPT;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < KB; ++k) {
-        const float p0 = __ldg(bp + (size_t)(k * 3 + 0) * Vp), p1 = __ldg(bp + (size_t)(k * 3 + 1) * Vp), p2 = __ldg(bp + (size_t)(k * 3 + 2) * Vp);
+        const float p0 = __ldg(bp + (size_t)(k * 3 + 0) * bstride), p1 = __ldg(bp + (size_t)(k * 3 + 1) * bstride), p2 = __ldg(bp + (size_t)(k * 3 + 2) * bstride);
         const float4 f = *reinterpret_cast<const float4*>(fs + k * BW_TS);
         acc[0][0] = fmaf(p0, f.x, acc[0][0]); acc[0][1] = fmaf(p1, f.x, acc[0][1]); acc[0][2] = fmaf(p2, f.x, acc[0][2]);
         acc[1][0] = fmaf(p0, f.y, acc[1][0]); acc[1][1] = fmaf(p1, f.y, acc[1][1]); acc[1][2] = fmaf(p2, f.y, acc[1][2]);
@@ -1704,20 +1715,27 @@ lbs_bwd_vertex_kernel(const float* __restrict__ blend, const float* __restrict__
             while (todo) {
                 const int jj = __shfl_sync(0xffffffffu, j, __ffs(todo) - 1);
                 const bool mine = j == jj;
-                float c[12];
+                float c[16];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float wg = mine ? w * g[r] : 0.f;
                     c[r * 4 + 0] = wg * p[0]; c[r * 4 + 1] = wg * p[1]; c[r * 4 + 2] = wg * p[2]; c[r * 4 + 3] = wg;
                 }
+                c[12] = c[13] = c[14] = c[15] = 0.f;
+                // transpose-reduction: 8 + 4 + 2 + 1 + 1 shuffles instead of 12 x 5; afterwards lane l holds the warp sum of entry
+                // 8*b4 + 4*b3 + 2*b2 + b1 of its lane index
 #pragma unroll
-                for (int e = 0; e < 12; ++e)
+                for (int sft = 16, n = 8; sft >= 2; sft >>= 1, n >>= 1) {
+                    const bool up = (lane & sft) != 0;
 #pragma unroll
-                    for (int sft = 16; sft > 0; sft >>= 1) c[e] += __shfl_xor_sync(0xffffffffu, c[e], sft);
-                float mineval = 0.f;
-#pragma unroll
-                for (int e = 0; e < 12; ++e) mineval = (lane == e) ? c[e] : mineval;
-                if (lane < 12) atomicAdd(gAs + sl * J12 + jj * 12 + lane, mineval);
+                    for (int i = 0; i < n; ++i) {
+                        const float keep = up ? c[i + n] : c[i], send = up ? c[i] : c[i + n];
+                        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                    }
+                }
+                c[0] += __shfl_xor_sync(0xffffffffu, c[0], 1);
+                const int ent = lane >> 1;       // = 8*b4 + 4*b3 + 2*b2 + b1
+                if ((lane & 1) == 0 && ent < 12) atomicAdd(gAs + sl * J12 + jj * 12 + ent, c[0]);
                 todo &= ~__ballot_sync(0xffffffffu, mine);
             }
         }
@@ -1756,6 +1774,16 @@ __global__ void lbs_blend_split_kernel(const float* __restrict__ blend, int KB, 
         const float hi = __uint_as_float(hb);
         out[(size_t)k * 2 * Vp3 + c] = hi;
         out[(size_t)k * 2 * Vp3 + Vp3 + c] = x - hi;
+    }
+}
+
+__global__ void lbs_blend_compact_kernel(const float* __restrict__ blend, int KB, int Vp, const int* __restrict__ vmap, int ncols,
+                                         float* __restrict__ out) {
+    const size_t total = (size_t)KB * 3 * ncols;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int kc = (int)(e / ncols), slot = (int)(e - (size_t)kc * ncols);
+        const int v = vmap[slot];
+        out[e] = v >= 0 ? blend[(size_t)kc * Vp + v] : 0.f;
     }
 }
 
@@ -2095,6 +2123,11 @@ extern "C" int hf_lbs_backward(hf_smpl_t* h, const float* betas, const float* ro
         const uint64_t dims[2] = {(uint64_t)(2 * C3), 256}, st[1] = {(uint64_t)(2 * C3) * 4};
         const uint32_t box[2] = {32, (uint32_t)GB_BN};
         if ((rc = encode_map(&mapBs, bsplit, 2, dims, st, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
+        if (!dense) {
+            HF_CUDA(cudaMalloc(&h->blend_c, (size_t)h->KB * 3 * L.ncols * sizeof(float)));
+            lbs_blend_compact_kernel<<<256, 256, 0, stream>>>(h->blend, h->KB, h->Vp, h->fvert, L.ncols, h->blend_c);
+            HF_LAUNCH_CHECK();
+        }
     }
     const void*& mapG_ptr = dense ? h->mapG_ptr : h->mapGc_ptr;
     int& mapG_M = dense ? h->mapG_M : h->mapGc_M;
@@ -2114,7 +2147,7 @@ extern "C" int hf_lbs_backward(hf_smpl_t* h, const float* betas, const float* ro
     {
         const size_t smem = ((size_t)h->KP * BW_TS + 2 * (size_t)BW_TS * h->J * 12 + (size_t)BW_TS * (J_out - h->J) * 3) * sizeof(float);
         HF_CUDA(cudaFuncSetAttribute(lbs_bwd_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HF_CUDA(hf::launch_pdl(lbs_bwd_vertex_kernel, dim3(L.nvt, hf::div_up(M, BW_TS)), dim3(128 * BW_SG), smem, stream, h->blend, h->vtemp, h->sj, h->sw,
+        HF_CUDA(hf::launch_pdl(lbs_bwd_vertex_kernel, dim3(L.nvt, hf::div_up(M, BW_TS)), dim3(128 * BW_SG), smem, stream, dense ? (const float*)h->blend : (const float*)h->blend_c, h->vtemp, h->sj, h->sw,
                                (const float*)F, (const float*)A, h->csc_ptr, h->csc_row, h->csc_val, grad_vertices, grad_joints, M, h->V, h->Vp, h->KB, h->KP,
                                h->J, J_out, h->nslots, dense ? (const int*)nullptr : (const int*)h->fvert, L.ncols, G2, part));
         HF_LAUNCH_CHECK();
