@@ -2,7 +2,6 @@
 // utils/rigid_transform_utils.py:86-100).  M is the image batch (tens of rows): these are latency-bound
 // GEMVs, written for coalesced weight streaming rather than tensor cores.
 #include "common.cuh"
-#include <mutex>
 
 namespace {
 
@@ -206,38 +205,31 @@ extern "C" int hf_heads_finish(const float* heads, const float* init_glob, const
 }
 
 namespace {
-// Partial-sum buffer of the K-sliced layers: one per (device, stream), grown on demand, so that calls on different streams never
-// share it; calls on ONE stream are ordered by the stream.  Growing frees the old buffer (cudaFree synchronises the device) and is
-// not possible during stream capture -- the warm-up replay before a capture sizes it (CudaGraphRunner does three).
-int slice_scratch(cudaStream_t stream, size_t floats, float** out) {
-    struct Slot { int dev; cudaStream_t stream; float* p; size_t n; };
-    static Slot slots[64];
-    static int nslots = 0;
-    static std::mutex mu;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(mu);
-    Slot* sl = nullptr;
-    for (int i = 0; i < nslots; ++i)
-        if (slots[i].dev == dev && slots[i].stream == stream) sl = &slots[i];
-    if (!sl) {
-        if (nslots == 64) return hf::fail(HF_ERR_UNSUPPORTED, "hf_linear: more than 64 (device, stream) pairs in use");
-        sl = &slots[nslots++];
-        *sl = Slot{dev, stream, nullptr, 0};
-    }
-    if (sl->n < floats) {
-        if (sl->p) cudaFree(sl->p);
-        sl->p = nullptr; sl->n = 0;
-        HF_CUDA(cudaMalloc(&sl->p, floats * sizeof(float)));
-        sl->n = floats;
-    }
-    *out = sl->p;
-    return HF_OK;
+// K-slices of a layer: up to one CTA per SM (255 registers x 256 threads: one CTA per SM, stay within one wave), slices a multiple
+// of 128 floats
+int linear_slices(int M, int K, int O) {
+    const bool vec4 = (K % 4 == 0) && (K >= 64);
+    if (!vec4) return 1;
+    const int ctas = hf::div_up(O, LW * LNB) * hf::div_up(M, 32);
+    int nz = 1;
+    while (nz < 8 && ctas * nz * 2 <= 148 && (K % (nz * 2 * 128)) == 0) nz *= 2;
+    return nz;
 }
 }  // namespace
 
+extern "C" size_t hf_linear_workspace_bytes(int M, int K, int O) {
+    if (M <= 0 || K <= 0 || O <= 0) return 0;
+    const int nz = linear_slices(M, K, O);
+    return nz > 1 ? (size_t)nz * M * O * sizeof(float) : 0;
+}
+
 extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const float* b, float* y, int ldy,
                          int M, int K, int O, int act, int accumulate, void* stream) {
+    return hf_linear_ws(x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate, nullptr, 0, stream);
+}
+
+extern "C" int hf_linear_ws(const float* x, int ldx, const float* W, int ldw, const float* b, float* y, int ldy,
+                            int M, int K, int O, int act, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
     if (!x || !W || !y) return hf::fail(HF_ERR_INVALID, "hf_linear: null argument");
     if (M <= 0 || O <= 0) return HF_OK;
     if (K < 0 || ldx < K || ldw < K || ldy < O) return hf::fail(HF_ERR_INVALID, "hf_linear: bad strides");
@@ -246,14 +238,14 @@ extern "C" int hf_linear(const float* x, int ldx, const float* W, int ldw, const
         const int smem = 2 * 32 * KC * (int)sizeof(float);
         // per device / context attribute: set on every call (cheap), not cached in a process-wide static
         HF_CUDA(cudaFuncSetAttribute(linear_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        // K-slices: up to one CTA per SM, slices a multiple of 128 floats
-        const int ctas = hf::div_up(O, LW * LNB) * hf::div_up(M, 32);
-        int nz = 1;
-        while (nz < 8 && ctas * nz * 2 <= 148 && (K % (nz * 2 * 128)) == 0) nz *= 2;   // one CTA per SM (255 registers x 256 threads): stay within one wave
+        // K-sliced across CTAs when the caller provides room for the partial sums (hf_linear_workspace_bytes); otherwise one CTA
+        // per output tile walks the whole K
+        int nz = workspace ? linear_slices(M, K, O) : 1;
         float* part = nullptr;
         if (nz > 1) {
-            int rc = slice_scratch((cudaStream_t)stream, (size_t)nz * M * O, &part);
-            if (rc) return rc;
+            if (workspace_bytes < (size_t)nz * M * O * sizeof(float) || ((uintptr_t)workspace & 15))
+                return hf::fail(HF_ERR_INVALID, "hf_linear_ws: workspace too small or unaligned (%zu < %zu)", workspace_bytes, (size_t)nz * M * O * sizeof(float));
+            part = static_cast<float*>(workspace);
         }
         dim3 grid(hf::div_up(O, LW * LNB), hf::div_up(M, 32), nz);
         HF_CUDA(hf::launch_pdl(linear_vec_kernel, grid, dim3(LW * 32), (size_t)smem, (cudaStream_t)stream, x, ldx, W, ldw, b, y, ldy, M, K, O, act, accumulate,

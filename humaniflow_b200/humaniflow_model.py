@@ -220,8 +220,14 @@ class HumaniflowModel(nn.Module):
     def _linear(self, x, W, b, out, K, O, act=0, accumulate=0, w_offset=0):
         lib = _lib.load()
         wp = ctypes.c_void_p(W.data_ptr() + 4 * w_offset)
-        _lib.check(lib.hf_linear(_lib.ptr(x), x.stride(0), wp, W.stride(0), _lib.ptr(b), _lib.ptr(out), out.stride(0),
-                                 x.shape[0], K, O, act, accumulate, _lib.stream()))
+        M = x.shape[0]
+        nbytes = lib.hf_linear_workspace_bytes(M, K, O)         # partial sums of the K-sliced layers (one buffer per model: single stream)
+        ws = getattr(self, '_lin_ws', None)
+        if nbytes and (ws is None or ws.numel() < nbytes or ws.device != x.device):
+            ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+            self._lin_ws = ws
+        _lib.check(lib.hf_linear_ws(_lib.ptr(x), x.stride(0), wp, W.stride(0), _lib.ptr(b), _lib.ptr(out), out.stride(0),
+                                    M, K, O, act, accumulate, _lib.ptr(ws) if nbytes else None, ws.numel() if nbytes else 0, _lib.stream()))
 
     def _img_base(self, input_feats, glob_R, cam):
         """W[:, feats|glob|cam] . [feats, vec(glob_R), cam] + b : the beta-independent part of

@@ -223,6 +223,12 @@ int hf_flow_algebra_log_prob(const hf_flow_t* h, const float* ctx, int ctx_row_s
  * b may be NULL.  If accumulate != 0, y += instead of = (activation applied to the sum). */
 int hf_linear(const float* x, int ldx, const float* W, int ldw, const float* b, float* y, int ldy,
               int M, int K, int O, int act, int accumulate, void* stream);
+/* Same, with room for partial sums: a layer with few output tiles (M <= 32 rows x O outputs) is then split along K across CTAs
+ * (slices summed in index order by a second small launch: deterministic).  workspace: hf_linear_workspace_bytes(M, K, O) bytes,
+ * 16-byte aligned, private to the stream the call is issued on; NULL = hf_linear. */
+size_t hf_linear_workspace_bytes(int M, int K, int O);
+int hf_linear_ws(const float* x, int ldx, const float* W, int ldw, const float* b, float* y, int ldy,
+                 int M, int K, int O, int act, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Head post-processing (models/humaniflow_model.py:237-258).  heads (B, 2*nb+9) = one Linear over the
  * concatenated [fc_shape | fc_glob | fc_cam] rows.  cam (B,3) = cam head + init_cam; glob6 (B,6) = glob head +

@@ -186,10 +186,12 @@ def test_state_dict_roundtrip_and_repack():
 
 
 @pytest.mark.parametrize('M,K,O,act,acc', [(32, 2048, 512, 1, 0), (32, 2048, 256, 0, 0), (5, 512, 29, 0, 0), (33, 128, 7, 2, 1),
-                                            (1, 64, 4, 0, 0), (32, 9, 256, 0, 1)])
+                                            (1, 64, 4, 0, 0), (32, 9, 256, 0, 1), (32, 2048, 1024, 1, 0), (32, 1024, 29, 0, 1),
+                                            (70, 1024, 40, 2, 0)])
 def test_linear_layers(M, K, O, act, acc):
-    """hf_linear (humaniflow_model.py:232-258 fc1 / heads / image-level features) against torch fp32 on the CPU:
-    ragged row tiles, neuron counts that are not a multiple of the CTA tile, ELU / ReLU, accumulate-into-output."""
+    """hf_linear / hf_linear_ws (humaniflow_model.py:232-258 fc1 / heads / image-level features) against torch fp32 on the CPU:
+    ragged row tiles, neuron counts that are not a multiple of the CTA tile, ELU / ReLU, accumulate-into-output; with a
+    workspace the layer is K-sliced across CTAs (same tolerance, and the same result on every call)."""
     import torch.nn.functional as F
     from humaniflow_b200 import _lib
     lib = _lib.load()
@@ -204,3 +206,14 @@ def test_linear_layers(M, K, O, act, acc):
     _lib.check(lib.hf_linear(_lib.ptr(xd), K, _lib.ptr(Wd), K, _lib.ptr(bd), _lib.ptr(yd), O, M, K, O, act, acc, _lib.stream()))
     torch.cuda.synchronize()
     assert (yd.cpu().double() - ref).abs().max().item() <= 2e-5
+    nbytes = lib.hf_linear_workspace_bytes(M, K, O)
+    ws = torch.empty(max(nbytes, 16), device='cuda', dtype=torch.uint8)
+    outs = []
+    for _ in range(2):
+        y2 = y0.clone().cuda()
+        _lib.check(lib.hf_linear_ws(_lib.ptr(xd), K, _lib.ptr(Wd), K, _lib.ptr(bd), _lib.ptr(y2), O, M, K, O, act, acc,
+                                    _lib.ptr(ws), nbytes, _lib.stream()))
+        torch.cuda.synchronize()
+        outs.append(y2.cpu())
+    assert (outs[0].double() - ref).abs().max().item() <= 2e-5
+    assert torch.equal(outs[0], outs[1])
