@@ -50,6 +50,8 @@ SIGNATURES = {
     'hf_smpl_dims': (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 5),
     'hf_vertex_variance': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'hf_pointset_errors': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'hf_pointset_errors_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'hf_pointset_errors_ws': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'hf_sample_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'hf_samples_reduce': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'hf_proxy_rep': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_float, c_int, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -252,6 +252,164 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
 #undef LDP
 }
 
+// ---- the same computation as three launches, for many point sets --------------------------------------------------------
+// In the fused kernel 255 threads of every block wait while thread 0 solves the 3x3 problem (ncu: ~40 % of the warp samples sit at
+// that barrier, and shared-memory staging limits an SM to two sets in flight).  With thousands of sets the passes run as their own
+// memory-bound kernels (four blocks per SM, nothing staged) around a solve kernel with one THREAD per set:
+//   pse_pass_kernel<1>  moments about the first point of each set -> mom[m][18] (fp64)
+//   pse_solve_kernel    SC / PA transforms -> xfg[m][20] = [s, mu1 (3), mu2 (3), scale*R (9), t (3), plain error]
+//   pse_pass_kernel<2>  the two aligned errors; walks the sets in REVERSE so that it starts on the ones pass 1 left in L2
+struct Pts4 { float x[12]; };
+__device__ __forceinline__ Pts4 load4(const float* q) {      // 4 points = 48 contiguous bytes, 8-byte aligned
+    const float2* g = reinterpret_cast<const float2*>(q);
+    Pts4 r;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const float2 u = __ldg(g + i); r.x[2 * i] = u.x; r.x[2 * i + 1] = u.y; }
+    return r;
+}
+
+__device__ void pse_solve(const double* v, int P, const float* p0, const float* t0, float* xf /* [20] */) {
+    const double n = (double)P;
+    double mu1[3], mu2[3];
+    for (int i = 0; i < 3; ++i) { mu1[i] = v[i] / n; mu2[i] = v[3 + i] / n; }
+    const double var1 = v[6] - n * (mu1[0] * mu1[0] + mu1[1] * mu1[1] + mu1[2] * mu1[2]);
+    const double var2 = v[7] - n * (mu2[0] * mu2[0] + mu2[1] * mu2[1] + mu2[2] * mu2[2]);
+    const double o1[3] = {(double)p0[0], (double)p0[1], (double)p0[2]}, o2[3] = {(double)t0[0], (double)t0[1], (double)t0[2]};
+    xf[0] = (float)sqrt(var2 / var1);
+    for (int i = 0; i < 3; ++i) { xf[1 + i] = (float)(mu1[i] + o1[i]); xf[4 + i] = (float)(mu2[i] + o2[i]); }
+    double K[3][3], KtK[3][3], V[3][3], w[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) K[i][j] = v[8 + i * 3 + j] - n * mu1[i] * mu2[j];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) KtK[i][j] = K[0][i] * K[0][j] + K[1][i] * K[1][j] + K[2][i] * K[2][j];
+    eig_sym3(KtK, V, w);
+    int order[3] = {0, 1, 2};
+    for (int a = 0; a < 2; ++a)
+        for (int c = a + 1; c < 3; ++c)
+            if (w[order[c]] > w[order[a]]) { const int tmp = order[a]; order[a] = order[c]; order[c] = tmp; }
+    const double detK = K[0][0] * (K[1][1] * K[2][2] - K[1][2] * K[2][1]) - K[0][1] * (K[1][0] * K[2][2] - K[1][2] * K[2][0]) +
+                        K[0][2] * (K[1][0] * K[2][1] - K[1][1] * K[2][0]);
+    const double d = detK < 0.0 ? -1.0 : 1.0;
+    double sv[3], g[3];
+    for (int a = 0; a < 3; ++a) sv[a] = sqrt(fmax(w[order[a]], 0.0));
+    const double tiny = 1e-30;
+    g[0] = 1.0 / fmax(sv[0], tiny); g[1] = 1.0 / fmax(sv[1], tiny); g[2] = d / fmax(sv[2], tiny);
+    double Mm[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double sacc = 0.0;
+            for (int a = 0; a < 3; ++a) sacc += V[i][order[a]] * g[a] * V[j][order[a]];
+            Mm[i][j] = sacc;
+        }
+    double R[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[i][j] = Mm[i][0] * K[j][0] + Mm[i][1] * K[j][1] + Mm[i][2] * K[j][2];
+    const double scale = (sv[0] + sv[1] + d * sv[2]) / var1;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) xf[7 + i * 3 + j] = (float)(scale * R[i][j]);
+    for (int i = 0; i < 3; ++i)
+        xf[16 + i] = (float)((mu2[i] + o2[i]) - scale * (R[i][0] * (mu1[0] + o1[0]) + R[i][1] * (mu1[1] + o1[1]) + R[i][2] * (mu1[2] + o1[2])));
+    xf[19] = (float)(v[17] / n);
+}
+
+__global__ void __launch_bounds__(128)
+pse_solve_kernel(const float* __restrict__ pred, const float* __restrict__ target, const double* __restrict__ mom, int N, int P, int M,
+                 float* __restrict__ xfg) {
+    HF_PDL_SYNC();
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double v[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) v[i] = mom[(size_t)m * 18 + i];
+    const float* p = pred + (size_t)m * P * 3;
+    const float* t = target + (size_t)(m / N) * P * 3;
+    const float p0[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)}, t0[3] = {__ldg(t), __ldg(t + 1), __ldg(t + 2)};
+    float xf[20];
+    pse_solve(v, P, p0, t0, xf);
+#pragma unroll
+    for (int i = 0; i < 20; ++i) xfg[(size_t)m * 20 + i] = xf[i];
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(ME_THREADS, 4)
+pse_pass_kernel(const float* __restrict__ pred, const float* __restrict__ target, int N, int P, double* __restrict__ mom,
+                const float* __restrict__ xfg, float* __restrict__ out) {
+    HF_PDL_SYNC();
+    __shared__ double scratch[(ME_THREADS / 32 + 1) * 18];
+    const int m = PASS == 1 ? blockIdx.x : gridDim.x - 1 - blockIdx.x, b = m / N;
+    const float* p = pred + (size_t)m * P * 3;
+    const float* t = target + (size_t)b * P * 3;
+    const int ng = P >> 2;
+    if (PASS == 1) {
+        const float p0x = __ldg(p), p0y = __ldg(p + 1), p0z = __ldg(p + 2), t0x = __ldg(t), t0y = __ldg(t + 1), t0z = __ldg(t + 2);
+        float sp[3] = {0.f, 0.f, 0.f}, st[3] = {0.f, 0.f, 0.f}, spp = 0.f, stt = 0.f, k[9], e = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) k[i] = 0.f;
+        auto acc1 = [&](float qx, float qy, float qz, float ux, float uy, float uz) {
+            const float dx = qx - ux, dy = qy - uy, dz = qz - uz;
+            const float px = qx - p0x, py = qy - p0y, pz = qz - p0z;
+            const float tx = ux - t0x, ty = uy - t0y, tz = uz - t0z;
+            sp[0] += px; sp[1] += py; sp[2] += pz;
+            st[0] += tx; st[1] += ty; st[2] += tz;
+            spp += px * px + py * py + pz * pz;
+            stt += tx * tx + ty * ty + tz * tz;
+            k[0] += px * tx; k[1] += px * ty; k[2] += px * tz;
+            k[3] += py * tx; k[4] += py * ty; k[5] += py * tz;
+            k[6] += pz * tx; k[7] += pz * ty; k[8] += pz * tz;
+            e += sqrtf(dx * dx + dy * dy + dz * dz);
+        };
+#pragma unroll 2
+        for (int gq = threadIdx.x; gq < ng; gq += ME_THREADS) {
+            const Pts4 a = load4(p + gq * 12), u = load4(t + gq * 12);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc1(a.x[3 * q], a.x[3 * q + 1], a.x[3 * q + 2], u.x[3 * q], u.x[3 * q + 1], u.x[3 * q + 2]);
+        }
+        for (int i = (ng << 2) + threadIdx.x; i < P; i += ME_THREADS)
+            acc1(__ldg(p + i * 3), __ldg(p + i * 3 + 1), __ldg(p + i * 3 + 2), __ldg(t + i * 3), __ldg(t + i * 3 + 1), __ldg(t + i * 3 + 2));
+        double v[18];
+        for (int i = 0; i < 3; ++i) { v[i] = sp[i]; v[3 + i] = st[i]; }
+        v[6] = spp; v[7] = stt;
+        for (int i = 0; i < 9; ++i) v[8 + i] = k[i];
+        v[17] = e;
+        block_sum<18>(v, scratch);
+        if (threadIdx.x < 18) {
+            double mine = 0.0;
+#pragma unroll
+            for (int i = 0; i < 18; ++i) mine = (threadIdx.x == i) ? v[i] : mine;
+            mom[(size_t)m * 18 + threadIdx.x] = mine;
+        }
+    } else {
+        const float* xf = xfg + (size_t)m * 20;
+        const float s_sc = __ldg(xf), m1x = __ldg(xf + 1), m1y = __ldg(xf + 2), m1z = __ldg(xf + 3), m2x = __ldg(xf + 4), m2y = __ldg(xf + 5), m2z = __ldg(xf + 6);
+        const float r0 = __ldg(xf + 7), r1 = __ldg(xf + 8), r2 = __ldg(xf + 9), r3 = __ldg(xf + 10), r4 = __ldg(xf + 11), r5 = __ldg(xf + 12),
+                    r6 = __ldg(xf + 13), r7 = __ldg(xf + 14), r8 = __ldg(xf + 15), t0 = __ldg(xf + 16), t1 = __ldg(xf + 17), t2 = __ldg(xf + 18);
+        float esc = 0.f, epa = 0.f;
+        auto acc2 = [&](float px, float py, float pz, float tx, float ty, float tz) {
+            float dx = (px - m1x) * s_sc + m2x - tx, dy = (py - m1y) * s_sc + m2y - ty, dz = (pz - m1z) * s_sc + m2z - tz;
+            esc += sqrtf(dx * dx + dy * dy + dz * dz);
+            dx = r0 * px + r1 * py + r2 * pz + t0 - tx;
+            dy = r3 * px + r4 * py + r5 * pz + t1 - ty;
+            dz = r6 * px + r7 * py + r8 * pz + t2 - tz;
+            epa += sqrtf(dx * dx + dy * dy + dz * dz);
+        };
+#pragma unroll 2
+        for (int gq = threadIdx.x; gq < ng; gq += ME_THREADS) {
+            const Pts4 a = load4(p + gq * 12), u = load4(t + gq * 12);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc2(a.x[3 * q], a.x[3 * q + 1], a.x[3 * q + 2], u.x[3 * q], u.x[3 * q + 1], u.x[3 * q + 2]);
+        }
+        for (int i = (ng << 2) + threadIdx.x; i < P; i += ME_THREADS)
+            acc2(__ldg(p + i * 3), __ldg(p + i * 3 + 1), __ldg(p + i * 3 + 2), __ldg(t + i * 3), __ldg(t + i * 3 + 1), __ldg(t + i * 3 + 2));
+        double e2[2] = {esc, epa};
+        block_sum<2>(e2, scratch);
+        if (threadIdx.x == 0) {
+            out[(size_t)m * 3 + 0] = __ldg(xf + 19);
+            out[(size_t)m * 3 + 1] = (float)(e2[0] / (double)P);
+            out[(size_t)m * 3 + 2] = (float)(e2[1] / (double)P);
+        }
+    }
+}
+
 // Per-image sample statistics of point sets (B, N, P, D), D in {2, 3} (metrics/eval_metrics_tracker.py:330-433):
 //   out[b][0] = mean over (samples, points) of w_p ||x_{n,p} - mean_n x_{.,p}||            sample diversity (:397-433)
 //   out[b][1] = sum over (samples, points) of w_p ||x_{n,p} - t_p|| / (N * sum_p w_p)       samples-L2E (:339-374); 0 without target
@@ -357,11 +515,36 @@ extern "C" int hf_sample_stats(const float* points, const float* target, const f
     return HF_OK;
 }
 
+extern "C" size_t hf_pointset_errors_workspace_bytes(int B, int N) {
+    if (B <= 0 || N <= 0) return 0;
+    return (size_t)B * N * (18 * sizeof(double) + 20 * sizeof(float));
+}
+
 extern "C" int hf_pointset_errors(const float* pred, const float* target, int B, int N, int P, float* out, void* stream) {
+    return hf_pointset_errors_ws(pred, target, B, N, P, out, nullptr, 0, stream);
+}
+
+extern "C" int hf_pointset_errors_ws(const float* pred, const float* target, int B, int N, int P, float* out, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
     if (!pred || !target || !out) return hf::fail(HF_ERR_INVALID, "hf_pointset_errors: null argument");
     if (B <= 0 || N <= 0) return HF_OK;
     if (P < 3) return hf::fail(HF_ERR_INVALID, "hf_pointset_errors: at least 3 points per set are needed (got %d)", P);
     const size_t stage_bytes = (size_t)P * 3 * sizeof(float);
+    const int M = B * N;
+    if (workspace && M >= 512 && ((uintptr_t)pred & 7) == 0 && ((uintptr_t)target & 7) == 0 && (P * 3) % 2 == 0) {
+        // many sets: moments / solve / errors as three launches (see pse_pass_kernel)
+        if (workspace_bytes < hf_pointset_errors_workspace_bytes(B, N) || ((uintptr_t)workspace & 7))
+            return hf::fail(HF_ERR_INVALID, "hf_pointset_errors_ws: workspace too small or unaligned (%zu < %zu)", workspace_bytes, hf_pointset_errors_workspace_bytes(B, N));
+        double* mom = static_cast<double*>(workspace);
+        float* xfg = reinterpret_cast<float*>(mom + (size_t)M * 18);
+        HF_CUDA(hf::launch_pdl(pse_pass_kernel<1>, dim3(M), dim3(ME_THREADS), 0, (cudaStream_t)stream, pred, target, N, P, mom, (const float*)nullptr, (float*)nullptr));
+        HF_LAUNCH_CHECK();
+        HF_CUDA(hf::launch_pdl(pse_solve_kernel, dim3(hf::div_up(M, 128)), dim3(128), 0, (cudaStream_t)stream, pred, target, (const double*)mom, N, P, M, xfg));
+        HF_LAUNCH_CHECK();
+        HF_CUDA(hf::launch_pdl(pse_pass_kernel<2>, dim3(M), dim3(ME_THREADS), 0, (cudaStream_t)stream, pred, target, N, P, (double*)nullptr, (const float*)xfg, out));
+        HF_LAUNCH_CHECK();
+        return HF_OK;
+    }
     if (stage_bytes <= 100 * 1024 && ((uintptr_t)pred & 7) == 0 && ((uintptr_t)target & 7) == 0 && (P * 3 * sizeof(float)) % 8 == 0) {    // two sets per SM
         HF_CUDA(cudaFuncSetAttribute(pointset_errors_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         HF_CUDA(hf::launch_pdl(pointset_errors_kernel<true>, dim3(B * N), dim3(ME_THREADS), stage_bytes, (cudaStream_t)stream, pred, target, N, P, out));

@@ -10,6 +10,12 @@ import torch
 from . import _lib
 
 
+def _pse(lib, p, t, B, N, P, out):
+    nbytes = lib.hf_pointset_errors_workspace_bytes(B, N)
+    ws = torch.empty(nbytes, device=p.device, dtype=torch.uint8)      # torch's caching allocator: a pointer bump, capturable
+    _lib.check(lib.hf_pointset_errors_ws(_lib.ptr(p), _lib.ptr(t), B, N, P, _lib.ptr(out), _lib.ptr(ws), nbytes, _lib.stream()))
+
+
 def pointset_errors(pred, target):
     """pred (B,N,P,3) or (B,P,3) CUDA fp32; target (B,P,3) -> dict of (B,N) (or (B,)) tensors 'plain', 'sc', 'pa':
     mean over the P points of ||pred - target|| without alignment, after scale-and-translation correction and after
@@ -27,7 +33,7 @@ def pointset_errors(pred, target):
         raise ValueError('target shape %s does not match predictions %s' % (tuple(t.shape), tuple(p.shape)))
     out = torch.empty(B, N, 3, device=p.device, dtype=torch.float32)
     with torch.cuda.device(p.device):
-        _lib.check(_lib.load().hf_pointset_errors(_lib.ptr(p), _lib.ptr(t), B, N, P, _lib.ptr(out), _lib.stream()))
+        _pse(_lib.load(), p, t, B, N, P, out)
     res = {'plain': out[..., 0], 'sc': out[..., 1], 'pa': out[..., 2]}
     return {k: v[:, 0] for k, v in res.items()} if squeeze else res
 
@@ -48,7 +54,7 @@ def pointset_error_rows(pred, target):
     rows = torch.empty(B, 6, device=p.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(p.device):
-        _lib.check(lib.hf_pointset_errors(_lib.ptr(p), _lib.ptr(t), B, N, P, _lib.ptr(err), _lib.stream()))
+        _pse(lib, p, t, B, N, P, err)
         _lib.check(lib.hf_samples_reduce(_lib.ptr(err), B, N, 3, _lib.ptr(rows), _lib.stream()))
     return rows
 

@@ -117,6 +117,12 @@ int hf_project_joints2d(const float* joints, const float* cam_wp, const int* joi
  * (PVE, PVE-SC, PVE-PA, PVE-T(-SC), MPJPE(-SC/-PA) and their samples_min forms are sums / minima of these values).
  * ---------------------------------------------------------------------------------------------- */
 int hf_pointset_errors(const float* pred, const float* target, int B, int N, int P, float* out, void* stream);
+/* Same with a scratch buffer (hf_pointset_errors_workspace_bytes(B, N) bytes, 8-byte aligned): with >= 512 point sets the two
+ * passes over the points run as their own memory-bound launches around a one-thread-per-set solve, instead of one block per
+ * set in which 255 threads wait for the 3x3 solve.  Same values (same per-thread arithmetic; block sums in the same order). */
+size_t hf_pointset_errors_workspace_bytes(int B, int N);
+int hf_pointset_errors_ws(const float* pred, const float* target, int B, int N, int P, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* Per-image reduction over the samples of per-sample error values: err (B,N,K) -> out (B,2K) = [min over n (K) | mean over n (K)].
  * The "samples_min" metrics of metrics/eval_metrics_tracker.py:201-280 are the minimum over the samples of the per-sample mean

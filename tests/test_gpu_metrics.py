@@ -94,3 +94,30 @@ def test_pointset_error_rows_is_min_and_mean_of_the_per_sample_errors():
         for k, name in enumerate(('plain', 'sc', 'pa')):
             assert torch.equal(rows[:, k], err[name].min(dim=1).values)
             assert torch.allclose(rows[:, 3 + k], err[name].double().mean(dim=1).float(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('B,N,P', [(6, 100, 6890), (40, 16, 17), (3, 171, 301)])
+def test_three_launch_form_equals_the_fused_kernel(B, N, P):
+    """>= 512 point sets with a workspace run as moments / solve / errors launches (hf_pointset_errors_ws); the per-thread
+    arithmetic and the block-sum order are those of the fused kernel, so meshes (staged fused path) agree bit for bit and the other
+    shapes to fp32 rounding; both agree with the oracle."""
+    from humaniflow_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B + N + P)
+    target = torch.randn(B, P, 3, generator=g) * 0.3 + torch.tensor([0.1, -0.2, 2.5])
+    pred = target[:, None] * (1 + 0.1 * torch.randn(B, N, 1, 1, generator=g)) + 0.05 * torch.randn(B, N, P, 3, generator=g)
+    pd, td = pred.cuda().contiguous(), target.cuda().contiguous()
+    fused = torch.empty(B, N, 3, device='cuda')
+    split = torch.empty(B, N, 3, device='cuda')
+    _lib.check(lib.hf_pointset_errors(_lib.ptr(pd), _lib.ptr(td), B, N, P, _lib.ptr(fused), _lib.stream()))
+    nbytes = lib.hf_pointset_errors_workspace_bytes(B, N)
+    ws = torch.empty(nbytes, device='cuda', dtype=torch.uint8)
+    _lib.check(lib.hf_pointset_errors_ws(_lib.ptr(pd), _lib.ptr(td), B, N, P, _lib.ptr(split), _lib.ptr(ws), nbytes, _lib.stream()))
+    torch.cuda.synchronize()
+    if P == 6890:
+        assert torch.equal(fused, split)
+    assert torch.allclose(fused, split, rtol=2e-6, atol=1e-7)
+    rows = [0, B - 1]
+    ref = omet.pointset_errors(pred[rows].numpy(), target[rows].numpy())
+    for i, k in enumerate(('plain', 'sc', 'pa')):
+        assert _close(split[rows, :, i].cpu().numpy(), ref[k]), k
