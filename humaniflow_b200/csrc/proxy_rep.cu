@@ -36,9 +36,9 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
     __shared__ float s_gx[MH][MW], s_gy[MH][MW];
     __shared__ float s_mag[MH][MW];
     __shared__ float s_edge[PT_H][PT_W];
-    // heatmaps are separable: exp(-(a*a)/2 - (c*c)/2) with a = (row - v)/std, c = (col - u)/std.  The two halves are computed once
-    // per (joint, tile row) and (joint, tile column) -- same operations in the same order as the per-pixel formula, so the
-    // values are bit-identical -- and a pixel costs one subtraction and one expf per joint instead of two divisions as well.
+    // heatmaps are separable: exp(-(a*a)/2 - (c*c)/2) = exp(-(a*a)/2) exp(-(c*c)/2) with a = (row - v)/std, c = (col - u)/std.  The
+    // two factors are computed once per (joint, tile row) and (joint, tile column); a pixel then costs ONE multiplication per joint
+    // instead of two divisions and an expf (the product differs from the single exponential by <= 2 ulp: tolerance 2e-6).
     __shared__ float s_hrow[32][PT_H], s_hcol[32][PT_W], s_vis[32];
     const int b = blockIdx.z, x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
     const int tid = threadIdx.x;
@@ -46,10 +46,10 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
         const int j = i / (PT_H + PT_W), k = i - j * (PT_H + PT_W);
         if (k < PT_H) {
             const float a = ((float)(y0 + k) - __ldg(joints2D + ((size_t)b * J + j) * 2 + 1)) / prm.heat_std;
-            s_hrow[j][k] = -(a * a) / 2.f;
+            s_hrow[j][k] = expf(-(a * a) / 2.f);
         } else {
             const float c2 = ((float)(x0 + k - PT_H) - __ldg(joints2D + ((size_t)b * J + j) * 2)) / prm.heat_std;
-            s_hcol[j][k - PT_H] = (c2 * c2) / 2.f;
+            s_hcol[j][k - PT_H] = expf(-(c2 * c2) / 2.f);
         }
     }
     if (tid < J) s_vis[tid] = vis ? __ldg(vis + (size_t)b * J + tid) : 1.f;
@@ -128,7 +128,7 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
         if (dbg_ori) dbg_ori[(size_t)b * HWp + pix] = ori;
         // heatmaps: exp(-((row - v) / std)^2 / 2 - ((col - u) / std)^2 / 2), joints2D = (u, v) = (column, row)
         for (int j = 0; j < J; ++j) {
-            float h = expf(s_hrow[j][r] - s_hcol[j][q]);
+            float h = s_hrow[j][r] * s_hcol[j][q];
             if (vis) h *= s_vis[j];
             out[((size_t)b * (1 + J) + 1 + j) * HWp + pix] = h;
         }
@@ -138,29 +138,34 @@ proxy_rep_kernel(const float* __restrict__ rgb, const float* __restrict__ joints
         // zero border of the (Hp, Wp) padded image.  One 16-byte store per (pixel, group of 8 channels); consecutive threads write
         // consecutive 16-byte pieces, so a warp writes 512 contiguous bytes.
         __syncthreads();
+        // a thread owns a pixel and writes its Cp channels as Cp/8 16-byte pieces (the lanes of a warp cover 32 consecutive pixels
+        // = one contiguous 32*Cp*2-byte run across the pieces)
         const int G = Cp >> 3;
-        for (int i = tid; i < PT_H * PT_W * G; i += PR_THREADS) {
-            const int pixl = i / G, grp = i - pixl * G;
-            const int r = pixl / PT_W, q = pixl - r * PT_W, y = y0 + r, x = x0 + q;
+        for (int i = tid; i < PT_H * PT_W; i += PR_THREADS) {
+            const int r = i / PT_W, q = i - r * PT_W, y = y0 + r, x = x0 + q;
             if (y >= H || x >= W) continue;
-            float ch[8];
+            __nv_bfloat16* dst = staged + (((size_t)b * Hp + y + top) * Wp + x + left) * Cp;
+            for (int grp = 0; grp < G; ++grp) {
+                float ch[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                // branch-free: channel 0 = edge map, 1..J = heatmaps, the rest zero padding (grp differs between neighbouring threads)
-                const int cc = grp * 8 + c;
-                const bool heat = cc >= 1 && cc <= J;
-                const int j = heat ? cc - 1 : 0;
-                float val = expf(s_hrow[j][r] - s_hcol[j][q]);
-                if (vis) val *= s_vis[j];
-                ch[c] = heat ? val : (cc == 0 ? s_edge[r][q] : 0.f);
-            }
-            uint32_t pk[4];
+                for (int c = 0; c < 8; ++c) {
+                    const int cc = grp * 8 + c;            // warp-uniform
+                    float val = 0.f;
+                    if (cc == 0) val = s_edge[r][q];
+                    else if (cc <= J) {
+                        val = s_hrow[cc - 1][r] * s_hcol[cc - 1][q];
+                        if (vis) val *= s_vis[cc - 1];
+                    }
+                    ch[c] = val;
+                }
+                uint32_t pk[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(ch[2 * c], ch[2 * c + 1]);
-                pk[c] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int c = 0; c < 4; ++c) {
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(ch[2 * c], ch[2 * c + 1]);
+                    pk[c] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(dst + grp * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            *reinterpret_cast<uint4*>(staged + (((size_t)b * Hp + y + top) * Wp + x + left) * Cp + grp * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
     }
 }
