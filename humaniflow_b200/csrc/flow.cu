@@ -790,6 +790,324 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
                tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6]);
 }
 
+// =====================================  sampling, level-parallel  =====================================
+// The chain above walks the joints in index order, but the kinematic tree only has a few dependency LEVELS (SMPL: {1,2,3},
+// {4,5,6}, {7,8,9}, {10..14}, ... : 9 rounds of <= 3 joints instead of 23 steps), and every phase of the chain is latency-bound.
+// Here the CTA is three independent groups of 192 threads; in a round each group takes one joint of the level through its
+// context layer, couplings, spline and exp map with GROUP barriers (bar.sync id, 192) only; rounds end with a CTA barrier that
+// publishes the new rotations.  A joint's weights (~100 KB) do not fit three times next to the activations, so each group streams
+// them LAYER BY LAYER: the [W | b] block of layer l+1 (<= 17.9 KB) is fetched with cp.async into the other half of the group's
+// double buffer while layer l computes.  U_j (the precomputed image-feature term) is added straight from the L2-resident scratch.
+constexpr int LG = 3, LGT = 192, LNT = LG * LGT;
+constexpr int LWB = 65 * (64 + WPAD) + 64;        // largest [W | b] block in floats: first coupling layer; the ancestor block is <= 63*68 + 64
+
+struct LevelSched { int nrounds; signed char joint[HF_FJ][LG]; };      // joint index per (round, group), -1 = idle
+
+template <int NR>
+struct LevelSmem {
+    static constexpr int ActFloats = (CTX + 1 + 64 + 32 + 32 + 64 + 4) * NR;      // Cs | Ha | Hb | Hc | Raw | Zs of one group
+    static constexpr int Ps = 0;                                                  // [HF_FJ*9][NR], shared by the groups
+    static constexpr int Act = Ps + HF_FJ * 9 * NR;
+    static constexpr int Wb = Act + LG * ActFloats;                               // [LG][2][LWB]
+    static constexpr int Total = Wb + LG * 2 * LWB;
+};
+
+// dense layer of ONE thread group: same tile mapping and arithmetic as dense_layer (4 outputs x 4 rows per 4 lanes), tiles
+// strided over the group's LGT / 4 tile slots; weights and bias in shared memory; `add` (optional) is read from global memory
+// first so that its latency hides behind the k loop.  No barrier inside.
+template <int NR, int OT, int ACT, typename XRow>
+__device__ __forceinline__ void dense_layer_g(const float* __restrict__ W, const float* __restrict__ bias, int K, XRow xrow,
+                                              float* dst, const float* __restrict__ add, int lt) {
+    constexpr int O = OT * 32, LDW = O + 4, RG = NR / 4, NTILE = (O / 4) * RG;
+    const int ks = lt & 3;
+    for (int tile = lt >> 2; tile < NTILE; tile += LGT / 4) {        // whole warps: NTILE and LGT / 4 are multiples of 8
+        const int og = tile / RG, rg = tile - og * RG;
+        const int o = og * 4 + ks;
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add) a4 = __ldg(reinterpret_cast<const float4*>(add + o * NR + rg * 4));
+        float2 acc[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+        const float* wp = W + og * 4;
+#pragma unroll 4
+        for (int k = ks; k < K; k += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(wp + (size_t)k * LDW);
+            const float4 x = *reinterpret_cast<const float4*>(xrow(k) + rg * 4);
+            const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+            const float2 w0 = make_float2(w.x, w.x), w1 = make_float2(w.y, w.y), w2 = make_float2(w.z, w.z), w3 = make_float2(w.w, w.w);
+            acc[0][0] = fma2(w0, xa, acc[0][0]); acc[0][1] = fma2(w0, xb, acc[0][1]);
+            acc[1][0] = fma2(w1, xa, acc[1][0]); acc[1][1] = fma2(w1, xb, acc[1][1]);
+            acc[2][0] = fma2(w2, xa, acc[2][0]); acc[2][1] = fma2(w2, xb, acc[2][1]);
+            acc[3][0] = fma2(w3, xa, acc[3][0]); acc[3][1] = fma2(w3, xb, acc[3][1]);
+        }
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float vx = acc[i][h].x, vy = acc[i][h].y;
+                vx += __shfl_xor_sync(0xffffffffu, vx, 1); vy += __shfl_xor_sync(0xffffffffu, vy, 1);
+                vx += __shfl_xor_sync(0xffffffffu, vx, 2); vy += __shfl_xor_sync(0xffffffffu, vy, 2);
+                if (i == ks) { r[2 * h] = vx; r[2 * h + 1] = vy; }
+            }
+        }
+        const float b = bias[o];
+        float v[4] = {r[0] + b + a4.x, r[1] + b + a4.y, r[2] + b + a4.z, r[3] + b + a4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (ACT == 1) v[q] = elu(v[q]);
+            if (ACT == 2) v[q] = fmaxf(v[q], 0.f);
+        }
+        *reinterpret_cast<float4*>(dst + o * NR + rg * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// Dense layer of one thread group with a LARGER register tile: 8 (OT = 2) or 4 (OT = 1) outputs x 8 rows per tile, the 8 lanes of a
+// tile take every eighth k.  The 4 x 4 tile of dense_layer moves 8 floats from shared memory per 16 FMAs and is bound by the
+// shared-memory pipe (two 4-wavefront LDS.128 per 8 FFMA2); this one moves 16 (12) floats per 64 (32) FMAs, and the three tiles
+// that share an output group sit in the same warp, so their weight loads are broadcasts.  The 8 k-slices are combined by a
+// transpose-reduction (N/2 + N/4 + N/8 shuffles for N accumulators) that leaves lane kl with output og*OW + kl (OT = 2: all 8
+// rows; OT = 1: output og*4 + kl/2, rows (kl&1)*4..).  24 tiles x 8 lanes = the 192 threads of a group at NR = 24.
+template <int NR, int OT, int ACT, typename XRow>
+__device__ __forceinline__ void dense_layer_g8(const float* __restrict__ W, const float* __restrict__ bias, int K, XRow xrow,
+                                               float* dst, const float* __restrict__ add, int lt) {
+    constexpr int O = OT * 32, LDW = O + 4, RG = NR / 8, OW = O / 8, N = OW * 8;
+    static_assert(NR % 8 == 0 && 8 * RG * 8 <= LGT, "dense_layer_g8 tile mapping");
+    const int kl = lt & 7, tile = lt >> 3;
+    if (tile < 8 * RG) {                         // whole warps (4 tiles per warp; 8 * RG is a multiple of 4)
+        const int og = tile / RG, rg = tile - og * RG;
+        float f[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) f[i] = 0.f;
+        float2* acc = reinterpret_cast<float2*>(f);          // acc[o * 4 + rp]: output o, row pair rp
+        const float* wp = W + og * OW;
+#pragma unroll 2
+        for (int k = kl; k < K; k += 8) {
+            float w[OW];
+#pragma unroll
+            for (int q = 0; q < OW / 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(wp + (size_t)k * LDW + q * 4);
+                w[q * 4] = t.x; w[q * 4 + 1] = t.y; w[q * 4 + 2] = t.z; w[q * 4 + 3] = t.w;
+            }
+            const float* xr = xrow(k) + rg * 8;
+            const float4 x0 = *reinterpret_cast<const float4*>(xr), x1 = *reinterpret_cast<const float4*>(xr + 4);
+            const float2 xp[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
+#pragma unroll
+            for (int o = 0; o < OW; ++o) {
+                const float2 ww = make_float2(w[o], w[o]);
+#pragma unroll
+                for (int rp = 0; rp < 4; ++rp) acc[o * 4 + rp] = fma2(ww, xp[rp], acc[o * 4 + rp]);
+            }
+        }
+        // transpose-reduction over the 8 k-lanes
+#pragma unroll
+        for (int sft = 4, n = N / 2; sft >= 1; sft >>= 1, n >>= 1) {
+            const bool up = (kl & sft) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const float keep = up ? f[i + n] : f[i], send = up ? f[i] : f[i + n];
+                f[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+            }
+        }
+        // lane kl now holds entries [kl * N/8, +N/8) of the tile's (output, row) grid
+        constexpr int PER = N / 8;                          // 8 (one output, 8 rows) or 4 (half an output row block)
+        const int o = og * OW + (kl * PER) / 8, rbase = rg * 8 + (kl * PER) % 8;
+        const float b = bias[o];
+#pragma unroll
+        for (int q = 0; q < PER / 4; ++q) {
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add) a4 = __ldg(reinterpret_cast<const float4*>(add + o * NR + rbase + q * 4));
+            float v[4] = {f[q * 4] + b + a4.x, f[q * 4 + 1] + b + a4.y, f[q * 4 + 2] + b + a4.z, f[q * 4 + 3] + b + a4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (ACT == 1) v[e] = elu(v[e]);
+                if (ACT == 2) v[e] = fmaxf(v[e], 0.f);
+            }
+            *reinterpret_cast<float4*>(dst + o * NR + rbase + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// spline_knots_full for one thread group (no barrier)
+template <int NR>
+__device__ __forceinline__ void spline_knots_full_g(const float* __restrict__ raw, float bound, float* __restrict__ KN, int lt) {
+    const float lo = -bound, hi = bound;
+    for (int t = lt; t < NR * 16; t += LGT) {
+        const int g = t >> 3, b = t & 7;
+        const int row = g >> 1, d = g & 1;
+        const float xw = raw[(d * NBINS + b) * NR + row], xh = raw[(2 * NBINS + d * NBINS + b) * NR + row];
+        const float xd = raw[(4 * NBINS + d * (NBINS - 1) + min(b, NBINS - 2)) * NR + row];
+        const float xl = raw[(4 * NBINS + 2 * (NBINS - 1) + d * NBINS + b) * NR + row];
+        float mw = xw, mh = xh;
+#pragma unroll
+        for (int sft = 1; sft < 8; sft <<= 1) {
+            mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, sft, 8));
+            mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, sft, 8));
+        }
+        const float ew = expf(xw - mw), eh = expf(xh - mh);
+        float sw = ew, sh = eh;
+#pragma unroll
+        for (int sft = 1; sft < 8; sft <<= 1) {
+            sw += __shfl_xor_sync(0xffffffffu, sw, sft, 8);
+            sh += __shfl_xor_sync(0xffffffffu, sh, sft, 8);
+        }
+        float cw = 1e-3f + 0.992f * (ew / sw), ch = 1e-3f + 0.992f * (eh / sh);
+#pragma unroll
+        for (int sft = 1; sft < 8; sft <<= 1) {
+            const float uw = __shfl_up_sync(0xffffffffu, cw, sft, 8), uh = __shfl_up_sync(0xffffffffu, ch, sft, 8);
+            if (b >= sft) { cw += uw; ch += uh; }
+        }
+        const float sp = (xd > 20.f) ? xd : log1pf(expf(xd));
+        const float lam = 0.95f * (1.f / (1.f + expf(-xl))) + 0.025f;
+        float* k = KN + g * KNF;
+        k[b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * cw + lo;
+        k[9 + b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * ch + lo;
+        k[18 + b + 1] = (b == NBINS - 1) ? 0.999f : 1e-3f + sp;
+        k[27 + b] = lam;
+        if (b == 0) { k[0] = lo; k[9] = lo; k[18] = 0.999f; }
+    }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(LNT, 1)
+flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_constant__ LevelSched S, const float* __restrict__ base_noise,
+                          int R, int Rn, float* __restrict__ rotmats, float* __restrict__ axisangle_pe, const float* __restrict__ U) {
+    using LS = LevelSmem<NR>;
+    extern __shared__ __align__(16) float smraw[];
+    const int tid = threadIdx.x, g = tid / LGT, lt = tid - g * LGT;
+    float* Ps = smraw + LS::Ps;
+    float* Cs = smraw + LS::Act + g * LS::ActFloats;
+    float* Ha = Cs + (CTX + 1) * NR;
+    float* Hb = Ha + 64 * NR;
+    float* Hc = Hb + 32 * NR;
+    float* Raw = Hc + 32 * NR;
+    float* Zs = Raw + 64 * NR;
+    float* wb = smraw + LS::Wb + g * 2 * LWB;
+    const int r0 = blockIdx.x * NR;
+    const float* Ucta = U + (size_t)blockIdx.x * P.J * CTX * NR;
+    const int NL = 1 + 4 * P.T;                  // layers per joint: ancestor block, then 4 per coupling
+    auto gbar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(LGT) : "memory"); };
+    auto prefetch = [&](int j, int l) {          // [W | b] block of layer l of joint j -> buffer l & 1
+        const float* jb = P.jpack + P.off_jb[j];
+        const int na = 9 * P.anc_cnt[j] * CTXP + CTX;
+        const float* src = jb;
+        int n = na;
+        if (l > 0) {
+            const int t = (l - 1) >> 2, q = (l - 1) & 3;
+            const int off = q == 0 ? OFF_W0 : (q == 1 ? OFF_W1 : (q == 2 ? OFF_W2 : OFF_W3));
+            const int end = q == 0 ? OFF_W1 : (q == 1 ? OFF_W2 : (q == 2 ? OFF_W3 : COUPLING_FLOATS));
+            src = jb + na + t * COUPLING_FLOATS + off;
+            n = end - off;
+        }
+        float* dst = wb + (l & 1) * LWB;
+        for (int i = lt; i < (n >> 2); i += LGT) cp_async16(dst + i * 4, src + i * 4);
+        cp_async_commit();
+    };
+    auto wait_layer = [&](bool more) {           // the oldest outstanding block has landed and is visible to the group
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        gbar();
+    };
+    if (S.joint[0][g] >= 0) prefetch(S.joint[0][g], 0);      // weights: constant, no dependency on the predecessor
+    HF_PDL_SYNC();
+    for (int rd = 0; rd < S.nrounds; ++rd) {
+        const int j = S.joint[rd][g];
+        if (j >= 0) {
+            const int Ka = 9 * P.anc_cnt[j];
+            if (lt < NR) {       // base sample (zero for point-estimate rows); the first permutation is the identity
+                const int r = r0 + lt;
+                float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+                if (r < Rn) {
+                    const float* z = base_noise + ((size_t)r * P.J + j) * 3;
+                    z0 = z[0]; z1 = z[1]; z2 = z[2];
+                }
+                Zs[lt] = z0; Zs[NR + lt] = z1; Zs[2 * NR + lt] = z2;
+                Cs[CTX * NR + lt] = z0;
+            }
+            // context = ELU(U_j + b + Wanc . vec(ancestor rotations)); every layer: request the next block, wait for this one
+            prefetch(j, 1);
+            wait_layer(true);
+            dense_layer_g<NR, 2, 1>(wb, wb + Ka * CTXP, Ka, AncRow{Ps, P.anc[j], NR}, Cs, Ucta + (size_t)j * CTX * NR, lt);
+            gbar();
+            for (int t = 0; t < P.T; ++t) {
+                const int l0 = 1 + 4 * t;
+                {
+                    const float* w = wb + (l0 & 1) * LWB;
+                    prefetch(j, l0 + 1); wait_layer(true);
+                    dense_layer_g<NR, 2, 2>(w, w + (OFF_B0 - OFF_W0), CTX + 1, PlainRow{Cs, NR}, Ha, nullptr, lt);
+                    gbar();
+                }
+                {
+                    const float* w = wb + ((l0 + 1) & 1) * LWB;
+                    prefetch(j, l0 + 2); wait_layer(true);
+                    dense_layer_g<NR, 1, 2>(w, w + (OFF_B1 - OFF_W1), H1, PlainRow{Ha, NR}, Hb, nullptr, lt);
+                    gbar();
+                }
+                {
+                    const float* w = wb + ((l0 + 2) & 1) * LWB;
+                    prefetch(j, l0 + 3); wait_layer(true);
+                    dense_layer_g<NR, 1, 2>(w, w + (OFF_B2 - OFF_W2), H2, PlainRow{Hb, NR}, Hc, nullptr, lt);
+                    gbar();
+                }
+                {
+                    const float* w = wb + ((l0 + 3) & 1) * LWB;
+                    const bool more = l0 + 4 < NL;
+                    if (more) prefetch(j, l0 + 4);
+                    wait_layer(more);
+                    dense_layer_g<NR, 2, 0>(w, w + (OFF_B3 - OFF_W3), H3, PlainRow{Hc, NR}, Raw, nullptr, lt);
+                    gbar();
+                }
+                spline_knots_full_g<NR>(Raw, P.radius, Ha, lt);          // 72 x NR floats over Ha and the start of Hb (both free here)
+                gbar();
+                if (lt < 2 * NR) {
+                    const int s = lt >> 1, d = lt & 1;
+                    const float x = Zs[(1 + d) * NR + s];
+                    const float y0 = Zs[s];
+                    const float mine = spline_forward_pre(x, P.radius, Ha + (s * 2 + d) * KNF);
+                    const unsigned act = __activemask();
+                    const float other = __shfl_xor_sync(act, mine, 1);
+                    if (d == 0) {
+                        const float y1 = mine, y2 = other;
+                        if (t + 1 < P.T) {     // next permutation relative to the current order is always [1,2,0]
+                            Zs[s] = y1; Zs[NR + s] = y2; Zs[2 * NR + s] = y0;
+                            Cs[CTX * NR + s] = y1;
+                        } else {
+                            Zs[NR + s] = y1; Zs[2 * NR + s] = y2;
+                        }
+                    }
+                }
+                gbar();
+            }
+            // radial tanh -> exp map -> store (the shared copy feeds the descendants' contexts after the round barrier)
+            if (lt < NR) {
+                const int r = r0 + lt;
+                float x = Zs[lt], y = Zs[NR + lt], z = Zs[2 * NR + lt];
+                const float n = sqrtf(x * x + y * y + z * z);
+                if (n > 1e-7f) {
+                    const float th = tanhf(n / P.radius);
+                    x = th * (x / n) * P.radius; y = th * (y / n) * P.radius; z = th * (z / n) * P.radius;
+                }
+                float Rm[9];
+                if (r < Rn) so3_exp_f64((double)x, (double)y, (double)z, Rm);
+                else rodrigues_f32(x, y, z, Rm);
+#pragma unroll
+                for (int e = 0; e < 9; ++e) Ps[(j * 9 + e) * NR + lt] = Rm[e];
+                if (r < R) {
+                    float* o = rotmats + ((size_t)r * P.J + j) * 9;
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) o[e] = Rm[e];
+                    if (r >= Rn && axisangle_pe) {
+                        float* a = axisangle_pe + ((size_t)(r - Rn) * P.J + j) * 3;
+                        a[0] = x; a[1] = y; a[2] = z;
+                    }
+                }
+            }
+        }
+        if (rd + 1 < S.nrounds && S.joint[rd + 1][g] >= 0) prefetch(S.joint[rd + 1][g], 0);
+        __syncthreads();
+    }
+}
+
 // =====================================  contexts for teacher forcing  =====================================
 template <int NR>
 __global__ void __launch_bounds__(HF_NT, 1)
@@ -952,6 +1270,7 @@ struct hf_flow {
     float* betaW;
     float* wfeat;
     float* jpack;
+    LevelSched sched;             // level-parallel sampling kernel: joints per (round, group)
     float* wsplit;                // [J*64][512] = [tf32 hi (256) | lo (256)] of the feature part of every context Linear
     CUtensorMap mapW;
     const void* mapF_ptr; int mapF_R; CUtensorMap mapF;     // cached activation map (workspace pointer and row count)
@@ -1043,6 +1362,28 @@ extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const 
             else jpack.resize(jpack.size() + COUPLING_FLOATS, 0.f);
         }
     }
+    {   // dependency levels of the tree (a joint's context reads its ancestors' rotations), packed into rounds of <= LG joints
+        int level[HF_FJ];
+        int maxl = 0;
+        for (int j = 0; j < P.J; ++j) {
+            int l = 0;
+            for (int q = 0; q < P.anc_cnt[j]; ++q) l = std::max(l, level[(int)P.anc[j][q]] + 1);
+            level[j] = l;
+            maxl = std::max(maxl, l);
+        }
+        LevelSched& S = h->sched;
+        S.nrounds = 0;
+        for (int l = 0; l <= maxl; ++l) {
+            int cnt = 0;
+            for (int j = 0; j < P.J; ++j) {
+                if (level[j] != l) continue;
+                if (cnt == 0) { for (int q = 0; q < LG; ++q) S.joint[S.nrounds][q] = -1; }
+                S.joint[S.nrounds][cnt++] = (signed char)j;
+                if (cnt == LG) { ++S.nrounds; cnt = 0; }
+            }
+            if (cnt) ++S.nrounds;
+        }
+    }
     std::vector<float> wsplit((size_t)P.J * CTX * 2 * FEATS);
     for (int j = 0; j < P.J; ++j) {
         const int Kc = FEATS + 9 * P.anc_cnt[j];
@@ -1128,6 +1469,18 @@ extern "C" int hf_flow_sample(const hf_flow_t* h, const float* img_base, const f
         HF_CUDA(hf::launch_pdl(flow_ctx_gemm_kernel, dim3(hf::div_up(R, 128), hf::div_up(h->P.J * CTX, CG_BN)), dim3(CG_THREADS), gsmem, (cudaStream_t)stream, h->mapF, h->mapW, R,
                                h->P.J, nr, (float*)workspace));
         HF_LAUNCH_CHECK();
+    }
+    const bool levels = have_U && getenv("HF_FLOW_CHAIN") == nullptr;      // HF_FLOW_CHAIN=1: the joint-by-joint kernel (cross-check)
+    if (levels) {
+        HF_DISPATCH_ROWS(nr, {
+            const size_t smem = LevelSmem<NR>::Total * sizeof(float);
+            int rc = set_smem(flow_sample_levels_kernel<NR>, smem);
+            if (rc) return rc;
+            HF_CUDA(hf::launch_pdl(flow_sample_levels_kernel<NR>, dim3(hf::div_up(R, NR)), dim3(LNT), smem, (cudaStream_t)stream, h->P, h->sched, base_noise,
+                                   R, Rn, rotmats, axisangle_pe, (const float*)workspace));
+        });
+        HF_LAUNCH_CHECK();
+        return HF_OK;
     }
     HF_DISPATCH_ROWS(nr, {
         const size_t smem = SampleSmem<NR>::Total * sizeof(float);

@@ -73,6 +73,23 @@ def test_tensor_core_prologue_against_the_cuda_core_prologue(monkeypatch):
     assert e_tc <= ROT_TOL and e_simt <= ROT_TOL and d <= ROT_TOL
 
 
+@pytest.mark.parametrize('B,N', [(32, 100), (3, 5), (9, 40)])
+def test_level_parallel_kernel_equals_the_joint_by_joint_kernel(B, N, monkeypatch):
+    """The product sampler walks the kinematic tree level by level (three thread groups, one joint each per round, weights
+    streamed layer by layer); the joint-by-joint kernel (HF_FLOW_CHAIN=1) does the same arithmetic in the same order, so the two
+    agree bit for bit -- at all three rows-per-CTA variants (8 / 16 / 24)."""
+    m, sd, cfg = make_model(50, seed=5)
+    m = m.cuda()
+    feats, z, se = _noise(B, N, seed=B + N, feat_dim=m.input_feats_dim)
+    lev = _run(m, feats, z, se)
+    lev = {k: lev[k].clone() for k in ('pose_rotmats_samples', 'pose_rotmats_point_est', 'pose_axisangle_point_est')}
+    monkeypatch.setenv('HF_FLOW_CHAIN', '1')
+    chain = _run(m, feats, z, se)
+    monkeypatch.delenv('HF_FLOW_CHAIN')
+    for k in lev:
+        assert torch.equal(lev[k], chain[k]), k
+
+
 def test_modes_of_forward():
     m, sd, cfg = make_model(18, seed=2)
     m = m.cuda()
