@@ -496,6 +496,12 @@ struct AncRow {
     }
 };
 
+// same rows through a per-k offset table in shared memory (no division in the k loop)
+struct TabRow {
+    const float* Ps; const int* off;
+    __device__ __forceinline__ const float* operator()(int k) const { return Ps + off[k]; }
+};
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -928,6 +934,66 @@ __device__ __forceinline__ void dense_layer_g8(const float* __restrict__ W, cons
     }
 }
 
+// 64-output layers of one thread group: tile = 8 outputs x 4 rows, 4 k-lanes (48 tiles x 4 = the 192 threads at NR = 24: ONE pass).
+// Per k a lane loads 8 weights (two LDS.128 that are broadcasts for the six tiles of an output group sharing a warp) and 4 row
+// values for 16 FFMA2: 5 shared-memory wavefronts per 16 FFMA2 against 8 per 8 for the 4 x 4 tile, which keeps the shared-memory
+// pipe (60 % busy with the small tile) off the critical path.  The 4 k-slices are combined by a transpose-reduction (16 + 8
+// shuffles) that leaves every lane with two outputs of the tile's 4 rows.
+template <int NR, int ACT, typename XRow>
+__device__ __forceinline__ void dense_layer_g84(const float* __restrict__ W, const float* __restrict__ bias, int K, XRow xrow,
+                                                float* dst, const float* __restrict__ add, int lt) {
+    constexpr int O = 64, LDW = O + 4, RG = NR / 4, NTILE = 8 * RG;
+    const int ks = lt & 3;
+    for (int tile = lt >> 2; tile < NTILE; tile += LGT / 4) {
+        const int og = tile / RG, rg = tile - og * RG;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = 0.f;
+        float2* acc = reinterpret_cast<float2*>(f);          // acc[o * 2 + rp]: output o (0..7), row pair rp
+        const float* wp = W + og * 8;
+#pragma unroll 4
+        for (int k = ks; k < K; k += 4) {
+            const float4 wa = *reinterpret_cast<const float4*>(wp + (size_t)k * LDW), wc = *reinterpret_cast<const float4*>(wp + (size_t)k * LDW + 4);
+            const float4 x = *reinterpret_cast<const float4*>(xrow(k) + rg * 4);
+            const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const float2 ww = make_float2(w[o], w[o]);
+                acc[o * 2] = fma2(ww, xa, acc[o * 2]);
+                acc[o * 2 + 1] = fma2(ww, xb, acc[o * 2 + 1]);
+            }
+        }
+        // (lanes 0+1 and 2+3 first, then the pairs: the summation order of dense_layer, so both kernels agree bit for bit)
+#pragma unroll
+        for (int step = 0; step < 2; ++step) {
+            const int sft = 1 << step, n = 16 >> step;
+            const bool up = (ks & sft) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const float keep = up ? f[i + n] : f[i], send = up ? f[i] : f[i + n];
+                f[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+            }
+        }
+        // lane ks holds entries [e8*8, +8) of the (output, row) grid with e8 = 2*(ks&1) + (ks>>1): outputs og*8 + 2*e8 and +1, 4 rows each
+        const int e8 = 2 * (ks & 1) + (ks >> 1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int o = og * 8 + 2 * e8 + q;
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add) a4 = __ldg(reinterpret_cast<const float4*>(add + o * NR + rg * 4));
+            const float b = bias[o];
+            float v[4] = {f[q * 4] + b + a4.x, f[q * 4 + 1] + b + a4.y, f[q * 4 + 2] + b + a4.z, f[q * 4 + 3] + b + a4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (ACT == 1) v[e] = elu(v[e]);
+                if (ACT == 2) v[e] = fmaxf(v[e], 0.f);
+            }
+            *reinterpret_cast<float4*>(dst + o * NR + rg * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 // spline_knots_full for one thread group (no barrier)
 template <int NR>
 __device__ __forceinline__ void spline_knots_full_g(const float* __restrict__ raw, float bound, float* __restrict__ KN, int lt) {
@@ -971,8 +1037,10 @@ __device__ __forceinline__ void spline_knots_full_g(const float* __restrict__ ra
 template <int NR>
 __global__ void __launch_bounds__(LNT, 1)
 flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_constant__ LevelSched S, const float* __restrict__ base_noise,
-                          int R, int Rn, float* __restrict__ rotmats, float* __restrict__ axisangle_pe, const float* __restrict__ U) {
+                          int R, int Rn, float* __restrict__ rotmats, float* __restrict__ axisangle_pe, const float* __restrict__ U, int dbg) {
     using LS = LevelSmem<NR>;
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    auto lap = [&](int c) { if (dbg) { const long long tt = clock64(); tph[c] += tt - tlast; tlast = tt; } };
     extern __shared__ __align__(16) float smraw[];
     const int tid = threadIdx.x, g = tid / LGT, lt = tid - g * LGT;
     float* Ps = smraw + LS::Ps;
@@ -987,29 +1055,43 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
     const float* Ucta = U + (size_t)blockIdx.x * P.J * CTX * NR;
     const int NL = 1 + 4 * P.T;                  // layers per joint: ancestor block, then 4 per coupling
     auto gbar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(LGT) : "memory"); };
+    // weight blocks arrive by ONE bulk copy each (issued by the group's first thread, completion on the group's mbarrier of that
+    // buffer): 192 threads issuing six 16-byte cp.async each cost ~600 cycles of issue time per layer
+    __shared__ __align__(8) uint64_t lbar[LG][2];
+    __shared__ int anc_off[LG][64];              // row offset into Ps of every input k of the group's context layer
+    const uint32_t bar_g = smem_u32(&lbar[g][0]);
+    if (lt == 0) {
+        mbar_init(bar_g, 1); mbar_init(bar_g + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t phase[2] = {0u, 0u};                // parity of the next completion of each buffer (tracked identically by all threads)
     auto prefetch = [&](int j, int l) {          // [W | b] block of layer l of joint j -> buffer l & 1
-        const float* jb = P.jpack + P.off_jb[j];
-        const int na = 9 * P.anc_cnt[j] * CTXP + CTX;
-        const float* src = jb;
-        int n = na;
-        if (l > 0) {
-            const int t = (l - 1) >> 2, q = (l - 1) & 3;
-            const int off = q == 0 ? OFF_W0 : (q == 1 ? OFF_W1 : (q == 2 ? OFF_W2 : OFF_W3));
-            const int end = q == 0 ? OFF_W1 : (q == 1 ? OFF_W2 : (q == 2 ? OFF_W3 : COUPLING_FLOATS));
-            src = jb + na + t * COUPLING_FLOATS + off;
-            n = end - off;
+        if (lt == 0) {
+            const float* jb = P.jpack + P.off_jb[j];
+            const int na = 9 * P.anc_cnt[j] * CTXP + CTX;
+            const float* src = jb;
+            int n = na;
+            if (l > 0) {
+                const int tt = (l - 1) >> 2, q = (l - 1) & 3;
+                const int off = q == 0 ? OFF_W0 : (q == 1 ? OFF_W1 : (q == 2 ? OFF_W2 : OFF_W3));
+                const int end = q == 0 ? OFF_W1 : (q == 1 ? OFF_W2 : (q == 2 ? OFF_W3 : COUPLING_FLOATS));
+                src = jb + na + tt * COUPLING_FLOATS + off;
+                n = end - off;
+            }
+            const uint32_t bar = bar_g + 8 * (l & 1);
+            mbar_expect_tx(bar, (uint32_t)n * 4u);
+            bulk_load_1d(smem_u32(wb + (l & 1) * LWB), src, (uint32_t)n * 4u, bar);
         }
-        float* dst = wb + (l & 1) * LWB;
-        for (int i = lt; i < (n >> 2); i += LGT) cp_async16(dst + i * 4, src + i * 4);
-        cp_async_commit();
     };
-    auto wait_layer = [&](bool more) {           // the oldest outstanding block has landed and is visible to the group
-        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    auto wait_layer = [&](int l) {               // block l has landed (one thread observes the barrier) and is visible to the group
+        if (lt == 0) mbar_wait(bar_g + 8 * (l & 1), phase[l & 1]);
+        phase[l & 1] ^= 1u;
         gbar();
     };
+    __syncthreads();                             // barrier inits visible before the first bulk copy can complete on them
     if (S.joint[0][g] >= 0) prefetch(S.joint[0][g], 0);      // weights: constant, no dependency on the predecessor
     HF_PDL_SYNC();
+    lap(0);
     for (int rd = 0; rd < S.nrounds; ++rd) {
         const int j = S.joint[rd][g];
         if (j >= 0) {
@@ -1024,41 +1106,56 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
                 Zs[lt] = z0; Zs[NR + lt] = z1; Zs[2 * NR + lt] = z2;
                 Cs[CTX * NR + lt] = z0;
             }
+            if (lt >= 64 && lt < 64 + Ka) {          // (another warp than the base-sample one)
+                const int k = lt - 64, a = k / 9;
+                anc_off[g][k] = (P.anc[j][a] * 9 + (k - a * 9)) * NR;
+            }
             // context = ELU(U_j + b + Wanc . vec(ancestor rotations)); every layer: request the next block, wait for this one
             prefetch(j, 1);
-            wait_layer(true);
-            dense_layer_g<NR, 2, 1>(wb, wb + Ka * CTXP, Ka, AncRow{Ps, P.anc[j], NR}, Cs, Ucta + (size_t)j * CTX * NR, lt);
+            wait_layer(0);
+            lap(1);
+            dense_layer_g84<NR, 1>(wb, wb + Ka * CTXP, Ka, TabRow{Ps, anc_off[g]}, Cs, Ucta + (size_t)j * CTX * NR, lt);
             gbar();
+            lap(2);
             for (int t = 0; t < P.T; ++t) {
                 const int l0 = 1 + 4 * t;
                 {
                     const float* w = wb + (l0 & 1) * LWB;
-                    prefetch(j, l0 + 1); wait_layer(true);
-                    dense_layer_g<NR, 2, 2>(w, w + (OFF_B0 - OFF_W0), CTX + 1, PlainRow{Cs, NR}, Ha, nullptr, lt);
+                    prefetch(j, l0 + 1); wait_layer(l0);
+                    lap(1);
+                    dense_layer_g84<NR, 2>(w, w + (OFF_B0 - OFF_W0), CTX + 1, PlainRow{Cs, NR}, Ha, nullptr, lt);
                     gbar();
+                    lap(3);
                 }
                 {
                     const float* w = wb + ((l0 + 1) & 1) * LWB;
-                    prefetch(j, l0 + 2); wait_layer(true);
+                    prefetch(j, l0 + 2); wait_layer(l0 + 1);
+                    lap(1);
                     dense_layer_g<NR, 1, 2>(w, w + (OFF_B1 - OFF_W1), H1, PlainRow{Ha, NR}, Hb, nullptr, lt);
                     gbar();
+                    lap(3);
                 }
                 {
                     const float* w = wb + ((l0 + 2) & 1) * LWB;
-                    prefetch(j, l0 + 3); wait_layer(true);
+                    prefetch(j, l0 + 3); wait_layer(l0 + 2);
+                    lap(1);
                     dense_layer_g<NR, 1, 2>(w, w + (OFF_B2 - OFF_W2), H2, PlainRow{Hb, NR}, Hc, nullptr, lt);
                     gbar();
+                    lap(3);
                 }
                 {
                     const float* w = wb + ((l0 + 3) & 1) * LWB;
                     const bool more = l0 + 4 < NL;
                     if (more) prefetch(j, l0 + 4);
-                    wait_layer(more);
-                    dense_layer_g<NR, 2, 0>(w, w + (OFF_B3 - OFF_W3), H3, PlainRow{Hc, NR}, Raw, nullptr, lt);
+                    wait_layer(l0 + 3);
+                    lap(1);
+                    dense_layer_g84<NR, 0>(w, w + (OFF_B3 - OFF_W3), H3, PlainRow{Hc, NR}, Raw, nullptr, lt);
                     gbar();
+                    lap(3);
                 }
                 spline_knots_full_g<NR>(Raw, P.radius, Ha, lt);          // 72 x NR floats over Ha and the start of Hb (both free here)
                 gbar();
+                lap(4);
                 if (lt < 2 * NR) {
                     const int s = lt >> 1, d = lt & 1;
                     const float x = Zs[(1 + d) * NR + s];
@@ -1077,6 +1174,7 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
                     }
                 }
                 gbar();
+                lap(5);
             }
             // radial tanh -> exp map -> store (the shared copy feeds the descendants' contexts after the round barrier)
             if (lt < NR) {
@@ -1103,9 +1201,14 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
                 }
             }
         }
+        lap(6);
         if (rd + 1 < S.nrounds && S.joint[rd + 1][g] >= 0) prefetch(S.joint[rd + 1][g], 0);
         __syncthreads();
+        lap(7);
     }
+    if (dbg && blockIdx.x == 0 && lt == 0)
+        printf("flow levels group %d (cycles): start %lld | weight waits %lld | context %lld | coupling layers %lld | knots %lld | spline %lld | exp map %lld | round barrier %lld\n",
+               g, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7]);
 }
 
 // =====================================  contexts for teacher forcing  =====================================
@@ -1477,7 +1580,7 @@ extern "C" int hf_flow_sample(const hf_flow_t* h, const float* img_base, const f
             int rc = set_smem(flow_sample_levels_kernel<NR>, smem);
             if (rc) return rc;
             HF_CUDA(hf::launch_pdl(flow_sample_levels_kernel<NR>, dim3(hf::div_up(R, NR)), dim3(LNT), smem, (cudaStream_t)stream, h->P, h->sched, base_noise,
-                                   R, Rn, rotmats, axisangle_pe, (const float*)workspace));
+                                   R, Rn, rotmats, axisangle_pe, (const float*)workspace, getenv("HF_FLOW_DBG") ? 1 : 0));
         });
         HF_LAUNCH_CHECK();
         return HF_OK;
