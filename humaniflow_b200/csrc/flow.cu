@@ -799,11 +799,14 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
 // =====================================  sampling, level-parallel  =====================================
 // The chain above walks the joints in index order, but the kinematic tree only has a few dependency LEVELS (SMPL: {1,2,3},
 // {4,5,6}, {7,8,9}, {10..14}, ... : 9 rounds of <= 3 joints instead of 23 steps), and every phase of the chain is latency-bound.
-// Here the CTA is three independent groups of 192 threads; in a round each group takes one joint of the level through its
-// context layer, couplings, spline and exp map with GROUP barriers (bar.sync id, 192) only; rounds end with a CTA barrier that
-// publishes the new rotations.  A joint's weights (~100 KB) do not fit three times next to the activations, so each group streams
-// them LAYER BY LAYER: the [W | b] block of layer l+1 (<= 17.9 KB) is fetched with cp.async into the other half of the group's
-// double buffer while layer l computes.  U_j (the precomputed image-feature term) is added straight from the L2-resident scratch.
+// Here the CTA is three independent groups of 192 threads (+ one producer warp each); in a round each group takes one joint of the
+// level through its context layer, couplings, spline and exp map with GROUP barriers (bar.sync id, 192) only; rounds end with a
+// barrier over the consumer threads that publishes the new rotations.  A joint's weights (~100 KB) do not fit three times next to
+// the activations, so each group streams them LAYER BY LAYER: the [W | b] block of the layer after next (<= 17.9 KB) is fetched
+// by the group's producer warp with one bulk copy into a two-deep ring (full / empty mbarriers) while the current layer computes.
+// U_j (the precomputed image-feature term) is added straight from the L2-resident scratch.  64-output layers use an 8 x 4
+// register tile (dense_layer_g84), 32-output layers the 4 x 4 tile; the arithmetic and its order are those of the joint-by-joint
+// kernel, so both produce the same bits.
 constexpr int LG = 3, LGT = 192, LNT = LG * LGT;
 constexpr int LWB = 65 * (64 + WPAD) + 64;        // largest [W | b] block in floats: first coupling layer; the ancestor block is <= 63*68 + 64
 
@@ -1035,14 +1038,59 @@ __device__ __forceinline__ void spline_knots_full_g(const float* __restrict__ ra
 }
 
 template <int NR>
-__global__ void __launch_bounds__(LNT, 1)
+__global__ void __launch_bounds__(LNT + 32 * LG, 1)
 flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_constant__ LevelSched S, const float* __restrict__ base_noise,
                           int R, int Rn, float* __restrict__ rotmats, float* __restrict__ axisangle_pe, const float* __restrict__ U, int dbg) {
     using LS = LevelSmem<NR>;
     long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
     auto lap = [&](int c) { if (dbg) { const long long tt = clock64(); tph[c] += tt - tlast; tlast = tt; } };
     extern __shared__ __align__(16) float smraw[];
-    const int tid = threadIdx.x, g = tid / LGT, lt = tid - g * LGT;
+    // weight blocks: one bulk copy each, issued by the group's PRODUCER warp (warps 18..20; issuing a bulk copy costs the issuing
+    // thread ~500 cycles, which sat on every layer's critical path when the group's first thread did it) into a two-deep ring
+    // guarded by full / empty mbarriers
+    __shared__ __align__(8) uint64_t lbar[LG][4];         // full[0..1], empty[0..1]
+    __shared__ int anc_off[LG][64];                        // row offset into Ps of every input k of the group's context layer
+    const int tid = threadIdx.x;
+    const int NL = 1 + 4 * P.T;                            // layers per joint: ancestor block, then 4 per coupling
+    if (tid < LG) {
+        const uint32_t bb = smem_u32(&lbar[tid][0]);
+        for (int i = 0; i < 4; ++i) mbar_init(bb + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid >= LNT) {
+        // ---------------- producer warps ----------------
+        const int g = (tid - LNT) >> 5;
+        if ((tid & 31) == 0) {
+            const uint32_t bar_g = smem_u32(&lbar[g][0]);
+            float* wb = smraw + LS::Wb + g * 2 * LWB;
+            int blk = 0;                                   // running block counter of the group: buffer = blk & 1, use = blk >> 1
+            for (int rd = 0; rd < S.nrounds; ++rd) {
+                const int j = S.joint[rd][g];
+                if (j < 0) continue;
+                const float* jb = P.jpack + P.off_jb[j];
+                const int na = 9 * P.anc_cnt[j] * CTXP + CTX;
+                for (int l = 0; l < NL; ++l, ++blk) {
+                    const float* src = jb;
+                    int n = na;
+                    if (l > 0) {
+                        const int tt = (l - 1) >> 2, q = (l - 1) & 3;
+                        const int off = q == 0 ? OFF_W0 : (q == 1 ? OFF_W1 : (q == 2 ? OFF_W2 : OFF_W3));
+                        const int end = q == 0 ? OFF_W1 : (q == 1 ? OFF_W2 : (q == 2 ? OFF_W3 : COUPLING_FLOATS));
+                        src = jb + na + tt * COUPLING_FLOATS + off;
+                        n = end - off;
+                    }
+                    const int buf = blk & 1;
+                    mbar_wait_long(bar_g + 8 * (2 + buf), (uint32_t)(((blk >> 1) & 1) ^ 1));       // buffer released by the consumers
+                    mbar_expect_tx(bar_g + 8 * buf, (uint32_t)n * 4u);
+                    bulk_load_1d(smem_u32(wb + buf * LWB), src, (uint32_t)n * 4u, bar_g + 8 * buf);
+                }
+            }
+        }
+        return;
+    }
+    // ---------------- consumer groups ----------------
+    const int g = tid / LGT, lt = tid - g * LGT;
     float* Ps = smraw + LS::Ps;
     float* Cs = smraw + LS::Act + g * LS::ActFloats;
     float* Ha = Cs + (CTX + 1) * NR;
@@ -1053,43 +1101,25 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
     float* wb = smraw + LS::Wb + g * 2 * LWB;
     const int r0 = blockIdx.x * NR;
     const float* Ucta = U + (size_t)blockIdx.x * P.J * CTX * NR;
-    const int NL = 1 + 4 * P.T;                  // layers per joint: ancestor block, then 4 per coupling
-    auto gbar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(LGT) : "memory"); };
-    // weight blocks arrive by ONE bulk copy each (issued by the group's first thread, completion on the group's mbarrier of that
-    // buffer): 192 threads issuing six 16-byte cp.async each cost ~600 cycles of issue time per layer
-    __shared__ __align__(8) uint64_t lbar[LG][2];
-    __shared__ int anc_off[LG][64];              // row offset into Ps of every input k of the group's context layer
     const uint32_t bar_g = smem_u32(&lbar[g][0]);
-    if (lt == 0) {
-        mbar_init(bar_g, 1); mbar_init(bar_g + 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    uint32_t phase[2] = {0u, 0u};                // parity of the next completion of each buffer (tracked identically by all threads)
-    auto prefetch = [&](int j, int l) {          // [W | b] block of layer l of joint j -> buffer l & 1
-        if (lt == 0) {
-            const float* jb = P.jpack + P.off_jb[j];
-            const int na = 9 * P.anc_cnt[j] * CTXP + CTX;
-            const float* src = jb;
-            int n = na;
-            if (l > 0) {
-                const int tt = (l - 1) >> 2, q = (l - 1) & 3;
-                const int off = q == 0 ? OFF_W0 : (q == 1 ? OFF_W1 : (q == 2 ? OFF_W2 : OFF_W3));
-                const int end = q == 0 ? OFF_W1 : (q == 1 ? OFF_W2 : (q == 2 ? OFF_W3 : COUPLING_FLOATS));
-                src = jb + na + tt * COUPLING_FLOATS + off;
-                n = end - off;
-            }
-            const uint32_t bar = bar_g + 8 * (l & 1);
-            mbar_expect_tx(bar, (uint32_t)n * 4u);
-            bulk_load_1d(smem_u32(wb + (l & 1) * LWB), src, (uint32_t)n * 4u, bar);
-        }
-    };
-    auto wait_layer = [&](int l) {               // block l has landed (one thread observes the barrier) and is visible to the group
-        if (lt == 0) mbar_wait(bar_g + 8 * (l & 1), phase[l & 1]);
-        phase[l & 1] ^= 1u;
+    auto gbar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(LGT) : "memory"); };
+    auto cbar = [&]() { asm volatile("bar.sync %0, %1;" ::"n"(LG + 1), "n"(LNT) : "memory"); };      // all consumer threads (round barrier)
+    int blk = 0;
+    // ONE group barrier per layer (a bar.sync costs ~300 cycles on this loaded SM): it publishes the layer's outputs and, because
+    // the group's first thread has observed the next block's mbarrier just before it, the next layer's weights; the finished
+    // buffer goes back to the producer right behind it
+    auto first_block = [&]() -> const float* {
+        if (lt == 0) mbar_wait(bar_g + 8 * (blk & 1), (uint32_t)((blk >> 1) & 1));
         gbar();
+        return wb + (blk & 1) * LWB;
     };
-    __syncthreads();                             // barrier inits visible before the first bulk copy can complete on them
-    if (S.joint[0][g] >= 0) prefetch(S.joint[0][g], 0);      // weights: constant, no dependency on the predecessor
+    auto next_block = [&](bool has_next) -> const float* {
+        if (lt == 0 && has_next) mbar_wait(bar_g + 8 * ((blk + 1) & 1), (uint32_t)(((blk + 1) >> 1) & 1));
+        gbar();
+        if (lt == 0) mbar_arrive(bar_g + 8 * (2 + (blk & 1)));
+        ++blk;
+        return wb + (blk & 1) * LWB;
+    };
     HF_PDL_SYNC();
     lap(0);
     for (int rd = 0; rd < S.nrounds; ++rd) {
@@ -1110,49 +1140,22 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
                 const int k = lt - 64, a = k / 9;
                 anc_off[g][k] = (P.anc[j][a] * 9 + (k - a * 9)) * NR;
             }
-            // context = ELU(U_j + b + Wanc . vec(ancestor rotations)); every layer: request the next block, wait for this one
-            prefetch(j, 1);
-            wait_layer(0);
+            const float* w = first_block();
             lap(1);
-            dense_layer_g84<NR, 1>(wb, wb + Ka * CTXP, Ka, TabRow{Ps, anc_off[g]}, Cs, Ucta + (size_t)j * CTX * NR, lt);
-            gbar();
+            // context = ELU(U_j + b + Wanc . vec(ancestor rotations))
+            dense_layer_g84<NR, 1>(w, w + Ka * CTXP, Ka, TabRow{Ps, anc_off[g]}, Cs, Ucta + (size_t)j * CTX * NR, lt);
+            w = next_block(true);
             lap(2);
             for (int t = 0; t < P.T; ++t) {
-                const int l0 = 1 + 4 * t;
-                {
-                    const float* w = wb + (l0 & 1) * LWB;
-                    prefetch(j, l0 + 1); wait_layer(l0);
-                    lap(1);
-                    dense_layer_g84<NR, 2>(w, w + (OFF_B0 - OFF_W0), CTX + 1, PlainRow{Cs, NR}, Ha, nullptr, lt);
-                    gbar();
-                    lap(3);
-                }
-                {
-                    const float* w = wb + ((l0 + 1) & 1) * LWB;
-                    prefetch(j, l0 + 2); wait_layer(l0 + 1);
-                    lap(1);
-                    dense_layer_g<NR, 1, 2>(w, w + (OFF_B1 - OFF_W1), H1, PlainRow{Ha, NR}, Hb, nullptr, lt);
-                    gbar();
-                    lap(3);
-                }
-                {
-                    const float* w = wb + ((l0 + 2) & 1) * LWB;
-                    prefetch(j, l0 + 3); wait_layer(l0 + 2);
-                    lap(1);
-                    dense_layer_g<NR, 1, 2>(w, w + (OFF_B2 - OFF_W2), H2, PlainRow{Hb, NR}, Hc, nullptr, lt);
-                    gbar();
-                    lap(3);
-                }
-                {
-                    const float* w = wb + ((l0 + 3) & 1) * LWB;
-                    const bool more = l0 + 4 < NL;
-                    if (more) prefetch(j, l0 + 4);
-                    wait_layer(l0 + 3);
-                    lap(1);
-                    dense_layer_g84<NR, 0>(w, w + (OFF_B3 - OFF_W3), H3, PlainRow{Hc, NR}, Raw, nullptr, lt);
-                    gbar();
-                    lap(3);
-                }
+                dense_layer_g84<NR, 2>(w, w + (OFF_B0 - OFF_W0), CTX + 1, PlainRow{Cs, NR}, Ha, nullptr, lt);
+                w = next_block(true);
+                dense_layer_g<NR, 1, 2>(w, w + (OFF_B1 - OFF_W1), H1, PlainRow{Ha, NR}, Hb, nullptr, lt);
+                w = next_block(true);
+                dense_layer_g<NR, 1, 2>(w, w + (OFF_B2 - OFF_W2), H2, PlainRow{Hb, NR}, Hc, nullptr, lt);
+                w = next_block(true);
+                dense_layer_g84<NR, 0>(w, w + (OFF_B3 - OFF_W3), H3, PlainRow{Hc, NR}, Raw, nullptr, lt);
+                w = next_block(t + 1 < P.T);                 // (also the barrier between the raw outputs and the knot pass)
+                lap(3);
                 spline_knots_full_g<NR>(Raw, P.radius, Ha, lt);          // 72 x NR floats over Ha and the start of Hb (both free here)
                 gbar();
                 lap(4);
@@ -1202,8 +1205,7 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
             }
         }
         lap(6);
-        if (rd + 1 < S.nrounds && S.joint[rd + 1][g] >= 0) prefetch(S.joint[rd + 1][g], 0);
-        __syncthreads();
+        cbar();
         lap(7);
     }
     if (dbg && blockIdx.x == 0 && lt == 0)
@@ -1579,8 +1581,8 @@ extern "C" int hf_flow_sample(const hf_flow_t* h, const float* img_base, const f
             const size_t smem = LevelSmem<NR>::Total * sizeof(float);
             int rc = set_smem(flow_sample_levels_kernel<NR>, smem);
             if (rc) return rc;
-            HF_CUDA(hf::launch_pdl(flow_sample_levels_kernel<NR>, dim3(hf::div_up(R, NR)), dim3(LNT), smem, (cudaStream_t)stream, h->P, h->sched, base_noise,
-                                   R, Rn, rotmats, axisangle_pe, (const float*)workspace, getenv("HF_FLOW_DBG") ? 1 : 0));
+            HF_CUDA(hf::launch_pdl(flow_sample_levels_kernel<NR>, dim3(hf::div_up(R, NR)), dim3(LNT + 32 * LG), smem, (cudaStream_t)stream, h->P, h->sched, base_noise,
+                                   R, Rn, rotmats, axisangle_pe, (const float*)workspace, getenv("HF_FLOW_DBG") ? atoi(getenv("HF_FLOW_DBG")) : 0));
         });
         HF_LAUNCH_CHECK();
         return HF_OK;
