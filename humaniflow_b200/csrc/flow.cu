@@ -810,7 +810,7 @@ flow_sample_kernel(const __grid_constant__ FlowParams P, const float* __restrict
 constexpr int LG = 3, LGT = 192, LNT = LG * LGT;
 constexpr int LWB = 65 * (64 + WPAD) + 64;        // largest [W | b] block in floats: first coupling layer; the ancestor block is <= 63*68 + 64
 
-struct LevelSched { int nrounds; signed char joint[HF_FJ][LG]; };      // joint index per (round, group), -1 = idle
+struct LevelSched { int count[LG]; signed char joint[LG][HF_FJ]; };      // the joints of every group in execution order (a static list schedule)
 
 template <int NR>
 struct LevelSmem {
@@ -1050,8 +1050,10 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
     // guarded by full / empty mbarriers
     __shared__ __align__(8) uint64_t lbar[LG][4];         // full[0..1], empty[0..1]
     __shared__ int anc_off[LG][64];                        // row offset into Ps of every input k of the group's context layer
+    __shared__ volatile int jdone[HF_FJ];                  // joint finished: its rotations are in Ps
     const int tid = threadIdx.x;
     const int NL = 1 + 4 * P.T;                            // layers per joint: ancestor block, then 4 per coupling
+    if (tid < HF_FJ) jdone[tid] = 0;
     if (tid < LG) {
         const uint32_t bb = smem_u32(&lbar[tid][0]);
         for (int i = 0; i < 4; ++i) mbar_init(bb + 8 * i, 1);
@@ -1065,9 +1067,8 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
             const uint32_t bar_g = smem_u32(&lbar[g][0]);
             float* wb = smraw + LS::Wb + g * 2 * LWB;
             int blk = 0;                                   // running block counter of the group: buffer = blk & 1, use = blk >> 1
-            for (int rd = 0; rd < S.nrounds; ++rd) {
-                const int j = S.joint[rd][g];
-                if (j < 0) continue;
+            for (int rd = 0; rd < S.count[g]; ++rd) {
+                const int j = S.joint[g][rd];
                 const float* jb = P.jpack + P.off_jb[j];
                 const int na = 9 * P.anc_cnt[j] * CTXP + CTX;
                 for (int l = 0; l < NL; ++l, ++blk) {
@@ -1103,7 +1104,6 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
     const float* Ucta = U + (size_t)blockIdx.x * P.J * CTX * NR;
     const uint32_t bar_g = smem_u32(&lbar[g][0]);
     auto gbar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(LGT) : "memory"); };
-    auto cbar = [&]() { asm volatile("bar.sync %0, %1;" ::"n"(LG + 1), "n"(LNT) : "memory"); };      // all consumer threads (round barrier)
     int blk = 0;
     // ONE group barrier per layer (a bar.sync costs ~300 cycles on this loaded SM): it publishes the layer's outputs and, because
     // the group's first thread has observed the next block's mbarrier just before it, the next layer's weights; the finished
@@ -1122,10 +1122,17 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
     };
     HF_PDL_SYNC();
     lap(0);
-    for (int rd = 0; rd < S.nrounds; ++rd) {
-        const int j = S.joint[rd][g];
-        if (j >= 0) {
+    for (int rd = 0; rd < S.count[g]; ++rd) {
+        const int j = S.joint[g][rd];
+        {
             const int Ka = 9 * P.anc_cnt[j];
+            // the ancestors' rotations must be in Ps: they were produced earlier by this or another group (the deepest ancestor
+            // finishing implies the others); one thread polls, the group barrier in first_block() publishes it
+            if (lt == 0 && Ka > 0) {
+                for (int q = 0; q < P.anc_cnt[j]; ++q)
+                    while (!jdone[(int)P.anc[j][q]]) {}
+                __threadfence_block();
+            }
             if (lt < NR) {       // base sample (zero for point-estimate rows); the first permutation is the identity
                 const int r = r0 + lt;
                 float z0 = 0.f, z1 = 0.f, z2 = 0.f;
@@ -1204,9 +1211,9 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
                 }
             }
         }
+        gbar();                                  // the joint's rotations are written by every row thread of the group ...
+        if (lt == 0) { __threadfence_block(); jdone[j] = 1; }      // ... before the flag goes up
         lap(6);
-        cbar();
-        lap(7);
     }
     if (dbg && blockIdx.x == 0 && lt == 0)
         printf("flow levels group %d (cycles): start %lld | weight waits %lld | context %lld | coupling layers %lld | knots %lld | spline %lld | exp map %lld | round barrier %lld\n",
@@ -1467,26 +1474,35 @@ extern "C" int hf_flow_create(hf_flow_t** out, const hf_flow_config* cfg, const 
             else jpack.resize(jpack.size() + COUPLING_FLOATS, 0.f);
         }
     }
-    {   // dependency levels of the tree (a joint's context reads its ancestors' rotations), packed into rounds of <= LG joints
-        int level[HF_FJ];
-        int maxl = 0;
-        for (int j = 0; j < P.J; ++j) {
-            int l = 0;
-            for (int q = 0; q < P.anc_cnt[j]; ++q) l = std::max(l, level[(int)P.anc[j][q]] + 1);
-            level[j] = l;
-            maxl = std::max(maxl, l);
+    {   // static list schedule of the joints on LG workers: a joint is ready when all its ancestors are done (its context reads
+        // their rotations); among the ready joints the one with the longest chain of descendants goes first.  Unit joint cost.
+        // (SMPL: 8 steps for 23 joints on 3 workers; the kernel's groups follow their lists and wait on per-joint flags.)
+        int height[HF_FJ], done_at[HF_FJ];
+        for (int j = P.J - 1; j >= 0; --j) {
+            height[j] = 1;
+            for (int c = j + 1; c < P.J; ++c)
+                for (int q = 0; q < P.anc_cnt[c]; ++q)
+                    if (P.anc[c][q] == j) height[j] = std::max(height[j], height[c] + 1);
+            done_at[j] = -1;
         }
         LevelSched& S = h->sched;
-        S.nrounds = 0;
-        for (int l = 0; l <= maxl; ++l) {
-            int cnt = 0;
-            for (int j = 0; j < P.J; ++j) {
-                if (level[j] != l) continue;
-                if (cnt == 0) { for (int q = 0; q < LG; ++q) S.joint[S.nrounds][q] = -1; }
-                S.joint[S.nrounds][cnt++] = (signed char)j;
-                if (cnt == LG) { ++S.nrounds; cnt = 0; }
+        for (int g = 0; g < LG; ++g) S.count[g] = 0;
+        int left = P.J;
+        for (int step = 0; left > 0; ++step) {
+            bool taken[HF_FJ] = {};
+            for (int g = 0; g < LG; ++g) {
+                int best = -1;
+                for (int j = 0; j < P.J; ++j) {
+                    if (done_at[j] >= 0 || taken[j]) continue;
+                    bool ready = true;
+                    for (int q = 0; q < P.anc_cnt[j]; ++q) { const int a = P.anc[j][q]; if (done_at[a] < 0 || done_at[a] > step) ready = false; }
+                    if (ready && (best < 0 || height[j] > height[best])) best = j;
+                }
+                if (best < 0) continue;
+                taken[best] = true;
+                S.joint[g][S.count[g]++] = (signed char)best;
             }
-            if (cnt) ++S.nrounds;
+            for (int j = 0; j < P.J; ++j) if (taken[j]) { done_at[j] = step + 1; --left; }
         }
     }
     std::vector<float> wsplit((size_t)P.J * CTX * 2 * FEATS);
