@@ -250,48 +250,56 @@ __device__ __forceinline__ float spline_forward(const float* raw, int rs, int d,
     return num / den;
 }
 
-// Sampling-kernel variant: one pass over 8 lanes per (row, d) computes BOTH softmax / cumulative-knot vectors plus every bin's
-// derivative (softplus) and lambda (sigmoid), so that the two threads per row that evaluate the spline afterwards only search the
-// bin and do the rational arithmetic.  KN[(row*2 + d)*36 + ...] = [widths 9 | heights 9 | derivatives 9 | lambdas 8 | pad].
-// Same per-element formulas as spline_knots / spline_select (bit-identical results).  Ends with __syncthreads().
 constexpr int KNF = 36;
+// One knot task of the sampling kernels: 4 lanes per (row, dimension), lane q takes bins 2q and 2q + 1 of BOTH softmax / cumulative
+// vectors plus their derivative (softplus) and lambda (sigmoid) entries: 8 * NR tasks (one pass of a 192-thread group at NR = 24;
+// the 8-lanes-per-vector form needed two), two shuffle steps per reduction instead of three.
+//   KN[(row*2 + d)*KNF + ...] = [widths 9 | heights 9 | derivatives 9 | lambdas 8 | pad]
+template <int NR>
+__device__ __forceinline__ void knot_task(const float* __restrict__ raw, float bound, float* __restrict__ KN, int t) {
+    const float lo = -bound, hi = bound;
+    const int g = t >> 2, q = t & 3, row = g >> 1, d = g & 1, b0 = 2 * q;
+    const float* r0 = raw + row;
+    float x[2][2], e[2][2], c[2][2];          // [vector: widths / heights][bin]
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        x[v][0] = r0[(v * 2 * NBINS + d * NBINS + b0) * NR];
+        x[v][1] = r0[(v * 2 * NBINS + d * NBINS + b0 + 1) * NR];
+    }
+    const float xd0 = r0[(4 * NBINS + d * (NBINS - 1) + b0) * NR], xd1 = r0[(4 * NBINS + d * (NBINS - 1) + min(b0 + 1, NBINS - 2)) * NR];
+    const float xl0 = r0[(4 * NBINS + 2 * (NBINS - 1) + d * NBINS + b0) * NR], xl1 = r0[(4 * NBINS + 2 * (NBINS - 1) + d * NBINS + b0 + 1) * NR];
+    float* k = KN + g * KNF;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        float m = fmaxf(x[v][0], x[v][1]);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2, 4));
+        e[v][0] = expf(x[v][0] - m); e[v][1] = expf(x[v][1] - m);
+        float s = e[v][0] + e[v][1];
+        s += __shfl_xor_sync(0xffffffffu, s, 1, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2, 4);
+        c[v][0] = 1e-3f + 0.992f * (e[v][0] / s);
+        c[v][1] = 1e-3f + 0.992f * (e[v][1] / s);
+        float p = c[v][0] + c[v][1];                      // inclusive scan of the pair sums over the 4 lanes
+        float u = __shfl_up_sync(0xffffffffu, p, 1, 4); if (q >= 1) p += u;
+        u = __shfl_up_sync(0xffffffffu, p, 2, 4); if (q >= 2) p += u;
+        u = __shfl_up_sync(0xffffffffu, p, 1, 4);
+        const float excl = q >= 1 ? u : 0.f;
+        k[v * 9 + b0 + 1] = (hi - lo) * (excl + c[v][0]) + lo;
+        k[v * 9 + b0 + 2] = (q == 3) ? hi : (hi - lo) * p + lo;
+        if (q == 0) k[v * 9] = lo;
+    }
+    const float sp0 = (xd0 > 20.f) ? xd0 : log1pf(expf(xd0)), sp1 = (xd1 > 20.f) ? xd1 : log1pf(expf(xd1));
+    k[18 + b0 + 1] = 1e-3f + sp0;
+    k[18 + b0 + 2] = (q == 3) ? 0.999f : 1e-3f + sp1;
+    if (q == 0) k[18] = 0.999f;
+    k[27 + b0] = 0.95f * (1.f / (1.f + expf(-xl0))) + 0.025f;
+    k[27 + b0 + 1] = 0.95f * (1.f / (1.f + expf(-xl1))) + 0.025f;
+}
+
 template <int NR>
 __device__ __forceinline__ void spline_knots_full(const float* __restrict__ raw, float bound, float* __restrict__ KN) {
-    const float lo = -bound, hi = bound;
-    for (int t = threadIdx.x; t < NR * 16; t += HF_NT) {      // NR*2 groups of 8 lanes
-        const int g = t >> 3, b = t & 7;
-        const int row = g >> 1, d = g & 1;
-        const float xw = raw[(d * NBINS + b) * NR + row], xh = raw[(2 * NBINS + d * NBINS + b) * NR + row];
-        const float xd = raw[(4 * NBINS + d * (NBINS - 1) + min(b, NBINS - 2)) * NR + row];
-        const float xl = raw[(4 * NBINS + 2 * (NBINS - 1) + d * NBINS + b) * NR + row];
-        float mw = xw, mh = xh;
-#pragma unroll
-        for (int sft = 1; sft < 8; sft <<= 1) {
-            mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, sft, 8));
-            mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, sft, 8));
-        }
-        const float ew = expf(xw - mw), eh = expf(xh - mh);
-        float sw = ew, sh = eh;
-#pragma unroll
-        for (int sft = 1; sft < 8; sft <<= 1) {
-            sw += __shfl_xor_sync(0xffffffffu, sw, sft, 8);
-            sh += __shfl_xor_sync(0xffffffffu, sh, sft, 8);
-        }
-        float cw = 1e-3f + 0.992f * (ew / sw), ch = 1e-3f + 0.992f * (eh / sh);
-#pragma unroll
-        for (int sft = 1; sft < 8; sft <<= 1) {              // inclusive scans over the 8 lanes
-            const float uw = __shfl_up_sync(0xffffffffu, cw, sft, 8), uh = __shfl_up_sync(0xffffffffu, ch, sft, 8);
-            if (b >= sft) { cw += uw; ch += uh; }
-        }
-        const float sp = (xd > 20.f) ? xd : log1pf(expf(xd));
-        const float lam = 0.95f * (1.f / (1.f + expf(-xl))) + 0.025f;
-        float* k = KN + g * KNF;
-        k[b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * cw + lo;
-        k[9 + b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * ch + lo;
-        k[18 + b + 1] = (b == NBINS - 1) ? 0.999f : 1e-3f + sp;
-        k[27 + b] = lam;
-        if (b == 0) { k[0] = lo; k[9] = lo; k[18] = 0.999f; }
-    }
+    for (int t = threadIdx.x; t < NR * 8; t += HF_NT) knot_task<NR>(raw, bound, KN, t);      // whole warps: NR * 8 is a multiple of 32
     __syncthreads();
 }
 
@@ -871,72 +879,6 @@ __device__ __forceinline__ void dense_layer_g(const float* __restrict__ W, const
     }
 }
 
-// Dense layer of one thread group with a LARGER register tile: 8 (OT = 2) or 4 (OT = 1) outputs x 8 rows per tile, the 8 lanes of a
-// tile take every eighth k.  The 4 x 4 tile of dense_layer moves 8 floats from shared memory per 16 FMAs and is bound by the
-// shared-memory pipe (two 4-wavefront LDS.128 per 8 FFMA2); this one moves 16 (12) floats per 64 (32) FMAs, and the three tiles
-// that share an output group sit in the same warp, so their weight loads are broadcasts.  The 8 k-slices are combined by a
-// transpose-reduction (N/2 + N/4 + N/8 shuffles for N accumulators) that leaves lane kl with output og*OW + kl (OT = 2: all 8
-// rows; OT = 1: output og*4 + kl/2, rows (kl&1)*4..).  24 tiles x 8 lanes = the 192 threads of a group at NR = 24.
-template <int NR, int OT, int ACT, typename XRow>
-__device__ __forceinline__ void dense_layer_g8(const float* __restrict__ W, const float* __restrict__ bias, int K, XRow xrow,
-                                               float* dst, const float* __restrict__ add, int lt) {
-    constexpr int O = OT * 32, LDW = O + 4, RG = NR / 8, OW = O / 8, N = OW * 8;
-    static_assert(NR % 8 == 0 && 8 * RG * 8 <= LGT, "dense_layer_g8 tile mapping");
-    const int kl = lt & 7, tile = lt >> 3;
-    if (tile < 8 * RG) {                         // whole warps (4 tiles per warp; 8 * RG is a multiple of 4)
-        const int og = tile / RG, rg = tile - og * RG;
-        float f[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) f[i] = 0.f;
-        float2* acc = reinterpret_cast<float2*>(f);          // acc[o * 4 + rp]: output o, row pair rp
-        const float* wp = W + og * OW;
-#pragma unroll 2
-        for (int k = kl; k < K; k += 8) {
-            float w[OW];
-#pragma unroll
-            for (int q = 0; q < OW / 4; ++q) {
-                const float4 t = *reinterpret_cast<const float4*>(wp + (size_t)k * LDW + q * 4);
-                w[q * 4] = t.x; w[q * 4 + 1] = t.y; w[q * 4 + 2] = t.z; w[q * 4 + 3] = t.w;
-            }
-            const float* xr = xrow(k) + rg * 8;
-            const float4 x0 = *reinterpret_cast<const float4*>(xr), x1 = *reinterpret_cast<const float4*>(xr + 4);
-            const float2 xp[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
-#pragma unroll
-            for (int o = 0; o < OW; ++o) {
-                const float2 ww = make_float2(w[o], w[o]);
-#pragma unroll
-                for (int rp = 0; rp < 4; ++rp) acc[o * 4 + rp] = fma2(ww, xp[rp], acc[o * 4 + rp]);
-            }
-        }
-        // transpose-reduction over the 8 k-lanes
-#pragma unroll
-        for (int sft = 4, n = N / 2; sft >= 1; sft >>= 1, n >>= 1) {
-            const bool up = (kl & sft) != 0;
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-                const float keep = up ? f[i + n] : f[i], send = up ? f[i] : f[i + n];
-                f[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
-            }
-        }
-        // lane kl now holds entries [kl * N/8, +N/8) of the tile's (output, row) grid
-        constexpr int PER = N / 8;                          // 8 (one output, 8 rows) or 4 (half an output row block)
-        const int o = og * OW + (kl * PER) / 8, rbase = rg * 8 + (kl * PER) % 8;
-        const float b = bias[o];
-#pragma unroll
-        for (int q = 0; q < PER / 4; ++q) {
-            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (add) a4 = __ldg(reinterpret_cast<const float4*>(add + o * NR + rbase + q * 4));
-            float v[4] = {f[q * 4] + b + a4.x, f[q * 4 + 1] + b + a4.y, f[q * 4 + 2] + b + a4.z, f[q * 4 + 3] + b + a4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (ACT == 1) v[e] = elu(v[e]);
-                if (ACT == 2) v[e] = fmaxf(v[e], 0.f);
-            }
-            *reinterpret_cast<float4*>(dst + o * NR + rbase + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-    }
-}
-
 // 64-output layers of one thread group: tile = 8 outputs x 4 rows, 4 k-lanes (48 tiles x 4 = the 192 threads at NR = 24: ONE pass).
 // Per k a lane loads 8 weights (two LDS.128 that are broadcasts for the six tiles of an output group sharing a warp) and 4 row
 // values for 16 FFMA2: 5 shared-memory wavefronts per 16 FFMA2 against 8 per 8 for the 4 x 4 tile, which keeps the shared-memory
@@ -1000,41 +942,7 @@ __device__ __forceinline__ void dense_layer_g84(const float* __restrict__ W, con
 // spline_knots_full for one thread group (no barrier)
 template <int NR>
 __device__ __forceinline__ void spline_knots_full_g(const float* __restrict__ raw, float bound, float* __restrict__ KN, int lt) {
-    const float lo = -bound, hi = bound;
-    for (int t = lt; t < NR * 16; t += LGT) {
-        const int g = t >> 3, b = t & 7;
-        const int row = g >> 1, d = g & 1;
-        const float xw = raw[(d * NBINS + b) * NR + row], xh = raw[(2 * NBINS + d * NBINS + b) * NR + row];
-        const float xd = raw[(4 * NBINS + d * (NBINS - 1) + min(b, NBINS - 2)) * NR + row];
-        const float xl = raw[(4 * NBINS + 2 * (NBINS - 1) + d * NBINS + b) * NR + row];
-        float mw = xw, mh = xh;
-#pragma unroll
-        for (int sft = 1; sft < 8; sft <<= 1) {
-            mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, sft, 8));
-            mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, sft, 8));
-        }
-        const float ew = expf(xw - mw), eh = expf(xh - mh);
-        float sw = ew, sh = eh;
-#pragma unroll
-        for (int sft = 1; sft < 8; sft <<= 1) {
-            sw += __shfl_xor_sync(0xffffffffu, sw, sft, 8);
-            sh += __shfl_xor_sync(0xffffffffu, sh, sft, 8);
-        }
-        float cw = 1e-3f + 0.992f * (ew / sw), ch = 1e-3f + 0.992f * (eh / sh);
-#pragma unroll
-        for (int sft = 1; sft < 8; sft <<= 1) {
-            const float uw = __shfl_up_sync(0xffffffffu, cw, sft, 8), uh = __shfl_up_sync(0xffffffffu, ch, sft, 8);
-            if (b >= sft) { cw += uw; ch += uh; }
-        }
-        const float sp = (xd > 20.f) ? xd : log1pf(expf(xd));
-        const float lam = 0.95f * (1.f / (1.f + expf(-xl))) + 0.025f;
-        float* k = KN + g * KNF;
-        k[b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * cw + lo;
-        k[9 + b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * ch + lo;
-        k[18 + b + 1] = (b == NBINS - 1) ? 0.999f : 1e-3f + sp;
-        k[27 + b] = lam;
-        if (b == 0) { k[0] = lo; k[9] = lo; k[18] = 0.999f; }
-    }
+    for (int t = lt; t < NR * 8; t += LGT) knot_task<NR>(raw, bound, KN, t);
 }
 
 template <int NR>
