@@ -54,6 +54,30 @@ if os.path.exists(lst):
         for r in step:
             w.writerow([r['ID'], r['Kernel Name'].split('(')[0], r['Grid Size'], r['Block Size'], r['Metric Value'], r['Metric Unit']])
 
+lst2 = os.path.join(G, 'launches_e2e_%s.csv' % suffix)
+if os.path.exists(lst2):
+    rows = rows_of(lst2)
+    starts = [i for i, r in enumerate(rows) if 'proxy_rep_kernel' in r['Kernel Name']]
+    ends = [i for i, r in enumerate(rows) if 'samples_reduce_kernel' in r['Kernel Name']]
+    if starts and ends and ends[-1] > starts[-1]:
+        step = rows[starts[-1]:ends[-1] + 1]
+        agg = collections.OrderedDict()
+        tot = 0.0
+        for r in step:
+            name = r['Kernel Name'].split('(')[0].replace('void ', '').replace('<unnamed>::', '')
+            v = float(r['Metric Value'].replace(',', ''))
+            v = v / 1000 if r['Metric Unit'] == 'ns' else (v * 1000 if r['Metric Unit'] == 'ms' else v)
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += v
+            tot += v
+        out += ['## Launch list of one END-TO-END step (`python tools/e2e_launches.py 2`: RGB + 2-D joints -> staged proxy representation -> the step -> per-image metric rows)', '',
+                '%d launches, %.1f us of kernel time under ncu.' % (len(step), tot), '',
+                '| kernel | launches | us | share |', '|---|---:|---:|---:|']
+        for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            out.append('| `%s` | %d | %.1f | %.1f%% |' % (k[:70], c, t, 100 * t / tot))
+        out.append('')
+
 WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
