@@ -9,11 +9,12 @@
 // the host (2 x 265 MB per batch) and runs numpy incl. one 3x3 SVD per mesh; here a block per sample reads the mesh twice
 // from HBM and nothing but 3 floats per sample leaves the GPU.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
 constexpr int ME_THREADS = 256;     // block per point set; eight such blocks per SM overlap the single-thread 3x3 solve of one set with the passes of the others
-constexpr int SS_THREADS = 256;     // sample_stats
+constexpr int SS_THREADS = 1024;    // sample_stats
 
 // Jacobi eigen-decomposition of a symmetric 3x3 matrix (fp64): A = V diag(w) V^T, columns of V orthonormal.
 __device__ void eig_sym3(double A[3][3], double V[3][3], double w[3]) {
@@ -418,36 +419,65 @@ pse_pass_kernel(const float* __restrict__ pred, const float* __restrict__ target
 template <int D>
 __global__ void __launch_bounds__(SS_THREADS)
 sample_stats_kernel(const float* __restrict__ pts, const float* __restrict__ target, const float* __restrict__ weights, int N, int P,
-                    float* __restrict__ out) {
+                    int parts, float* __restrict__ out) {
+    // `parts` threads share a point: thread (p, part) takes the samples n = part, part + parts, ...  (joint sets have fewer points
+    // than the block has threads; one thread per point walked 2 x N dependent loads and took 20 us for 100 x 90 joints).  The
+    // partial sums of the mean meet in shared memory and are added in part order.
     HF_PDL_SYNC();
+    extern __shared__ float mu_part[];                       // [parts][P][D]
     __shared__ double scratch[(SS_THREADS / 32) * 3 + 3];
     const int b = blockIdx.x;
     const float* xb = pts + (size_t)b * N * P * D;
     double v[3] = {0.0, 0.0, 0.0};       // diversity sum, L2E sum, weight sum
-    for (int p = threadIdx.x; p < P; p += SS_THREADS) {
-        const float w = weights ? __ldg(weights + (size_t)b * P + p) : 1.f;
+    const int npp = P * parts;
+    for (int base = 0; base < npp; base += SS_THREADS) {
+        const int i = base + threadIdx.x;
+        const bool act = i < npp;
+        const int p = act ? i / parts : 0, part = act ? i - p * parts : 0;
         float mu[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) mu[d] = 0.f;
-        for (int n = 0; n < N; ++n) {
-            const float* x = xb + ((size_t)n * P + p) * D;
+        if (act) {
+            for (int n = part; n < N; n += parts) {
+                const float* x = xb + ((size_t)n * P + p) * D;
 #pragma unroll
-            for (int d = 0; d < D; ++d) mu[d] += __ldg(x + d);
+                for (int d = 0; d < D; ++d) mu[d] += __ldg(x + d);
+            }
+            if (parts > 1) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) mu_part[((size_t)part * P + p) * D + d] = mu[d];
+            }
         }
+        if (parts > 1) {
+            __syncthreads();
+            if (act) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) mu[d] /= (float)N;
-        float t[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) t[d] = target ? __ldg(target + ((size_t)b * P + p) * D + d) : 0.f;
-        float div = 0.f, l2e = 0.f;
-        for (int n = 0; n < N; ++n) {
-            const float* x = xb + ((size_t)n * P + p) * D;
-            float a = 0.f, c = 0.f;
-#pragma unroll
-            for (int d = 0; d < D; ++d) { const float xv = __ldg(x + d); a += (xv - mu[d]) * (xv - mu[d]); c += (xv - t[d]) * (xv - t[d]); }
-            div += sqrtf(a); l2e += sqrtf(c);
+                for (int d = 0; d < D; ++d) {
+                    float a = 0.f;
+                    for (int q = 0; q < parts; ++q) a += mu_part[((size_t)q * P + p) * D + d];
+                    mu[d] = a;
+                }
+            }
+            __syncthreads();
         }
-        v[0] += (double)(w * div); v[1] += (double)(w * l2e); v[2] += (double)w;
+        if (act) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) mu[d] /= (float)N;
+            const float w = weights ? __ldg(weights + (size_t)b * P + p) : 1.f;
+            float t[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) t[d] = target ? __ldg(target + ((size_t)b * P + p) * D + d) : 0.f;
+            float div = 0.f, l2e = 0.f;
+            for (int n = part; n < N; n += parts) {
+                const float* x = xb + ((size_t)n * P + p) * D;
+                float a = 0.f, c = 0.f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) { const float xv = __ldg(x + d); a += (xv - mu[d]) * (xv - mu[d]); c += (xv - t[d]) * (xv - t[d]); }
+                div += sqrtf(a); l2e += sqrtf(c);
+            }
+            v[0] += (double)(w * div); v[1] += (double)(w * l2e);
+            if (part == 0) v[2] += (double)w;
+        }
     }
     block_sum<3, SS_THREADS>(v, scratch);
     if (threadIdx.x == 0) {
@@ -508,8 +538,11 @@ extern "C" int hf_sample_stats(const float* points, const float* target, const f
                                void* stream) {
     if (!points || !out) return hf::fail(HF_ERR_INVALID, "hf_sample_stats: null argument");
     if (B <= 0 || N <= 0 || P <= 0) return HF_OK;
-    if (D == 3) HF_CUDA(hf::launch_pdl(sample_stats_kernel<3>, dim3(B), dim3(SS_THREADS), 0, (cudaStream_t)stream, points, target, weights, N, P, out));
-    else if (D == 2) HF_CUDA(hf::launch_pdl(sample_stats_kernel<2>, dim3(B), dim3(SS_THREADS), 0, (cudaStream_t)stream, points, target, weights, N, P, out));
+    int parts = std::max(1, std::min(SS_THREADS / P, std::min(N, 16)));
+    while (parts > 1 && (size_t)parts * P * D * sizeof(float) > 40 * 1024) --parts;
+    const size_t smem = parts > 1 ? (size_t)parts * P * D * sizeof(float) : 0;
+    if (D == 3) HF_CUDA(hf::launch_pdl(sample_stats_kernel<3>, dim3(B), dim3(SS_THREADS), smem, (cudaStream_t)stream, points, target, weights, N, P, parts, out));
+    else if (D == 2) HF_CUDA(hf::launch_pdl(sample_stats_kernel<2>, dim3(B), dim3(SS_THREADS), smem, (cudaStream_t)stream, points, target, weights, N, P, parts, out));
     else return hf::fail(HF_ERR_INVALID, "hf_sample_stats: D must be 2 or 3");
     HF_LAUNCH_CHECK();
     return HF_OK;
