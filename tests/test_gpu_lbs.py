@@ -270,3 +270,39 @@ def test_fitting_step_through_axis_angle_pose():
             bc -= 0.02 * bc.grad
             thc -= 0.02 * thc.grad
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_argument_errors_are_reported_not_crashed():
+    """Bad calls through the C-ABI come back as error codes with a message (hf_last_error), never as a crashed launch: both
+    incoming gradients NULL, workspaces that are too small."""
+    from humaniflow_b200 import _lib
+    lib = _lib.load()
+    smpl = _smpl()
+    dev = torch.device('cuda')
+    h = smpl._handle(dev)
+    M = 3
+    betas = torch.zeros(M, 10, device=dev)
+    R = torch.eye(3, device=dev).expand(M, 24, 3, 3).contiguous()
+    gb, gr = torch.empty_like(betas), torch.empty_like(R)
+    ws = torch.empty(lib.hf_lbs_backward_workspace_bytes(h, M), device=dev, dtype=torch.uint8)
+    rc = lib.hf_lbs_backward(h, _lib.ptr(betas), _lib.ptr(R), None, None, _lib.ptr(gb), _lib.ptr(gr), _lib.ptr(ws), ws.numel(), M, _lib.stream())
+    assert rc != 0 and b'NULL' in lib.hf_last_error()
+    gj = torch.zeros(M, 90, 3, device=dev)
+    rc = lib.hf_lbs_backward(h, _lib.ptr(betas), _lib.ptr(R), None, _lib.ptr(gj), _lib.ptr(gb), _lib.ptr(gr), _lib.ptr(ws), 16, M, _lib.stream())
+    assert rc != 0 and b'workspace' in lib.hf_last_error()
+    x = torch.zeros(32, 2048, device=dev)
+    W = torch.zeros(1024, 2048, device=dev)
+    y = torch.zeros(32, 1024, device=dev)
+    small = torch.empty(64, device=dev, dtype=torch.uint8)
+    assert lib.hf_linear_workspace_bytes(32, 2048, 1024) > 64
+    rc = lib.hf_linear_ws(_lib.ptr(x), 2048, _lib.ptr(W), 2048, None, _lib.ptr(y), 1024, 32, 2048, 1024, 0, 0, _lib.ptr(small), 64, _lib.stream())
+    assert rc != 0 and b'workspace' in lib.hf_last_error()
+    pred = torch.zeros(8, 100, 20, 3, device=dev)
+    tgt = torch.zeros(8, 20, 3, device=dev)
+    out = torch.empty(8, 100, 3, device=dev)
+    rc = lib.hf_pointset_errors_ws(_lib.ptr(pred), _lib.ptr(tgt), 8, 100, 20, _lib.ptr(out), _lib.ptr(small), 64, _lib.stream())
+    assert rc != 0 and b'workspace' in lib.hf_last_error()
+    # zero gradients in: zero gradients out (and a finite result for identity poses)
+    rc = lib.hf_lbs_backward(h, _lib.ptr(betas), _lib.ptr(R), None, _lib.ptr(gj), _lib.ptr(gb), _lib.ptr(gr), _lib.ptr(ws), ws.numel(), M, _lib.stream())
+    torch.cuda.synchronize()
+    assert rc == 0 and gb.abs().max().item() == 0.0 and gr.abs().max().item() == 0.0
