@@ -64,6 +64,8 @@ SIGNATURES = {
     'hf_flow_context': (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_void_p]),
     'hf_flow_log_prob': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'hf_flow_algebra_log_prob': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'hf_flow_log_prob_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'hf_flow_algebra_log_prob_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'hf_linear': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'hf_linear_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'hf_linear_ws': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),

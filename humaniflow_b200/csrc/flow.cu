@@ -1569,3 +1569,388 @@ extern "C" int hf_flow_algebra_log_prob(const hf_flow_t* h, const float* ctx, in
     HF_LAUNCH_CHECK();
     return HF_OK;
 }
+
+
+// =====================================================================================================================
+// Backward of the log-densities w.r.t. their INPUTS: d log_prob / d (context row, target rotation or algebra
+// vector), weights fixed -- what a fitting loop needs from the pose prior (optimise/optimise_humaniflow.py:96-114: the loss is
+// -sum_j log p_j(R_j | ctx_j), and ctx_j depends on the ancestors' rotations, the shape and the global rotation).  The reference gets
+// it from torch.autograd through pyro's SplineCoupling / ConditionalDenseNN and local_diffeo_transformed_distribution.py:84-142.
+// Correctness-first form: ONE THREAD per (row, joint) recomputes the forward chain with all activations in local memory and
+// walks it backwards (these calls see a few dozen rows, not thousands); every formula is the derivative of the forward code in
+// flow_logprob_kernel / spline_inverse above.  fp32 like the forward, fp64 for the exp / log-map parts.
+namespace {
+
+struct CplActs { float in[CTX + 1], h1[64], h2[32], h3[32], raw[64]; };
+
+template <int O>
+__device__ void ref_dense_fwd(const float* __restrict__ W, const float* __restrict__ b, int K, const float* x, float* y, bool relu) {
+    constexpr int LDW = O + WPAD;
+    float acc[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) acc[o] = __ldg(b + o);
+    for (int k = 0; k < K; ++k) {
+        const float xv = x[k];
+        const float4* wr = reinterpret_cast<const float4*>(W + (size_t)k * LDW);
+#pragma unroll
+        for (int q = 0; q < O / 4; ++q) {
+            const float4 w = __ldg(wr + q);
+            acc[q * 4] = fmaf(w.x, xv, acc[q * 4]); acc[q * 4 + 1] = fmaf(w.y, xv, acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(w.z, xv, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(w.w, xv, acc[q * 4 + 3]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < O; ++o) y[o] = relu ? fmaxf(acc[o], 0.f) : acc[o];
+}
+
+// gx[k] = sum_o W[k][o] gy[o]   (gy = gradient w.r.t. the layer's pre-activation)
+template <int O>
+__device__ void ref_dense_bwd(const float* __restrict__ W, int K, const float* gy, float* gx) {
+    constexpr int LDW = O + WPAD;
+    for (int k = 0; k < K; ++k) {
+        const float4* wr = reinterpret_cast<const float4*>(W + (size_t)k * LDW);
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < O / 4; ++q) {
+            const float4 w = __ldg(wr + q);
+            a = fmaf(w.x, gy[q * 4], a); a = fmaf(w.y, gy[q * 4 + 1], a); a = fmaf(w.z, gy[q * 4 + 2], a); a = fmaf(w.w, gy[q * 4 + 3], a);
+        }
+        gx[k] = a;
+    }
+}
+
+__device__ void ref_mlp_fwd(const float* __restrict__ cw, CplActs& A) {
+    ref_dense_fwd<64>(cw + OFF_W0, cw + OFF_B0, CTX + 1, A.in, A.h1, true);
+    ref_dense_fwd<32>(cw + OFF_W1, cw + OFF_B1, H1, A.h1, A.h2, true);
+    ref_dense_fwd<32>(cw + OFF_W2, cw + OFF_B2, H2, A.h2, A.h3, true);
+    ref_dense_fwd<64>(cw + OFF_W3, cw + OFF_B3, H3, A.h3, A.raw, false);
+}
+
+// g_raw[64] (entries >= NRAW ignored) -> g_in[CTX + 1]
+__device__ void ref_mlp_bwd(const float* __restrict__ cw, const CplActs& A, float* g_raw, float* g_in) {
+    float g3[32], g2[32], g1[64];
+    g_raw[62] = 0.f; g_raw[63] = 0.f;
+    ref_dense_bwd<64>(cw + OFF_W3, H3, g_raw, g3);
+    for (int k = 0; k < 32; ++k) g3[k] = A.h3[k] > 0.f ? g3[k] : 0.f;
+    ref_dense_bwd<32>(cw + OFF_W2, H2, g3, g2);
+    for (int k = 0; k < 32; ++k) g2[k] = A.h2[k] > 0.f ? g2[k] : 0.f;
+    ref_dense_bwd<32>(cw + OFF_W1, H1, g2, g1);
+    for (int k = 0; k < 64; ++k) g1[k] = A.h1[k] > 0.f ? g1[k] : 0.f;
+    ref_dense_bwd<64>(cw + OFF_W0, CTX + 1, g1, g_in);
+}
+
+// Inverse rational-linear spline of dimension d for one scalar, from the raw NN outputs (the arithmetic of spline_knots +
+// spline_inverse); with g_raw != nullptr also the backward: upstream gx (on the returned x) and gld (on *ld) -> *gy += d/dy,
+// g_raw[...] += d/d(raw outputs).
+__device__ float ref_spline_inverse(const float* raw, int d, float y, float bound, float* ld, float* g_raw, float gx, float gld, float* gy) {
+    const float lo = -bound, hi = bound;
+    if (!(y >= -bound && y <= bound)) { *ld = 0.f; if (g_raw) *gy += gx; return y; }
+    float sm[2][NBINS], kn[2][NBINS + 1];            // [widths / heights]
+    for (int v = 0; v < 2; ++v) {
+        const float* r = raw + v * 2 * NBINS + d * NBINS;
+        float m = r[0];
+        for (int b = 1; b < NBINS; ++b) m = fmaxf(m, r[b]);
+        float ssum = 0.f;
+        for (int b = 0; b < NBINS; ++b) { sm[v][b] = expf(r[b] - m); ssum += sm[v][b]; }
+        float cum = 0.f;
+        kn[v][0] = lo;
+        for (int b = 0; b < NBINS; ++b) {
+            sm[v][b] /= ssum;
+            cum += 1e-3f + 0.992f * sm[v][b];
+            kn[v][b + 1] = (b == NBINS - 1) ? hi : (hi - lo) * cum + lo;
+        }
+    }
+    int idx = -1;
+    for (int b = 0; b <= NBINS; ++b) idx += (y >= kn[1][b] + 1e-6f) ? 1 : 0;
+    idx = max(0, min(idx, NBINS - 1));
+    const float in_cw = kn[0][idx], in_w = kn[0][idx + 1] - kn[0][idx], in_ch = kn[1][idx], in_h = kn[1][idx + 1] - kn[1][idx];
+    auto deriv_raw = [&](int i) { return raw[4 * NBINS + d * (NBINS - 1) + (i - 1)]; };
+    auto deriv = [&](int i) -> float {
+        if (i == 0 || i == NBINS) return 0.999f;
+        const float u = deriv_raw(i);
+        return 1e-3f + ((u > 20.f) ? u : log1pf(expf(u)));
+    };
+    const float d0 = deriv(idx), d1 = deriv(idx + 1);
+    const float lraw = raw[4 * NBINS + 2 * (NBINS - 1) + d * NBINS + idx];
+    const float sg = 1.f / (1.f + expf(-lraw));
+    const float lam = 0.95f * sg + 0.025f;
+    const float delta = in_h / in_w;
+    const float wb = sqrtf(d0 / d1);
+    const float C = lam * d0 + (1.f - lam) * wb * d1;
+    const float wc = C / delta;
+    const float ya = in_ch, yb = in_h + in_ch;
+    const float Aq = (1.f - lam) * ya + lam * wb * yb, Bq = (1.f - lam) + lam * wb;
+    const float yc = Aq / Bq;
+    const bool left = y <= yc;
+    float num, den, dnum;
+    if (left) {
+        num = lam * (ya - y);
+        den = (wc - 1.f) * y + ya - wc * yc;
+        dnum = wc * lam * (yc - ya) * in_w;
+    } else {
+        num = (wc - lam * wb) * y + lam * wb * yb - wc * yc;
+        den = (wc - wb) * y + wb * yb - wc * yc;
+        dnum = wb * wc * (1.f - lam) * (yb - yc) * in_w;
+    }
+    const float theta = num / den;
+    *ld = -(logf(dnum) - 2.f * logf(fabsf(den)));
+    const float x = theta * in_w + in_cw;
+    if (!g_raw) return x;
+    // ---- backward ----
+    float g_in_w = gx * theta, g_in_cw = gx, g_in_h = 0.f, g_in_ch = 0.f;
+    const float g_theta = gx * in_w;
+    const float g_num = g_theta / den;
+    const float g_den = -g_theta * num / (den * den) + gld * 2.f / den;
+    const float g_dnum = -gld / dnum;
+    float g_lam = 0.f, g_ya = 0.f, g_yb = 0.f, g_yc = 0.f, g_wc = 0.f, g_wb = 0.f, g_y = 0.f;
+    if (left) {
+        g_lam += g_num * (ya - y); g_ya += g_num * lam; g_y -= g_num * lam;
+        g_wc += g_den * (y - yc); g_y += g_den * (wc - 1.f); g_ya += g_den; g_yc -= g_den * wc;
+        const float e = (yc - ya) * in_w;
+        g_wc += g_dnum * lam * e; g_lam += g_dnum * wc * e;
+        g_yc += g_dnum * wc * lam * in_w; g_ya -= g_dnum * wc * lam * in_w; g_in_w += g_dnum * wc * lam * (yc - ya);
+    } else {
+        g_wc += g_num * (y - yc); g_lam += g_num * wb * (yb - y); g_wb += g_num * lam * (yb - y);
+        g_y += g_num * (wc - lam * wb); g_yb += g_num * lam * wb; g_yc -= g_num * wc;
+        g_wc += g_den * (y - yc); g_wb += g_den * (yb - y); g_y += g_den * (wc - wb); g_yb += g_den * wb; g_yc -= g_den * wc;
+        const float e = (yb - yc) * in_w;
+        g_wb += g_dnum * wc * (1.f - lam) * e; g_wc += g_dnum * wb * (1.f - lam) * e; g_lam -= g_dnum * wb * wc * e;
+        g_yb += g_dnum * wb * wc * (1.f - lam) * in_w; g_yc -= g_dnum * wb * wc * (1.f - lam) * in_w;
+        g_in_w += g_dnum * wb * wc * (1.f - lam) * (yb - yc);
+    }
+    {   // yc = Aq / Bq
+        const float g_A = g_yc / Bq, g_B = -g_yc * Aq / (Bq * Bq);
+        g_lam += g_A * (wb * yb - ya) + g_B * (wb - 1.f);
+        g_ya += g_A * (1.f - lam);
+        g_wb += g_A * lam * yb + g_B * lam;
+        g_yb += g_A * lam * wb;
+    }
+    g_in_ch += g_ya + g_yb; g_in_h += g_yb;
+    float g_d0 = 0.f, g_d1 = 0.f;
+    {   // wc = C / delta, C = lam d0 + (1 - lam) wb d1
+        const float g_C = g_wc / delta, g_delta = -g_wc * C / (delta * delta);
+        g_lam += g_C * (d0 - wb * d1); g_d0 += g_C * lam; g_wb += g_C * (1.f - lam) * d1; g_d1 += g_C * (1.f - lam) * wb;
+        g_in_h += g_delta / in_w; g_in_w -= g_delta * in_h / (in_w * in_w);
+    }
+    g_d0 += g_wb * 0.5f * wb / d0; g_d1 -= g_wb * 0.5f * wb / d1;
+    *gy += g_y;
+    // lambda, derivatives
+    g_raw[4 * NBINS + 2 * (NBINS - 1) + d * NBINS + idx] += g_lam * 0.95f * sg * (1.f - sg);
+    if (idx >= 1) { const float u = deriv_raw(idx); g_raw[4 * NBINS + d * (NBINS - 1) + idx - 1] += g_d0 * ((u > 20.f) ? 1.f : 1.f / (1.f + expf(-u))); }
+    if (idx + 1 <= NBINS - 1) { const float u = deriv_raw(idx + 1); g_raw[4 * NBINS + d * (NBINS - 1) + idx] += g_d1 * ((u > 20.f) ? 1.f : 1.f / (1.f + expf(-u))); }
+    // knots: in_cw = kw[idx], in_w = kw[idx+1] - kw[idx] (heights alike); kn[i] = (hi - lo) cum_i + lo for 1 <= i <= 7, ends pinned
+    for (int v = 0; v < 2; ++v) {
+        const float g_lo_knot = v == 0 ? (g_in_cw - g_in_w) : (g_in_ch - g_in_h), g_hi_knot = v == 0 ? g_in_w : g_in_h;
+        float g_c[NBINS];                // gradient w.r.t. the bin lengths c_b = 1e-3 + 0.992 softmax_b
+        for (int b = 0; b < NBINS; ++b) {
+            float a = 0.f;               // c_b enters every knot i > b (i <= 7)
+            if (idx >= 1 && idx <= NBINS - 1 && idx > b) a += g_lo_knot;
+            if (idx + 1 <= NBINS - 1 && idx + 1 > b) a += g_hi_knot;
+            g_c[b] = a * (hi - lo) * 0.992f;
+        }
+        float dot = 0.f;
+        for (int b = 0; b < NBINS; ++b) dot += sm[v][b] * g_c[b];
+        for (int b = 0; b < NBINS; ++b) g_raw[v * 2 * NBINS + d * NBINS + b] += sm[v][b] * (g_c[b] - dot);
+    }
+    return x;
+}
+
+// Algebra-space log-density of joint j for one vector y (fp32), context ctx[CTX]; returns lp.  With g != 0 also accumulates
+// g * d lp / d ctx into g_ctx[CTX] and writes g * d lp / d y into g_y[3].
+__device__ float ref_algebra_lp(const FlowParams& P, int j, const float* ctx, const float* y, float g, float* g_ctx, float* g_y) {
+    const float rad = P.radius;
+    // radial tanh inverse (fp64 like the forward)
+    const double dy0 = y[0], dy1 = y[1], dy2 = y[2];
+    const double yn = sqrt(dy0 * dy0 + dy1 * dy1 + dy2 * dy2);
+    float z[3] = {y[0], y[1], y[2]};
+    double a_th = 0.0;
+    if (yn > 1e-7) {
+        a_th = atanh(yn / (double)rad);
+        z[0] = (float)(a_th * (dy0 / yn) * (double)rad); z[1] = (float)(a_th * (dy1 / yn) * (double)rad); z[2] = (float)(a_th * (dy2 / yn) * (double)rad);
+    }
+    const float xn32 = sqrtf(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]), yn32 = sqrtf(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+    float lp = 0.f;
+    if (yn32 > 1e-7f) {
+        const float q = yn32 / rad;
+        lp -= 2.f * (logf(yn32) - logf(xn32)) + log1pf(-(q * q));
+    }
+    CplActs A[2];
+    float zin[2][3];                  // state entering stage i (stage i handles coupling t = T-1-i)
+    for (int i = 0; i < P.T; ++i) {
+        const int t = P.T - 1 - i;
+        zin[i][0] = z[0]; zin[i][1] = z[1]; zin[i][2] = z[2];
+        for (int k = 0; k < CTX; ++k) A[i].in[k] = ctx[k];
+        A[i].in[CTX] = z[0];
+        ref_mlp_fwd(P.pack + P.off_nn[j][t], A[i]);
+        float ld0, ld1;
+        const float x1 = ref_spline_inverse(A[i].raw, 0, z[1], rad, &ld0, nullptr, 0.f, 0.f, nullptr);
+        const float x2 = ref_spline_inverse(A[i].raw, 1, z[2], rad, &ld1, nullptr, 0.f, 0.f, nullptr);
+        lp -= ld0 + ld1;
+        const float x0 = z[0];
+        if (t > 0) { z[0] = x2; z[1] = x0; z[2] = x1; } else { z[0] = x0; z[1] = x1; z[2] = x2; }
+    }
+    const float sc = P.base_std;
+    for (int e = 0; e < 3; ++e) lp += -(z[e] * z[e]) / (2.f * sc * sc) - logf(sc) - 0.91893853320467274178f;
+    if (g == 0.f) return lp;
+    // ---- backward ----
+    float gz[3];
+    for (int e = 0; e < 3; ++e) gz[e] = g * (-z[e] / (sc * sc));
+    for (int i = P.T - 1; i >= 0; --i) {
+        const int t = P.T - 1 - i;
+        float gx0, gx1, gx2;
+        if (t > 0) { gx2 = gz[0]; gx0 = gz[1]; gx1 = gz[2]; } else { gx0 = gz[0]; gx1 = gz[1]; gx2 = gz[2]; }
+        float g_raw[64];
+        for (int k = 0; k < 64; ++k) g_raw[k] = 0.f;
+        float gz1 = 0.f, gz2 = 0.f, ldd;
+        ref_spline_inverse(A[i].raw, 0, zin[i][1], rad, &ldd, g_raw, gx1, -g, &gz1);
+        ref_spline_inverse(A[i].raw, 1, zin[i][2], rad, &ldd, g_raw, gx2, -g, &gz2);
+        float g_in[CTX + 1];
+        ref_mlp_bwd(P.pack + P.off_nn[j][t], A[i], g_raw, g_in);
+        for (int k = 0; k < CTX; ++k) g_ctx[k] += g_in[k];
+        gz[0] = gx0 + g_in[CTX]; gz[1] = gz1; gz[2] = gz2;
+    }
+    // radial tanh inverse: z = f(n) y / n, f = r atanh(n / r); lp term -ld(n), ld = 2 log n - 2 log f + log(1 - (n/r)^2)
+    if (yn > 1e-7) {
+        const double r = rad, s = yn / r, f = r * a_th, fp = 1.0 / (1.0 - s * s);
+        const double yh[3] = {dy0 / yn, dy1 / yn, dy2 / yn};
+        const double dotg = yh[0] * gz[0] + yh[1] * gz[1] + yh[2] * gz[2];
+        const double dld = 2.0 / yn - 2.0 * fp / f - 2.0 * s * fp / r;
+        for (int e = 0; e < 3; ++e) g_y[e] = (float)((f / yn) * gz[e] + (fp - f / yn) * dotg * yh[e] - (double)g * dld * yh[e]);
+    } else {
+        for (int e = 0; e < 3; ++e) g_y[e] = gz[e];
+    }
+    return lp;
+}
+
+template <bool ALGEBRA>
+__global__ void __launch_bounds__(64)
+flow_logprob_bwd_kernel(const __grid_constant__ FlowParams P, const float* __restrict__ ctx, int ctx_row_stride, int joint_first, int joint_count,
+                        const double* __restrict__ rot, const float* __restrict__ valg, const float* __restrict__ g_out, int R,
+                        float* __restrict__ g_ctx_out, double* __restrict__ g_rot, float* __restrict__ g_valg) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y, j = joint_first + jj;
+    if (r >= R) return;
+    const double PI = 3.14159265358979323846;
+    float c[CTX], gc[CTX];
+    for (int k = 0; k < CTX; ++k) { c[k] = ctx[(size_t)r * ctx_row_stride + j * CTX + k]; gc[k] = 0.f; }
+    const float g = g_out[(size_t)r * joint_count + jj];
+    if (ALGEBRA) {
+        const float* v = valg + ((size_t)r * joint_count + jj) * 3;
+        const float y[3] = {v[0], v[1], v[2]};
+        float gy[3] = {0.f, 0.f, 0.f};
+        if (g != 0.f) ref_algebra_lp(P, j, c, y, g, gc, gy);
+        for (int e = 0; e < 3; ++e) g_valg[((size_t)r * joint_count + jj) * 3 + e] = gy[e];
+    } else {
+        double rm[9], x[3];
+        const double* rp = rot + ((size_t)r * joint_count + jj) * 9;
+        for (int e = 0; e < 9; ++e) rm[e] = rp[e];
+        so3_log_f64(rm, x);
+        const double n = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+        double vc[3][3];
+        int mask[3] = {1, 0, 0};
+        float term[3];
+        for (int cnd = 0; cnd < 3; ++cnd) {
+            if (cnd > 0) {   // the arithmetic of flow_logprob_kernel (the mask is a comparison at the edge of the support)
+                const double fk = n + 2.0 * PI * (cnd == 1 ? -1.0 : 1.0);
+                double v[3] = {x[0] / n * fk, x[1] / n * fk, x[2] / n * fk};
+                const double vn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+                mask[cnd] = (vn < (double)P.radius) ? 1 : 0;          // NaN (n == 0) compares false
+                for (int e = 0; e < 3; ++e) vc[cnd][e] = mask[cnd] ? v[e] : 0.0;
+            } else {
+                for (int e = 0; e < 3; ++e) vc[cnd][e] = x[e];
+            }
+            term[cnd] = -INFINITY;
+            if (mask[cnd]) {
+                const float y[3] = {(float)vc[cnd][0], (float)vc[cnd][1], (float)vc[cnd][2]};
+                term[cnd] = -(float)so3_log_abs_det(vc[cnd][0], vc[cnd][1], vc[cnd][2]) + ref_algebra_lp(P, j, c, y, 0.f, nullptr, nullptr);
+            }
+        }
+        float m = fmaxf(term[0], fmaxf(term[1], term[2]));
+        if (isinf(m)) m = 0.f;
+        float ssum = 0.f;
+        for (int cnd = 0; cnd < 3; ++cnd) ssum += expf(term[cnd] - m);
+        double gx[3] = {0.0, 0.0, 0.0};
+        for (int cnd = 0; cnd < 3; ++cnd) {
+            if (!mask[cnd]) continue;
+            const float gcnd = g * expf(term[cnd] - m) / ssum;
+            if (gcnd == 0.f) continue;
+            const float y[3] = {(float)vc[cnd][0], (float)vc[cnd][1], (float)vc[cnd][2]};
+            float gy[3] = {0.f, 0.f, 0.f};
+            ref_algebra_lp(P, j, c, y, gcnd, gc, gy);
+            // -log|det J_exp|(v): L(n) = log((2 - 2 cos n) / n^2), dL/dn = sin n / (1 - cos n) - 2 / n
+            const double vn = sqrt(vc[cnd][0] * vc[cnd][0] + vc[cnd][1] * vc[cnd][1] + vc[cnd][2] * vc[cnd][2]);
+            double gv[3] = {gy[0], gy[1], gy[2]};
+            if (vn > 1e-10) {
+                const double dL = sin(vn) / (1.0 - cos(vn)) - 2.0 / vn;
+                for (int e = 0; e < 3; ++e) gv[e] -= (double)gcnd * dL * vc[cnd][e] / vn;
+            }
+            if (cnd == 0) { for (int e = 0; e < 3; ++e) gx[e] += gv[e]; }
+            else {   // v = f(n) x, f = 1 + 2 pi k / n
+                const double k2 = 2.0 * PI * (cnd == 1 ? -1.0 : 1.0), f = 1.0 + k2 / n, fp = -k2 / (n * n);
+                const double dotg = (x[0] * gv[0] + x[1] * gv[1] + x[2] * gv[2]) / n;
+                for (int e = 0; e < 3; ++e) gx[e] += f * gv[e] + fp * dotg * x[e];
+            }
+        }
+        // x = so3_log(R): generic branch x = (theta / sin theta) w, w = 0.5 vee(R - R^T), theta = acos((tr R - 1) / 2)
+        double gr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        double cth = 0.5 * (rm[0] + rm[4] + rm[8] - 1.0);
+        const bool clamped = cth < -1.0 || cth > 1.0;
+        cth = fmin(fmax(cth, -1.0), 1.0);
+        const double th = acos(cth);
+        if (fabs(PI - th) < 1e-2) {
+            // near pi the forward takes a_i = sqrt(max(q_i', 1e-8) / 2) with the sign pattern that reproduces R best
+            const double k = th * th / (1.0 - cos(th));
+            const double q1 = k * (rm[0] - 1.0), q2 = k * (rm[4] - 1.0), q3 = k * (rm[8] - 1.0);
+            const double s1 = q1 - q2 - q3, s2 = -q1 + q2 - q3, s3 = -q1 - q2 + q3;
+            const double ga1 = (x[0] != 0.0 && s1 > 1e-8) ? gx[0] * ((x[0] > 0) ? 1.0 : -1.0) / (4.0 * sqrt(s1 / 2.0)) : 0.0;
+            const double ga2 = (x[1] != 0.0 && s2 > 1e-8) ? gx[1] * ((x[1] > 0) ? 1.0 : -1.0) / (4.0 * sqrt(s2 / 2.0)) : 0.0;
+            const double ga3 = (x[2] != 0.0 && s3 > 1e-8) ? gx[2] * ((x[2] > 0) ? 1.0 : -1.0) / (4.0 * sqrt(s3 / 2.0)) : 0.0;
+            const double gq1 = ga1 - ga2 - ga3, gq2 = -ga1 + ga2 - ga3, gq3 = -ga1 - ga2 + ga3;
+            gr[0] += gq1 * k; gr[4] += gq2 * k; gr[8] += gq3 * k;
+            const double gk = gq1 * (rm[0] - 1.0) + gq2 * (rm[4] - 1.0) + gq3 * (rm[8] - 1.0);
+            // k(theta) = theta^2 / (1 - cos theta)
+            const double dk = (2.0 * th * (1.0 - cos(th)) - th * th * sin(th)) / ((1.0 - cos(th)) * (1.0 - cos(th)));
+            if (!clamped) { const double gcth = gk * dk * (-1.0 / sin(th)); gr[0] += 0.5 * gcth; gr[4] += 0.5 * gcth; gr[8] += 0.5 * gcth; }
+        } else {
+            const double sn = sin(th);
+            const double ratio = (th < 1e-20) ? 1.0 : th / sn;
+            const double w[3] = {-0.5 * (rm[5] - rm[7]), 0.5 * (rm[2] - rm[6]), -0.5 * (rm[1] - rm[3])};
+            const double gw[3] = {ratio * gx[0], ratio * gx[1], ratio * gx[2]};
+            gr[5] += -0.5 * gw[0]; gr[7] += 0.5 * gw[0]; gr[2] += 0.5 * gw[1]; gr[6] += -0.5 * gw[1]; gr[1] += -0.5 * gw[2]; gr[3] += 0.5 * gw[2];
+            if (!clamped && th > 1e-6) {
+                // d ratio / d cos(theta) = (d ratio / d theta) (-1 / sin theta), d ratio / d theta = (sin - theta cos) / sin^2
+                const double dr = (sn - th * cos(th)) / (sn * sn);
+                const double gcth = (w[0] * gx[0] + w[1] * gx[1] + w[2] * gx[2]) * dr * (-1.0 / sn);
+                gr[0] += 0.5 * gcth; gr[4] += 0.5 * gcth; gr[8] += 0.5 * gcth;
+            }
+        }
+        for (int e = 0; e < 9; ++e) g_rot[((size_t)r * joint_count + jj) * 9 + e] = gr[e];
+    }
+    for (int k = 0; k < CTX; ++k) g_ctx_out[((size_t)r * joint_count + jj) * CTX + k] = gc[k];
+}
+
+}  // namespace
+
+extern "C" int hf_flow_log_prob_backward(const hf_flow_t* h, const float* ctx, int ctx_row_stride, int joint_first, int joint_count,
+                                         const double* rot_f64, const float* grad_out, int R, float* grad_ctx, double* grad_rot, void* stream) {
+    if (!h || !ctx || !rot_f64 || !grad_out || !grad_ctx || !grad_rot) return hf::fail(HF_ERR_INVALID, "hf_flow_log_prob_backward: null argument");
+    if (joint_first < 0 || joint_count < 1 || joint_first + joint_count > h->P.J)
+        return hf::fail(HF_ERR_INVALID, "hf_flow_log_prob_backward: joints [%d,%d) out of range", joint_first, joint_first + joint_count);
+    if (R <= 0) return HF_OK;
+    HF_CUDA(cudaFuncSetAttribute(flow_logprob_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 0));
+    flow_logprob_bwd_kernel<false><<<dim3(hf::div_up(R, 64), joint_count), 64, 0, (cudaStream_t)stream>>>(h->P, ctx, ctx_row_stride, joint_first, joint_count, rot_f64,
+                                                                                                     nullptr, grad_out, R, grad_ctx, grad_rot, nullptr);
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}
+
+extern "C" int hf_flow_algebra_log_prob_backward(const hf_flow_t* h, const float* ctx, int ctx_row_stride, int joint_first, int joint_count,
+                                                 const float* v, const float* grad_out, int R, float* grad_ctx, float* grad_v, void* stream) {
+    if (!h || !ctx || !v || !grad_out || !grad_ctx || !grad_v) return hf::fail(HF_ERR_INVALID, "hf_flow_algebra_log_prob_backward: null argument");
+    if (joint_first < 0 || joint_count < 1 || joint_first + joint_count > h->P.J)
+        return hf::fail(HF_ERR_INVALID, "hf_flow_algebra_log_prob_backward: joints [%d,%d) out of range", joint_first, joint_first + joint_count);
+    if (R <= 0) return HF_OK;
+    flow_logprob_bwd_kernel<true><<<dim3(hf::div_up(R, 64), joint_count), 64, 0, (cudaStream_t)stream>>>(h->P, ctx, ctx_row_stride, joint_first, joint_count, nullptr,
+                                                                                                    v, grad_out, R, grad_ctx, nullptr, grad_v);
+    HF_LAUNCH_CHECK();
+    return HF_OK;
+}

@@ -56,6 +56,95 @@ class ConditionalSplineCoupling(nn.Module):
         self.count_bins, self.bound = count_bins, bound
 
 
+class _FlowLogProbFunction(torch.autograd.Function):
+    """log_prob of joints [joint_first, joint_first + joint_count) with a CUDA backward w.r.t. the contexts and the targets
+    (hf_flow_log_prob_backward / hf_flow_algebra_log_prob_backward; weights are constants here)."""
+
+    @staticmethod
+    def forward(ctx_, model, joint_first, joint_count, on_group, ctx_all, value):
+        lib = _lib.load()
+        R = ctx_all.shape[0]
+        dev = ctx_all.device
+        c = _lib.f32c(ctx_all)
+        v = value.detach().to(dev, torch.float64 if on_group else torch.float32).contiguous()
+        out = torch.empty(R, joint_count, device=dev, dtype=torch.float32)
+        stride = c.shape[1] * c.shape[2]
+        with torch.cuda.device(dev):
+            fn = lib.hf_flow_log_prob if on_group else lib.hf_flow_algebra_log_prob
+            _lib.check(fn(model._flow, _lib.ptr(c), stride, joint_first, joint_count, _lib.ptr(v), R, _lib.ptr(out), _lib.stream()))
+        ctx_.model, ctx_.jf, ctx_.jc, ctx_.on_group, ctx_.vdtype = model, joint_first, joint_count, on_group, value.dtype
+        ctx_.save_for_backward(c, v)
+        return out
+
+    @staticmethod
+    def backward(ctx_, g):
+        lib = _lib.load()
+        c, v = ctx_.saved_tensors
+        model, jf, jc = ctx_.model, ctx_.jf, ctx_.jc
+        R, dev = c.shape[0], c.device
+        g = _lib.f32c(g)
+        g_part = torch.empty(R, jc, c.shape[2], device=dev, dtype=torch.float32)
+        g_val = torch.empty_like(v)
+        stride = c.shape[1] * c.shape[2]
+        with torch.cuda.device(dev):
+            fn = lib.hf_flow_log_prob_backward if ctx_.on_group else lib.hf_flow_algebra_log_prob_backward
+            _lib.check(fn(model._flow, _lib.ptr(c), stride, jf, jc, _lib.ptr(v), _lib.ptr(g), R, _lib.ptr(g_part), _lib.ptr(g_val), _lib.stream()))
+        g_ctx = torch.zeros_like(c)
+        g_ctx[:, jf:jf + jc] = g_part
+        return None, None, None, None, g_ctx, g_val.to(ctx_.vdtype)
+
+
+class _FlowContextFunction(torch.autograd.Function):
+    """Teacher-forced contexts (models/humaniflow_model.py:133-148, 277-283) with a backward w.r.t. the image features, the camera,
+    the shape, the ancestors' rotations and the global rotation.  Forward: the library's kernels.  Backward: a handful of small
+    dense products with the model's own weight tensors (torch matmuls: glue, 32 x 256-sized)."""
+
+    @staticmethod
+    def forward(ctx_, model, input_feats, cam, shape, pose_R, glob_R):
+        lib = _lib.load()
+        dev = input_feats.device
+        B, J = input_feats.shape[0], model.num_bodyparts
+        base_ll = model._img_base(input_feats, glob_R, cam)
+        betas_ll = _lib.f32c(shape, dev)
+        anc_R = _lib.f32c(pose_R, dev)
+        assert anc_R.shape == (B, J, 3, 3)
+        out = torch.empty(B, J, model.cfg.NORM_FLOW.CONTEXT_DIM, device=dev, dtype=torch.float32)
+        idx = model._img_index(B, 1, False, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hf_flow_context(model._flow, _lib.ptr(base_ll), _lib.ptr(betas_ll), _lib.ptr(idx), _lib.ptr(anc_R),
+                                           B, _lib.ptr(out), _lib.stream()))
+        ctx_.model = model
+        ctx_.dtypes = (input_feats.dtype, cam.dtype, shape.dtype, pose_R.dtype, glob_R.dtype)
+        ctx_.save_for_backward(base_ll, betas_ll, out)
+        return out
+
+    @staticmethod
+    def backward(ctx_, g_ctx):
+        model = ctx_.model
+        base_ll, betas, out = ctx_.saved_tensors
+        B, J = out.shape[0], out.shape[1]
+        Fd = model.cfg.INPUT_SHAPE_GLOB_CAM_FEATS_DIM
+        Fin, nb = model.input_feats_dim, model.num_shape_params
+        with torch.no_grad():
+            one = torch.ones((), device=out.device)
+            g_pre = g_ctx.float() * torch.where(out > 0, one, out + 1)             # ELU'(pre) = 1 or exp(pre) = ELU(pre) + 1
+            g_F = torch.zeros(B, Fd, device=out.device)
+            g_pose = torch.zeros(B, J, 3, 3, device=out.device)
+            for j in range(J):
+                W = model.fc_flow_context[j].weight.detach().float()
+                ga = g_pre[:, j] @ W                                                # (B, Fd + 9 * ancestors)
+                g_F += ga[:, :Fd]
+                for q, a in enumerate(model.ancestors_dict[j]):
+                    g_pose[:, a] += ga[:, Fd + 9 * q:Fd + 9 * q + 9].view(B, 3, 3)
+            Wimg = model.fc_input_shape_glob_cam_feats.weight.detach().float()
+            Wf, Wb, Wg, Wc = Wimg[:, :Fin], Wimg[:, Fin:Fin + nb], Wimg[:, Fin + nb:Fin + nb + 9], Wimg[:, Fin + nb + 9:]
+            preF = base_ll + betas @ Wb.t()
+            g_preF = g_F * torch.where(preF > 0, one, torch.exp(preF))
+            dt = ctx_.dtypes
+            return (None, (g_preF @ Wf).to(dt[0]), (g_preF @ Wc).to(dt[1]), (g_preF @ Wb).to(dt[2]), g_pose.to(dt[3]),
+                    (g_preF @ Wg).view(B, 3, 3).to(dt[4]))
+
+
 class ConditionedSO3FlowDist:
     """One joint's flow conditioned on a batch of contexts: the object the reference returns in
     ``conditioned_pose_SO3flow_dists_for_loglik`` (group=True) / ``..._so3flow_...`` (group=False).
@@ -71,17 +160,20 @@ class ConditionedSO3FlowDist:
             raise RuntimeError('humaniflow_b200: the model was re-packed (weights changed or moved) after this conditioned '
                                'distribution was created; call forward(compute_for_loglik=True) again')
         R = self.ctx_all.shape[0]
+        if torch.is_grad_enabled() and (self.ctx_all.requires_grad or (torch.is_tensor(value) and value.requires_grad)):
+            # a gradient w.r.t. the contexts and / or the target is wanted (fitting loops): CUDA forward + CUDA backward
+            return _FlowLogProbFunction.apply(m, self.joint, 1, self.on_group, self.ctx_all, value.to(self.ctx_all.device))[:, 0]
         out = torch.empty(R, device=self.ctx_all.device, dtype=torch.float32)
         with torch.cuda.device(out.device):
             if self.on_group:
                 v = value.detach().to(self.ctx_all.device, torch.float64).contiguous()
                 assert v.shape == (R, 3, 3)
-                _lib.check(lib.hf_flow_log_prob(m._flow, _lib.ptr(self.ctx_all), self.ctx_all.shape[1] * self.ctx_all.shape[2],
+                _lib.check(lib.hf_flow_log_prob(m._flow, _lib.ptr(_lib.f32c(self.ctx_all)), self.ctx_all.shape[1] * self.ctx_all.shape[2],
                                                 self.joint, 1, _lib.ptr(v), R, _lib.ptr(out), _lib.stream()))
             else:
                 v = _lib.f32c(value, self.ctx_all.device)
                 assert v.shape == (R, 3)
-                _lib.check(lib.hf_flow_algebra_log_prob(m._flow, _lib.ptr(self.ctx_all), self.ctx_all.shape[1] * self.ctx_all.shape[2],
+                _lib.check(lib.hf_flow_algebra_log_prob(m._flow, _lib.ptr(_lib.f32c(self.ctx_all)), self.ctx_all.shape[1] * self.ctx_all.shape[2],
                                                         self.joint, 1, _lib.ptr(v), R, _lib.ptr(out), _lib.stream()))
         return out
 
@@ -252,12 +344,19 @@ class HumaniflowModel(nn.Module):
         return self._index_cache[key]
 
     # ------------------------------------------------------------------ forward
+    def forward(self, *args, **kwargs):
+        """See models/humaniflow_model.py:188-340 for the argument meaning.  The network itself runs without an autograd graph
+        (inference kernels); when autograd is recording, the teacher-forced contexts of ``compute_for_loglik=True`` stay
+        differentiable w.r.t. shape_for_loglik / pose_R_for_loglik / glob_R_for_loglik (and input_feats), and the returned
+        conditioned distributions' ``log_prob`` w.r.t. their contexts and targets: the pose-prior term of a fitting loop
+        (optimise/optimise_humaniflow.py:96-114) can be back-propagated to the pose, shape and global rotation."""
+        return self._forward(torch.is_grad_enabled(), *args, **kwargs)
+
     @torch.no_grad()
-    def forward(self, input, compute_point_est=True, num_samples=0, use_shape_mode_for_samples=False,
-                compute_for_loglik=False, shape_for_loglik=None, pose_R_for_loglik=None, glob_R_for_loglik=None,
-                input_feats=None, grad_for_pose_point_est=False, return_input_feats=False,
-                return_input_feats_only=False, *, base_noise=None, shape_eps=None):
-        """See models/humaniflow_model.py:188-340 for the argument meaning."""
+    def _forward(self, grad_on, input, compute_point_est=True, num_samples=0, use_shape_mode_for_samples=False,
+                 compute_for_loglik=False, shape_for_loglik=None, pose_R_for_loglik=None, glob_R_for_loglik=None,
+                 input_feats=None, grad_for_pose_point_est=False, return_input_feats=False,
+                 return_input_feats_only=False, *, base_noise=None, shape_eps=None):
         _lib.require_cuda('HumaniflowModel.forward')
         lib = _lib.load()
         if input_feats is None:
@@ -326,14 +425,12 @@ class HumaniflowModel(nn.Module):
                     out['shape_samples'] = shape_rows[:Rn].view(B, N, nb)
             # teacher-forced contexts for the log-likelihood (:277-283, :314-320)
             if compute_for_loglik:
-                base_ll = self._img_base(input_feats, glob_R_for_loglik, cam)
-                betas_ll = _lib.f32c(shape_for_loglik, dev)
-                anc_R = _lib.f32c(pose_R_for_loglik, dev)
-                assert anc_R.shape == (B, J, 3, 3)
-                ctx = torch.empty(B, J, nf.CONTEXT_DIM, device=dev, dtype=torch.float32)
-                idx = self._img_index(B, 1, False, dev)
-                _lib.check(lib.hf_flow_context(self._flow, _lib.ptr(base_ll), _lib.ptr(betas_ll), _lib.ptr(idx), _lib.ptr(anc_R),
-                                               B, _lib.ptr(ctx), st))
+                wants_grad = grad_on and any(torch.is_tensor(t) and t.requires_grad
+                                             for t in (shape_for_loglik, pose_R_for_loglik, glob_R_for_loglik, input_feats))
+                to_dev = lambda t: t.to(dev)
+                with torch.set_grad_enabled(wants_grad):
+                    ctx = _FlowContextFunction.apply(self, input_feats, cam, to_dev(shape_for_loglik), to_dev(pose_R_for_loglik),
+                                                     to_dev(glob_R_for_loglik))
                 out['conditioned_pose_so3flow_dists_for_loglik'] = [ConditionedSO3FlowDist(self, j, ctx, False) for j in range(J)]
                 out['conditioned_pose_SO3flow_dists_for_loglik'] = [ConditionedSO3FlowDist(self, j, ctx, True) for j in range(J)]
                 out['flow_contexts_for_loglik'] = ctx
@@ -346,6 +443,9 @@ class HumaniflowModel(nn.Module):
         (= stacking ``dist_j.log_prob(pose_R[:, j].double())`` as losses/humaniflow_loss.py:25-35 does)."""
         lib = _lib.load()
         B, J = ctx.shape[0], self.num_bodyparts
+        if torch.is_grad_enabled() and (ctx.requires_grad or pose_R.requires_grad):
+            return _FlowLogProbFunction.apply(self, 0, J, True, ctx, pose_R.to(ctx.device))
+        ctx = _lib.f32c(ctx)
         v = pose_R.detach().to(ctx.device, torch.float64).contiguous()
         out = torch.empty(B, J, device=ctx.device, dtype=torch.float32)
         with torch.cuda.device(ctx.device):

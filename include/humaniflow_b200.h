@@ -222,6 +222,17 @@ int hf_flow_log_prob(const hf_flow_t* h, const float* ctx, int ctx_row_stride, i
 int hf_flow_algebra_log_prob(const hf_flow_t* h, const float* ctx, int ctx_row_stride, int joint_first,
                              int joint_count, const float* v, int R, float* out, void* stream);
 
+/* Backward of the two log-densities w.r.t. their INPUTS, weights fixed (the reference: torch.autograd through
+ * local_diffeo_transformed_distribution.py:84-142 and pyro's conditional spline coupling, as used by
+ * optimise/optimise_humaniflow.py:96-114).  grad_out (R,joint_count) = d loss / d log_prob;
+ * grad_ctx (R,joint_count,context_dim) = d loss / d (context row of that joint);
+ * grad_rot (R,joint_count,3,3) fp64 = d loss / d target rotation (entries treated as free variables, like autograd does);
+ * grad_v (R,joint_count,3) = d loss / d algebra vector. */
+int hf_flow_log_prob_backward(const hf_flow_t* h, const float* ctx, int ctx_row_stride, int joint_first, int joint_count,
+                              const double* rot_f64, const float* grad_out, int R, float* grad_ctx, double* grad_rot, void* stream);
+int hf_flow_algebra_log_prob_backward(const hf_flow_t* h, const float* ctx, int ctx_row_stride, int joint_first, int joint_count,
+                                      const float* v, const float* grad_out, int R, float* grad_ctx, float* grad_v, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Heads (models/humaniflow_model.py:232-258, 116-150) and small dense layers.
  * ---------------------------------------------------------------------------------------------- */

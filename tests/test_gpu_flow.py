@@ -234,3 +234,115 @@ def test_linear_layers(M, K, O, act, acc):
         outs.append(y2.cpu())
     assert (outs[0].double() - ref).abs().max().item() <= 2e-5
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize('scale', [1.0, 1.5])
+def test_log_prob_backward_against_autograd_through_the_oracle(scale):
+    """d log_prob / d (context, target) of both densities (hf_flow_log_prob_backward,
+    hf_flow_algebra_log_prob_backward) against torch.autograd through the oracle, weights fixed: rotations incl. theta ~ 0 and
+    theta ~ pi/2, random contexts, random upstream weights.  Tolerance: 2e-3 of the largest gradient entry per tensor (fp32
+    chain of two spline couplings; autograd differentiates the same fp32 arithmetic in a different order)."""
+    from humaniflow_b200 import _lib
+    from oracle import flow as oflow
+    lib = _lib.load()
+    m, sd, cfg = make_model(18, seed=8, flow_scale=scale)
+    m = m.cuda()
+    m._ensure_packed(torch.device('cuda'))
+    nf = cfg.NORM_FLOW
+    J, T = 23, nf.NUM_TRANSFORMS
+    g = torch.Generator().manual_seed(3)
+    from oracle import so3
+    import numpy as np
+    rs = np.random.RandomState(11)
+    axes = rs.standard_normal((16, 3))
+    axes /= np.linalg.norm(axes, axis=1, keepdims=True)
+    # (theta = pi / 2 exactly puts the second pre-image ON the edge of the support, where the density diverges and the mask is a
+    #  rounding decision: not a point to compare gradients at)
+    ang = np.concatenate([rs.uniform(0.05, 3.0, 9), [1e-3, math.pi / 2 - 1e-3, math.pi / 2 + 1e-3, 1.9, 2.0, 2.5, 3.0]])
+    Rt = so3.so3_exp(torch.tensor(axes * ang[:, None], dtype=torch.float64))
+    Rn = Rt.shape[0]
+    perm = torch.stack([torch.randperm(Rn, generator=g) for _ in range(J)], 1)
+    pose = Rt[perm].double().contiguous()                                   # (Rn,J,3,3)
+    ctx = (torch.randn(Rn, J, 64, generator=g) * 0.5).float()
+    w = torch.randn(Rn, J, generator=g).float()
+    valg = (torch.randn(Rn, J, 3, generator=g) * 0.8).float()
+
+    ctx_r = ctx.clone().requires_grad_()
+    pose_r = pose.clone().requires_grad_()
+    valg_r = valg.clone().requires_grad_()
+    ctx_a = ctx.clone().requires_grad_()
+    tot = 0.
+    tot_a = 0.
+    for j in range(J):
+        cpl = om.joint_couplings(sd, j, T)
+        tot = tot + (w[:, j] * oflow.so3_log_prob(cpl, pose_r[:, j], ctx_r[:, j], nf.COMPACT_SUPPORT_RADIUS, nf.BASE_DIST_STD)).sum()
+        tot_a = tot_a + (w[:, j] * oflow.algebra_log_prob(cpl, valg_r[:, j], ctx_a[:, j], nf.COMPACT_SUPPORT_RADIUS, nf.BASE_DIST_STD)).sum()
+    tot.backward()
+    tot_a.backward()
+
+    cd, pd, wd, vd = ctx.cuda().contiguous(), pose.cuda().contiguous(), w.cuda().contiguous(), valg.cuda().contiguous()
+    g_ctx = torch.empty(Rn, J, 64, device='cuda')
+    g_rot = torch.empty(Rn, J, 3, 3, device='cuda', dtype=torch.float64)
+    _lib.check(lib.hf_flow_log_prob_backward(m._flow, _lib.ptr(cd), J * 64, 0, J, _lib.ptr(pd), _lib.ptr(wd), Rn, _lib.ptr(g_ctx), _lib.ptr(g_rot),
+                                             _lib.stream()))
+    g_ctx_a = torch.empty(Rn, J, 64, device='cuda')
+    g_v = torch.empty(Rn, J, 3, device='cuda')
+    _lib.check(lib.hf_flow_algebra_log_prob_backward(m._flow, _lib.ptr(cd), J * 64, 0, J, _lib.ptr(vd), _lib.ptr(wd), Rn, _lib.ptr(g_ctx_a),
+                                                     _lib.ptr(g_v), _lib.stream()))
+    torch.cuda.synchronize()
+    for name, got, ref in (('algebra ctx', g_ctx_a, ctx_a.grad), ('algebra v', g_v, valg_r.grad), ('SO3 ctx', g_ctx, ctx_r.grad),
+                           ('SO3 rot', g_rot, pose_r.grad)):
+        err = (got.double().cpu() - ref.double()).abs().max().item()
+        sc = ref.abs().max().item()
+        print('%-12s max err %.2e of %.2e' % (name, err, sc))
+        assert err <= 2e-3 * sc, (name, err, sc)
+
+
+def test_pose_prior_gradient_of_a_fitting_loop():
+    """The pose-prior term of optimise/optimise_humaniflow.py:96-114 end to end: axis-angle pose, shape and global rotation are
+    leaf tensors; contexts come from forward(compute_for_loglik=True), the loss is -sum_j log p_j(R_j | ctx_j).  Gradients through
+    hf_flow_log_prob_backward + the context backward against torch.autograd through the oracle; then a few descent steps raise
+    the log-likelihood."""
+    from oracle import so3
+    m, sd, cfg = make_model(18, seed=12)
+    m = m.cuda()
+    B = 6
+    g = torch.Generator().manual_seed(21)
+    feats = torch.randn(B, 512, generator=g).abs()
+    pose_aa = (torch.randn(B, 23, 3, generator=g) * 0.3)
+    glob_aa = (torch.randn(B, 3, generator=g) * 0.3)
+    shape = torch.randn(B, 10, generator=g)
+
+    def rodrigues(aa):                 # differentiable torch Rodrigues (the fitting script uses smplx's batch_rodrigues)
+        if aa.is_cuda:
+            from humaniflow_b200.smpl import _rodrigues_torch
+            return _rodrigues_torch(aa.reshape(-1, 3)).view(*aa.shape[:-1], 3, 3)
+        return so3.batch_rodrigues(aa.reshape(-1, 3)).view(*aa.shape[:-1], 3, 3)
+
+    pa, ga, sh = pose_aa.clone().requires_grad_(), glob_aa.clone().requires_grad_(), shape.clone().requires_grad_()
+    ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, compute_point_est=False, shape_for_loglik=sh,
+                     pose_R_for_loglik=rodrigues(pa), glob_R_for_loglik=rodrigues(ga))
+    (-ref['pose_loglik'].sum() / B).backward()
+
+    pc, gc, sc = pose_aa.clone().cuda().requires_grad_(), glob_aa.clone().cuda().requires_grad_(), shape.clone().cuda().requires_grad_()
+    fc = feats.cuda()
+    vals = []
+    for it in range(4):
+        pose_R = rodrigues(pc)
+        out = m(None, input_feats=fc, compute_point_est=False, compute_for_loglik=True, shape_for_loglik=sc, pose_R_for_loglik=pose_R,
+                glob_R_for_loglik=rodrigues(gc))
+        dists = out['conditioned_pose_SO3flow_dists_for_loglik']
+        lp = sum(dists[j].log_prob(pose_R[:, j].double()).sum() for j in range(23))
+        loss = -lp / B
+        pc.grad = gc.grad = sc.grad = None
+        loss.backward()
+        if it == 0:
+            assert abs(loss.item() - (-ref['pose_loglik'].sum().item() / B)) <= 1e-3 * abs(loss.item())
+            for name, got, want in (('pose', pc.grad, pa.grad), ('glob', gc.grad, ga.grad), ('shape', sc.grad, sh.grad)):
+                err = (got.cpu() - want).abs().max().item()
+                print('%-6s max err %.2e of %.2e' % (name, err, want.abs().max().item()))
+                assert err <= 3e-3 * want.abs().max().item(), (name, err)
+        vals.append(loss.item())
+        with torch.no_grad():
+            pc -= 0.01 * pc.grad
+    assert vals[-1] < vals[0], vals
