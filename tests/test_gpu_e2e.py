@@ -155,3 +155,72 @@ def test_image_shards_reproduce_the_unsharded_rows_exactly(layers, size, B, worl
         assert torch.equal(torch.cat([p[k] for p in parts], 0), full[k]), k
     assert torch.isfinite(v_full).all() and torch.isfinite(j_full).all()
     assert torch.equal(torch.cat(vparts, 0), v_full) and torch.equal(torch.cat(jparts, 0), j_full)
+
+
+def test_optimise_pattern_end_to_end():
+    """SURVEY 8f N3, the fitting loop of optimise/optimise_humaniflow.py:71-135 on the CUDA path: axis-angle pose, global rotation,
+    shape and camera are leaf tensors; loss = w1 * 2-D joint error through SMPL (hf_lbs_forward / hf_lbs_backward) and the
+    orthographic projection - w2 * pose prior (contexts + hf_flow_log_prob, CUDA backward) - w3 * shape prior.  The gradients of the
+    first iteration match torch.autograd through the oracle (LBS + flow); a few descent steps lower the loss."""
+    import humaniflow_b200 as hb
+    from humaniflow_b200.smpl import _rodrigues_torch
+    from oracle import so3, smpl as osmpl
+    from util import smpl_data
+    m, sd, cfg = make_model(18, seed=31)
+    m = m.cuda()
+    data = smpl_data()
+    smpl = hb.SMPL.from_arrays(data, create_transl=False).cuda()
+    B = 4
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn(B, 512, generator=g).abs()
+    pose0 = torch.randn(B, 69, generator=g) * 0.25
+    glob0 = torch.randn(B, 3, generator=g) * 0.2
+    shape0 = torch.randn(B, 10, generator=g) * 0.5
+    cam0 = torch.tensor([[0.9, 0.0, 0.0]]).repeat(B, 1)
+    target = torch.rand(B, 17, 2, generator=g) * 256
+    joint_map = list(range(17, 34))            # any fixed 17 of the 90 output joints (picked + regressed ones)
+    W1, W2, W3, IMG = 1e-4, 0.05, 0.1, 256.0
+
+    def project(j3d, cam):                     # x-flip about pi + orthographic projection + undo normalisation (:80-88)
+        j = torch.stack([j3d[..., 0], -j3d[..., 1]], -1)
+        return (cam[:, None, :1] * (j + cam[:, None, 1:]) + 1.0) * 0.5 * IMG
+
+    # ---- oracle
+    po, go, so_, co = (t.clone().requires_grad_() for t in (pose0, glob0, shape0, cam0))
+    _, j_ref = osmpl.smpl_forward(data, so_, po, go, pose2rot=True)
+    j2d = ((project(j_ref[:, joint_map], co) - target) ** 2).mean()
+    pose_R = so3.batch_rodrigues(po.reshape(-1, 3)).view(B, 23, 3, 3)
+    ref = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats, compute_point_est=False, shape_for_loglik=so_, pose_R_for_loglik=pose_R,
+                     glob_R_for_loglik=so3.batch_rodrigues(go))
+    heads = om.forward(sd, cfg, SMPL_PARENTS, input_feats=feats)
+    shape_lp = torch.distributions.Normal(heads['shape_mode'], torch.exp(heads['shape_log_std'])).log_prob(so_).sum() / B
+    loss_ref = W1 * j2d - W2 * ref['pose_loglik'].sum() / B - W3 * shape_lp
+    loss_ref.backward()
+
+    # ---- CUDA
+    pc, gc, sc, cc = (t.clone().cuda().requires_grad_() for t in (pose0, glob0, shape0, cam0))
+    fc, tc = feats.cuda(), target.cuda()
+    losses = []
+    for it in range(5):
+        out_s = smpl(body_pose=pc, global_orient=gc, betas=sc, pose2rot=True)
+        j2d = ((project(out_s.joints[:, joint_map], cc) - tc) ** 2).mean()
+        pose_R = _rodrigues_torch(pc.reshape(-1, 3)).view(B, 23, 3, 3)
+        out = m(None, input_feats=fc, compute_point_est=False, num_samples=0, compute_for_loglik=True, shape_for_loglik=sc,
+                pose_R_for_loglik=pose_R, glob_R_for_loglik=_rodrigues_torch(gc))
+        dists = out['conditioned_pose_SO3flow_dists_for_loglik']
+        pose_lp = sum(dists[j].log_prob(pose_R[:, j].double()).sum() for j in range(23)) / B
+        shape_lp = out['shape_dist_for_loglik'].log_prob(sc).sum() / B
+        loss = W1 * j2d - W2 * pose_lp - W3 * shape_lp
+        for t in (pc, gc, sc, cc):
+            t.grad = None
+        loss.backward()
+        if it == 0:
+            assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item())
+            for name, got, want in (('pose', pc.grad, po.grad), ('glob', gc.grad, go.grad), ('shape', sc.grad, so_.grad), ('cam', cc.grad, co.grad)):
+                err = (got.cpu() - want).abs().max().item()
+                assert err <= 5e-3 * want.abs().max().item(), (name, err, want.abs().max().item())
+        losses.append(loss.item())
+        with torch.no_grad():
+            for t, lr in ((pc, 0.02), (gc, 0.02), (sc, 0.02), (cc, 1e-3)):
+                t -= lr * t.grad / (t.grad.abs().max() + 1e-12)
+    assert losses[-1] < losses[0], losses
