@@ -346,3 +346,32 @@ def test_pose_prior_gradient_of_a_fitting_loop():
         with torch.no_grad():
             pc -= 0.01 * pc.grad
     assert vals[-1] < vals[0], vals
+
+
+def test_log_prob_backward_at_the_log_map_edge_cases():
+    """The same gradients where the log map switches formulas: theta within 1e-2 of pi (the reference's sqrt-of-diagonal branch),
+    theta -> 0 (series branch).  Per-row tolerance 1e-3 of that row's largest entry (near pi the rotation gradient is ~1e4-1e5)."""
+    from humaniflow_b200 import _lib
+    from oracle import flow as oflow, so3
+    lib = _lib.load()
+    m, sd, cfg = make_model(18, seed=8)
+    m = m.cuda()
+    m._ensure_packed(torch.device('cuda'))
+    nf = cfg.NORM_FLOW
+    ang = torch.tensor([3.1, math.pi - 9e-3, math.pi - 5e-3, math.pi - 1e-3, math.pi - 1e-4, 1e-4, 1e-6, 1e-3], dtype=torch.float64)
+    axes = torch.nn.functional.normalize(torch.randn(8, 3, generator=torch.Generator().manual_seed(1)), dim=1).double()
+    Rt = so3.so3_exp(axes * ang[:, None])
+    Rn, J, j = 8, 23, 5
+    pose = Rt[:, None].expand(Rn, J, 3, 3).contiguous()
+    ctx = torch.randn(Rn, J, 64, generator=torch.Generator().manual_seed(3)) * 0.5
+    ctx_r, pose_r = ctx.clone().requires_grad_(), pose.clone().requires_grad_()
+    oflow.so3_log_prob(om.joint_couplings(sd, j, 2), pose_r[:, j], ctx_r[:, j], nf.COMPACT_SUPPORT_RADIUS, nf.BASE_DIST_STD).sum().backward()
+    cd, pd, wd = ctx.cuda(), pose.cuda(), torch.ones(Rn, J, device='cuda')
+    g_ctx = torch.zeros(Rn, J, 64, device='cuda')
+    g_rot = torch.zeros(Rn, J, 3, 3, device='cuda', dtype=torch.float64)
+    _lib.check(lib.hf_flow_log_prob_backward(m._flow, _lib.ptr(cd), J * 64, 0, J, _lib.ptr(pd), _lib.ptr(wd), Rn, _lib.ptr(g_ctx), _lib.ptr(g_rot),
+                                             _lib.stream()))
+    torch.cuda.synchronize()
+    for r in range(Rn):
+        for got, ref in ((g_ctx[r, j].cpu(), ctx_r.grad[r, j]), (g_rot[r, j].cpu(), pose_r.grad[r, j])):
+            assert (got.double() - ref.double()).abs().max().item() <= 1e-3 * ref.abs().max().item(), (r, ang[r].item())
