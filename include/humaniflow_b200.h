@@ -82,7 +82,10 @@ int hf_lbs_forward_split(const hf_smpl_t* h, const float* betas, const float* bo
  * [upstream] smplx lbs.lbs, e.g. in a fitting loop that optimises pose / shape against 2-D joints):
  *   grad_vertices (M,V,3) or NULL, grad_joints (M,J_out,3) or NULL  ->  grad_betas (M,num_betas), grad_rotmats (M,J,3,3).
  * A translation only shifts the outputs: d loss / d transl = sum over vertices and joints of the incoming gradients (caller).
- * fp32; the per-joint sums over the vertices use shared-memory atomics (run-to-run differences at the rounding level). */
+ * fp32; the per-joint sums over the vertices use shared-memory atomics (run-to-run differences at the rounding level).
+ * The first call on a handle builds the split-tf32 copies of the blend basis (cudaMalloc + one kernel: not capturable in a CUDA
+ * graph; later calls only launch kernels).  A joints-only call (grad_vertices == NULL) touches only the ~4 % of the vertices that a
+ * joint pick / regressor row reads. */
 size_t hf_lbs_backward_workspace_bytes(const hf_smpl_t* h, int M);
 int hf_lbs_backward(hf_smpl_t* h, const float* betas, const float* rotmats, const float* grad_vertices, const float* grad_joints,
                     float* grad_betas, float* grad_rotmats, void* workspace, size_t workspace_bytes, int M, void* stream);
