@@ -69,7 +69,7 @@ SIGNATURES = {
     'hf_linear': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'hf_linear_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'hf_linear_ws': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    'hf_heads_finish': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int] + [c_void_p] * 4),
+    'hf_heads_finish': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int] + [c_void_p] * 6),
     'hf_rot6d_to_rotmat': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'hf_encoder_create': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(EncOp), c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
     'hf_encoder_destroy': (None, [c_void_p]),

@@ -2,6 +2,7 @@
 // utils/rigid_transform_utils.py:86-100).  M is the image batch (tens of rows): these are latency-bound
 // GEMVs, written for coalesced weight streaming rather than tensor cores.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -139,12 +140,8 @@ linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restric
     *dst = act_fn(a, act);
 }
 
-__global__ void rot6d_kernel(const float* __restrict__ x6, float* __restrict__ R, int n) {
-    HF_PDL_SYNC();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    // x.view(-1,3,2): a1 = (x0,x2,x4), a2 = (x1,x3,x5); F.normalize eps 1e-12; columns b1,b2,b3
-    const float* x = x6 + (size_t)i * 6;
+// x.view(-1,3,2): a1 = (x0,x2,x4), a2 = (x1,x3,x5); F.normalize eps 1e-12; columns b1,b2,b3
+__device__ __forceinline__ void rot6d_one(const float* x, float* o) {
     float a1[3] = {x[0], x[2], x[4]}, a2[3] = {x[1], x[3], x[5]};
     float n1 = fmaxf(sqrtf(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), 1e-12f);
     float b1[3] = {a1[0] / n1, a1[1] / n1, a1[2] / n1};
@@ -153,8 +150,14 @@ __global__ void rot6d_kernel(const float* __restrict__ x6, float* __restrict__ R
     float n2 = fmaxf(sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), 1e-12f);
     float b2[3] = {u[0] / n2, u[1] / n2, u[2] / n2};
     float b3[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2], b1[0] * b2[1] - b1[1] * b2[0]};
-    float* o = R + (size_t)i * 9;
     for (int r = 0; r < 3; ++r) { o[r * 3 + 0] = b1[r]; o[r * 3 + 1] = b2[r]; o[r * 3 + 2] = b3[r]; }
+}
+
+__global__ void rot6d_kernel(const float* __restrict__ x6, float* __restrict__ R, int n) {
+    HF_PDL_SYNC();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rot6d_one(x6 + (size_t)i * 6, R + (size_t)i * 9);
 }
 
 // heads (B, 2*nb + 6 + 3) = [shape_mode | shape_log_std | glob6 | cam]  ->  cam + init, rot6d(glob6 + init),
@@ -163,7 +166,7 @@ __global__ void rot6d_kernel(const float* __restrict__ x6, float* __restrict__ R
 __global__ void heads_finish_kernel(const float* __restrict__ heads, const float* __restrict__ init_glob,
                                     const float* __restrict__ init_cam, const float* __restrict__ shape_eps,
                                     int B, int N, int nb, float* __restrict__ cam, float* __restrict__ glob6,
-                                    float* __restrict__ shape_rows) {
+                                    float* __restrict__ shape_rows, float* __restrict__ glob_R, float* __restrict__ shape_std) {
     HF_PDL_SYNC();
     const int ld = 2 * nb + 9;
     const int total = B * N * nb + B * nb;
@@ -185,21 +188,27 @@ __global__ void heads_finish_kernel(const float* __restrict__ heads, const float
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < B * 6) { const int b = t / 6, c = t - b * 6; glob6[t] = heads[b * ld + 2 * nb + c] + init_glob[c]; }
     if (t < B * 3) { const int b = t / 3, c = t - b * 3; cam[t] = heads[b * ld + 2 * nb + 6 + c] + init_cam[c]; }
+    if (glob_R && t < B) {            // rot6d -> matrix of the global rotation (from the heads directly: glob6 is written by other threads)
+        float x6[6];
+        for (int c = 0; c < 6; ++c) x6[c] = heads[t * ld + 2 * nb + c] + init_glob[c];
+        rot6d_one(x6, glob_R + (size_t)t * 9);
+    }
+    if (shape_std && t < B * nb) { const int b = t / nb, l = t - b * nb; shape_std[t] = expf(heads[b * ld + nb + l]); }
 }
 
 }  // namespace
 
 extern "C" int hf_heads_finish(const float* heads, const float* init_glob, const float* init_cam,
                                const float* shape_eps, int B, int N, int nb, float* cam, float* glob6,
-                               float* shape_rows, void* stream) {
+                               float* shape_rows, float* glob_R, float* shape_std, void* stream) {
     if (!heads || !init_glob || !init_cam || !cam || !glob6 || !shape_rows) return hf::fail(HF_ERR_INVALID, "hf_heads_finish: null argument");
     if (B <= 0) return HF_OK;
     const int total = B * N * nb + B * nb;
-    int blocks = hf::div_up(total > B * 6 ? total : B * 6, 256);
+    int blocks = hf::div_up(std::max(total, B * std::max(6, nb)), 256);
     if (blocks > 1024) blocks = 1024;
-    if (blocks * 256 < B * 6) return hf::fail(HF_ERR_UNSUPPORTED, "hf_heads_finish: batch too large");
+    if (blocks * 256 < B * 6 || blocks * 256 < B * nb) return hf::fail(HF_ERR_UNSUPPORTED, "hf_heads_finish: batch too large");
     HF_CUDA(hf::launch_pdl(heads_finish_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, heads, init_glob, init_cam, shape_eps, B, N,
-                           nb, cam, glob6, shape_rows));
+                           nb, cam, glob6, shape_rows, glob_R, shape_std));
     HF_LAUNCH_CHECK();
     return HF_OK;
 }

@@ -390,12 +390,13 @@ class HumaniflowModel(nn.Module):
             if N > 0 and not use_shape_mode_for_samples:
                 eps = torch.randn(B, N, nb, device=dev) if shape_eps is None else _lib.f32c(shape_eps, dev)
                 assert eps.shape == (B, N, nb)
-            _lib.check(lib.hf_heads_finish(_lib.ptr(heads), _lib.ptr(P['init_glob']), _lib.ptr(P['init_cam']), _lib.ptr(eps),
-                                           B, N, nb, _lib.ptr(cam), _lib.ptr(glob6), _lib.ptr(shape_rows), st))
             glob_R = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
-            _lib.check(lib.hf_rot6d_to_rotmat(_lib.ptr(glob6), _lib.ptr(glob_R), B, st))
+            shape_std = torch.empty(B, nb, device=dev, dtype=torch.float32)
+            _lib.check(lib.hf_heads_finish(_lib.ptr(heads), _lib.ptr(P['init_glob']), _lib.ptr(P['init_cam']), _lib.ptr(eps),
+                                           B, N, nb, _lib.ptr(cam), _lib.ptr(glob6), _lib.ptr(shape_rows), _lib.ptr(glob_R),
+                                           _lib.ptr(shape_std), st))
             shape_mode, shape_log_std = heads[:, :nb], heads[:, nb:2 * nb]
-            shape_dist = Normal(loc=shape_mode, scale=torch.exp(shape_log_std), validate_args=False)
+            shape_dist = Normal(loc=shape_mode, scale=shape_std, validate_args=False)
             out = {'cam_wp': cam, 'glob_rotmat': glob_R, 'shape_mode': shape_mode, 'shape_log_std': shape_log_std,
                    'shape_dist_for_loglik': shape_dist}
             # pose: one launch walks all 23 joints for the N samples and the point estimate (:263-311)

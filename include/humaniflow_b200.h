@@ -253,9 +253,12 @@ int hf_linear_ws(const float* x, int ldx, const float* W, int ldw, const float* 
 /* Head post-processing (models/humaniflow_model.py:237-258).  heads (B, 2*nb+9) = one Linear over the
  * concatenated [fc_shape | fc_glob | fc_cam] rows.  cam (B,3) = cam head + init_cam; glob6 (B,6) = glob head +
  * init_glob; shape_rows (B*N + B, nb): rows [0,B*N) = shape_mode + exp(shape_log_std) * shape_eps (shape_eps
- * (B,N,nb) ~ N(0,1); NULL = use the mode, `use_shape_mode_for_samples`), rows [B*N, B*N+B) = shape_mode. */
+ * (B,N,nb) ~ N(0,1); NULL = use the mode, `use_shape_mode_for_samples`), rows [B*N, B*N+B) = shape_mode.
+ * Optional (NULL to skip): glob_R (B,3,3) = rot6d_to_rotmat(glob6) (utils/rigid_transform_utils.py:86-100) and shape_std (B,nb) =
+ * exp(shape_log_std) (the scale of `shape_dist_for_loglik`), so that the step needs no separate launches for them. */
 int hf_heads_finish(const float* heads, const float* init_glob, const float* init_cam, const float* shape_eps,
-                    int B, int N, int nb, float* cam, float* glob6, float* shape_rows, void* stream);
+                    int B, int N, int nb, float* cam, float* glob6, float* shape_rows, float* glob_R, float* shape_std,
+                    void* stream);
 
 /* glob6 (B,6) -> rotation matrices (B,3,3): utils/rigid_transform_utils.py:86-100. */
 int hf_rot6d_to_rotmat(const float* rot6d, float* rotmats, int n, void* stream);
