@@ -1037,8 +1037,17 @@ flow_sample_levels_kernel(const __grid_constant__ FlowParams P, const __grid_con
             // the ancestors' rotations must be in Ps: they were produced earlier by this or another group (the deepest ancestor
             // finishing implies the others); one thread polls, the group barrier in first_block() publishes it
             if (lt == 0 && Ka > 0) {
-                for (int q = 0; q < P.anc_cnt[j]; ++q)
-                    while (!jdone[(int)P.anc[j][q]]) {}
+                for (int q = 0; q < P.anc_cnt[j]; ++q) {
+                    // bounded like every wait of this library: a schedule bug must surface as a trapped launch, never as a hung GPU
+                    unsigned long long t0 = 0, t1;
+                    for (unsigned spin = 0; !jdone[(int)P.anc[j][q]]; ++spin) {
+                        if ((spin & 0xffffu) == 0xffffu) {
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                            if (t0 == 0) t0 = t1;
+                            if (t1 - t0 > 2000000000ull) __trap();     // 2 s
+                        }
+                    }
+                }
                 __threadfence_block();
             }
             if (lt < NR) {       // base sample (zero for point-estimate rows); the first permutation is the identity
