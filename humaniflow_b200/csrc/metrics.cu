@@ -262,10 +262,16 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
 //   pse_pass_kernel<2>  the two aligned errors; walks the sets in REVERSE so that it starts on the ones pass 1 left in L2
 struct Pts4 { float x[12]; };
 __device__ __forceinline__ Pts4 load4(const float* q) {      // 4 points = 48 contiguous bytes, 8-byte aligned
-    const float2* g = reinterpret_cast<const float2*>(q);
     Pts4 r;
+    if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {         // (uniform per block: a set's base is either 16- or only 8-byte aligned)
+        const float4* g = reinterpret_cast<const float4*>(q);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { const float2 u = __ldg(g + i); r.x[2 * i] = u.x; r.x[2 * i + 1] = u.y; }
+        for (int i = 0; i < 3; ++i) { const float4 u = __ldg(g + i); r.x[4 * i] = u.x; r.x[4 * i + 1] = u.y; r.x[4 * i + 2] = u.z; r.x[4 * i + 3] = u.w; }
+    } else {
+        const float2* g = reinterpret_cast<const float2*>(q);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const float2 u = __ldg(g + i); r.x[2 * i] = u.x; r.x[2 * i + 1] = u.y; }
+    }
     return r;
 }
 
