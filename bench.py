@@ -14,6 +14,7 @@ there is no data-path collective; one all_gather collects the per-image metric r
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -259,12 +260,15 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    gc.collect()
+    gc.disable()                      # a collector pause of the issuing thread inside a 30 ms timed region starves the GPU queue
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(args.steps):
         step_and_gather()
     e1.record()
     sync_all()
+    gc.enable()
     ms_step = maxms(e0.elapsed_time(e1)) / args.steps
     value = world * B * N / (ms_step * 1e-3)
     # the same step issued eagerly (one driver call per kernel), for the record
@@ -409,11 +413,14 @@ def run_ours(args):
         for n in steps_list:
             run(3)
             sync_all()
+            gc.collect()
+            gc.disable()
             a, b2 = ev(), ev()
             a.record()
             run(n)
             b2.record()
             sync_all()
+            gc.enable()
             res.append(maxms(a.elapsed_time(b2)) / n)
         return res[0]
 

@@ -259,7 +259,8 @@ pointset_errors_kernel(const float* __restrict__ pred, const float* __restrict__
 // memory-bound kernels (four blocks per SM, nothing staged) around a solve kernel with one THREAD per set:
 //   pse_pass_kernel<1>  moments about the first point of each set -> mom[m][18] (fp64)
 //   pse_solve_kernel    SC / PA transforms -> xfg[m][20] = [s, mu1 (3), mu2 (3), scale*R (9), t (3), plain error]
-//   pse_pass_kernel<2>  the two aligned errors; walks the sets in REVERSE so that it starts on the ones pass 1 left in L2
+//   pse_pass_kernel<2>  the two aligned errors; pass 1 walks the sets downwards, pass 2 upwards, so that each starts on what its
+//                       predecessor left in L2
 struct Pts4 { float x[12]; };
 __device__ __forceinline__ Pts4 load4(const float* q) {      // 4 points = 48 contiguous bytes, 8-byte aligned
     Pts4 r;
@@ -343,7 +344,9 @@ pse_pass_kernel(const float* __restrict__ pred, const float* __restrict__ target
                 const float* __restrict__ xfg, float* __restrict__ out) {
     HF_PDL_SYNC();
     __shared__ double scratch[(ME_THREADS / 32 + 1) * 18];
-    const int m = PASS == 1 ? blockIdx.x : gridDim.x - 1 - blockIdx.x, b = m / N;
+    // pass 1 walks the sets from the LAST one down (the producer -- the skinning kernel -- wrote them in ascending order, so the tail is
+    // what L2 still holds), pass 2 from the first one up (what pass 1 read last)
+    const int m = PASS == 1 ? gridDim.x - 1 - blockIdx.x : blockIdx.x, b = m / N;
     const float* p = pred + (size_t)m * P * 3;
     const float* t = target + (size_t)b * P * 3;
     const int ng = P >> 2;
